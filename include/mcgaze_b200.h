@@ -1,0 +1,106 @@
+/*
+ * mcgaze_b200 — C ABI of the B200-native MCGaze per-clip forward.
+ *
+ * The reference (zgchen33/MCGaze) has no FFI today: the hot path is pure Python on top of
+ * torch/cuDNN/mmcv.  This header is the boundary a maintainer would bind from the reference's
+ * `MultiClueGaze.simple_test` (mmdet/models/detectors/multiclue_gaze.py:105-131); each entry
+ * point cites the reference interface it replaces.  See INTEGRATION.md for the ctypes stub.
+ *
+ * Conventions: plain C, no torch types.  Every function returns 0 on success or a negative
+ * error code; the message is available from mcg_last_error() (thread-local).  Nothing throws
+ * across the ABI.  One handle per (device, stream); a handle is not re-entrant.
+ */
+#ifndef MCGAZE_B200_H_
+#define MCGAZE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcg_engine* mcg_handle;
+
+/* One named fp32 tensor of a reference checkpoint `state_dict` (HOST memory, contiguous).
+ * Key layout: SURVEY.md section 8b, i.e. exactly what mmcv.runner.load_checkpoint feeds
+ * `MultiClueGaze` (mmdet/apis/inference.py:45). Unknown keys are ignored (non-strict). */
+typedef struct {
+  const char* name;
+  const float* data;
+  int ndim;
+  int64_t shape[4];
+} mcg_tensor;
+
+enum {
+  MCG_PRECISION_FP16X3 = 0, /* tcgen05, split-fp16 operands (hi+lo), 3 MMAs/k-step: fp32-equivalent; parity mode */
+  MCG_PRECISION_FP16 = 1,   /* tcgen05, single fp16 operands, fp32 accumulate: fast mode */
+  MCG_PRECISION_SIMT = 2    /* fp32 CUDA-core kernels only (cross-check / bring-up) */
+};
+
+enum {
+  MCG_OK = 0,
+  MCG_ERR_INVALID = -1,
+  MCG_ERR_CUDA = -2,
+  MCG_ERR_MISSING_WEIGHT = -3,
+  MCG_ERR_UNSUPPORTED = -4
+};
+
+/* Replaces build_detector(cfg.model) + load_checkpoint (mmdet/apis/inference.py:17-56):
+ * folds BN into the convolutions, repacks weights to K-major split-fp16 and uploads them. */
+int mcg_create(mcg_handle* out, int device, const mcg_tensor* weights, int n_weights, int precision);
+int mcg_destroy(mcg_handle h);
+
+/* Replaces MultiClueGaze.forward(return_loss=False) -> simple_test
+ * (mmdet/models/detectors/multiclue_gaze.py:105-131 -> roi_heads/multiclue_gaze_roi_head.py:287-384)
+ * for B clips of T frames each (the reference's test path is B == 1; B > 1 uses clip_length = T
+ * exactly like forward_train, multiclue_gaze_roi_head.py:229).
+ *   img          DEVICE fp32 [B*T, 3, H, W]   (NCHW, the reference layout; H, W multiples of 32)
+ *   img_hw       HOST   fp32 [B*T, 2]         unpadded (h, w) = meta['img_shape'] ; NULL -> (H, W)
+ *   scale_factor HOST   fp32 [B*T, 4]         meta['scale_factor'] (rescale=True) ; NULL -> no rescale
+ *   out_gaze     DEVICE fp32 [B*T, 4, 3]      unit vectors: fused, face, eyes, head
+ *   out_boxes    DEVICE fp32 [B*T, 3, 4]      xyxy (face, eyes, head)
+ *   out_scores   DEVICE fp32 [B*T, 3]         sigmoid scores
+ * Asynchronous on `stream` (a cudaStream_t). */
+int mcg_forward(mcg_handle h, const float* img, int B, int T, int H, int W, const float* img_hw,
+                const float* scale_factor, float* out_gaze, float* out_boxes, float* out_scores, void* stream);
+
+/* Same, with HOST input/output buffers: copies img host->device, runs, copies results back and
+ * synchronises.  This is the call tools/test_gaze360_gaze.py:107 maps to (scatter + forward +
+ * .cpu()).  Pinned host memory gives asynchronous copies. */
+int mcg_forward_host(mcg_handle h, const float* img_host, int B, int T, int H, int W, const float* img_hw,
+                     const float* scale_factor, float* out_gaze_host, float* out_boxes_host,
+                     float* out_scores_host);
+
+/* Per-op parity support: copy a named intermediate of the LAST forward as dense fp32 into `dst`
+ * (DEVICE).  Activations are returned NCHW like the reference's tensors.  Names: "stem", "pool",
+ * "layer{1-4}.{i}", "fpn{0-3}", "stage{0-3}.roi_feat" ([R,49,256]), "stage{s}.attn",
+ * "stage{s}.obj", "stage{s}.boxes", "stage{s}.delta", "stage{s}.cls".  shape_out receives up to
+ * 4 dims (unused = 0).  Returns MCG_ERR_INVALID for unknown names or too small capacity. */
+int mcg_get_intermediate(mcg_handle h, const char* name, float* dst, int64_t capacity, int64_t shape_out[4]);
+
+/* Number of kernels this library launched in the last forward. */
+int mcg_last_launch_count(mcg_handle h);
+
+/* Capture the forward for the current shape in a CUDA graph and replay it on later calls
+ * (on = 1) or launch kernels eagerly (on = 0, default). */
+int mcg_set_graph_mode(mcg_handle h, int on);
+
+/* Options: "keep_intermediates" (1: snapshot per-stage head buffers for mcg_get_intermediate),
+ * "head_tensor_cores" (0: run the head's large Linear layers on the fp32 CUDA-core kernel). */
+int mcg_set_option(mcg_handle h, const char* key, int value);
+
+/* Stand-alone convolution / GEMM with the fused epilogue, for kernel-level parity tests.
+ *   engine: MCG_PRECISION_*    x: DEVICE fp32 NHWC [NB,H,W,C]    w: DEVICE fp32 [Cout, R*S*C] (r,s,c order)
+ *   res: DEVICE fp32 NHWC residual or NULL; res_mode 0 none / 1 same size / 2 nearest 2x upsample
+ *   out: DEVICE fp32 NHWC [NB,P,Q,Cout].  force_im2col != 0 routes 1x1/s1 through the im2col TMA path. */
+int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, const float* w, int Cout, int R, int S,
+                   int stride, int pad, const float* bias, const float* res, int res_mode, int relu,
+                   int force_im2col, int force_block_n, float* out, void* stream);
+
+const char* mcg_last_error(void);
+const char* mcg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCGAZE_B200_H_ */

@@ -1,0 +1,464 @@
+// Non-GEMM kernels of the MCGaze forward: stem im2col, max-pool, RoIAlign, LayerNorm,
+// the 3-token / T-token self-attention core, DynamicConv interaction, box decode,
+// initial proposals and the final gaze fusion.  All HBM-bound or latency-bound; layouts are
+// NHWC / row-major so that every warp access is contiguous along channels.
+#pragma once
+#include "common.cuh"
+
+namespace mcg {
+
+// ---------------------------------------------------------------------------------------
+// stem: explicit im2col of the fp32 NCHW input for the 7x7/2 pad-3 convolution
+// (mmdet/models/backbones/resnet.py:599-611, :636).  A[m, k], k = (r*7+s)*3 + c for k < 147,
+// zero for 147 <= k < 192, written as split-fp16 planes so the stem runs on the GEMM kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int kStemK = 192;
+
+__global__ void stem_im2col_kernel(const float* __restrict__ img, int NB, int H, int W, int P, int Q,
+                                   __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
+  const long long total = static_cast<long long>(NB) * P * Q * (kStemK / 8);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k8 = static_cast<int>(i % (kStemK / 8));
+    const long long m = i / (kStemK / 8);
+    const int q = static_cast<int>(m % Q);
+    const long long t = m / Q;
+    const int p = static_cast<int>(t % P);
+    const int n = static_cast<int>(t / P);
+    __align__(16) __half hh[8];
+    __align__(16) __half hl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k8 * 8 + j;
+      float v = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int r = tap / 7, s = tap - r * 7;
+        const int h = p * 2 - 3 + r, w = q * 2 - 3 + s;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = img[((static_cast<long long>(n) * 3 + c) * H + h) * W + w];
+      }
+      const __half h = __float2half_rn(v);
+      hh[j] = h;
+      hl[j] = __float2half_rn(v - __half2float(h));
+    }
+    *reinterpret_cast<uint4*>(a_hi + m * kStemK + k8 * 8) = *reinterpret_cast<const uint4*>(hh);
+    if (a_lo) *reinterpret_cast<uint4*>(a_lo + m * kStemK + k8 * 8) = *reinterpret_cast<const uint4*>(hl);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// max-pool 3x3 stride 2 pad 1 over NHWC split-fp16 planes (resnet.py:611,639)
+// ---------------------------------------------------------------------------------------
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int NB,
+                                    int H, int W, int C, int P, int Q, __half* __restrict__ out_hi,
+                                    __half* __restrict__ out_lo) {
+  const int c8n = C / 8;
+  const long long total = static_cast<long long>(NB) * P * Q * c8n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % c8n);
+    long long t = i / c8n;
+    const int q = static_cast<int>(t % Q);
+    t /= Q;
+    const int p = static_cast<int>(t % P);
+    const int n = static_cast<int>(t / P);
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int h = p * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = q * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        const long long idx = ((static_cast<long long>(n) * H + h) * W + w) * C + c8 * 8;
+        const uint4 uh = *reinterpret_cast<const uint4*>(in_hi + idx);
+        const __half* ph = reinterpret_cast<const __half*>(&uh);
+        uint4 ul = make_uint4(0, 0, 0, 0);
+        if (in_lo) ul = *reinterpret_cast<const uint4*>(in_lo + idx);
+        const __half* pl = reinterpret_cast<const __half*>(&ul);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], __half2float(ph[j]) + __half2float(pl[j]));
+      }
+    }
+    __align__(16) __half hh[8];
+    __align__(16) __half hl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half h = __float2half_rn(best[j]);
+      hh[j] = h;
+      hl[j] = __float2half_rn(best[j] - __half2float(h));
+    }
+    const long long o = ((static_cast<long long>(n) * P + p) * Q + q) * C + c8 * 8;
+    *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(hl);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// initial proposals (mmdet/models/dense_heads/fixed_embedding_rpn_head.py:55-94)
+// ---------------------------------------------------------------------------------------
+__global__ void init_proposals_kernel(const float* __restrict__ init_boxes /*[3,4] cxcywh*/,
+                                      const float* __restrict__ init_feats /*[3,256]*/,
+                                      const float* __restrict__ img_hw /*[N,2]*/, int N,
+                                      float* __restrict__ boxes /*[N,3,4]*/, float* __restrict__ obj /*[N,3,256]*/) {
+  const int n = blockIdx.x;
+  const float h = img_hw[n * 2], w = img_hw[n * 2 + 1];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) obj[static_cast<long long>(n) * 768 + i] = init_feats[i];
+  if (threadIdx.x < 3) {
+    const float* b = init_boxes + threadIdx.x * 4;
+    float* o = boxes + (n * 3 + threadIdx.x) * 4;
+    o[0] = (b[0] - 0.5f * b[2]) * w;
+    o[1] = (b[1] - 0.5f * b[3]) * h;
+    o[2] = (b[0] + 0.5f * b[2]) * w;
+    o[3] = (b[1] + 0.5f * b[3]) * h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// RoIAlign 7x7, sampling_ratio 2, aligned=True, avg  +  FPN level mapping
+// (single_level_roi_extractor.py:36-115; mmcv.ops.RoIAlign semantics).
+// One block per (roi, bin); thread = channel, so every bilinear tap is a 512 B coalesced row.
+// Output X[r, bin, c] fp32 == the [R,49,256] operand of DynamicConv's first bmm
+// (transformer.py:1131-1133).
+// ---------------------------------------------------------------------------------------
+struct FpnLevels {
+  const __half* hi[4];
+  const __half* lo[4];
+  int H[4];
+  int W[4];
+};
+
+__device__ __forceinline__ int roi_level(float x1, float y1, float x2, float y2) {
+  const float scale = sqrtf((x2 - x1) * (y2 - y1));
+  float lvl = floorf(log2f(scale / 56.f + 1e-6f));
+  lvl = fminf(fmaxf(lvl, 0.f), 3.f);
+  return static_cast<int>(lvl);
+}
+
+__global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const float* __restrict__ boxes /*[R,4]*/,
+                                                        int R, float* __restrict__ out /*[R,49,256]*/) {
+  const int r = blockIdx.x / 49;
+  const int bin = blockIdx.x - r * 49;
+  const int ph = bin / 7, pw = bin - ph * 7;
+  const int c = threadIdx.x;
+  const int n = r / 3;
+  const float bx1 = boxes[r * 4 + 0], by1 = boxes[r * 4 + 1], bx2 = boxes[r * 4 + 2], by2 = boxes[r * 4 + 3];
+  const int lvl = roi_level(bx1, by1, bx2, by2);
+  const float scale = 1.f / static_cast<float>(4 << lvl);
+  const int H = f.H[lvl], W = f.W[lvl];
+  const __half* fhi = f.hi[lvl];
+  const __half* flo = f.lo[lvl];
+  const float x1 = bx1 * scale - 0.5f, y1 = by1 * scale - 0.5f;
+  const float bw = (bx2 * scale - 0.5f - x1) / 7.f;
+  const float bh = (by2 * scale - 0.5f - y1) / 7.f;
+  float acc = 0.f;
+#pragma unroll
+  for (int iy = 0; iy < 2; ++iy) {
+    float y = y1 + ph * bh + (iy + 0.5f) * bh / 2.f;
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) {
+      float x = x1 + pw * bw + (ix + 0.5f) * bw / 2.f;
+      float yy = y;
+      if (yy < -1.f || yy > H || x < -1.f || x > W) continue;
+      yy = fmaxf(yy, 0.f);
+      x = fmaxf(x, 0.f);
+      int yl = static_cast<int>(yy), xl = static_cast<int>(x);
+      int yh, xh;
+      if (yl >= H - 1) {
+        yh = yl = H - 1;
+        yy = static_cast<float>(yl);
+      } else {
+        yh = yl + 1;
+      }
+      if (xl >= W - 1) {
+        xh = xl = W - 1;
+        x = static_cast<float>(xl);
+      } else {
+        xh = xl + 1;
+      }
+      const float ly = yy - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+      const long long base = static_cast<long long>(n) * H * W;
+      const long long i00 = (base + static_cast<long long>(yl) * W + xl) * 256 + c;
+      const long long i01 = (base + static_cast<long long>(yl) * W + xh) * 256 + c;
+      const long long i10 = (base + static_cast<long long>(yh) * W + xl) * 256 + c;
+      const long long i11 = (base + static_cast<long long>(yh) * W + xh) * 256 + c;
+      float v00 = __half2float(fhi[i00]), v01 = __half2float(fhi[i01]);
+      float v10 = __half2float(fhi[i10]), v11 = __half2float(fhi[i11]);
+      if (flo) {
+        v00 += __half2float(flo[i00]);
+        v01 += __half2float(flo[i01]);
+        v10 += __half2float(flo[i10]);
+        v11 += __half2float(flo[i11]);
+      }
+      acc += hy * hx * v00 + hy * lx * v01 + ly * hx * v10 + ly * lx * v11;
+    }
+  }
+  out[(static_cast<long long>(r) * 49 + bin) * 256 + c] = acc * 0.25f;
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over rows of width C (64 or 256), eps 1e-5, optional residual add before the
+// norm and ReLU after it.  One warp per row; rows may be strided (per-clue views).
+// y[row] = act( LN(x[row] (+ res[row])) * gamma + beta )
+// ---------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res,
+                                 long long ldres, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* __restrict__ y, long long ldy, long long rows, int C, int relu) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int per = C / 32;  // 2 or 8
+  float v[8];
+  float s = 0.f;
+  for (int j = 0; j < per; ++j) {
+    const int c = j * 32 + lane;
+    float t = x[row * ldx + c];
+    if (res) t += res[row * ldres + c];
+    v[j] = t;
+    s += t;
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int j = 0; j < per; ++j) {
+    const float d = v[j] - mean;
+    q += d * d;
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+  for (int j = 0; j < per; ++j) {
+    const int c = j * 32 + lane;
+    float t = (v[j] - mean) * rstd * gamma[c] + beta[c];
+    if (relu) t = fmaxf(t, 0.f);
+    y[row * ldy + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// self-attention core for the shared spatial / temporal MHA (gaze_stqi_head.py:148-166):
+// 8 heads x head_dim 32 == one warp lane per head channel.  One warp per (query row, head).
+// rows are laid out [frame, clue] (row = frame*3 + clue).  mode 0 (spatial): keys = the 3
+// clues of the same frame.  mode 1 (temporal): keys = the T frames of the same clip & clue.
+// qkv [R,768] -> out [R,256] (pre out_proj).  Online softmax, fp32.
+// ---------------------------------------------------------------------------------------
+__global__ void attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int R, int T, int mode) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= R * 8) return;
+  const int row = gw >> 3, head = gw & 7;
+  const int frame = row / 3, clue = row - frame * 3;
+  int first, step, L;
+  if (mode == 0) {
+    first = frame * 3;
+    step = 1;
+    L = 3;
+  } else {
+    const int clip = frame / T;
+    first = clip * T * 3 + clue;
+    step = 3;
+    L = T;
+  }
+  const float qv = qkv[static_cast<long long>(row) * 768 + head * 32 + lane] * 0.17677669529663687f;  // 1/sqrt(32)
+  float mx = -INFINITY, den = 0.f, acc = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const long long kr = static_cast<long long>(first + l * step) * 768;
+    float s = qv * qkv[kr + 256 + head * 32 + lane];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(mx, s);
+    const float corr = __expf(mx - nm);
+    const float pexp = __expf(s - nm);
+    den = den * corr + pexp;
+    acc = acc * corr + pexp * qkv[kr + 512 + head * 32 + lane];
+    mx = nm;
+  }
+  out[static_cast<long long>(row) * 256 + head * 32 + lane] = acc / den;
+}
+
+// ---------------------------------------------------------------------------------------
+// DynamicConv interaction (mmdet/models/utils/transformer.py:1136-1156), one CTA per RoI:
+//   F1 = relu(LN64 (X[49,256]  . Pin [256,64]))
+//   F2 = relu(LN256(F1[49,64]  . Pout[64,256]))   -> out[r, p*256 + c]  (flatten order :1158)
+// X comes from RoIAlign, Pin/Pout are this RoI's row of dynamic_layer's output.
+// ---------------------------------------------------------------------------------------
+constexpr int kDynSmemFloats = 49 * 256 + 256 * 64 + 49 * 64;
+constexpr int kDynSmemBytes = kDynSmemFloats * 4;
+
+__global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ X /*[R,49,256]*/,
+                                                      const float* __restrict__ params /*[R,32768]*/,
+                                                      const float* __restrict__ g_in, const float* __restrict__ b_in,
+                                                      const float* __restrict__ g_out, const float* __restrict__ b_out,
+                                                      float* __restrict__ out /*[R,12544]*/) {
+  extern __shared__ float dsm[];
+  float* sX = dsm;                 // [49][256]   (later reused for F2)
+  float* sP = dsm + 49 * 256;      // [256][64] then [64][256]
+  float* sF = sP + 256 * 64;       // [49][64]
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* gx = reinterpret_cast<const float4*>(X + static_cast<long long>(r) * 12544);
+  const float4* gp = reinterpret_cast<const float4*>(params + static_cast<long long>(r) * 32768);
+  for (int i = tid; i < 12544 / 4; i += 256) reinterpret_cast<float4*>(sX)[i] = gx[i];
+  for (int i = tid; i < 16384 / 4; i += 256) reinterpret_cast<float4*>(sP)[i] = gp[i];
+  __syncthreads();
+  {  // F1[p][f] : thread -> feature f = tid%64, positions p = tid/64 + 4*i
+    const int f = tid & 63, pg = tid >> 6;
+    float acc[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) acc[i] = 0.f;
+    for (int k = 0; k < 256; ++k) {
+      const float w = sP[k * 64 + f];
+#pragma unroll
+      for (int i = 0; i < 13; ++i) {
+        const int p = pg + 4 * i;
+        if (p < 49) acc[i] = fmaf(sX[p * 256 + k], w, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      const int p = pg + 4 * i;
+      if (p < 49) sF[p * 64 + f] = acc[i];
+    }
+  }
+  __syncthreads();
+  // LN(64) + ReLU per position (one warp per position), and load Pout into sP
+  for (int p = warp; p < 49; p += 8) {
+    float a = sF[p * 64 + lane], b = sF[p * 64 + 32 + lane];
+    float s = a + b;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / 64.f;
+    float q = (a - mean) * (a - mean) + (b - mean) * (b - mean);
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / 64.f + 1e-5f);
+    sF[p * 64 + lane] = fmaxf((a - mean) * rstd * g_in[lane] + b_in[lane], 0.f);
+    sF[p * 64 + 32 + lane] = fmaxf((b - mean) * rstd * g_in[32 + lane] + b_in[32 + lane], 0.f);
+  }
+  for (int i = tid; i < 16384 / 4; i += 256) reinterpret_cast<float4*>(sP)[i] = gp[16384 / 4 + i];
+  __syncthreads();
+  {  // F2[p][c] : thread -> channel c = tid, all 49 positions
+    const int c = tid;
+    float acc[49];
+#pragma unroll
+    for (int p = 0; p < 49; ++p) acc[p] = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      const float w = sP[k * 256 + c];
+#pragma unroll
+      for (int p = 0; p < 49; ++p) acc[p] = fmaf(sF[p * 64 + k], w, acc[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < 49; ++p) sX[p * 256 + c] = acc[p];
+  }
+  __syncthreads();
+  for (int p = warp; p < 49; p += 8) {
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = sX[p * 256 + j * 32 + lane];
+      s += v[j];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / 256.f;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / 256.f + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = j * 32 + lane;
+      out[static_cast<long long>(r) * 12544 + p * 256 + c] = fmaxf((v[j] - mean) * rstd * g_out[c] + b_out[c], 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// box refinement: delta2bbox with stds (0.5,0.5,1,1), |dwh| <= |ln(16/1000)|, no border clip
+// (mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:224-260; bbox_head.py:380-497)
+// ---------------------------------------------------------------------------------------
+__global__ void box_decode_kernel(const float* __restrict__ boxes_in, const float* __restrict__ delta, int R,
+                                  float* __restrict__ boxes_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float x1 = boxes_in[r * 4], y1 = boxes_in[r * 4 + 1], x2 = boxes_in[r * 4 + 2], y2 = boxes_in[r * 4 + 3];
+  const float dx = delta[r * 4] * 0.5f, dy = delta[r * 4 + 1] * 0.5f;
+  const float max_ratio = 4.135166556742356f;
+  const float dw = fminf(fmaxf(delta[r * 4 + 2], -max_ratio), max_ratio);
+  const float dh = fminf(fmaxf(delta[r * 4 + 3], -max_ratio), max_ratio);
+  const float pw = x2 - x1, ph = y2 - y1;
+  const float gx = (x1 + x2) * 0.5f + pw * dx, gy = (y1 + y2) * 0.5f + ph * dy;
+  const float gw = pw * expf(dw), gh = ph * expf(dh);
+  boxes_out[r * 4 + 0] = gx - gw * 0.5f;
+  boxes_out[r * 4 + 1] = gy - gh * 0.5f;
+  boxes_out[r * 4 + 2] = gx + gw * 0.5f;
+  boxes_out[r * 4 + 3] = gy + gh * 0.5f;
+}
+
+// ---------------------------------------------------------------------------------------
+// output packing (multiclue_gaze_roi_head.py:351-366) + gaze fusion (gaze_head.py:186-200)
+// gvec / conf: [3 clues][N][3].  out_gaze [N,4,3] = fused, face, eyes, head (unit vectors).
+// ---------------------------------------------------------------------------------------
+__global__ void finalize_kernel(const float* __restrict__ gvec, const float* __restrict__ conf,
+                                const float* __restrict__ wg /*[3,9]*/, const float* __restrict__ bg /*[3]*/,
+                                const float* __restrict__ cls_logit /*[N,3]*/, const float* __restrict__ boxes /*[N,3,4]*/,
+                                const float* __restrict__ scale_factor /*[N,4] or null*/, int N,
+                                float* __restrict__ out_gaze, float* __restrict__ out_boxes,
+                                float* __restrict__ out_scores) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float feat[9];
+  for (int c = 0; c < 3; ++c) {
+    const float* g = gvec + (static_cast<long long>(c) * N + n) * 3;
+    const float* cf = conf + (static_cast<long long>(c) * N + n) * 3;
+    for (int j = 0; j < 3; ++j) feat[c * 3 + j] = cf[j] * g[j];
+    const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    for (int j = 0; j < 3; ++j) out_gaze[(static_cast<long long>(n) * 4 + 1 + c) * 3 + j] = g[j] / nrm;
+  }
+  float fz[3];
+  for (int j = 0; j < 3; ++j) {
+    float s = bg[j];
+    for (int k = 0; k < 9; ++k) s = fmaf(wg[j * 9 + k], feat[k], s);
+    fz[j] = s;
+  }
+  const float nrm = sqrtf(fz[0] * fz[0] + fz[1] * fz[1] + fz[2] * fz[2]);
+  for (int j = 0; j < 3; ++j) out_gaze[static_cast<long long>(n) * 12 + j] = fz[j] / nrm;
+  for (int c = 0; c < 3; ++c) {
+    out_scores[n * 3 + c] = 1.f / (1.f + expf(-cls_logit[n * 3 + c]));
+    for (int j = 0; j < 4; ++j) {
+      float b = boxes[(n * 3 + c) * 4 + j];
+      if (scale_factor) b /= scale_factor[n * 4 + j];
+      out_boxes[(n * 3 + c) * 4 + j] = b;
+    }
+  }
+}
+
+// fp32 [rows, C] (row stride ld) -> split-fp16 planes [rows, C] (dense)
+__global__ void split_planes_kernel(const float* __restrict__ x, long long ld, long long rows, int C,
+                                    __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    split_store(x[r * ld + c], hi, lo, i);
+  }
+}
+
+// split-fp16 NHWC planes -> fp32 NCHW (debug / intermediate export only)
+__global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int NB, int H,
+                                      int W, int C, float* __restrict__ out) {
+  const long long total = static_cast<long long>(NB) * H * W * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long t = i / C;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float v = __half2float(hi[i]);
+    if (lo) v += __half2float(lo[i]);
+    out[((static_cast<long long>(n) * C + c) * H + h) * W + w] = v;
+  }
+}
+
+}  // namespace mcg

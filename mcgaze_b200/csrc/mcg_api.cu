@@ -1,0 +1,1104 @@
+// mcgaze_b200 engine + C ABI (include/mcgaze_b200.h).
+//
+// Host-side runtime for the MCGaze per-clip forward: checkpoint ingestion (BN folding, K-major
+// repack, split-fp16), workspace arena, launch schedule of the trunk (ResNet-50 + FPN) and of the
+// 4-stage query head, intermediates registry for per-op parity tests, optional CUDA-graph replay.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mcgaze_b200.h"
+#include "common.cuh"
+#include "head_kernels.cuh"
+#include "simt_gemm.cuh"
+#include "umma_gemm.cuh"
+
+namespace mcg {
+
+static thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------------------------ memory
+struct DeviceBlock {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DeviceBlock() = default;
+  explicit DeviceBlock(size_t n) : bytes(n) { MCG_CUDA(cudaMalloc(&p, n ? n : 16)); }
+  DeviceBlock(const DeviceBlock&) = delete;
+  DeviceBlock& operator=(const DeviceBlock&) = delete;
+  ~DeviceBlock() {
+    if (p) cudaFree(p);
+  }
+};
+
+// Bump allocator over one cudaMalloc; reset when the forward shape changes.
+class Arena {
+ public:
+  // measuring pass: alloc() only adds up sizes (returns a fake, never dereferenced pointer)
+  void begin_measure() {
+    measuring_ = true;
+    off_ = 0;
+  }
+  size_t end_measure() {
+    measuring_ = false;
+    const size_t n = off_;
+    off_ = 0;
+    return n;
+  }
+  void reserve(size_t bytes) {
+    if (bytes > cap_) {
+      block_.reset();
+      block_.reset(new DeviceBlock(bytes));
+      cap_ = bytes;
+    }
+    off_ = 0;
+  }
+  template <typename T>
+  T* alloc(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 1023) & ~static_cast<size_t>(1023);
+    if (measuring_) {
+      off_ += bytes;
+      return reinterpret_cast<T*>(static_cast<uintptr_t>(1024));
+    }
+    MCG_CHECK(off_ + bytes <= cap_, "arena overflow");
+    T* r = reinterpret_cast<T*>(static_cast<uint8_t*>(block_->p) + off_);
+    off_ += bytes;
+    return r;
+  }
+  size_t used() const { return off_; }
+
+ private:
+  std::unique_ptr<DeviceBlock> block_;
+  size_t cap_ = 0, off_ = 0;
+  bool measuring_ = false;
+};
+
+template <typename T>
+static T* upload(std::vector<std::unique_ptr<DeviceBlock>>& keep, const std::vector<T>& host) {
+  keep.emplace_back(new DeviceBlock(host.size() * sizeof(T)));
+  MCG_CUDA(cudaMemcpy(keep.back()->p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return reinterpret_cast<T*>(keep.back()->p);
+}
+
+static inline __half h_from_float(float v) { return __float2half_rn(v); }
+
+// ------------------------------------------------------------------------------------ weights
+struct GemmW {  // packed [N, K] weight (+ bias) on device
+  int N = 0, K = 0;
+  const float* w_f32 = nullptr;
+  Planes w;
+  const float* bias = nullptr;
+};
+struct LnW {
+  const float* g = nullptr;
+  const float* b = nullptr;
+  int C = 0;
+};
+struct ConvW {
+  GemmW g;
+  int Cin = 0, Cout = 0, R = 1, S = 1, stride = 1, pad = 0;
+};
+struct BlockW {
+  ConvW c1, c2, c3, ds;
+  bool has_ds = false;
+};
+struct StageW {
+  GemmW in_proj, out_proj, dyn, fc, ffn1, ffn2, cls_fc, reg_fc[3], fc_cls[3], fc_reg[3];
+  LnW attn_norm, norm_in, norm_out, fc_norm, iic_norm, ffn_norm, cls_ln, reg_ln[3];
+};
+struct GazeW {
+  GemmW tower[3][2], ctower[3][2], fc[3], fc_conf[3];
+  LnW tower_ln[3][2], ctower_ln[3][2];
+  const float* wg = nullptr;
+  const float* bg = nullptr;
+};
+
+struct Interm {
+  int kind = 0;  // 0 = fp32 dense, 1 = NHWC planes
+  const float* f32 = nullptr;
+  Planes pl;
+  int64_t shape[4] = {0, 0, 0, 0};  // kind 1: NB,H,W,C
+};
+
+// ------------------------------------------------------------------------------------ engine
+class Engine {
+ public:
+  Engine(int device, const mcg_tensor* w, int n, int precision) : device_(device), precision_(precision) {
+    MCG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MCG_CUDA(cudaGetDeviceProperties(&prop, device));
+    num_sms_ = prop.multiProcessorCount;
+    if (precision != MCG_PRECISION_SIMT)
+      MCG_CHECK(prop.major == 10, "tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor));
+    for (int i = 0; i < n; ++i) {
+      size_t cnt = 1;
+      for (int d = 0; d < w[i].ndim; ++d) cnt *= static_cast<size_t>(w[i].shape[d]);
+      host_[w[i].name] = {w[i].data, cnt};
+    }
+    load_weights();
+    host_.clear();
+    MCG_CUDA(cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+    if (precision != MCG_PRECISION_SIMT) umma_set_attrs();
+  }
+
+  ~Engine() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    if (pin_out_) cudaFreeHost(pin_out_);
+    if (pin_meta_) cudaFreeHost(pin_meta_);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+  }
+  void set_option(const std::string& k, int v) {
+    if (k == "keep_intermediates") keep_stage_interm_ = v != 0;
+    else if (k == "head_tensor_cores") { head_tc_ = v != 0; plans_.clear(); drop_graph(); }
+    else throw CudaError("check failed: unknown option " + k);
+  }
+
+  void set_graph_mode(int on) {
+    graph_mode_ = on != 0;
+    drop_graph();
+  }
+  int last_launches() const { return launches_; }
+
+  void forward(const float* img, int B, int T, int H, int W, const float* img_hw, const float* scale_factor,
+               float* out_gaze, float* out_boxes, float* out_scores, cudaStream_t stream) {
+    MCG_CUDA(cudaSetDevice(device_));
+    MCG_CHECK(B > 0 && T > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
+    const int NB = B * T;
+    ensure_workspace(NB, T, H, W);
+    // per-call host metadata -> device (tiny)
+    std::vector<float> meta(static_cast<size_t>(NB) * 6);
+    for (int i = 0; i < NB; ++i) {
+      meta[i * 2] = img_hw ? img_hw[i * 2] : static_cast<float>(H);
+      meta[i * 2 + 1] = img_hw ? img_hw[i * 2 + 1] : static_cast<float>(W);
+      for (int j = 0; j < 4; ++j) meta[NB * 2 + i * 4 + j] = scale_factor ? scale_factor[i * 4 + j] : 1.f;
+    }
+    if (meta != meta_host_) {
+      // rare (metadata changed): make sure no earlier async copy still reads the pinned buffer
+      MCG_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(pin_meta_, meta.data(), meta.size() * sizeof(float));
+      MCG_CUDA(cudaMemcpyAsync(d_meta_, pin_meta_, meta.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      meta_host_ = meta;
+    }
+    has_scale_ = scale_factor != nullptr;
+
+    const bool same_io = img == g_img_ && out_gaze == g_gaze_ && out_boxes == g_boxes_ && out_scores == g_scores_ &&
+                         has_scale_ == g_has_scale_;
+    if (graph_mode_ && graph_exec_ && same_io) {
+      MCG_CUDA(cudaGraphLaunch(graph_exec_, stream));
+      return;
+    }
+    if (graph_mode_) {
+      drop_graph();
+      cudaGraph_t graph = nullptr;
+      MCG_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        schedule(img, out_gaze, out_boxes, out_scores, stream);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      MCG_CUDA(cudaStreamEndCapture(stream, &graph));
+      MCG_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+      MCG_CUDA(cudaGraphDestroy(graph));
+      g_img_ = img;
+      g_gaze_ = out_gaze;
+      g_boxes_ = out_boxes;
+      g_scores_ = out_scores;
+      g_has_scale_ = has_scale_;
+      MCG_CUDA(cudaGraphLaunch(graph_exec_, stream));
+      return;
+    }
+    schedule(img, out_gaze, out_boxes, out_scores, stream);
+  }
+
+  void forward_host(const float* img_host, int B, int T, int H, int W, const float* img_hw,
+                    const float* scale_factor, float* out_gaze, float* out_boxes, float* out_scores) {
+    MCG_CUDA(cudaSetDevice(device_));
+    const int NB = B * T;
+    const size_t in_bytes = static_cast<size_t>(NB) * 3 * H * W * sizeof(float);
+    const size_t out_floats = static_cast<size_t>(NB) * (12 + 12 + 3);
+    if (!own_stream_) MCG_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    if (in_bytes > io_in_bytes_) {
+      io_in_.reset(new DeviceBlock(in_bytes));
+      io_in_bytes_ = in_bytes;
+      drop_graph();
+    }
+    if (out_floats * sizeof(float) > io_out_bytes_) {
+      io_out_.reset(new DeviceBlock(out_floats * sizeof(float)));
+      io_out_bytes_ = out_floats * sizeof(float);
+      if (pin_out_) cudaFreeHost(pin_out_);
+      MCG_CUDA(cudaMallocHost(&pin_out_, io_out_bytes_));
+      drop_graph();
+    }
+    float* d_in = reinterpret_cast<float*>(io_in_->p);
+    float* d_out = reinterpret_cast<float*>(io_out_->p);
+    // async when the caller's buffer is pinned; otherwise the runtime stages it
+    MCG_CUDA(cudaMemcpyAsync(d_in, img_host, in_bytes, cudaMemcpyHostToDevice, own_stream_));
+    forward(d_in, B, T, H, W, img_hw, scale_factor, d_out, d_out + NB * 12, d_out + NB * 24, own_stream_);
+    MCG_CUDA(cudaMemcpyAsync(pin_out_, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, own_stream_));
+    MCG_CUDA(cudaStreamSynchronize(own_stream_));
+    const float* po = reinterpret_cast<const float*>(pin_out_);
+    std::memcpy(out_gaze, po, static_cast<size_t>(NB) * 12 * sizeof(float));
+    std::memcpy(out_boxes, po + NB * 12, static_cast<size_t>(NB) * 12 * sizeof(float));
+    std::memcpy(out_scores, po + NB * 24, static_cast<size_t>(NB) * 3 * sizeof(float));
+  }
+
+  int get_intermediate(const char* name, float* dst, int64_t capacity, int64_t shape_out[4]) {
+    auto it = interm_.find(name);
+    if (it == interm_.end()) return MCG_ERR_INVALID;
+    const Interm& t = it->second;
+    int64_t cnt = 1;
+    for (int i = 0; i < 4; ++i)
+      if (t.shape[i] > 0) cnt *= t.shape[i];
+    if (cnt > capacity) return MCG_ERR_INVALID;
+    if (t.kind == 0) {
+      MCG_CUDA(cudaMemcpy(dst, t.f32, cnt * sizeof(float), cudaMemcpyDeviceToDevice));
+      for (int i = 0; i < 4; ++i) shape_out[i] = t.shape[i];
+    } else {
+      const int NB = static_cast<int>(t.shape[0]), H = static_cast<int>(t.shape[1]), W = static_cast<int>(t.shape[2]),
+                C = static_cast<int>(t.shape[3]);
+      planes_to_nchw_kernel<<<1024, 256>>>(t.pl.hi, t.pl.lo, NB, H, W, C, dst);
+      MCG_CUDA(cudaGetLastError());
+      MCG_CUDA(cudaDeviceSynchronize());
+      shape_out[0] = NB;
+      shape_out[1] = C;
+      shape_out[2] = H;
+      shape_out[3] = W;
+    }
+    return MCG_OK;
+  }
+
+ private:
+  // -------------------------------------------------------------------------- weight loading
+  struct HostT {
+    const float* p;
+    size_t n;
+  };
+  const HostT& need(const std::string& k, size_t count) {
+    auto it = host_.find(k);
+    if (it == host_.end()) throw CudaError("missing checkpoint key: " + k);
+    if (it->second.n != count)
+      throw CudaError("checkpoint key " + k + " has " + std::to_string(it->second.n) + " elements, expected " +
+                      std::to_string(count));
+    return it->second;
+  }
+  bool has(const std::string& k) const { return host_.count(k) != 0; }
+
+  GemmW pack_gemm(const std::vector<float>& w, int N, int K, const float* bias) {
+    GemmW g;
+    g.N = N;
+    g.K = K;
+    g.w_f32 = upload(keep_, w);
+    std::vector<__half> hi(w.size()), lo(w.size());
+    for (size_t i = 0; i < w.size(); ++i) {
+      const __half h = h_from_float(w[i]);
+      hi[i] = h;
+      lo[i] = h_from_float(w[i] - __half2float(h));
+    }
+    g.w.hi = upload(keep_, hi);
+    g.w.lo = upload(keep_, lo);
+    if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
+    return g;
+  }
+
+  // conv weight [Cout,Cin,R,S] (+ optional BN, + optional conv bias) -> [Cout, (r,s,c)] scaled, bias folded
+  ConvW pack_conv(const std::string& wkey, const std::string& bnkey, const std::string& biaskey, int Cout, int Cin,
+                  int R, int S, int stride, int pad, int Kpad = 0) {
+    const float* w = need(wkey, static_cast<size_t>(Cout) * Cin * R * S).p;
+    std::vector<float> scale(Cout, 1.f), shift(Cout, 0.f);
+    if (!bnkey.empty()) {
+      const float* g = need(bnkey + ".weight", Cout).p;
+      const float* b = need(bnkey + ".bias", Cout).p;
+      const float* m = need(bnkey + ".running_mean", Cout).p;
+      const float* v = need(bnkey + ".running_var", Cout).p;
+      for (int o = 0; o < Cout; ++o) {
+        // eval-mode BN (eps 1e-5) folded in double, as tools/test.py --fuse-conv-bn sanctions
+        const double s = static_cast<double>(g[o]) / std::sqrt(static_cast<double>(v[o]) + 1e-5);
+        scale[o] = static_cast<float>(s);
+        shift[o] = static_cast<float>(static_cast<double>(b[o]) - static_cast<double>(m[o]) * s);
+      }
+    }
+    if (!biaskey.empty()) {
+      const float* cb = need(biaskey, Cout).p;
+      for (int o = 0; o < Cout; ++o) shift[o] += cb[o] * scale[o];
+    }
+    const int K = R * S * Cin;
+    const int Kp = Kpad > 0 ? Kpad : K;
+    std::vector<float> packed(static_cast<size_t>(Cout) * Kp, 0.f);
+    for (int o = 0; o < Cout; ++o)
+      for (int c = 0; c < Cin; ++c)
+        for (int r = 0; r < R; ++r)
+          for (int s = 0; s < S; ++s)
+            packed[static_cast<size_t>(o) * Kp + (r * S + s) * Cin + c] =
+                w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s] * scale[o];
+    ConvW cw;
+    cw.g = pack_gemm(packed, Cout, Kp, shift.data());
+    cw.Cin = Cin;
+    cw.Cout = Cout;
+    cw.R = R;
+    cw.S = S;
+    cw.stride = stride;
+    cw.pad = pad;
+    return cw;
+  }
+
+  GemmW pack_linear(const std::string& wkey, const std::string& bkey, int N, int K) {
+    const float* w = need(wkey, static_cast<size_t>(N) * K).p;
+    const float* b = bkey.empty() ? nullptr : need(bkey, N).p;
+    return pack_gemm(std::vector<float>(w, w + static_cast<size_t>(N) * K), N, K, b);
+  }
+  LnW pack_ln(const std::string& key, int C) {
+    LnW l;
+    l.C = C;
+    l.g = upload(keep_, std::vector<float>(need(key + ".weight", C).p, need(key + ".weight", C).p + C));
+    l.b = upload(keep_, std::vector<float>(need(key + ".bias", C).p, need(key + ".bias", C).p + C));
+    return l;
+  }
+
+  void load_weights() {
+    stem_ = pack_conv("backbone.conv1.weight", "backbone.bn1", "", 64, 3, 7, 7, 2, 3, kStemK);
+    const int nblk[4] = {3, 4, 6, 3};
+    const int planes[4] = {64, 128, 256, 512};
+    int cin = 64;
+    for (int l = 0; l < 4; ++l) {
+      for (int b = 0; b < nblk[l]; ++b) {
+        const std::string p = "backbone.layer" + std::to_string(l + 1) + "." + std::to_string(b);
+        const int stride = (b == 0 && l > 0) ? 2 : 1;
+        BlockW bw;
+        bw.c1 = pack_conv(p + ".conv1.weight", p + ".bn1", "", planes[l], cin, 1, 1, 1, 0);
+        bw.c2 = pack_conv(p + ".conv2.weight", p + ".bn2", "", planes[l], planes[l], 3, 3, stride, 1);
+        bw.c3 = pack_conv(p + ".conv3.weight", p + ".bn3", "", planes[l] * 4, planes[l], 1, 1, 1, 0);
+        bw.has_ds = has(p + ".downsample.0.weight");
+        if (bw.has_ds)
+          bw.ds = pack_conv(p + ".downsample.0.weight", p + ".downsample.1", "", planes[l] * 4, cin, 1, 1, stride, 0);
+        blocks_[l].push_back(bw);
+        cin = planes[l] * 4;
+      }
+    }
+    const int fin[4] = {256, 512, 1024, 2048};
+    for (int i = 0; i < 4; ++i) {
+      const std::string l = "neck.lateral_convs." + std::to_string(i) + ".conv";
+      const std::string f = "neck.fpn_convs." + std::to_string(i) + ".conv";
+      lateral_[i] = pack_conv(l + ".weight", "", l + ".bias", 256, fin[i], 1, 1, 1, 0);
+      fpnconv_[i] = pack_conv(f + ".weight", "", f + ".bias", 256, 256, 3, 3, 1, 1);
+    }
+    init_boxes_ = upload(keep_, std::vector<float>(need("rpn_head.init_proposal_bboxes.weight", 12).p,
+                                                   need("rpn_head.init_proposal_bboxes.weight", 12).p + 12));
+    init_feats_ = upload(keep_, std::vector<float>(need("rpn_head.init_proposal_features.weight", 768).p,
+                                                   need("rpn_head.init_proposal_features.weight", 768).p + 768));
+    const char* clue[3] = {"face", "eyes", "head"};
+    for (int s = 0; s < 4; ++s) {
+      const std::string p = "roi_head.bbox_head." + std::to_string(s);
+      StageW& st = stage_[s];
+      st.in_proj = pack_linear(p + ".attention.attn.in_proj_weight", p + ".attention.attn.in_proj_bias", 768, 256);
+      st.out_proj = pack_linear(p + ".attention.attn.out_proj.weight", p + ".attention.attn.out_proj.bias", 256, 256);
+      st.attn_norm = pack_ln(p + ".attention_norm", 256);
+      const std::string q = p + ".instance_interactive_conv";
+      st.dyn = pack_linear(q + ".dynamic_layer.weight", q + ".dynamic_layer.bias", 32768, 256);
+      st.norm_in = pack_ln(q + ".norm_in", 64);
+      st.norm_out = pack_ln(q + ".norm_out", 256);
+      st.fc = pack_linear(q + ".fc_layer.weight", q + ".fc_layer.bias", 256, 12544);
+      st.fc_norm = pack_ln(q + ".fc_norm", 256);
+      st.iic_norm = pack_ln(p + ".instance_interactive_conv_norm", 256);
+      st.ffn1 = pack_linear(p + ".ffn.layers.0.0.weight", p + ".ffn.layers.0.0.bias", 2048, 256);
+      st.ffn2 = pack_linear(p + ".ffn.layers.1.weight", p + ".ffn.layers.1.bias", 256, 2048);
+      st.ffn_norm = pack_ln(p + ".ffn_norm", 256);
+      st.cls_fc = pack_linear(p + ".cls_fcs.0.weight", "", 256, 256);
+      st.cls_ln = pack_ln(p + ".cls_fcs.1", 256);
+      for (int j = 0; j < 3; ++j) {
+        st.reg_fc[j] = pack_linear(p + ".reg_fcs." + std::to_string(3 * j) + ".weight", "", 256, 256);
+        st.reg_ln[j] = pack_ln(p + ".reg_fcs." + std::to_string(3 * j + 1), 256);
+        st.fc_cls[j] = pack_linear(p + "." + clue[j] + "_fc_cls.weight", p + "." + clue[j] + "_fc_cls.bias", 1, 256);
+        st.fc_reg[j] = pack_linear(p + "." + clue[j] + "_fc_reg.weight", p + "." + clue[j] + "_fc_reg.bias", 4, 256);
+      }
+    }
+    {  // only the last stage's gaze head runs at test time (multiclue_gaze_roi_head.py:377-378)
+      const std::string h = "roi_head.gaze_head.3";
+      for (int c = 0; c < 3; ++c) {
+        const std::string t = h + ".gaze_" + clue[c] + "_fcs";
+        const std::string ct = h + ".gaze_" + clue[c] + "_confidence";
+        for (int j = 0; j < 2; ++j) {
+          gaze_.tower[c][j] = pack_linear(t + "." + std::to_string(3 * j) + ".weight", "", 256, 256);
+          gaze_.tower_ln[c][j] = pack_ln(t + "." + std::to_string(3 * j + 1), 256);
+          gaze_.ctower[c][j] = pack_linear(ct + "." + std::to_string(3 * j) + ".weight", "", 256, 256);
+          gaze_.ctower_ln[c][j] = pack_ln(ct + "." + std::to_string(3 * j + 1), 256);
+        }
+        gaze_.fc[c] = pack_linear(h + ".fc_" + clue[c] + ".weight", h + ".fc_" + clue[c] + ".bias", 3, 256);
+        gaze_.fc_conf[c] = pack_linear(h + ".fc_" + clue[c] + "_confidence.weight",
+                                       h + ".fc_" + clue[c] + "_confidence.bias", 3, 256);
+      }
+      gaze_.wg = upload(keep_, std::vector<float>(need(h + ".fc_gaze.weight", 27).p, need(h + ".fc_gaze.weight", 27).p + 27));
+      gaze_.bg = upload(keep_, std::vector<float>(need(h + ".fc_gaze.bias", 3).p, need(h + ".fc_gaze.bias", 3).p + 3));
+    }
+  }
+
+  // -------------------------------------------------------------------------- workspace
+  struct Act {  // NHWC planes
+    Planes pl;
+    int NB = 0, H = 0, W = 0, C = 0;
+    long long rows() const { return static_cast<long long>(NB) * H * W; }
+  };
+  Act new_act(int NB, int H, int W, int C) {
+    Act a;
+    a.NB = NB;
+    a.H = H;
+    a.W = W;
+    a.C = C;
+    const size_t n = static_cast<size_t>(NB) * H * W * C;
+    a.pl.hi = arena_.alloc<__half>(n);
+    a.pl.lo = two_planes() ? arena_.alloc<__half>(n) : nullptr;
+    return a;
+  }
+  bool two_planes() const { return precision_ != MCG_PRECISION_FP16; }
+
+  void ensure_workspace(int NB, int T, int H, int W) {
+    if (NB == ws_NB_ && T == ws_T_ && H == ws_H_ && W == ws_W_) return;
+    MCG_CUDA(cudaDeviceSynchronize());
+    drop_graph();
+    plans_.clear();
+    interm_.clear();
+    dbg_.clear();
+    arena_.begin_measure();
+    layout_workspace(NB, H, W);
+    const size_t bytes = arena_.end_measure();
+    arena_.reserve(bytes + 4096);
+    layout_workspace(NB, H, W);
+    ws_NB_ = NB;
+    ws_T_ = T;
+    ws_H_ = H;
+    ws_W_ = W;
+    if (pin_meta_) cudaFreeHost(pin_meta_);
+    MCG_CUDA(cudaMallocHost(&pin_meta_, static_cast<size_t>(NB) * 6 * sizeof(float)));
+    meta_host_.clear();
+  }
+
+  void layout_workspace(int NB, int H, int W) {
+    const int P1 = H / 2, Q1 = W / 2, P2 = H / 4, Q2 = W / 4;
+    stemA_.hi = arena_.alloc<__half>(static_cast<size_t>(NB) * P1 * Q1 * kStemK);
+    stemA_.lo = two_planes() ? arena_.alloc<__half>(static_cast<size_t>(NB) * P1 * Q1 * kStemK) : nullptr;
+    stem_out_ = new_act(NB, P1, Q1, 64);
+    pool_out_ = new_act(NB, P2, Q2, 64);
+    int h = P2, w = Q2;
+    const int planes_c[4] = {64, 128, 256, 512};
+    for (int l = 0; l < 4; ++l) {
+      blk_act_[l].clear();
+      for (size_t b = 0; b < blocks_[l].size(); ++b) {
+        const int stride = blocks_[l][b].c2.stride;
+        BlkAct ba;
+        ba.t1 = new_act(NB, h, w, planes_c[l]);
+        ba.t2 = new_act(NB, h / stride, w / stride, planes_c[l]);
+        if (blocks_[l][b].has_ds) ba.ds = new_act(NB, h / stride, w / stride, planes_c[l] * 4);
+        ba.out = new_act(NB, h / stride, w / stride, planes_c[l] * 4);
+        h /= stride;
+        w /= stride;
+        blk_act_[l].push_back(ba);
+      }
+    }
+    for (int i = 0; i < 4; ++i) {
+      lat_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256);
+      fpn_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256);
+    }
+    const size_t Rr = static_cast<size_t>(NB) * 3;
+    boxes_[0] = arena_.alloc<float>(Rr * 4);
+    boxes_[1] = arena_.alloc<float>(Rr * 4);
+    obj_[0] = arena_.alloc<float>(Rr * 256);
+    obj_[1] = arena_.alloc<float>(Rr * 256);
+    qkv_ = arena_.alloc<float>(Rr * 768);
+    att_ = arena_.alloc<float>(Rr * 256);
+    xa_ = arena_.alloc<float>(Rr * 256);
+    xb_ = arena_.alloc<float>(Rr * 256);
+    xc_ = arena_.alloc<float>(Rr * 256);
+    params_ = arena_.alloc<float>(Rr * 32768);
+    roi_ = arena_.alloc<float>(Rr * 12544);
+    dynf_ = arena_.alloc<float>(Rr * 12544);
+    fc_ = arena_.alloc<float>(Rr * 256);
+    ffn_h_ = arena_.alloc<float>(Rr * 2048);
+    t256a_ = arena_.alloc<float>(Rr * 256);
+    t256b_ = arena_.alloc<float>(Rr * 256);
+    cls_logit_ = arena_.alloc<float>(Rr);
+    delta_ = arena_.alloc<float>(Rr * 4);
+    gz_a_ = arena_.alloc<float>(static_cast<size_t>(NB) * 256);
+    gz_b_ = arena_.alloc<float>(static_cast<size_t>(NB) * 256);
+    gvec_ = arena_.alloc<float>(static_cast<size_t>(NB) * 9);
+    conf_ = arena_.alloc<float>(static_cast<size_t>(NB) * 9);
+    d_meta_ = arena_.alloc<float>(static_cast<size_t>(NB) * 6);
+    // split-fp16 staging for the head's tensor-core GEMM operands
+    hq_.hi = arena_.alloc<__half>(Rr * 256);
+    hq_.lo = arena_.alloc<__half>(Rr * 256);
+    hh_.hi = arena_.alloc<__half>(Rr * 2048);
+    hh_.lo = arena_.alloc<__half>(Rr * 2048);
+    hf_.hi = arena_.alloc<__half>(Rr * 12544);
+    hf_.lo = arena_.alloc<__half>(Rr * 12544);
+  }
+
+  void drop_graph() {
+    if (graph_exec_) {
+      cudaGraphExecDestroy(graph_exec_);
+      graph_exec_ = nullptr;
+    }
+    g_img_ = nullptr;
+  }
+
+  // -------------------------------------------------------------------------- op helpers
+  void count() { ++launches_; }
+
+  // generic GEMM dispatch.  A: planes (kind 0/1) or fp32 (kind 0).
+  // terms: 0 = CUDA-core fp32 kernel, 1 / 3 = tcgen05 kernel with 1 / 3 MMAs per k-step
+  int trunk_terms() const {
+    return precision_ == MCG_PRECISION_SIMT ? 0 : (precision_ == MCG_PRECISION_FP16X3 ? 3 : 1);
+  }
+  void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
+            long long M, const Epilogue& ep, cudaStream_t st, int terms) {
+    const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
+                        (terms == 1 || A->lo != nullptr);
+    if (tensor) {
+      auto it = plans_.find(key);
+      if (it == plans_.end()) {
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_);
+        it = plans_.emplace(key, pl).first;
+      }
+      launch_umma(it->second, st);
+    } else {
+      SimtParams p;
+      p.M = M;
+      p.N = w.N;
+      p.K = w.K;
+      p.a = geom;
+      if (A) {
+        p.a_hi = A->hi;
+        p.a_lo = A->lo;
+      } else {
+        p.a_f32 = A_f32;
+      }
+      p.w_f32 = w.w_f32;
+      p.ep = ep;
+      launch_simt_gemm(p, st);
+    }
+    count();
+  }
+
+  // convolution over NHWC planes -> NHWC planes
+  void conv(const std::string& key, const Act& x, const ConvW& cw, const Act& y, bool relu, const Act* res,
+            int res_mode, cudaStream_t st) {
+    AGeom g;
+    const bool plain = cw.R == 1 && cw.S == 1 && cw.stride == 1 && cw.pad == 0;
+    g.kind = plain ? 0 : 1;
+    g.lda = x.C;
+    g.NB = x.NB;
+    g.H = x.H;
+    g.W = x.W;
+    g.C = x.C;
+    g.R = cw.R;
+    g.S = cw.S;
+    g.stride = cw.stride;
+    g.pad = cw.pad;
+    g.P = y.H;
+    g.Q = y.W;
+    Epilogue ep;
+    ep.bias = cw.g.bias;
+    ep.relu = relu ? 1 : 0;
+    ep.out_hi = y.pl.hi;
+    ep.out_lo = y.pl.lo;
+    ep.ldo = y.C;
+    if (res) {
+      ep.res_hi = res->pl.hi;
+      ep.res_lo = res->pl.lo;
+      ep.res_mode = res_mode;
+      ep.ldr = res->C;
+      ep.P = y.H;
+      ep.Q = y.W;
+    }
+    gemm(key, &x.pl, nullptr, g, cw.g, y.rows(), ep, st, trunk_terms());
+  }
+
+  // fp32 linear on (possibly strided) rows: y = x W^T + b (+res) (relu)
+  void linear(const float* x, long long ldx, const GemmW& w, long long M, float* y, long long ldy, bool relu,
+              const float* res, long long ldres, cudaStream_t st) {
+    AGeom g;
+    g.kind = 0;
+    g.lda = ldx;
+    Epilogue ep;
+    ep.bias = w.bias;
+    ep.relu = relu ? 1 : 0;
+    ep.out_f32 = y;
+    ep.ldo = ldy;
+    if (res) {
+      ep.res_f32 = res;
+      ep.res_mode = RES_SAME;
+      ep.ldr = ldres;
+    }
+    gemm("", nullptr, x, g, w, M, ep, st, 0);
+  }
+
+  // big head linears: split the fp32 activations into fp16 planes and run on tensor cores
+  void linear_tc(const std::string& key, const float* x, int K, const Planes& stage, const GemmW& w, long long M,
+                 float* y, bool relu, const float* res, cudaStream_t st) {
+    if (precision_ == MCG_PRECISION_SIMT || !head_tc_) {
+      linear(x, K, w, M, y, w.N, relu, res, w.N, st);
+      return;
+    }
+    split_planes_kernel<<<num_sms_ * 4, 256, 0, st>>>(x, K, M, K, stage.hi, stage.lo);
+    MCG_CUDA(cudaGetLastError());
+    count();
+    AGeom g;
+    g.kind = 0;
+    g.lda = K;
+    Epilogue ep;
+    ep.bias = w.bias;
+    ep.relu = relu ? 1 : 0;
+    ep.out_f32 = y;
+    ep.ldo = w.N;
+    if (res) {
+      ep.res_f32 = res;
+      ep.res_mode = RES_SAME;
+      ep.ldr = w.N;
+    }
+    // head GEMMs always use the 3-term split: the head is precision critical and only 2.5 % of the FLOPs
+    gemm(key, &stage, nullptr, g, w, M, ep, st, 3);
+  }
+
+  void ln(const float* x, long long ldx, const float* res, long long ldres, const LnW& w, float* y, long long ldy,
+          long long rows, bool relu, cudaStream_t st) {
+    const int wpb = 8;
+    layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, ldx, res, ldres, w.g, w.b, y,
+                                                                                       ldy, rows, w.C, relu ? 1 : 0);
+    MCG_CUDA(cudaGetLastError());
+    count();
+  }
+
+  const float* snapshot(const float* src, size_t n, cudaStream_t st) {
+    dbg_.emplace_back(new DeviceBlock(n * sizeof(float)));
+    MCG_CUDA(cudaMemcpyAsync(dbg_.back()->p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return reinterpret_cast<const float*>(dbg_.back()->p);
+  }
+  void reg_f32(const std::string& name, const float* p, int64_t a, int64_t b = 0, int64_t c = 0, int64_t d = 0) {
+    Interm t;
+    t.kind = 0;
+    t.f32 = p;
+    t.shape[0] = a;
+    t.shape[1] = b;
+    t.shape[2] = c;
+    t.shape[3] = d;
+    interm_[name] = t;
+  }
+  void reg_act(const std::string& name, const Act& a) {
+    Interm t;
+    t.kind = 1;
+    t.pl = a.pl;
+    t.shape[0] = a.NB;
+    t.shape[1] = a.H;
+    t.shape[2] = a.W;
+    t.shape[3] = a.C;
+    interm_[name] = t;
+  }
+
+  // -------------------------------------------------------------------------- the forward schedule
+  void schedule(const float* img, float* out_gaze, float* out_boxes, float* out_scores, cudaStream_t st) {
+    launches_ = 0;
+    if (!graph_mode_) dbg_.clear();
+    const int NB = ws_NB_, T = ws_T_, H = ws_H_, W = ws_W_;
+    const int ew_grid = num_sms_ * 8;
+    // ---- stem (resnet.py:636-639)
+    stem_im2col_kernel<<<ew_grid, 256, 0, st>>>(img, NB, H, W, H / 2, W / 2, stemA_.hi, stemA_.lo);
+    MCG_CUDA(cudaGetLastError());
+    count();
+    {
+      AGeom g;
+      g.kind = 0;
+      g.lda = kStemK;
+      Epilogue ep;
+      ep.bias = stem_.g.bias;
+      ep.relu = 1;
+      ep.out_hi = stem_out_.pl.hi;
+      ep.out_lo = stem_out_.pl.lo;
+      ep.ldo = 64;
+      gemm("stem", &stemA_, nullptr, g, stem_.g, stem_out_.rows(), ep, st, trunk_terms());
+    }
+    maxpool3x3s2_kernel<<<ew_grid, 256, 0, st>>>(stem_out_.pl.hi, stem_out_.pl.lo, NB, H / 2, W / 2, 64, H / 4, W / 4,
+                                                 pool_out_.pl.hi, pool_out_.pl.lo);
+    MCG_CUDA(cudaGetLastError());
+    count();
+    reg_act("stem", stem_out_);
+    reg_act("pool", pool_out_);
+    // ---- layer1..4 (resnet.py:263-302)
+    const Act* x = &pool_out_;
+    for (int l = 0; l < 4; ++l) {
+      for (size_t b = 0; b < blocks_[l].size(); ++b) {
+        const BlockW& bw = blocks_[l][b];
+        BlkAct& ba = blk_act_[l][b];
+        const std::string k = "l" + std::to_string(l) + "b" + std::to_string(b);
+        conv(k + "c1", *x, bw.c1, ba.t1, true, nullptr, RES_NONE, st);
+        conv(k + "c2", ba.t1, bw.c2, ba.t2, true, nullptr, RES_NONE, st);
+        const Act* idn = x;
+        if (bw.has_ds) {
+          conv(k + "ds", *x, bw.ds, ba.ds, false, nullptr, RES_NONE, st);
+          idn = &ba.ds;
+        }
+        conv(k + "c3", ba.t2, bw.c3, ba.out, true, idn, RES_SAME, st);
+        x = &ba.out;
+        reg_act("layer" + std::to_string(l + 1) + "." + std::to_string(b), ba.out);
+      }
+    }
+    // ---- FPN (fpn.py:151-180): lateral 1x1 (+ top-down nearest-2x add fused), then 3x3
+    for (int i = 3; i >= 0; --i) {
+      const Act& c = blk_act_[i].back().out;
+      conv("lat" + std::to_string(i), c, lateral_[i], lat_[i], false, i < 3 ? &lat_[i + 1] : nullptr,
+           i < 3 ? RES_UP2X : RES_NONE, st);
+    }
+    for (int i = 0; i < 4; ++i) {
+      conv("fpn" + std::to_string(i), lat_[i], fpnconv_[i], fpn_[i], false, nullptr, RES_NONE, st);
+      reg_act("fpn" + std::to_string(i), fpn_[i]);
+    }
+    // ---- query head (multiclue_gaze_roi_head.py:287-384)
+    const int R = NB * 3;
+    float* img_hw = d_meta_;
+    float* scale = d_meta_ + NB * 2;
+    init_proposals_kernel<<<NB, 256, 0, st>>>(init_boxes_, init_feats_, img_hw, NB, boxes_[0], obj_[0]);
+    MCG_CUDA(cudaGetLastError());
+    count();
+    FpnLevels fl;
+    for (int i = 0; i < 4; ++i) {
+      fl.hi[i] = fpn_[i].pl.hi;
+      fl.lo[i] = fpn_[i].pl.lo;
+      fl.H[i] = fpn_[i].H;
+      fl.W[i] = fpn_[i].W;
+    }
+    int cur = 0;
+    for (int s = 0; s < 4; ++s) {
+      const StageW& sw = stage_[s];
+      const std::string sk = "s" + std::to_string(s);
+      float* boxes_in = boxes_[cur];
+      float* boxes_out = boxes_[cur ^ 1];
+      float* obj_in = obj_[cur];
+      float* obj_out = obj_[cur ^ 1];
+      roi_align_kernel<<<R * 49, 256, 0, st>>>(fl, boxes_in, R, roi_);
+      MCG_CUDA(cudaGetLastError());
+      count();
+      // spatial then temporal self-attention with the SAME weights (gaze_stqi_head.py:148-166)
+      const float* xin = obj_in;
+      float* xout[2] = {xa_, xb_};
+      for (int mode = 0; mode < 2; ++mode) {
+        linear(xin, 256, sw.in_proj, R, qkv_, 768, false, nullptr, 0, st);
+        attention_kernel<<<(R * 8 * 32 + 255) / 256, 256, 0, st>>>(qkv_, att_, R, T, mode);
+        MCG_CUDA(cudaGetLastError());
+        count();
+        linear(att_, 256, sw.out_proj, R, xc_, 256, false, xin, 256, st);  // + identity (mmcv MHA)
+        ln(xc_, 256, nullptr, 0, sw.attn_norm, xout[mode], 256, R, false, st);
+        xin = xout[mode];
+      }
+      const float* attn = xb_;
+      // DynamicConv (transformer.py:1116-1164)
+      linear_tc(sk + "dyn", attn, 256, hq_, sw.dyn, R, params_, false, nullptr, st);
+      dynconv_kernel<<<R, 256, kDynSmemBytes, st>>>(roi_, params_, sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
+                                                    sw.norm_out.b, dynf_);
+      MCG_CUDA(cudaGetLastError());
+      count();
+      linear_tc(sk + "fc", dynf_, 12544, hf_, sw.fc, R, fc_, false, nullptr, st);
+      ln(fc_, 256, nullptr, 0, sw.fc_norm, fc_, 256, R, true, st);
+      ln(attn, 256, fc_, 256, sw.iic_norm, xa_, 256, R, false, st);  // obj = LN(attn + iic)
+      // FFN with identity (gaze_stqi_head.py:179)
+      linear_tc(sk + "ffn1", xa_, 256, hq_, sw.ffn1, R, ffn_h_, true, nullptr, st);
+      linear_tc(sk + "ffn2", ffn_h_, 2048, hh_, sw.ffn2, R, xc_, false, xa_, st);
+      ln(xc_, 256, nullptr, 0, sw.ffn_norm, obj_out, 256, R, false, st);
+      // cls / reg towers + per-clue heads (gaze_stqi_head.py:185-201)
+      linear(obj_out, 256, sw.cls_fc, R, t256a_, 256, false, nullptr, 0, st);
+      ln(t256a_, 256, nullptr, 0, sw.cls_ln, t256a_, 256, R, true, st);
+      for (int c = 0; c < 3; ++c) linear(t256a_ + c * 256, 768, sw.fc_cls[c], NB, cls_logit_ + c, 3, false, nullptr, 0, st);
+      const float* rin = obj_out;
+      float* rbuf[2] = {t256b_, xc_};
+      for (int j = 0; j < 3; ++j) {
+        float* ro = rbuf[j & 1];
+        linear(rin, 256, sw.reg_fc[j], R, ro, 256, false, nullptr, 0, st);
+        ln(ro, 256, nullptr, 0, sw.reg_ln[j], ro, 256, R, true, st);
+        rin = ro;
+      }
+      for (int c = 0; c < 3; ++c) linear(rin + c * 256, 768, sw.fc_reg[c], NB, delta_ + c * 4, 12, false, nullptr, 0, st);
+      box_decode_kernel<<<(R + 127) / 128, 128, 0, st>>>(boxes_in, delta_, R, boxes_out);
+      MCG_CUDA(cudaGetLastError());
+      count();
+      if (keep_stage_interm_ && !graph_mode_) {
+        // head buffers are reused by every stage: snapshot them for per-op parity tests
+        const std::string nm = "stage" + std::to_string(s);
+        reg_f32(nm + ".roi_feat", snapshot(roi_, static_cast<size_t>(R) * 12544, st), R, 49, 256);
+        reg_f32(nm + ".attn", snapshot(attn, static_cast<size_t>(R) * 256, st), NB, 3, 256);
+        reg_f32(nm + ".obj", snapshot(obj_out, static_cast<size_t>(R) * 256, st), NB, 3, 256);
+        reg_f32(nm + ".boxes", snapshot(boxes_out, static_cast<size_t>(R) * 4, st), NB, 3, 4);
+        reg_f32(nm + ".delta", snapshot(delta_, static_cast<size_t>(R) * 4, st), NB, 3, 4);
+        reg_f32(nm + ".cls", snapshot(cls_logit_, static_cast<size_t>(R), st), NB, 3);
+      }
+      cur ^= 1;
+    }
+    reg_f32("obj", obj_[cur], NB, 3, 256);
+    reg_f32("boxes", boxes_[cur], NB, 3, 4);
+    reg_f32("cls", cls_logit_, NB, 3);
+    // ---- gaze head on the last stage's object features (gaze_head.py:138-202)
+    const float* obj = obj_[cur];
+    for (int c = 0; c < 3; ++c) {
+      for (int branch = 0; branch < 2; ++branch) {
+        const GemmW* tw = branch == 0 ? gaze_.tower[c] : gaze_.ctower[c];
+        const LnW* tl = branch == 0 ? gaze_.tower_ln[c] : gaze_.ctower_ln[c];
+        linear(obj + c * 256, 768, tw[0], NB, gz_a_, 256, false, nullptr, 0, st);
+        ln(gz_a_, 256, nullptr, 0, tl[0], gz_a_, 256, NB, true, st);
+        linear(gz_a_, 256, tw[1], NB, gz_b_, 256, false, nullptr, 0, st);
+        ln(gz_b_, 256, nullptr, 0, tl[1], gz_b_, 256, NB, true, st);
+        const GemmW& head = branch == 0 ? gaze_.fc[c] : gaze_.fc_conf[c];
+        float* dst = (branch == 0 ? gvec_ : conf_) + static_cast<size_t>(c) * NB * 3;
+        linear(gz_b_, 256, head, NB, dst, 3, false, nullptr, 0, st);
+      }
+    }
+    finalize_kernel<<<(NB + 127) / 128, 128, 0, st>>>(gvec_, conf_, gaze_.wg, gaze_.bg, cls_logit_, boxes_[cur],
+                                                      has_scale_ ? scale : nullptr, NB, out_gaze, out_boxes, out_scores);
+    MCG_CUDA(cudaGetLastError());
+    count();
+  }
+
+  // -------------------------------------------------------------------------- state
+  int device_ = 0;
+  int precision_ = 0;
+  int num_sms_ = 148;
+  bool head_tc_ = true;
+  bool keep_stage_interm_ = false;
+  std::vector<std::unique_ptr<DeviceBlock>> dbg_;
+  std::vector<float> meta_host_;
+  std::unordered_map<std::string, HostT> host_;
+  std::vector<std::unique_ptr<DeviceBlock>> keep_;
+  ConvW stem_;
+  std::vector<BlockW> blocks_[4];
+  ConvW lateral_[4], fpnconv_[4];
+  const float* init_boxes_ = nullptr;
+  const float* init_feats_ = nullptr;
+  StageW stage_[4];
+  GazeW gaze_;
+
+  Arena arena_;
+  int ws_NB_ = 0, ws_T_ = 0, ws_H_ = 0, ws_W_ = 0;
+  struct BlkAct {
+    Act t1, t2, ds, out;
+  };
+  Planes stemA_;
+  Act stem_out_, pool_out_;
+  std::vector<BlkAct> blk_act_[4];
+  Act lat_[4], fpn_[4];
+  float *boxes_[2] = {nullptr, nullptr}, *obj_[2] = {nullptr, nullptr};
+  float *qkv_ = nullptr, *att_ = nullptr, *xa_ = nullptr, *xb_ = nullptr, *xc_ = nullptr, *params_ = nullptr,
+        *roi_ = nullptr, *dynf_ = nullptr, *fc_ = nullptr, *ffn_h_ = nullptr, *t256a_ = nullptr, *t256b_ = nullptr,
+        *cls_logit_ = nullptr, *delta_ = nullptr, *gz_a_ = nullptr, *gz_b_ = nullptr, *gvec_ = nullptr,
+        *conf_ = nullptr, *d_meta_ = nullptr;
+  Planes hq_, hh_, hf_;
+  float* pin_meta_ = nullptr;
+  bool has_scale_ = false;
+
+  std::map<std::string, UmmaPlan> plans_;
+  std::map<std::string, Interm> interm_;
+  int launches_ = 0;
+
+  bool graph_mode_ = false;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  const float* g_img_ = nullptr;
+  float *g_gaze_ = nullptr, *g_boxes_ = nullptr, *g_scores_ = nullptr;
+  bool g_has_scale_ = false;
+
+  cudaStream_t own_stream_ = nullptr;
+  std::unique_ptr<DeviceBlock> io_in_, io_out_;
+  size_t io_in_bytes_ = 0, io_out_bytes_ = 0;
+  void* pin_out_ = nullptr;
+};
+
+}  // namespace mcg
+
+// ========================================================================================
+// C ABI
+// ========================================================================================
+struct mcg_engine {
+  std::unique_ptr<mcg::Engine> impl;
+};
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const mcg::CudaError& e) {
+    mcg::g_last_error = e.what();
+    const std::string m = e.what();
+    if (m.find("missing checkpoint key") != std::string::npos) return MCG_ERR_MISSING_WEIGHT;
+    if (m.find("check failed") != std::string::npos) return MCG_ERR_INVALID;
+    return MCG_ERR_CUDA;
+  } catch (const std::exception& e) {
+    mcg::g_last_error = e.what();
+    return MCG_ERR_INVALID;
+  } catch (...) {
+    mcg::g_last_error = "unknown error";
+    return MCG_ERR_INVALID;
+  }
+}
+
+extern "C" {
+
+const char* mcg_last_error(void) { return mcg::g_last_error.c_str(); }
+const char* mcg_version(void) { return "mcgaze_b200 0.1 (sm_100a)"; }
+
+int mcg_create(mcg_handle* out, int device, const mcg_tensor* weights, int n_weights, int precision) {
+  return guarded([&]() -> int {
+    if (!out || !weights || n_weights <= 0 || precision < 0 || precision > 2) {
+      mcg::g_last_error = "mcg_create: invalid argument";
+      return MCG_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      mcg::g_last_error = "mcg_create: no CUDA device visible (this library has no CPU fallback)";
+      return MCG_ERR_CUDA;
+    }
+    std::unique_ptr<mcg_engine> h(new mcg_engine);
+    h->impl.reset(new mcg::Engine(device, weights, n_weights, precision));
+    *out = h.release();
+    return MCG_OK;
+  });
+}
+
+int mcg_destroy(mcg_handle h) {
+  return guarded([&]() -> int {
+    delete h;
+    return MCG_OK;
+  });
+}
+
+int mcg_forward(mcg_handle h, const float* img, int B, int T, int H, int W, const float* img_hw,
+                const float* scale_factor, float* out_gaze, float* out_boxes, float* out_scores, void* stream) {
+  return guarded([&]() -> int {
+    if (!h || !img || !out_gaze || !out_boxes || !out_scores) {
+      mcg::g_last_error = "mcg_forward: null argument";
+      return MCG_ERR_INVALID;
+    }
+    h->impl->forward(img, B, T, H, W, img_hw, scale_factor, out_gaze, out_boxes, out_scores,
+                     static_cast<cudaStream_t>(stream));
+    return MCG_OK;
+  });
+}
+
+int mcg_forward_host(mcg_handle h, const float* img_host, int B, int T, int H, int W, const float* img_hw,
+                     const float* scale_factor, float* out_gaze_host, float* out_boxes_host, float* out_scores_host) {
+  return guarded([&]() -> int {
+    if (!h || !img_host || !out_gaze_host || !out_boxes_host || !out_scores_host) {
+      mcg::g_last_error = "mcg_forward_host: null argument";
+      return MCG_ERR_INVALID;
+    }
+    h->impl->forward_host(img_host, B, T, H, W, img_hw, scale_factor, out_gaze_host, out_boxes_host, out_scores_host);
+    return MCG_OK;
+  });
+}
+
+int mcg_get_intermediate(mcg_handle h, const char* name, float* dst, int64_t capacity, int64_t shape_out[4]) {
+  return guarded([&]() -> int {
+    if (!h || !name || !dst || !shape_out) return MCG_ERR_INVALID;
+    const int r = h->impl->get_intermediate(name, dst, capacity, shape_out);
+    if (r != MCG_OK) mcg::g_last_error = std::string("mcg_get_intermediate: unknown name or capacity too small: ") + name;
+    return r;
+  });
+}
+
+int mcg_last_launch_count(mcg_handle h) { return h ? h->impl->last_launches() : -1; }
+
+int mcg_set_graph_mode(mcg_handle h, int on) {
+  return guarded([&]() -> int {
+    if (!h) return MCG_ERR_INVALID;
+    h->impl->set_graph_mode(on);
+    return MCG_OK;
+  });
+}
+
+int mcg_set_option(mcg_handle h, const char* key, int value) {
+  return guarded([&]() -> int {
+    if (!h || !key) return MCG_ERR_INVALID;
+    h->impl->set_option(key, value);
+    return MCG_OK;
+  });
+}
+
+int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, const float* w, int Cout, int R, int S,
+                   int stride, int pad, const float* bias, const float* res, int res_mode, int relu, int force_im2col,
+                   int force_block_n, float* out, void* stream) {
+  using namespace mcg;
+  return guarded([&]() -> int {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    const long long M = static_cast<long long>(NB) * P * Q;
+    const int K = R * S * C;
+    const size_t nx = static_cast<size_t>(NB) * H * W * C, nw = static_cast<size_t>(Cout) * K;
+    const size_t ny = static_cast<size_t>(M) * Cout;
+    int RH = P, RW = Q;
+    if (res_mode == RES_UP2X) {
+      RH = P / 2;
+      RW = Q / 2;
+    }
+    const size_t nr = res ? static_cast<size_t>(NB) * RH * RW * Cout : 0;
+    DeviceBlock bx(nx * 4), bw(nw * 4), br(nr * 4 + 16);
+    Planes px{reinterpret_cast<__half*>(bx.p), reinterpret_cast<__half*>(bx.p) + nx};
+    Planes pw{reinterpret_cast<__half*>(bw.p), reinterpret_cast<__half*>(bw.p) + nw};
+    Planes pr{reinterpret_cast<__half*>(br.p), reinterpret_cast<__half*>(br.p) + nr};
+    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, px.lo);
+    split_planes_kernel<<<1024, 256, 0, st>>>(w, K, Cout, K, pw.hi, pw.lo);
+    if (res) split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi, pr.lo);
+    MCG_CUDA(cudaGetLastError());
+    AGeom g;
+    const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col;
+    g.kind = plain ? 0 : 1;
+    g.lda = C;
+    g.NB = NB;
+    g.H = H;
+    g.W = W;
+    g.C = C;
+    g.R = R;
+    g.S = S;
+    g.stride = stride;
+    g.pad = pad;
+    g.P = P;
+    g.Q = Q;
+    Epilogue ep;
+    ep.bias = bias;
+    ep.relu = relu;
+    ep.out_f32 = out;
+    ep.ldo = Cout;
+    if (res) {
+      ep.res_hi = pr.hi;
+      ep.res_lo = pr.lo;
+      ep.res_mode = res_mode;
+      ep.ldr = Cout;
+      ep.P = P;
+      ep.Q = Q;
+    }
+    (void)ny;
+    if (engine == MCG_PRECISION_SIMT) {
+      SimtParams p;
+      p.M = M;
+      p.N = Cout;
+      p.K = K;
+      p.a = g;
+      p.a_hi = px.hi;
+      p.a_lo = px.lo;
+      p.w_hi = pw.hi;
+      p.w_lo = pw.lo;
+      p.ep = ep;
+      launch_simt_gemm(p, st);
+    } else {
+      int dev = 0, sms = 148;
+      MCG_CUDA(cudaGetDevice(&dev));
+      MCG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      if (!umma_supported(M, Cout, K, g)) {
+        g_last_error = "mcg_debug_conv: shape not supported by the tcgen05 kernel";
+        return MCG_ERR_UNSUPPORTED;
+      }
+      UmmaPlan pl = make_umma_plan(engine == MCG_PRECISION_FP16X3 ? 3 : 1, px, g, pw, M, Cout, K, ep, sms, force_block_n);
+      launch_umma(pl, st);
+    }
+    MCG_CUDA(cudaStreamSynchronize(st));
+    return MCG_OK;
+  });
+}
+
+}  // extern "C"

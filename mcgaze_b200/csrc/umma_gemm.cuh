@@ -1,0 +1,461 @@
+// tcgen05 / TMA / TMEM implicit-GEMM kernel for sm_100a.
+//
+//   D[m, n] = sum_k A[m, k] * W[n, k]   (+ fused epilogue, see common.cuh)
+//
+// A is either a plain row-major [M, K] split-fp16 matrix (1x1 stride-1 convolutions, the head's
+// Linear layers) or the implicit im2col view of an NHWC activation (3x3 / strided convolutions),
+// fetched by TMA in im2col mode.  W is the [N, K] K-major packed weight (BN folded).
+//
+// Precision: operands are split-fp16 (value = hi + lo).  kTerms == 1 issues one MMA per k-step
+// (hi*hi, "fast" mode); kTerms == 3 issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM
+// accumulator (~22-bit operand mantissa: fp32-equivalent products, the mode that meets the
+// 1e-3 (yaw,pitch) parity bar against the fp32 oracle).
+//
+// Structure (persistent, one CTA per SM, 256 threads):
+//   warp 0   : TMA producer  (one elected lane; A tile 128 x 64, W tile block_n x 64, SWIZZLE_128B)
+//   warp 1   : MMA issuer    (one lane issues tcgen05.mma M=128, N=block_n, K=16; commit -> mbarrier)
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator buffers of up to 256 fp32 columns)
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b.x32 -> bias/residual/ReLU -> split-fp16 or fp32 stores)
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mcg {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 fp16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 8;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kSmemBarrierBytes = 1024;
+constexpr int kMaxDynSmem = 229376;  // 224 KB (227 KB opt-in limit minus headroom for the 1 KB the runtime reserves)
+
+struct UmmaParams {
+  int M = 0, N = 0, K = 0;
+  int block_n = 0;
+  int num_stages = 0;
+  int num_kb = 0;
+  int m_tiles = 0, n_tiles = 0;
+  int cblocks = 1;  // C / 64 for im2col
+  AGeom a;
+  Epilogue ep;
+};
+
+template <int kTerms>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                 const UmmaParams p) {
+  constexpr int kPlanes = (kTerms == 3) ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* stage_base = smem + kSmemBarrierBytes;
+
+  const int w_tile_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = kPlanes * (kATileBytes + w_tile_bytes);
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA_hi);
+    ptx::prefetch_tmap(&tmW_hi);
+    if (kTerms == 3) {
+      ptx::prefetch_tmap(&tmA_lo);
+      ptx::prefetch_tmap(&tmW_lo);
+    }
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const long long m0 = static_cast<long long>(m_tile) * kBlockM;
+        int img_n = 0, base_h = 0, base_w = 0;
+        if (p.a.kind == 1) {
+          const long long pq = static_cast<long long>(p.a.P) * p.a.Q;
+          img_n = static_cast<int>(m0 / pq);
+          const int rem = static_cast<int>(m0 - img_n * pq);
+          const int p0 = rem / p.a.Q;
+          const int q0 = rem - p0 * p.a.Q;
+          base_h = p0 * p.a.stride - p.a.pad;
+          base_w = q0 * p.a.stride - p.a.pad;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* s = stage_base + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sA_hi = s;
+          uint8_t* sA_lo = s + kATileBytes;
+          uint8_t* sW_hi = s + kPlanes * kATileBytes;
+          uint8_t* sW_lo = sW_hi + w_tile_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          if (p.a.kind == 1) {
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int r = tap / p.a.S;
+            const int sx = tap - r * p.a.S;
+            ptx::tma_load_im2col_4d(sA_hi, &tmA_hi, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
+                                    static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+            if (kTerms == 3)
+              ptx::tma_load_im2col_4d(sA_lo, &tmA_lo, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
+                                      static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+          } else {
+            ptx::tma_load_2d(sA_hi, &tmA_hi, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+            if (kTerms == 3) ptx::tma_load_2d(sA_lo, &tmA_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+          }
+          ptx::tma_load_2d(sW_hi, &tmW_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (kTerms == 3) ptx::tma_load_2d(sW_lo, &tmW_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = ptx::make_idesc_f16_f32(kBlockM, p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t s = ptx::smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t aA_hi = s;
+          const uint32_t aA_lo = s + kATileBytes;
+          const uint32_t aW_hi = s + kPlanes * kATileBytes;
+          const uint32_t aW_lo = aW_hi + w_tile_bytes;
+#pragma unroll
+          for (int j = 0; j < kBlockK / kUmmaK; ++j) {
+            const uint32_t koff = j * kUmmaK * 2;  // bytes inside the 128 B swizzle row
+            const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(aA_hi + koff);
+            const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(aW_hi + koff);
+            uint32_t accum = (kb > 0 || j > 0) ? 1u : 0u;
+            if (kTerms == 3) {
+              const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(aA_lo + koff);
+              const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(aW_lo + koff);
+              ptx::umma_f16(tmem_d, dA_lo, dW_hi, idesc, accum);
+              ptx::umma_f16(tmem_d, dA_hi, dW_lo, idesc, 1u);
+              accum = 1u;
+            }
+            ptx::umma_f16(tmem_d, dA_hi, dW_hi, idesc, accum);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == p.num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp_idx & 3;
+    const Epilogue& ep = p.ep;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const long long m = static_cast<long long>(m_tile) * kBlockM + quarter * 32 + lane;
+      const bool valid = m < p.M;
+      const long long rrow = (valid && ep.res_mode != RES_NONE) ? res_row(ep, m) : 0;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c0), r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          const int n = n_tile * p.block_n + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
+            }
+          }
+          if (ep.res_mode != RES_NONE && ep.res_f32) {
+            const float4* rf = reinterpret_cast<const float4*>(ep.res_f32 + rrow * ep.ldr + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 f = __ldg(rf + j);
+              v[4 * j + 0] += f.x;
+              v[4 * j + 1] += f.y;
+              v[4 * j + 2] += f.z;
+              v[4 * j + 3] += f.w;
+            }
+          } else if (ep.res_mode != RES_NONE) {
+            const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(rh + j);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(h2[t]);
+                v[8 * j + 2 * t] += f.x;
+                v[8 * j + 2 * t + 1] += f.y;
+              }
+            }
+            if (ep.res_lo) {
+              const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = __ldg(rl + j);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(h2[t]);
+                  v[8 * j + 2 * t] += f.x;
+                  v[8 * j + 2 * t + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (ep.out_f32) {
+            float4* o = reinterpret_cast<float4*>(ep.out_f32 + m * ep.ldo + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* oh = reinterpret_cast<uint4*>(ep.out_hi + m * ep.ldo + n);
+            uint4* ol = ep.out_lo ? reinterpret_cast<uint4*>(ep.out_lo + m * ep.ldo + n) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 uh, ul;
+              __half2* hh = reinterpret_cast<__half2*>(&uh);
+              __half2* hl = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float a = v[8 * j + 2 * t], b = v[8 * j + 2 * t + 1];
+                const __half2 h = __floats2half2_rn(a, b);
+                const float2 hf = __half22float2(h);
+                hh[t] = h;
+                hl[t] = __floats2half2_rn(a - hf.x, b - hf.y);
+              }
+              oh[j] = uh;
+              if (ol) ol[j] = ul;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps + launch plan
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DriverApi {
+  PFN_encodeTiled encodeTiled = nullptr;
+  PFN_encodeIm2col encodeIm2col = nullptr;
+  static const DriverApi& get() {
+    static DriverApi api = [] {
+      DriverApi a;
+      cudaDriverEntryPointQueryResult qr;
+      void* fn = nullptr;
+      MCG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+      MCG_CHECK(fn != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+      a.encodeTiled = reinterpret_cast<PFN_encodeTiled>(fn);
+      fn = nullptr;
+      MCG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qr));
+      MCG_CHECK(fn != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col unavailable");
+      a.encodeIm2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+      return a;
+    }();
+    return api;
+  }
+};
+
+inline CUtensorMap make_tmap_2d(const __half* base, long long rows, long long cols, long long ld, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = DriverApi::get().encodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims,
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed, code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+inline CUtensorMap make_tmap_im2col(const __half* base, const AGeom& g) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H),
+                        static_cast<cuuint64_t>(g.NB)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.C) * 2, static_cast<cuuint64_t>(g.W) * g.C * 2,
+                           static_cast<cuuint64_t>(g.H) * g.W * g.C * 2};
+  int lower[2] = {-g.pad, -g.pad};                            // (W, H)
+  int upper[2] = {g.pad - (g.S - 1), g.pad - (g.R - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
+  CUresult r = DriverApi::get().encodeIm2col(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims,
+                                             strides, lower, upper, kBlockK, kBlockM, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed, code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+struct UmmaPlan {
+  CUtensorMap tmA_hi, tmA_lo, tmW_hi, tmW_lo;
+  UmmaParams p;
+  int terms = 3;
+  int grid = 0;
+  int smem = 0;
+};
+
+inline bool umma_supported(long long M, int N, int K, const AGeom& a) {
+  if (N % 64 != 0 || K % kBlockK != 0 || M <= 0) return false;
+  if (a.kind == 1 && (a.C % kBlockK != 0)) return false;
+  if (a.kind == 0 && (a.lda % 8 != 0)) return false;
+  return true;
+}
+
+// A planes: for kind 0 the [M,K] matrix, for kind 1 the NHWC activation.  W planes: [N,K].
+inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
+                               const Epilogue& ep, int num_sms, int force_block_n = 0) {
+  MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
+  MCG_CHECK(terms == 1 || (A.lo && W.lo), "3-term GEMM needs lo planes");
+  UmmaPlan pl;
+  pl.terms = terms;
+  UmmaParams& p = pl.p;
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.K = K;
+  const int planes = terms == 3 ? 2 : 1;
+  int bn = force_block_n;
+  if (bn == 0) {
+    // largest tile that divides N and still leaves >= 3 pipeline stages
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (N % c) continue;
+      const int sb = planes * (kATileBytes + c * kBlockK * 2);
+      if ((kMaxDynSmem - 2048) / sb >= 3 || c == 64) {
+        bn = c;
+        break;
+      }
+    }
+  }
+  MCG_CHECK(bn > 0 && N % bn == 0, "bad block_n");
+  p.block_n = bn;
+  const int stage_bytes = planes * (kATileBytes + bn * kBlockK * 2);
+  p.num_stages = (kMaxDynSmem - 2048) / stage_bytes;
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  MCG_CHECK(p.num_stages >= 2, "not enough shared memory for 2 stages");
+  p.num_kb = K / kBlockK;
+  p.m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+  p.n_tiles = N / bn;
+  p.a = a;
+  p.cblocks = a.kind == 1 ? a.C / kBlockK : 1;
+  if (a.kind == 1) MCG_CHECK(K == a.R * a.S * a.C, "im2col K mismatch");
+  p.ep = ep;
+  pl.smem = 1024 + kSmemBarrierBytes + p.num_stages * stage_bytes;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  pl.grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  if (a.kind == 1) {
+    pl.tmA_hi = make_tmap_im2col(A.hi, a);
+    pl.tmA_lo = terms == 3 ? make_tmap_im2col(A.lo, a) : pl.tmA_hi;
+  } else {
+    pl.tmA_hi = make_tmap_2d(A.hi, M, K, a.lda, kBlockM);
+    pl.tmA_lo = terms == 3 ? make_tmap_2d(A.lo, M, K, a.lda, kBlockM) : pl.tmA_hi;
+  }
+  pl.tmW_hi = make_tmap_2d(W.hi, N, K, K, bn);
+  pl.tmW_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : pl.tmW_hi;
+  return pl;
+}
+
+inline void umma_set_attrs() {
+  static bool done = false;
+  if (done) return;
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  done = true;
+}
+
+inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
+  umma_set_attrs();
+  if (pl.terms == 3)
+    umma_gemm_kernel<3><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tmA_hi, pl.tmA_lo, pl.tmW_hi, pl.tmW_lo, pl.p);
+  else
+    umma_gemm_kernel<1><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tmA_hi, pl.tmA_lo, pl.tmW_hi, pl.tmW_lo, pl.p);
+  MCG_CUDA(cudaGetLastError());
+}
+
+}  // namespace mcg

@@ -1,0 +1,224 @@
+"""ctypes binding of the C ABI declared in include/mcgaze_b200.h.
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is visible,
+every compute entry point raises.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libmcgaze_b200.so')
+
+PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2}
+
+# every symbol include/mcgaze_b200.h declares
+EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_get_intermediate',
+           'mcg_last_launch_count', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
+           'mcg_last_error', 'mcg_version')
+
+
+class McgError(RuntimeError):
+    pass
+
+
+class mcg_tensor(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char_p), ('data', ctypes.c_void_p), ('ndim', ctypes.c_int),
+                ('shape', ctypes.c_int64 * 4)]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libmcgaze_b200.so (built in-tree by `python -m mcgaze_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McgError(f'{LIB_PATH} not found: build it with `python -m mcgaze_b200.build` '
+                       '(there is no CPU fallback)')
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)
+    lib.mcg_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(mcg_tensor), ci, ci]
+    lib.mcg_destroy.argtypes = [vp]
+    lib.mcg_forward.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.mcg_forward_host.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+    lib.mcg_get_intermediate.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    lib.mcg_last_launch_count.argtypes = [vp]
+    lib.mcg_set_graph_mode.argtypes = [vp, ci]
+    lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_char_p if name in ('mcg_last_error', 'mcg_version') else ci
+    del cf
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().mcg_last_error()
+        raise McgError(f'{what} failed (code {rc}): {msg.decode() if msg else ""}')
+
+
+class Engine:
+    """Owns one `mcg_handle`: packed weights + workspace on one device.
+
+    `state_dict` is a reference-layout checkpoint dict (name -> CPU fp32 tensor / ndarray),
+    exactly what `mmcv.runner.load_checkpoint` would hand to the reference's `MultiClueGaze`.
+    """
+
+    def __init__(self, state_dict: Dict[str, object], device: int = 0, precision: str = 'fp16x3'):
+        import numpy as np
+        import torch
+        if not torch.cuda.is_available():
+            raise McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        if precision not in PRECISIONS:
+            raise McgError(f'unknown precision {precision!r}; choose from {sorted(PRECISIONS)}')
+        self._lib = load_library()
+        self.device = int(device)
+        self.precision = precision
+        keep, arr = [], []
+        for k, v in state_dict.items():
+            if hasattr(v, 'detach'):
+                if not v.is_floating_point():
+                    continue
+                v = v.detach().to('cpu', torch.float32).contiguous().numpy()
+            v = np.ascontiguousarray(v, dtype=np.float32)
+            if v.ndim > 4:
+                continue
+            keep.append(v)
+            t = mcg_tensor()
+            t.name = k.encode()
+            t.data = v.ctypes.data
+            t.ndim = v.ndim
+            for i in range(v.ndim):
+                t.shape[i] = v.shape[i]
+            arr.append(t)
+        tensors = (mcg_tensor * len(arr))(*arr)
+        h = ctypes.c_void_p()
+        _check(self._lib.mcg_create(ctypes.byref(h), self.device, tensors, len(arr), PRECISIONS[precision]),
+               'mcg_create')
+        self._h = h
+        del keep
+
+    def close(self) -> None:
+        if getattr(self, '_h', None):
+            self._lib.mcg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ options
+    def set_graph_mode(self, on: bool) -> None:
+        _check(self._lib.mcg_set_graph_mode(self._h, int(bool(on))), 'mcg_set_graph_mode')
+
+    def set_option(self, key: str, value: int) -> None:
+        _check(self._lib.mcg_set_option(self._h, key.encode(), int(value)), 'mcg_set_option')
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.mcg_last_launch_count(self._h))
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _meta(arr, n: int, width: int):
+        import numpy as np
+        if arr is None:
+            return None, None
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(n, width))
+        return a, a.ctypes.data
+
+    def forward(self, img, clip_length: Optional[int] = None, img_hw=None, scale_factor=None):
+        """img: CUDA fp32 [N,3,H,W] (N = B*clip_length).  Returns CUDA tensors
+        {'gaze' [N,4,3] (fused, face, eyes, head), 'boxes' [N,3,4], 'scores' [N,3]}; asynchronous on the
+        current torch stream."""
+        import torch
+        assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3
+        img = img.contiguous()
+        N, _, H, W = img.shape
+        T = N if clip_length is None else int(clip_length)
+        assert N % T == 0
+        gaze = torch.empty(N, 4, 3, device=img.device, dtype=torch.float32)
+        boxes = torch.empty(N, 3, 4, device=img.device, dtype=torch.float32)
+        scores = torch.empty(N, 3, device=img.device, dtype=torch.float32)
+        k1, p1 = self._meta(img_hw, N, 2)
+        k2, p2 = self._meta(scale_factor, N, 4)
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        _check(self._lib.mcg_forward(self._h, img.data_ptr(), N // T, T, H, W, p1, p2, gaze.data_ptr(),
+                                     boxes.data_ptr(), scores.data_ptr(), ctypes.c_void_p(stream)), 'mcg_forward')
+        del k1, k2
+        return {'gaze': gaze, 'boxes': boxes, 'scores': scores}
+
+    def forward_into(self, img, clip_length: int, out):
+        """Like forward() but writes into the preallocated dict `out` (stable pointers: lets the
+        CUDA-graph replay path engage)."""
+        import torch
+        N, _, H, W = img.shape
+        T = int(clip_length)
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        _check(self._lib.mcg_forward(self._h, img.data_ptr(), N // T, T, H, W, None, None, out['gaze'].data_ptr(),
+                                     out['boxes'].data_ptr(), out['scores'].data_ptr(), ctypes.c_void_p(stream)),
+               'mcg_forward')
+        return out
+
+    def forward_host(self, img, clip_length: Optional[int] = None, img_hw=None, scale_factor=None):
+        """img: CPU fp32 [N,3,H,W] (pinned memory gives async copies).  Host-to-device copy, forward,
+        device-to-host copy and a stream sync all happen inside the C call.  Returns CPU tensors."""
+        import torch
+        assert (not img.is_cuda) and img.dtype == torch.float32 and img.dim() == 4
+        img = img.contiguous()
+        N, _, H, W = img.shape
+        T = N if clip_length is None else int(clip_length)
+        gaze = torch.empty(N, 4, 3, dtype=torch.float32)
+        boxes = torch.empty(N, 3, 4, dtype=torch.float32)
+        scores = torch.empty(N, 3, dtype=torch.float32)
+        k1, p1 = self._meta(img_hw, N, 2)
+        k2, p2 = self._meta(scale_factor, N, 4)
+        _check(self._lib.mcg_forward_host(self._h, img.data_ptr(), N // T, T, H, W, p1, p2, gaze.data_ptr(),
+                                          boxes.data_ptr(), scores.data_ptr()), 'mcg_forward_host')
+        del k1, k2
+        return {'gaze': gaze, 'boxes': boxes, 'scores': scores}
+
+    def intermediate(self, name: str, max_elems: int = 1 << 28):
+        import torch
+        buf = torch.empty(max_elems, device=f'cuda:{self.device}', dtype=torch.float32)
+        shape = (ctypes.c_int64 * 4)()
+        _check(self._lib.mcg_get_intermediate(self._h, name.encode(), buf.data_ptr(), max_elems, shape),
+               f'mcg_get_intermediate({name})')
+        dims = [int(s) for s in shape if int(s) > 0]
+        n = 1
+        for d in dims:
+            n *= d
+        return buf[:n].reshape(dims).clone()
+
+
+def debug_conv(engine: str, x, w, stride: int, pad: int, bias=None, res=None, res_mode: int = 0, relu: bool = False,
+               force_im2col: bool = False, force_block_n: int = 0):
+    """Kernel-level entry: x CUDA fp32 NCHW, w CUDA fp32 [Cout,Cin,R,S] -> CUDA fp32 NCHW (torch layout in/out;
+    the NHWC / (r,s,c) repack the C ABI wants happens here)."""
+    import torch
+    lib = load_library()
+    NB, C, H, W = x.shape
+    Cout, _, R, S = w.shape
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - S) // stride + 1
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_p = w.permute(0, 2, 3, 1).contiguous().reshape(Cout, R * S * C)
+    res_nhwc = res.permute(0, 2, 3, 1).contiguous() if res is not None else None
+    out = torch.empty(NB, P, Q, Cout, device=x.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    rc = lib.mcg_debug_conv(PRECISIONS[engine], x_nhwc.data_ptr(), NB, H, W, C, w_p.data_ptr(), Cout, R, S, stride, pad,
+                            bias.data_ptr() if bias is not None else None,
+                            res_nhwc.data_ptr() if res_nhwc is not None else None, res_mode, int(relu),
+                            int(force_im2col), force_block_n, out.data_ptr(), ctypes.c_void_p(stream))
+    _check(rc, 'mcg_debug_conv')
+    return out.permute(0, 3, 1, 2).contiguous()
