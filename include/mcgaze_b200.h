@@ -81,11 +81,17 @@ int mcg_get_intermediate(mcg_handle h, const char* name, float* dst, int64_t cap
 /* Number of kernels this library launched in the last forward. */
 int mcg_last_launch_count(mcg_handle h);
 
+/* tcgen05 GEMM statistics of the last EAGER forward: out[0] = launches, out[1] = algorithmic FLOPs
+ * (2*M*N*K, independent of the precision mode), out[2] = summed device time in ms measured with
+ * CUDA events around each launch (needs option "time_kernels" = 1; synchronises). */
+int mcg_last_umma_stats(mcg_handle h, double out[3]);
+
 /* Capture the forward for the current shape in a CUDA graph and replay it on later calls
  * (on = 1) or launch kernels eagerly (on = 0, default). */
 int mcg_set_graph_mode(mcg_handle h, int on);
 
 /* Options: "keep_intermediates" (1: snapshot per-stage head buffers for mcg_get_intermediate),
+ * "time_kernels" (1: CUDA events around every tcgen05 GEMM launch),
  * "head_tensor_cores" (0: run the head's large Linear layers on the fp32 CUDA-core kernel). */
 int mcg_set_option(mcg_handle h, const char* key, int value);
 

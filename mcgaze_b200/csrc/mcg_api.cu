@@ -148,12 +148,15 @@ class Engine {
 
   ~Engine() {
     if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     if (pin_out_) cudaFreeHost(pin_out_);
     if (pin_meta_) cudaFreeHost(pin_meta_);
     if (own_stream_) cudaStreamDestroy(own_stream_);
+    if (cap_stream_) cudaStreamDestroy(cap_stream_);
   }
   void set_option(const std::string& k, int v) {
     if (k == "keep_intermediates") keep_stage_interm_ = v != 0;
+    else if (k == "time_kernels") time_kernels_ = v != 0;
     else if (k == "head_tensor_cores") { head_tc_ = v != 0; plans_.clear(); drop_graph(); }
     else throw CudaError("check failed: unknown option " + k);
   }
@@ -163,6 +166,22 @@ class Engine {
     drop_graph();
   }
   int last_launches() const { return launches_; }
+  // stats of the tcgen05 GEMM launches of the last eager forward: [0] launches, [1] algorithmic
+  // FLOPs, [2] summed device time in ms (needs option time_kernels=1; synchronises)
+  void umma_stats(double out[3]) {
+    out[0] = umma_launches_;
+    out[1] = umma_flops_;
+    double ms = 0.0;
+    if (ev_used_) {
+      MCG_CUDA(cudaEventSynchronize(ev_pool_[ev_used_ - 1]));
+      for (size_t i = 0; i + 1 < ev_used_; i += 2) {
+        float t = 0.f;
+        MCG_CUDA(cudaEventElapsedTime(&t, ev_pool_[i], ev_pool_[i + 1]));
+        ms += t;
+      }
+    }
+    out[2] = ms;
+  }
 
   void forward(const float* img, int B, int T, int H, int W, const float* img_hw, const float* scale_factor,
                float* out_gaze, float* out_boxes, float* out_scores, cudaStream_t stream) {
@@ -194,16 +213,20 @@ class Engine {
     }
     if (graph_mode_) {
       drop_graph();
+      // capture on a private stream (the caller's may be the legacy default stream, which cannot
+      // be captured), then replay the instantiated graph on the caller's stream
+      if (!cap_stream_) MCG_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+      MCG_CUDA(cudaStreamSynchronize(stream));
       cudaGraph_t graph = nullptr;
-      MCG_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      MCG_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
       try {
-        schedule(img, out_gaze, out_boxes, out_scores, stream);
+        schedule(img, out_gaze, out_boxes, out_scores, cap_stream_);
       } catch (...) {
-        cudaStreamEndCapture(stream, &graph);
+        cudaStreamEndCapture(cap_stream_, &graph);
         if (graph) cudaGraphDestroy(graph);
         throw;
       }
-      MCG_CUDA(cudaStreamEndCapture(stream, &graph));
+      MCG_CUDA(cudaStreamEndCapture(cap_stream_, &graph));
       MCG_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
       MCG_CUDA(cudaGraphDestroy(graph));
       g_img_ = img;
@@ -563,7 +586,23 @@ class Engine {
         UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_);
         it = plans_.emplace(key, pl).first;
       }
+      const bool timed = time_kernels_ && !graph_mode_;
+      if (timed) {
+        if (ev_used_ + 2 > ev_pool_.size()) {
+          ev_pool_.resize(ev_used_ + 2);
+          MCG_CUDA(cudaEventCreate(&ev_pool_[ev_used_]));
+          MCG_CUDA(cudaEventCreate(&ev_pool_[ev_used_ + 1]));
+        }
+        MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_], st));
+      }
       launch_umma(it->second, st);
+      if (timed) {
+        MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_ + 1], st));
+        ev_used_ += 2;
+      }
+      ++umma_launches_;
+      // algorithmic work: the stem's K is zero-padded from 147 to 192
+      umma_flops_ += 2.0 * static_cast<double>(M) * w.N * (key == "stem" ? 147 : w.K);
     } else {
       SimtParams p;
       p.M = M;
@@ -701,6 +740,9 @@ class Engine {
   // -------------------------------------------------------------------------- the forward schedule
   void schedule(const float* img, float* out_gaze, float* out_boxes, float* out_scores, cudaStream_t st) {
     launches_ = 0;
+    umma_launches_ = 0;
+    umma_flops_ = 0.0;
+    ev_used_ = 0;
     if (!graph_mode_) dbg_.clear();
     const int NB = ws_NB_, T = ws_T_, H = ws_H_, W = ws_W_;
     const int ew_grid = num_sms_ * 8;
@@ -864,6 +906,11 @@ class Engine {
   int num_sms_ = 148;
   bool head_tc_ = true;
   bool keep_stage_interm_ = false;
+  bool time_kernels_ = false;
+  std::vector<cudaEvent_t> ev_pool_;
+  size_t ev_used_ = 0;
+  int umma_launches_ = 0;
+  double umma_flops_ = 0.0;
   std::vector<std::unique_ptr<DeviceBlock>> dbg_;
   std::vector<float> meta_host_;
   std::unordered_map<std::string, HostT> host_;
@@ -905,6 +952,7 @@ class Engine {
   bool g_has_scale_ = false;
 
   cudaStream_t own_stream_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr;
   std::unique_ptr<DeviceBlock> io_in_, io_out_;
   size_t io_in_bytes_ = 0, io_out_bytes_ = 0;
   void* pin_out_ = nullptr;
@@ -1003,6 +1051,14 @@ int mcg_get_intermediate(mcg_handle h, const char* name, float* dst, int64_t cap
 }
 
 int mcg_last_launch_count(mcg_handle h) { return h ? h->impl->last_launches() : -1; }
+
+int mcg_last_umma_stats(mcg_handle h, double out[3]) {
+  return guarded([&]() -> int {
+    if (!h || !out) return MCG_ERR_INVALID;
+    h->impl->umma_stats(out);
+    return MCG_OK;
+  });
+}
 
 int mcg_set_graph_mode(mcg_handle h, int on) {
   return guarded([&]() -> int {

@@ -1,0 +1,220 @@
+"""Drop-in `MultiClueGaze` for the reference's config / registry surface, backed by the CUDA
+engine (include/mcgaze_b200.h).
+
+The classes registered here mirror the `type=` names of configs/multiclue_gaze/*.py
+(reference: mmdet/models/detectors/multiclue_gaze.py:8, backbones/resnet.py:305, necks/fpn.py:10,
+dense_heads/fixed_embedding_rpn_head.py:10, roi_heads/multiclue_gaze_roi_head.py:9,
+roi_extractors/single_level_roi_extractor.py, bbox_heads/gaze_stqi_head.py:17,
+mask_heads/gaze_head.py:16, utils/transformer.py:1054).  The sub-module classes only VALIDATE
+their config against what the sm_100a kernels implement (the architecture is compiled in) and
+describe the parameter layout; all arithmetic happens in libmcgaze_b200.so.  There is no CPU path:
+constructing the engine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .registry import (BACKBONES, DETECTORS, HEADS, LOSSES, NECKS, ROI_EXTRACTORS, TRANSFORMER, build_backbone,
+                       build_head, build_neck, build_roi_extractor, build_transformer)
+
+
+class _Spec:
+    """Config-carrying node; `expect` pins the hyper-parameters the kernels hard-wire."""
+    expect: Dict[str, Any] = {}
+
+    def __init__(self, **cfg):
+        cfg.pop('init_cfg', None)
+        cfg.pop('train_cfg', None)
+        cfg.pop('test_cfg', None)
+        for k, want in self.expect.items():
+            if k in cfg:
+                got = cfg[k]
+                got = list(got) if isinstance(got, (tuple, list)) else got
+                w = list(want) if isinstance(want, (tuple, list)) else want
+                if got != w:
+                    raise NotImplementedError(
+                        f'{type(self).__name__}: {k}={cfg[k]!r} is not supported by the sm_100a kernels '
+                        f'(compiled for {k}={want!r})')
+        self.cfg = cfg
+
+
+@BACKBONES.register_module()
+class ResNet(_Spec):
+    expect = dict(depth=50, num_stages=4, out_indices=(0, 1, 2, 3), style='pytorch')
+
+
+@NECKS.register_module()
+class FPN(_Spec):
+    expect = dict(in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=0, num_outs=4)
+
+
+@HEADS.register_module()
+class FixedEmbeddingRPNHead(_Spec):
+    expect = dict(proposal_feature_channel=256, num_proposals=3)
+
+
+@ROI_EXTRACTORS.register_module()
+class SingleRoIExtractor(_Spec):
+    expect = dict(out_channels=256, featmap_strides=[4, 8, 16, 32], finest_scale=56)
+
+    def __init__(self, **cfg):
+        super().__init__(**cfg)
+        rl = cfg.get('roi_layer', {})
+        if rl.get('type', 'RoIAlign') != 'RoIAlign' or rl.get('output_size', 7) != 7 or rl.get('sampling_ratio', 2) != 2:
+            raise NotImplementedError(f'roi_layer {rl!r} not supported (RoIAlign 7x7, sampling_ratio=2 only)')
+
+
+@TRANSFORMER.register_module()
+class DynamicConv(_Spec):
+    expect = dict(in_channels=256, feat_channels=64, out_channels=256, input_feat_shape=7, with_proj=True)
+
+
+@LOSSES.register_module(name=['FocalLoss', 'L1Loss', 'GIoULoss', 'GazeArccosLoss', 'GazeTempLoss', 'CrossEntropyLoss'])
+class _InferenceOnlyLoss(_Spec):
+    """Losses are training-only (out of scope); kept so that reference configs build."""
+
+
+@HEADS.register_module()
+class GazeSTQIHead(_Spec):
+    expect = dict(num_classes=3, num_ffn_fcs=2, num_heads=8, num_cls_fcs=1, num_reg_fcs=3, feedforward_channels=2048,
+                  in_channels=256, dropout=0.0)
+
+    def __init__(self, **cfg):
+        super().__init__(**cfg)
+        self.dynamic_conv = build_transformer(cfg.get('dynamic_conv_cfg', dict(type='DynamicConv')))
+        lc = cfg.get('loss_cls', dict(use_sigmoid=True))
+        if not lc.get('use_sigmoid', False):
+            raise NotImplementedError('GazeSTQIHead: only sigmoid classification is implemented')
+        bc = cfg.get('bbox_coder', {})
+        if bc and (list(bc.get('target_stds', [0.5, 0.5, 1., 1.])) != [0.5, 0.5, 1., 1.] or bc.get('clip_border', False)
+                   or list(bc.get('target_means', [0., 0., 0., 0.])) != [0., 0., 0., 0.]):
+            raise NotImplementedError(f'bbox_coder {bc!r} not supported')
+
+
+@HEADS.register_module()
+class GazeHead(_Spec):
+    expect = dict(in_channels=256, gaze_dim=3)
+
+
+@HEADS.register_module()
+class MultiClueGazeROIHead(_Spec):
+    expect = dict(num_stages=4, proposal_feature_channel=256)
+
+    def __init__(self, bbox_roi_extractor=None, bbox_head=None, gaze_head=None, **cfg):
+        super().__init__(**cfg)
+        n = cfg.get('num_stages', 4)
+        self.bbox_roi_extractor = build_roi_extractor(bbox_roi_extractor)
+        bbox_head = bbox_head if isinstance(bbox_head, (list, tuple)) else [bbox_head] * n
+        gaze_head = gaze_head if isinstance(gaze_head, (list, tuple)) else [gaze_head] * n
+        assert len(bbox_head) == n and len(gaze_head) == n
+        self.bbox_head = [build_head(h) for h in bbox_head]
+        self.gaze_head = [build_head(h) for h in gaze_head]
+
+
+@DETECTORS.register_module()
+class MultiClueGaze:
+    """reference: mmdet/models/detectors/multiclue_gaze.py:8-131 (+ base.py:112-174 dispatch)."""
+
+    CLASSES = ('face', 'eyes', 'head')
+
+    def __init__(self, backbone, rpn_head, roi_head, train_cfg=None, test_cfg=None, neck=None, pretrained=None,
+                 init_cfg=None, precision: str = 'fp16x3'):
+        self.backbone = build_backbone(backbone)
+        self.neck = build_neck(neck) if neck is not None else None
+        if self.neck is None:
+            raise NotImplementedError('MultiClueGaze without an FPN neck is not supported')
+        self.rpn_head = build_head(rpn_head)
+        self.roi_head = build_head(roi_head)
+        self.test_cfg = test_cfg
+        self.precision = precision
+        self.device_index = 0
+        self.cfg = None
+        self._sd: 'OrderedDict[str, Any]' = OrderedDict()
+        self._engine = None
+        self.training = False
+
+    # --- torch.nn.Module-like surface used by init_detector / load_checkpoint ---------------
+    def state_dict(self):
+        return self._sd
+
+    def load_state_dict(self, state_dict, strict: bool = False):
+        self._sd = OrderedDict(state_dict)
+        self._engine = None
+        return self
+
+    def to(self, device):
+        s = str(device)
+        if s.startswith('cpu'):
+            raise RuntimeError('mcgaze_b200 has no CPU path; use a cuda device')
+        self.device_index = int(s.split(':')[1]) if ':' in s else 0
+        self._engine = None
+        return self
+
+    def cuda(self, device=0):
+        return self.to(f'cuda:{device}')
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError('training is out of scope for the B200 inference backend')
+        return self
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            if not self._sd:
+                raise RuntimeError('MultiClueGaze: no weights loaded (call load_state_dict / init_detector)')
+            from .lib import Engine
+            self._engine = Engine(self._sd, self.device_index, self.precision)
+        return self._engine
+
+    # --- forward ------------------------------------------------------------------------------
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
+
+    def forward(self, img, img_metas, return_loss: bool = True, **kwargs):
+        if return_loss:
+            raise NotImplementedError('forward_train is out of scope for the B200 inference backend')
+        return self.forward_test(img, img_metas, **kwargs)
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """base.py:112-154: list-of-augmentations wrapper; exactly one augmentation is supported."""
+        for var, name in [(imgs, 'imgs'), (img_metas, 'img_metas')]:
+            if not isinstance(var, list):
+                raise TypeError(f'{name} must be a list, but got {type(var)}')
+        if len(imgs) != len(img_metas):
+            raise ValueError(f'num of augmentations ({len(imgs)}) != num of image meta ({len(img_metas)})')
+        if len(imgs) != 1:
+            raise NotImplementedError('test-time augmentation is not supported (the reference raises too)')
+        for img, metas in zip(imgs, img_metas):
+            for m in metas:
+                m['batch_input_shape'] = tuple(img.shape[-2:])
+        return self.simple_test(imgs[0], img_metas[0], **kwargs)
+
+    def simple_test(self, img, img_metas: Sequence[Dict[str, Any]], rescale: bool = False, format: bool = False,
+                    clip_length: Optional[int] = None):
+        """multiclue_gaze.py:105-131 -> multiclue_gaze_roi_head.py:287-384.  `img` [T,3,H,W] CUDA
+        fp32 is ONE clip unless `clip_length` says the batch holds several clips of that length."""
+        import torch
+        T = img.shape[0]
+        img_hw = np.array([[m['img_shape'][0], m['img_shape'][1]] for m in img_metas], dtype=np.float32)
+        scale = None
+        if rescale:
+            scale = np.stack([np.asarray(m['scale_factor'], dtype=np.float32).reshape(4) for m in img_metas])
+        out = self.engine.forward(img, clip_length=clip_length or T, img_hw=img_hw, scale_factor=scale)
+        gaze, boxes, scores = out['gaze'], out['boxes'], out['scores']
+        det_bboxes = [torch.cat([boxes[i], scores[i][:, None]], dim=1) for i in range(T)]
+        det_labels = [[0, 1, 2] for _ in range(T)]
+        if format:
+            bbox_results = [[det_bboxes[i][c:c + 1].cpu().numpy() for c in range(3)] for i in range(T)]
+        else:
+            bbox_results = (det_bboxes, det_labels)
+        gaze_results = {'gaze_score': gaze[:, 0], 'face_gaze_score': gaze[:, 1], 'eyes_gaze_score': gaze[:, 2],
+                        'head_gaze_score': gaze[:, 3]}
+        return bbox_results, gaze_results

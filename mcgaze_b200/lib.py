@@ -16,7 +16,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2}
 
 # every symbol include/mcgaze_b200.h declares
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_get_intermediate',
-           'mcg_last_launch_count', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
+           'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
            'mcg_last_error', 'mcg_version')
 
 
@@ -49,6 +49,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_get_intermediate.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     lib.mcg_last_launch_count.argtypes = [vp]
     lib.mcg_set_graph_mode.argtypes = [vp, ci]
+    lib.mcg_last_umma_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
@@ -127,6 +128,12 @@ class Engine:
     @property
     def last_launch_count(self) -> int:
         return int(self._lib.mcg_last_launch_count(self._h))
+
+    def umma_stats(self):
+        """(launches, algorithmic FLOPs, summed device ms) of the tcgen05 GEMMs of the last eager forward."""
+        out = (ctypes.c_double * 3)()
+        _check(self._lib.mcg_last_umma_stats(self._h, out), 'mcg_last_umma_stats')
+        return int(out[0]), float(out[1]), float(out[2])
 
     # ------------------------------------------------------------------ forward
     @staticmethod

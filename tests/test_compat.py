@@ -1,0 +1,107 @@
+"""CPU: config / registry / checkpoint / collate stand-ins and the drop-in detector surface."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mcgaze_b200.compat import (Config, DataContainer, DictAction, Registry, build_from_cfg, collate,
+                                load_checkpoint, scatter)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(ROOT, 'configs', 'multiclue_gaze', 'multiclue_gaze_r50_gaze360.py')
+REF_CFG = '/root/reference/configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'
+
+
+def test_config_inheritance_and_delete(tmp_path):
+    (tmp_path / 'base.py').write_text("a = dict(x=1, y=dict(p=1, q=2))\nlst = [1, 2, 3]\nkeep = 'k'\n")
+    (tmp_path / 'child.py').write_text(
+        "_base_ = './base.py'\na = dict(y=dict(_delete_=True, r=3), z=5)\nlst = [9]\n")
+    c = Config.fromfile(str(tmp_path / 'child.py'))
+    assert c.a.x == 1 and c.a.z == 5 and c.a.y == {'r': 3} and c.lst == [9] and c.keep == 'k'
+    c.merge_from_dict({'a.y.r': 7, 'new.k': 'v'})
+    assert c.a.y.r == 7 and c.new.k == 'v'
+    with pytest.raises(AttributeError):
+        c.a.nope
+
+
+def test_our_config_builds_the_detector():
+    from mcgaze_b200.apis import init_detector
+    m = init_detector(CFG, None, 'cuda:0')
+    assert type(m).__name__ == 'MultiClueGaze' and len(m.roi_head.bbox_head) == 4
+    assert m.cfg.data.samples_per_gpu == 32 and m.cfg.data.test.pipeline[2]['img_scale'] == (224, 224)
+    l2 = init_detector(CFG.replace('gaze360.py', 'l2cs.py'), None, 'cuda:0', cfg_options={'data.samples_per_gpu': 4})
+    assert l2.cfg.data.samples_per_gpu == 4 and l2.cfg.data.test.pipeline[1]['img_scale'] == (448, 448)
+    with pytest.raises(RuntimeError):
+        m.to('cpu')                                   # no CPU path
+    with pytest.raises(NotImplementedError):
+        m(img=[None], img_metas=[[{}]], return_loss=True)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason='reference tree not mounted')
+def test_reference_config_file_builds_unchanged():
+    from mcgaze_b200.apis import init_detector
+    ours, ref = Config.fromfile(CFG), Config.fromfile(REF_CFG)
+    assert ref.model.type == 'MultiClueGaze' and ref.optimizer.type == 'AdamW' and 'momentum' not in ref.optimizer
+    a, b = ours.model.to_dict(), ref.model.to_dict()
+    a.pop('train_cfg'), b.pop('train_cfg')
+    assert a == b                                      # same model keys / type strings as the reference
+    assert type(init_detector(REF_CFG, None, 'cuda:0')).__name__ == 'MultiClueGaze'
+
+
+def test_unsupported_architecture_fails_loudly():
+    from mcgaze_b200.registry import build_detector
+    from mcgaze_b200 import detector  # noqa: F401
+    cfg = Config.fromfile(CFG).model.to_dict()
+    cfg['backbone']['depth'] = 101
+    with pytest.raises(NotImplementedError):
+        build_detector(cfg)
+
+
+def test_registry_and_build_from_cfg():
+    R = Registry('things')
+    child = Registry('child', parent=R)
+
+    @R.register_module()
+    class A:
+        def __init__(self, v=1):
+            self.v = v
+
+    assert R.build(dict(type='A', v=3)).v == 3 and child.get('A') is A and 'A' in child
+    with pytest.raises(KeyError):
+        R.build(dict(type='B'))
+    with pytest.raises(KeyError):
+        R.register_module()(A)
+    with pytest.raises(TypeError):
+        build_from_cfg([1], R)
+
+
+def test_dict_action():
+    p = argparse.ArgumentParser()
+    p.add_argument('--cfg-options', nargs='+', action=DictAction)
+    ns = p.parse_args(['--cfg-options', 'a.b=1', 'c=[1,2]', 'd=x', 'e=True', 'f=(1.5,2)'])
+    assert ns.cfg_options == {'a.b': 1, 'c': [1, 2], 'd': 'x', 'e': True, 'f': (1.5, 2)}
+
+
+def test_load_checkpoint_revise_keys_nonstrict(tmp_path):
+    m = torch.nn.Linear(2, 2)
+    sd = {'module.weight': torch.ones(2, 2), 'module.extra': torch.zeros(1)}
+    f = str(tmp_path / 'c.pth')
+    torch.save({'state_dict': sd, 'meta': {'CLASSES': ('a',)}}, f)
+    ck = load_checkpoint(m, f, revise_keys=[(r'^module\.', '')])
+    assert ck['meta']['CLASSES'] == ('a',) and (m.weight == 1).all()
+    with pytest.raises(RuntimeError):
+        load_checkpoint(m, f, strict=True)
+
+
+def test_collate_scatter_like_the_slicer():
+    """tools/test_gaze360_gaze.py:98-101: T per-frame dicts -> one clip batch, metas list-of-list."""
+    T = 3
+    datas = [dict(img=DataContainer(torch.full((3, 4 + i, 6), float(i)), stack=True),
+                  img_metas=DataContainer(dict(filename=f'{i}.png'), cpu_only=True)) for i in range(T)]
+    b = collate(datas, samples_per_gpu=T)
+    b['img_metas'], b['img'] = b['img_metas'].data, b['img'].data
+    out = scatter(b, [-1])[0]
+    assert out['img'][0].shape == (T, 3, 6, 6) and out['img'][0][0, :, 4:, :].abs().sum() == 0
+    assert [m['filename'] for m in out['img_metas'][0]] == ['0.png', '1.png', '2.png']

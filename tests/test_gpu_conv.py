@@ -1,0 +1,82 @@
+"""GPU: kernel-level parity of the tcgen05/TMA implicit-GEMM convolution and of the CUDA-core
+cross-check kernel against torch (fp64 reference on the same inputs), through the C ABI
+(mcg_debug_conv)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, NB, C, H, W, Cout, k, stride, pad, res_mode, relu, force_im2col, block_n
+    ('1x1_plain', 2, 64, 56, 56, 256, 1, 1, 0, 0, 1, 0, 0),
+    ('1x1_tail_rows', 1, 256, 30, 30, 64, 1, 1, 0, 0, 1, 0, 0),       # M = 900: ragged last tile
+    ('1x1_tiny_M', 1, 64, 3, 3, 64, 1, 1, 0, 0, 0, 0, 0),             # M = 9 < one tile
+    ('1x1_residual', 2, 64, 28, 28, 256, 1, 1, 0, 1, 1, 0, 0),
+    ('1x1_fpn_topdown', 2, 512, 14, 14, 256, 1, 1, 0, 2, 0, 0, 0),
+    ('1x1_via_im2col', 2, 128, 28, 28, 128, 1, 1, 0, 0, 0, 1, 0),
+    ('1x1_stride2', 2, 256, 56, 56, 512, 1, 2, 0, 0, 0, 0, 0),
+    ('3x3_c64', 2, 64, 56, 56, 64, 3, 1, 1, 0, 1, 0, 0),
+    ('3x3_c256', 1, 256, 14, 14, 256, 3, 1, 1, 0, 0, 0, 0),
+    ('3x3_stride2', 2, 128, 56, 56, 128, 3, 2, 1, 0, 1, 0, 0),
+    ('3x3_7x7map', 3, 512, 7, 7, 512, 3, 1, 1, 0, 1, 0, 0),
+    ('3x3_nonsquare', 2, 64, 24, 40, 128, 3, 1, 1, 0, 1, 0, 0),
+    ('block_n64', 2, 256, 28, 28, 256, 1, 1, 0, 0, 0, 0, 64),
+    ('block_n128', 2, 256, 28, 28, 256, 1, 1, 0, 0, 0, 0, 128),
+    ('bigK', 1, 2048, 7, 7, 512, 1, 1, 0, 0, 1, 0, 0),
+]
+# max |err| relative to max |ref|: split-fp16 x3 and the fp32 CUDA-core kernel are fp32-class,
+# single fp16 carries 2^-11 operand rounding
+TOL = {'simt': 5e-6, 'fp16x3': 2e-5, 'fp16': 1e-3}
+
+
+def _run(engine, case):
+    from mcgaze_b200 import lib
+    name, NB, C, H, W, Cout, k, stride, pad, res_mode, relu, fim, bn = case
+    g = torch.Generator().manual_seed(len(name) * 7 + C)
+    x = torch.randn(NB, C, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = None
+    if res_mode == 1:
+        res = torch.randn(NB, Cout, P, Q, generator=g).cuda()
+    elif res_mode == 2:
+        res = torch.randn(NB, Cout, P // 2, Q // 2, generator=g).cuda()
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)
+    if res_mode == 1:
+        ref = ref + res.double()
+    elif res_mode == 2:
+        ref = ref + F.interpolate(res.double(), size=(P, Q), mode='nearest')
+    if relu:
+        ref = ref.relu()
+    out = lib.debug_conv(engine, x, w, stride, pad, bias=b, res=res, res_mode=res_mode, relu=bool(relu),
+                         force_im2col=bool(fim), force_block_n=bn)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    return (out.double() - ref).abs().max().item() / ref.abs().max().item()
+
+
+@pytest.mark.parametrize('engine', ['simt', 'fp16x3', 'fp16'])
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_conv_parity(engine, case):
+    assert _run(engine, case) < TOL[engine]
+
+
+def test_tensor_core_and_cuda_core_kernels_agree():
+    """x3 tcgen05 vs fp32 FFMA on identical split-fp16 operands: only summation order differs."""
+    from mcgaze_b200 import lib
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 128, 28, 28, generator=g).cuda()
+    w = (torch.randn(128, 128, 3, 3, generator=g) / 34.0).cuda()
+    a = lib.debug_conv('fp16x3', x, w, 1, 1)
+    b = lib.debug_conv('simt', x, w, 1, 1)
+    assert (a - b).abs().max().item() < 3e-5 * b.abs().max().item()
+
+
+def test_unsupported_shape_is_an_error_not_a_fallback():
+    from mcgaze_b200 import lib
+    x = torch.randn(1, 24, 8, 8).cuda()        # C not a multiple of 64
+    w = torch.randn(64, 24, 1, 1).cuda()
+    with pytest.raises(lib.McgError):
+        lib.debug_conv('fp16x3', x, w, 1, 0)

@@ -1,0 +1,176 @@
+"""GPU: end-to-end parity of the C-ABI forward against the CPU oracle and against the fixtures
+the reference's own code produced (tests/golden), plus size-independent properties at the
+BASELINE batch size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mcgaze_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# north_star: "within 1e-3 on the regressed (yaw, pitch)" -> the parity mode (fp16x3) and the fp32
+# CUDA-core mode must meet it; the single-fp16 fast mode is documented as ~3e-3 and only bounded.
+YAW_PITCH_TOL = {'fp16x3': 1e-3, 'simt': 1e-3, 'fp16': 2e-2}
+KEYS = ('gaze_score', 'face_gaze_score', 'eyes_gaze_score', 'head_gaze_score')
+
+
+def yaw_pitch_err(a, b):
+    d = (O.vector_to_yaw_pitch(a) - O.vector_to_yaw_pitch(b)).abs()
+    return torch.minimum(d, 2 * torch.pi - d).max().item()
+
+
+@pytest.fixture(scope='module')
+def engines(synthetic_sd):
+    from mcgaze_b200 import lib
+    cache = {}
+
+    def get(precision):
+        if precision not in cache:
+            cache[precision] = lib.Engine(synthetic_sd, 0, precision)
+        return cache[precision]
+
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+@pytest.mark.parametrize('precision', ['fp16x3', 'simt', 'fp16'])
+def test_single_clip_vs_oracle(engines, synthetic_sd, precision):
+    """BASELINE configs[0]: one 7-frame 224x224 clip, random weights, (yaw,pitch) vs the fp32 reference path."""
+    img = O.make_clip(0, 7)
+    ref = O.forward(synthetic_sd, img)
+    out = engines(precision).forward(img.cuda())
+    g = out['gaze'].cpu()
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(g[:, i], ref[k]) < YAW_PITCH_TOL[precision], (precision, k)
+    assert (g.norm(dim=-1) - 1).abs().max() < 1e-5
+    if precision != 'fp16':
+        assert (out['boxes'].cpu() - ref['boxes']).abs().max() < 0.05          # pixels
+        assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('name', ['t7_224', 't3_192x224_rescale', 't1_224'])
+def test_vs_reference_fixtures(engines, golden_dir, name):
+    """Outputs of the reference's own MultiClueGaze.forward (oracle/gen_golden.py) on the same inputs."""
+    g = np.load(os.path.join(golden_dir, f'golden_forward_{name}.npz'))
+    T, H, W = int(g['T']), int(g['H']), int(g['W'])
+    img = O.make_clip(int(g['seed']), T, H, W).cuda()
+    img_hw = np.array([[g['img_hw'][0], g['img_hw'][1]]] * T, dtype=np.float32)
+    scale = np.tile(g['scale'][None], (T, 1))
+    out = engines('fp16x3').forward(img, clip_length=T, img_hw=img_hw, scale_factor=scale)
+    gz = out['gaze'].cpu()
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(gz[:, i], torch.from_numpy(g[k])) < 1e-3, k
+    det = torch.from_numpy(g['det_bboxes'])
+    assert (out['boxes'].cpu() - det[..., :4]).abs().max() < 0.05
+    assert (out['scores'].cpu() - det[..., 4]).abs().max() < 1e-3
+
+
+def test_batched_clips_and_ragged_meta(engines, synthetic_sd):
+    """B=2 clips of T=3 on a non-square padded image with unpadded img_shape and rescale."""
+    T, H, W = 3, 160, 224
+    img = torch.cat([O.make_clip(21, T, H, W), O.make_clip(22, T, H, W)])
+    img_hw = torch.tensor([[150.0, 224.0]] * (2 * T))
+    scale = torch.tensor([[0.5, 0.6, 0.5, 0.6]] * (2 * T))
+    ref = O.forward(synthetic_sd, img, clip_length=T, img_hw=img_hw, scale_factor=scale)
+    out = engines('fp16x3').forward(img.cuda(), clip_length=T, img_hw=img_hw.numpy(), scale_factor=scale.numpy())
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(out['gaze'][:, i].cpu(), ref[k]) < 1e-3, k
+    assert (out['boxes'].cpu() - ref['boxes']).abs().max() < 0.1
+
+
+def test_intermediates_per_layer(engines, synthetic_sd):
+    """Per-op parity: every trunk / FPN / head stage tensor against the oracle's."""
+    img = O.make_clip(0, 7)
+    taps = {}
+    O.forward(synthetic_sd, img, hk=O.Hooks(tap=lambda n, t: taps.__setitem__(n, t.clone())))
+    eng = engines('fp16x3')
+    eng.set_option('keep_intermediates', 1)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    for n in ['stem', 'pool', 'layer1.2', 'layer2.3', 'layer3.5', 'layer4.2', 'fpn0', 'fpn1', 'fpn2', 'fpn3']:
+        got, r = eng.intermediate(n).cpu(), taps[n]
+        assert got.shape == r.shape
+        assert (got - r).abs().max() < 1e-4 * r.abs().max(), n
+    for s in range(4):
+        got = eng.intermediate(f'stage{s}.roi_feat').cpu()
+        r = taps[f'stage{s}.roi_feat'].flatten(2).permute(0, 2, 1)
+        assert (got - r).abs().max() < 2e-4 * r.abs().max(), s
+        for mine, theirs in ((f'stage{s}.attn', f'roi_head.bbox_head.{s}.attn'),
+                             (f'stage{s}.obj', f'roi_head.bbox_head.{s}.obj'), (f'stage{s}.boxes', f'stage{s}.boxes')):
+            got, r = eng.intermediate(mine).cpu(), taps[theirs]
+            assert (got - r).abs().max() < 5e-4 * max(r.abs().max().item(), 1.0), mine
+    eng.set_option('keep_intermediates', 0)
+
+
+def test_host_entry_and_graph_replay_match_eager(engines):
+    eng = engines('fp16x3')
+    img = O.make_clip(3, 14)
+    a = eng.forward(img.cuda(), clip_length=7)
+    torch.cuda.synchronize()
+    h = eng.forward_host(img.pin_memory(), clip_length=7)
+    for k in a:
+        assert torch.equal(a[k].cpu(), h[k]), k
+    out = {k: torch.empty_like(v) for k, v in a.items()}
+    x = img.cuda()
+    eng.set_graph_mode(True)
+    try:
+        for _ in range(3):
+            eng.forward_into(x, 7, out)
+        torch.cuda.synchronize()
+        for k in a:
+            assert torch.equal(a[k], out[k]), k
+    finally:
+        eng.set_graph_mode(False)
+
+
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16'])
+def test_full_batch_properties(engines, precision):
+    """BASELINE configs[1] size (32 clips x 7 frames x 224^2): clips are independent units, so
+    (a) a clip's result must not depend on its batch neighbours (bit-exact), (b) permuting clips
+    permutes results, (c) outputs are finite unit vectors."""
+    B, T = 32, 7
+    g = torch.Generator().manual_seed(99)
+    img = torch.randn(B * T, 3, 224, 224, generator=g).cuda()
+    eng = engines(precision)
+    full = eng.forward(img, clip_length=T)
+    gz = full['gaze'].clone()
+    assert torch.isfinite(gz).all() and (gz.norm(dim=-1) - 1).abs().max() < 1e-5
+    for c in (0, 17, 31):
+        one = eng.forward(img[c * T:(c + 1) * T].clone(), clip_length=T)
+        assert torch.equal(one['gaze'], gz[c * T:(c + 1) * T]), c
+    perm = torch.randperm(B, generator=g)
+    idx = (perm[:, None] * T + torch.arange(T)[None]).reshape(-1).cuda()
+    shuffled = eng.forward(img[idx].contiguous(), clip_length=T)
+    assert torch.equal(shuffled['gaze'], gz[idx])
+
+
+def test_errors_are_reported(engines):
+    from mcgaze_b200 import lib
+    eng = engines('fp16x3')
+    with pytest.raises(lib.McgError):
+        eng.forward(torch.zeros(7, 3, 100, 224, device='cuda'))        # H not a multiple of 32
+    with pytest.raises(lib.McgError):
+        lib.Engine({'backbone.conv1.weight': torch.zeros(64, 3, 7, 7)}, 0, 'fp16x3')   # missing keys
+
+
+def test_detector_surface_matches_reference_call(synthetic_sd):
+    """tools/test_gaze360_gaze.py:107-111 call shape and return structure through init_detector."""
+    from mcgaze_b200.apis import init_detector
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    model = init_detector(os.path.join(root, 'configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'), None, 'cuda:0')
+    model.load_state_dict(synthetic_sd)
+    T = 7
+    img = O.make_clip(0, T)
+    metas = [dict(img_shape=(224, 224, 3), ori_shape=(224, 224, 3), pad_shape=(224, 224, 3),
+                  scale_factor=np.ones(4, dtype=np.float32), flip=False, filename=f'{i}.png') for i in range(T)]
+    (det_bboxes, det_labels), gaze = model(return_loss=False, rescale=True, format=False, img=[img.cuda()],
+                                           img_metas=[metas])
+    assert len(det_bboxes) == T and det_bboxes[0].shape == (3, 5) and det_labels[0] == [0, 1, 2]
+    assert set(gaze) == {'gaze_score', 'face_gaze_score', 'eyes_gaze_score', 'head_gaze_score'}
+    ref = O.forward(synthetic_sd, img)
+    assert yaw_pitch_err(gaze['gaze_score'].cpu(), ref['gaze_score']) < 1e-3
+    assert metas[0]['batch_input_shape'] == (224, 224)
