@@ -49,7 +49,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reason_bits, self.max_mhz, self.power = [], 0, None, []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -62,17 +62,17 @@ class ClockSampler(threading.Thread):
             self.ok = False
 
     def run(self):
-        while self.ok and not self._stop.is_set():
+        while self.ok and not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 self.reason_bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=2)
         if not self.samples:

@@ -14,17 +14,30 @@ namespace mcg {
 // ---------------------------------------------------------------------------------------
 constexpr int kStemK = 192;
 
-__global__ void stem_im2col_kernel(const float* __restrict__ img, int NB, int H, int W, int P, int Q,
-                                   __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
-  const long long total = static_cast<long long>(NB) * P * Q * (kStemK / 8);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k8 = static_cast<int>(i % (kStemK / 8));
-    const long long m = i / (kStemK / 8);
-    const int q = static_cast<int>(m % Q);
-    const long long t = m / Q;
-    const int p = static_cast<int>(t % P);
-    const int n = static_cast<int>(t / P);
+// One CTA per (frame, output row): the 7 input rows it needs are staged in shared memory with
+// coalesced reads along W, then the 112 x 192 im2col rows are written as 16-byte vectors
+// (consecutive threads -> consecutive addresses: rows of A are contiguous in memory).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, int NB, int H, int W, int P,
+                                                          int Q, __half* __restrict__ a_hi,
+                                                          __half* __restrict__ a_lo) {
+  extern __shared__ float srow[];  // [3][7][W + 6], zero padded
+  const int WP = W + 6;
+  const int p = blockIdx.x % P;
+  const int n = blockIdx.x / P;
+  for (int i = threadIdx.x; i < 3 * 7 * WP; i += blockDim.x) {
+    const int wp = i % WP;
+    const int r = (i / WP) % 7;
+    const int c = i / (WP * 7);
+    const int h = p * 2 - 3 + r, w = wp - 3;
+    float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) v = img[((static_cast<long long>(n) * 3 + c) * H + h) * W + w];
+    srow[i] = v;
+  }
+  __syncthreads();
+  const long long m0 = (static_cast<long long>(n) * P + p) * Q;
+  for (int i = threadIdx.x; i < Q * (kStemK / 8); i += blockDim.x) {
+    const int k8 = i % (kStemK / 8);
+    const int q = i / (kStemK / 8);
     __align__(16) __half hh[8];
     __align__(16) __half hl[8];
 #pragma unroll
@@ -34,15 +47,15 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int NB, int H,
       if (k < 147) {
         const int tap = k / 3, c = k - tap * 3;
         const int r = tap / 7, s = tap - r * 7;
-        const int h = p * 2 - 3 + r, w = q * 2 - 3 + s;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = img[((static_cast<long long>(n) * 3 + c) * H + h) * W + w];
+        v = srow[(c * 7 + r) * WP + q * 2 + s];
       }
       const __half h = __float2half_rn(v);
       hh[j] = h;
       hl[j] = __float2half_rn(v - __half2float(h));
     }
-    *reinterpret_cast<uint4*>(a_hi + m * kStemK + k8 * 8) = *reinterpret_cast<const uint4*>(hh);
-    if (a_lo) *reinterpret_cast<uint4*>(a_lo + m * kStemK + k8 * 8) = *reinterpret_cast<const uint4*>(hl);
+    const long long o = (m0 + q) * kStemK + k8 * 8;
+    *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hh);
+    if (a_lo) *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(hl);
   }
 }
 

@@ -747,7 +747,8 @@ class Engine {
     const int NB = ws_NB_, T = ws_T_, H = ws_H_, W = ws_W_;
     const int ew_grid = num_sms_ * 8;
     // ---- stem (resnet.py:636-639)
-    stem_im2col_kernel<<<ew_grid, 256, 0, st>>>(img, NB, H, W, H / 2, W / 2, stemA_.hi, stemA_.lo);
+    stem_im2col_kernel<<<NB * (H / 2), 256, 3 * 7 * (W + 6) * sizeof(float), st>>>(img, NB, H, W, H / 2, W / 2,
+                                                                                   stemA_.hi, stemA_.lo);
     MCG_CUDA(cudaGetLastError());
     count();
     {
