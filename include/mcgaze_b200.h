@@ -98,10 +98,13 @@ int mcg_set_option(mcg_handle h, const char* key, int value);
 /* Stand-alone convolution / GEMM with the fused epilogue, for kernel-level parity tests.
  *   engine: MCG_PRECISION_*    x: DEVICE fp32 NHWC [NB,H,W,C]    w: DEVICE fp32 [Cout, R*S*C] (r,s,c order)
  *   res: DEVICE fp32 NHWC residual or NULL; res_mode 0 none / 1 same size / 2 nearest 2x upsample
- *   out: DEVICE fp32 NHWC [NB,P,Q,Cout].  force_im2col != 0 routes 1x1/s1 through the im2col TMA path. */
+ *   out: DEVICE fp32 NHWC [NB,P,Q,Cout].  force_im2col != 0 routes 1x1/s1 through the im2col TMA path.
+ *   out_mode 0: the tensor-core engines write split-fp16 planes through the smem-staged TMA-store epilogue (the
+ *   trunk's format; with single fp16 the result carries one fp16 rounding) and are converted to fp32 afterwards;
+ *   out_mode 1: fp32 direct-store epilogue (the head's format). */
 int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, const float* w, int Cout, int R, int S,
                    int stride, int pad, const float* bias, const float* res, int res_mode, int relu,
-                   int force_im2col, int force_block_n, float* out, void* stream);
+                   int force_im2col, int force_block_n, int out_mode, float* out, void* stream);
 
 const char* mcg_last_error(void);
 const char* mcg_version(void);

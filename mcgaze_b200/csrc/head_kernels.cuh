@@ -456,6 +456,14 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, l
   }
 }
 
+// split-fp16 planes -> dense fp32, same layout (debug only)
+__global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n,
+                                     float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f);
+}
+
 // split-fp16 NHWC planes -> fp32 NCHW (debug / intermediate export only)
 __global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int NB, int H,
                                       int W, int C, float* __restrict__ out) {

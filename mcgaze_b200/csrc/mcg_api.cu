@@ -1079,7 +1079,7 @@ int mcg_set_option(mcg_handle h, const char* key, int value) {
 
 int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, const float* w, int Cout, int R, int S,
                    int stride, int pad, const float* bias, const float* res, int res_mode, int relu, int force_im2col,
-                   int force_block_n, float* out, void* stream) {
+                   int force_block_n, int out_mode, float* out, void* stream) {
   using namespace mcg;
   return guarded([&]() -> int {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1116,10 +1116,20 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     g.pad = pad;
     g.P = P;
     g.Q = Q;
+    // tensor-core engines write split-fp16 planes (the trunk's real output format: smem-staged TMA
+    // stores); out_mode 1 forces the fp32 direct-store epilogue the head uses
+    const bool planes_out = engine != MCG_PRECISION_SIMT && out_mode == 0;
+    DeviceBlock bo(planes_out ? ny * 4 : 16);
+    Planes po{reinterpret_cast<__half*>(bo.p), reinterpret_cast<__half*>(bo.p) + ny};
     Epilogue ep;
     ep.bias = bias;
     ep.relu = relu;
-    ep.out_f32 = out;
+    if (planes_out) {
+      ep.out_hi = po.hi;
+      ep.out_lo = engine == MCG_PRECISION_FP16X3 ? po.lo : nullptr;
+    } else {
+      ep.out_f32 = out;
+    }
     ep.ldo = Cout;
     if (res) {
       ep.res_hi = pr.hi;
@@ -1129,7 +1139,6 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
       ep.P = P;
       ep.Q = Q;
     }
-    (void)ny;
     if (engine == MCG_PRECISION_SIMT) {
       SimtParams p;
       p.M = M;
@@ -1150,8 +1159,13 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
         g_last_error = "mcg_debug_conv: shape not supported by the tcgen05 kernel";
         return MCG_ERR_UNSUPPORTED;
       }
+      if (engine == MCG_PRECISION_FP16 && res) ep.res_lo = nullptr;
       UmmaPlan pl = make_umma_plan(engine == MCG_PRECISION_FP16X3 ? 3 : 1, px, g, pw, M, Cout, K, ep, sms, force_block_n);
       launch_umma(pl, st);
+      if (planes_out) {
+        planes_to_f32_kernel<<<1024, 256, 0, st>>>(po.hi, ep.out_lo, static_cast<long long>(ny), out);
+        MCG_CUDA(cudaGetLastError());
+      }
     }
     MCG_CUDA(cudaStreamSynchronize(st));
     return MCG_OK;

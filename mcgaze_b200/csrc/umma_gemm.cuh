@@ -15,9 +15,16 @@
 //   warp 0   : TMA producer  (one elected lane; A tile 128 x 64, W tile block_n x 64, SWIZZLE_128B)
 //   warp 1   : MMA issuer    (one lane issues tcgen05.mma M=128, N=block_n, K=16; commit -> mbarrier)
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator buffers of up to 256 fp32 columns)
-//   warps 4-7: epilogue      (tcgen05.ld 32x32b.x32 -> bias/residual/ReLU -> split-fp16 or fp32 stores)
-// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4-7: epilogue.  Each warp owns 32 accumulator rows (its TMEM lane quarter) and walks the
+//              tile in 32-column chunks: tcgen05.ld -> + bias -> + residual -> ReLU -> split to
+//              fp16 hi/lo -> 64B-swizzled smem staging -> TMA store (bulk async group), double
+//              buffered so the store of chunk c overlaps the math of chunk c+1.  A same-shape
+//              residual (bottleneck identity) is TMA-prefetched one chunk ahead into smem by the
+//              same warp, so neither stores nor residual reads are issued as per-thread strided
+//              global accesses.  fp32 outputs (head) and the FPN's 2x-upsampled residual use
+//              direct vector loads/stores.
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), per-warp
+// residual mbarriers, so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -32,7 +39,9 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSmemBarrierBytes = 1024;
-constexpr int kMaxDynSmem = 229376;  // 224 KB (227 KB opt-in limit minus headroom for the 1 KB the runtime reserves)
+constexpr int kMaxDynSmem = 232448;  // 227 KB: the sm_100 opt-in limit per block
+constexpr int kEpiChunk = 32;        // columns per epilogue chunk (64 B of fp16 per row)
+constexpr int kEpiBufBytes = 32 * kEpiChunk * 2;  // one warp's [32 rows x 32 cols] fp16 staging tile = 2 KB
 
 struct UmmaParams {
   int M = 0, N = 0, K = 0;
@@ -41,17 +50,26 @@ struct UmmaParams {
   int num_kb = 0;
   int m_tiles = 0, n_tiles = 0;
   int cblocks = 1;  // C / 64 for im2col
+  int out_tma = 0;  // planes output through smem staging + TMA store
+  int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
   AGeom a;
   Epilogue ep;
 };
 
+struct UmmaMaps {
+  CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, r_hi, r_lo;
+};
+
+// byte offset of logical 16-byte chunk j of row `row` in a 64B-swizzled [32][64 B] tile
+__device__ __forceinline__ uint32_t sw64_off(int row, int j) {
+  return static_cast<uint32_t>(row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+}
+
 template <int kTerms>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                 const UmmaParams p) {
+umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   constexpr int kPlanes = (kTerms == 3) ? 2 : 1;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
@@ -59,22 +77,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;  // [4 warps][2 buffers]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   const int w_tile_bytes = p.block_n * kBlockK * 2;
   const int stage_bytes = kPlanes * (kATileBytes + w_tile_bytes);
+  uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;  // [4][2 sets][planes][2 KB]
+  uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kPlanes * kEpiBufBytes : 0);  // [4][2 bufs][planes][2 KB]
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp_idx == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA_hi);
-    ptx::prefetch_tmap(&tmW_hi);
+    ptx::prefetch_tmap(&tm.a_hi);
+    ptx::prefetch_tmap(&tm.w_hi);
     if (kTerms == 3) {
-      ptx::prefetch_tmap(&tmA_lo);
-      ptx::prefetch_tmap(&tmW_lo);
+      ptx::prefetch_tmap(&tm.a_lo);
+      ptx::prefetch_tmap(&tm.w_lo);
     }
+    if (p.out_tma) ptx::prefetch_tmap(&tm.o_hi);
+    if (p.res_tma) ptx::prefetch_tmap(&tm.r_hi);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
@@ -85,6 +108,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -128,17 +152,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int cb = kb - tap * p.cblocks;
             const int r = tap / p.a.S;
             const int sx = tap - r * p.a.S;
-            ptx::tma_load_im2col_4d(sA_hi, &tmA_hi, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
+            ptx::tma_load_im2col_4d(sA_hi, &tm.a_hi, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
                                     static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
             if (kTerms == 3)
-              ptx::tma_load_im2col_4d(sA_lo, &tmA_lo, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
+              ptx::tma_load_im2col_4d(sA_lo, &tm.a_lo, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
                                       static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
           } else {
-            ptx::tma_load_2d(sA_hi, &tmA_hi, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
-            if (kTerms == 3) ptx::tma_load_2d(sA_lo, &tmA_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+            ptx::tma_load_2d(sA_hi, &tm.a_hi, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+            if (kTerms == 3) ptx::tma_load_2d(sA_lo, &tm.a_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
           }
-          ptx::tma_load_2d(sW_hi, &tmW_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-          if (kTerms == 3) ptx::tma_load_2d(sW_lo, &tmW_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          ptx::tma_load_2d(sW_hi, &tm.w_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (kTerms == 3) ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
@@ -196,39 +220,89 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // ===================== epilogue =====================
     const int quarter = warp_idx & 3;
     const Epilogue& ep = p.ep;
+    uint8_t* obuf = obuf_base + quarter * (2 * kPlanes * kEpiBufBytes);
+    uint8_t* rbuf = rbuf_base + quarter * (2 * kPlanes * kEpiBufBytes);
+    uint64_t* rbar = res_bar + quarter * 2;
+    uint32_t rphase0 = 0, rphase1 = 0;
+    int oset = 0;   // staging set used by the next chunk
+    int rcnt = 0;   // residual chunks consumed so far (buffer = rcnt & 1)
+    const int nchunks = p.block_n / kEpiChunk;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
+      const long long m_warp = static_cast<long long>(m_tile) * kBlockM + quarter * 32;  // first row of this warp
+      const long long m = m_warp + lane;
+      const bool valid = m < p.M;
+      const bool warp_live = m_warp < p.M;  // warp-uniform: at least one valid row
+      const int n_base = n_tile * p.block_n;
+      const bool use_rtma = p.res_tma && warp_live;
+      // the residual does not depend on the MMA: fetch the first chunk before waiting for the accumulator
+      if (use_rtma && lane == 0) {
+        uint8_t* dst = rbuf + (rcnt & 1) * (kPlanes * kEpiBufBytes);
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive_expect_tx(&rbar[rcnt & 1], kPlanes * kEpiBufBytes);
+        ptx::tma_load_2d(dst, &tm.r_hi, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
+        if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
+      }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const long long m = static_cast<long long>(m_tile) * kBlockM + quarter * 32 + lane;
-      const bool valid = m < p.M;
-      const long long rrow = (valid && ep.res_mode != RES_NONE) ? res_row(ep, m) : 0;
+      const long long rrow = (valid && ep.res_mode != RES_NONE && !p.res_tma) ? res_row(ep, m) : 0;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int n = n_base + c * kEpiChunk;
+        const uint8_t* rcur = nullptr;
+        if (use_rtma) {
+          const int b = rcnt & 1;
+          if (c + 1 < nchunks && lane == 0) {  // prefetch the next chunk's residual into the other buffer
+            const int nb = b ^ 1;
+            uint8_t* dst = rbuf + nb * (kPlanes * kEpiBufBytes);
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive_expect_tx(&rbar[nb], kPlanes * kEpiBufBytes);
+            ptx::tma_load_2d(dst, &tm.r_hi, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
+            if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
+          }
+          ptx::mbar_wait(&rbar[b], b ? rphase1 : rphase0);
+          if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
+          rcur = rbuf + b * (kPlanes * kEpiBufBytes);
+          ++rcnt;
+        }
         uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c0), r);
+        ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
         ptx::tmem_ld_wait();
-        if (valid) {
-          const int n = n_tile * p.block_n + c0;
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+        if (rcur) {
+#pragma unroll
+          for (int pl = 0; pl < kPlanes; ++pl) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiBufBytes + sw64_off(lane, j));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(h2[t]);
+                v[8 * j + 2 * t] += f.x;
+                v[8 * j + 2 * t + 1] += f.y;
+              }
             }
           }
-          if (ep.res_mode != RES_NONE && ep.res_f32) {
+        } else if (valid && ep.res_mode != RES_NONE && !p.res_tma) {
+          if (ep.res_f32) {
             const float4* rf = reinterpret_cast<const float4*>(ep.res_f32 + rrow * ep.ldr + n);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -238,24 +312,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               v[4 * j + 2] += f.z;
               v[4 * j + 3] += f.w;
             }
-          } else if (ep.res_mode != RES_NONE) {
-            const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(rh + j);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = __half22float2(h2[t]);
-                v[8 * j + 2 * t] += f.x;
-                v[8 * j + 2 * t + 1] += f.y;
-              }
-            }
-            if (ep.res_lo) {
-              const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n);
+            for (int pl = 0; pl < 2; ++pl) {
+              const __half* rp = pl == 0 ? ep.res_hi : ep.res_lo;
+              if (rp == nullptr) continue;
+              const uint4* rh = reinterpret_cast<const uint4*>(rp + rrow * ep.ldr + n);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(rl + j);
+                const uint4 u = __ldg(rh + j);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -266,10 +331,43 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               }
             }
           }
-          if (ep.relu) {
+        }
+        if (ep.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.out_tma) {
+          uint8_t* ob = obuf + oset * (kPlanes * kEpiBufBytes);
+          // the set was handed to TMA two chunks ago: wait until that store has finished reading it
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 uh, ul;
+            __half2* hh = reinterpret_cast<__half2*>(&uh);
+            __half2* hl = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float a = v[8 * j + 2 * t], b = v[8 * j + 2 * t + 1];
+              const __half2 h = __floats2half2_rn(a, b);
+              const float2 hf = __half22float2(h);
+              hh[t] = h;
+              hl[t] = __floats2half2_rn(a - hf.x, b - hf.y);
+            }
+            *reinterpret_cast<uint4*>(ob + sw64_off(lane, j)) = uh;
+            if (kTerms == 3) *reinterpret_cast<uint4*>(ob + kEpiBufBytes + sw64_off(lane, j)) = ul;
           }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (warp_live) {
+              ptx::tma_store_2d(&tm.o_hi, ob, n, static_cast<int>(m_warp));
+              if (kTerms == 3) ptx::tma_store_2d(&tm.o_lo, ob + kEpiBufBytes, n, static_cast<int>(m_warp));
+            }
+            ptx::tma_store_commit();  // one (possibly empty) group per chunk keeps wait_group counting uniform
+          }
+          oset ^= 1;
+        } else if (valid) {
           if (ep.out_f32) {
             float4* o = reinterpret_cast<float4*>(ep.out_f32 + m * ep.ldo + n);
 #pragma unroll
@@ -300,6 +398,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
     }
+    // smem must stay valid until every bulk store of this warp has been read out
+    if (p.out_tma && lane == 0) ptx::tma_store_wait_all<0>();
   }
 
   ptx::tc_fence_before();
@@ -342,16 +442,17 @@ struct DriverApi {
   }
 };
 
-inline CUtensorMap make_tmap_2d(const __half* base, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D row-major fp16 matrix [rows, cols] with row pitch ld; box = box_cols x box_rows
+inline CUtensorMap make_tmap_2d(const __half* base, long long rows, long long cols, long long ld, int box_rows,
+                                int box_cols = kBlockK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = DriverApi::get().encodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims,
-                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed, code " + std::to_string(static_cast<int>(r)));
   return m;
 }
@@ -374,7 +475,7 @@ inline CUtensorMap make_tmap_im2col(const __half* base, const AGeom& g) {
 }
 
 struct UmmaPlan {
-  CUtensorMap tmA_hi, tmA_lo, tmW_hi, tmW_lo;
+  UmmaMaps tm;
   UmmaParams p;
   int terms = 3;
   int grid = 0;
@@ -400,6 +501,15 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.N = N;
   p.K = K;
   const int planes = terms == 3 ? 2 : 1;
+  // epilogue staging (per CTA): TMA-store staging when the output is fp16 planes, plus residual
+  // prefetch buffers for the same-shape residual
+  p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 8 == 0 && (terms == 1 || ep.out_lo != nullptr)) ? 1 : 0;
+  p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 8 == 0 &&
+               (terms == 1 || ep.res_lo != nullptr))
+                  ? 1
+                  : 0;
+  const int epi_bytes = (p.out_tma ? 4 * 2 * planes * kEpiBufBytes : 0) + (p.res_tma ? 4 * 2 * planes * kEpiBufBytes : 0);
+  const int ring_budget = kMaxDynSmem - 1024 - kSmemBarrierBytes - epi_bytes;
   int bn = force_block_n;
   if (bn == 0) {
     // largest tile that divides N and still leaves >= 3 pipeline stages
@@ -407,7 +517,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     for (int c : cands) {
       if (N % c) continue;
       const int sb = planes * (kATileBytes + c * kBlockK * 2);
-      if ((kMaxDynSmem - 2048) / sb >= 3 || c == 64) {
+      // residual (bottleneck conv3) layers are HBM-bound with short K loops: 2 stages are enough there
+      if (ring_budget / sb >= (p.res_tma ? 2 : 3) || c == 64) {
         bn = c;
         break;
       }
@@ -416,7 +527,7 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   MCG_CHECK(bn > 0 && N % bn == 0, "bad block_n");
   p.block_n = bn;
   const int stage_bytes = planes * (kATileBytes + bn * kBlockK * 2);
-  p.num_stages = (kMaxDynSmem - 2048) / stage_bytes;
+  p.num_stages = ring_budget / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   MCG_CHECK(p.num_stages >= 2, "not enough shared memory for 2 stages");
   p.num_kb = K / kBlockK;
@@ -426,18 +537,29 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.cblocks = a.kind == 1 ? a.C / kBlockK : 1;
   if (a.kind == 1) MCG_CHECK(K == a.R * a.S * a.C, "im2col K mismatch");
   p.ep = ep;
-  pl.smem = 1024 + kSmemBarrierBytes + p.num_stages * stage_bytes;
+  pl.smem = 1024 + kSmemBarrierBytes + p.num_stages * stage_bytes + epi_bytes;
+  MCG_CHECK(pl.smem <= kMaxDynSmem, "shared memory plan exceeds the 227 KB limit");
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   pl.grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  UmmaMaps& tm = pl.tm;
   if (a.kind == 1) {
-    pl.tmA_hi = make_tmap_im2col(A.hi, a);
-    pl.tmA_lo = terms == 3 ? make_tmap_im2col(A.lo, a) : pl.tmA_hi;
+    tm.a_hi = make_tmap_im2col(A.hi, a);
+    tm.a_lo = terms == 3 ? make_tmap_im2col(A.lo, a) : tm.a_hi;
   } else {
-    pl.tmA_hi = make_tmap_2d(A.hi, M, K, a.lda, kBlockM);
-    pl.tmA_lo = terms == 3 ? make_tmap_2d(A.lo, M, K, a.lda, kBlockM) : pl.tmA_hi;
+    tm.a_hi = make_tmap_2d(A.hi, M, K, a.lda, kBlockM);
+    tm.a_lo = terms == 3 ? make_tmap_2d(A.lo, M, K, a.lda, kBlockM) : tm.a_hi;
   }
-  pl.tmW_hi = make_tmap_2d(W.hi, N, K, K, bn);
-  pl.tmW_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : pl.tmW_hi;
+  tm.w_hi = make_tmap_2d(W.hi, N, K, K, bn);
+  tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : tm.w_hi;
+  tm.o_hi = tm.o_lo = tm.r_hi = tm.r_lo = tm.w_hi;  // placeholders when unused
+  if (p.out_tma) {
+    tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
+    tm.o_lo = terms == 3 ? make_tmap_2d(ep.out_lo, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.o_hi;
+  }
+  if (p.res_tma) {
+    tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
+    tm.r_lo = terms == 3 ? make_tmap_2d(ep.res_lo, M, N, ep.ldr, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.r_hi;
+  }
   return pl;
 }
 
@@ -452,9 +574,9 @@ inline void umma_set_attrs() {
 inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   umma_set_attrs();
   if (pl.terms == 3)
-    umma_gemm_kernel<3><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tmA_hi, pl.tmA_lo, pl.tmW_hi, pl.tmW_lo, pl.p);
+    umma_gemm_kernel<3><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   else
-    umma_gemm_kernel<1><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tmA_hi, pl.tmA_lo, pl.tmW_hi, pl.tmW_lo, pl.p);
+    umma_gemm_kernel<1><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   MCG_CUDA(cudaGetLastError());
 }
 

@@ -51,7 +51,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_set_graph_mode.argtypes = [vp, ci]
     lib.mcg_last_umma_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
-    lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp, vp]
+    lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         fn.restype = ctypes.c_char_p if name in ('mcg_last_error', 'mcg_version') else ci
@@ -209,7 +209,7 @@ class Engine:
 
 
 def debug_conv(engine: str, x, w, stride: int, pad: int, bias=None, res=None, res_mode: int = 0, relu: bool = False,
-               force_im2col: bool = False, force_block_n: int = 0):
+               force_im2col: bool = False, force_block_n: int = 0, out_mode: int = 0):
     """Kernel-level entry: x CUDA fp32 NCHW, w CUDA fp32 [Cout,Cin,R,S] -> CUDA fp32 NCHW (torch layout in/out;
     the NHWC / (r,s,c) repack the C ABI wants happens here)."""
     import torch
@@ -226,6 +226,6 @@ def debug_conv(engine: str, x, w, stride: int, pad: int, bias=None, res=None, re
     rc = lib.mcg_debug_conv(PRECISIONS[engine], x_nhwc.data_ptr(), NB, H, W, C, w_p.data_ptr(), Cout, R, S, stride, pad,
                             bias.data_ptr() if bias is not None else None,
                             res_nhwc.data_ptr() if res_nhwc is not None else None, res_mode, int(relu),
-                            int(force_im2col), force_block_n, out.data_ptr(), ctypes.c_void_p(stream))
+                            int(force_im2col), force_block_n, int(out_mode), out.data_ptr(), ctypes.c_void_p(stream))
     _check(rc, 'mcg_debug_conv')
     return out.permute(0, 3, 1, 2).contiguous()

@@ -30,7 +30,7 @@ CASES = [
 TOL = {'simt': 5e-6, 'fp16x3': 2e-5, 'fp16': 1e-3}
 
 
-def _run(engine, case):
+def _run(engine, case, out_mode=0):
     from mcgaze_b200 import lib
     name, NB, C, H, W, Cout, k, stride, pad, res_mode, relu, fim, bn = case
     g = torch.Generator().manual_seed(len(name) * 7 + C)
@@ -51,7 +51,7 @@ def _run(engine, case):
     if relu:
         ref = ref.relu()
     out = lib.debug_conv(engine, x, w, stride, pad, bias=b, res=res, res_mode=res_mode, relu=bool(relu),
-                         force_im2col=bool(fim), force_block_n=bn)
+                         force_im2col=bool(fim), force_block_n=bn, out_mode=out_mode)
     torch.cuda.synchronize()
     assert not torch.isnan(out).any()
     return (out.double() - ref).abs().max().item() / ref.abs().max().item()
@@ -61,6 +61,13 @@ def _run(engine, case):
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_conv_parity(engine, case):
     assert _run(engine, case) < TOL[engine]
+
+
+@pytest.mark.parametrize('engine', ['fp16x3', 'fp16'])
+@pytest.mark.parametrize('case', [CASES[0], CASES[1], CASES[3], CASES[4], CASES[9]], ids=lambda c: c[0])
+def test_conv_parity_fp32_epilogue(engine, case):
+    """out_mode=1: the direct fp32 store epilogue the head's Linear layers use."""
+    assert _run(engine, case, out_mode=1) < TOL[engine]
 
 
 def test_tensor_core_and_cuda_core_kernels_agree():
