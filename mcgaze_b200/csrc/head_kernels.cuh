@@ -149,12 +149,26 @@ __device__ __forceinline__ int roi_level(float x1, float y1, float x2, float y2)
   return static_cast<int>(lvl);
 }
 
+__device__ __forceinline__ void acc8(float (&a)[8], const uint4& u, float w) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h2[t]);
+    a[2 * t] = fmaf(w, f.x, a[2 * t]);
+    a[2 * t + 1] = fmaf(w, f.y, a[2 * t + 1]);
+  }
+}
+
+// One warp per (roi, bin); each lane owns 8 consecutive channels, so every bilinear tap is one
+// 16-byte load per lane (512 B per warp) per plane and the output row is written as 2 float4.
 __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const float* __restrict__ boxes /*[R,4]*/,
                                                         int R, float* __restrict__ out /*[R,49,256]*/) {
-  const int r = blockIdx.x / 49;
-  const int bin = blockIdx.x - r * 49;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (gw >= R * 49) return;
+  const int lane = threadIdx.x & 31;
+  const int r = gw / 49;
+  const int bin = gw - r * 49;
   const int ph = bin / 7, pw = bin - ph * 7;
-  const int c = threadIdx.x;
   const int n = r / 3;
   const float bx1 = boxes[r * 4 + 0], by1 = boxes[r * 4 + 1], bx2 = boxes[r * 4 + 2], by2 = boxes[r * 4 + 3];
   const int lvl = roi_level(bx1, by1, bx2, by2);
@@ -165,10 +179,11 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
   const float x1 = bx1 * scale - 0.5f, y1 = by1 * scale - 0.5f;
   const float bw = (bx2 * scale - 0.5f - x1) / 7.f;
   const float bh = (by2 * scale - 0.5f - y1) / 7.f;
-  float acc = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long base = static_cast<long long>(n) * H * W;
 #pragma unroll
   for (int iy = 0; iy < 2; ++iy) {
-    float y = y1 + ph * bh + (iy + 0.5f) * bh / 2.f;
+    const float y = y1 + ph * bh + (iy + 0.5f) * bh / 2.f;
 #pragma unroll
     for (int ix = 0; ix < 2; ++ix) {
       float x = x1 + pw * bw + (ix + 0.5f) * bw / 2.f;
@@ -191,23 +206,25 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
         xh = xl + 1;
       }
       const float ly = yy - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
-      const long long base = static_cast<long long>(n) * H * W;
-      const long long i00 = (base + static_cast<long long>(yl) * W + xl) * 256 + c;
-      const long long i01 = (base + static_cast<long long>(yl) * W + xh) * 256 + c;
-      const long long i10 = (base + static_cast<long long>(yh) * W + xl) * 256 + c;
-      const long long i11 = (base + static_cast<long long>(yh) * W + xh) * 256 + c;
-      float v00 = __half2float(fhi[i00]), v01 = __half2float(fhi[i01]);
-      float v10 = __half2float(fhi[i10]), v11 = __half2float(fhi[i11]);
+      const long long i00 = (base + static_cast<long long>(yl) * W + xl) * 256 + lane * 8;
+      const long long i01 = (base + static_cast<long long>(yl) * W + xh) * 256 + lane * 8;
+      const long long i10 = (base + static_cast<long long>(yh) * W + xl) * 256 + lane * 8;
+      const long long i11 = (base + static_cast<long long>(yh) * W + xh) * 256 + lane * 8;
+      acc8(acc, __ldg(reinterpret_cast<const uint4*>(fhi + i00)), hy * hx);
+      acc8(acc, __ldg(reinterpret_cast<const uint4*>(fhi + i01)), hy * lx);
+      acc8(acc, __ldg(reinterpret_cast<const uint4*>(fhi + i10)), ly * hx);
+      acc8(acc, __ldg(reinterpret_cast<const uint4*>(fhi + i11)), ly * lx);
       if (flo) {
-        v00 += __half2float(flo[i00]);
-        v01 += __half2float(flo[i01]);
-        v10 += __half2float(flo[i10]);
-        v11 += __half2float(flo[i11]);
+        acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i00)), hy * hx);
+        acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i01)), hy * lx);
+        acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i10)), ly * hx);
+        acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i11)), ly * lx);
       }
-      acc += hy * hx * v00 + hy * lx * v01 + ly * hx * v10 + ly * lx * v11;
     }
   }
-  out[(static_cast<long long>(r) * 49 + bin) * 256 + c] = acc * 0.25f;
+  float4* o = reinterpret_cast<float4*>(out + (static_cast<long long>(r) * 49 + bin) * 256 + lane * 8);
+  o[0] = make_float4(acc[0] * 0.25f, acc[1] * 0.25f, acc[2] * 0.25f, acc[3] * 0.25f);
+  o[1] = make_float4(acc[4] * 0.25f, acc[5] * 0.25f, acc[6] * 0.25f, acc[7] * 0.25f);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -294,46 +311,65 @@ __global__ void attention_kernel(const float* __restrict__ qkv, float* __restric
 //   F2 = relu(LN256(F1[49,64]  . Pout[64,256]))   -> out[r, p*256 + c]  (flatten order :1158)
 // X comes from RoIAlign, Pin/Pout are this RoI's row of dynamic_layer's output.
 // ---------------------------------------------------------------------------------------
-constexpr int kDynSmemFloats = 49 * 256 + 256 * 64 + 49 * 64;
+constexpr int kDynSmemFloats = 49 * 256 + 256 * 64 + 64 * 256 + 49 * 64;
 constexpr int kDynSmemBytes = kDynSmemFloats * 4;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 224 of the 256 threads form a 7 x 32 grid: warp w < 7 owns positions 7w..7w+6 (so X / F1 reads
+// are warp-wide broadcasts), lane owns 2 features (bmm1) or 8 channels lane+32j (bmm2): 14 resp.
+// 56 accumulators per thread against 8 resp. 15 shared-memory loads per k.  X + Pin and Pout
+// arrive through two cp.async groups so Pout streams in while bmm1 runs.
 __global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ X /*[R,49,256]*/,
                                                       const float* __restrict__ params /*[R,32768]*/,
                                                       const float* __restrict__ g_in, const float* __restrict__ b_in,
                                                       const float* __restrict__ g_out, const float* __restrict__ b_out,
                                                       float* __restrict__ out /*[R,12544]*/) {
-  extern __shared__ float dsm[];
-  float* sX = dsm;                 // [49][256]   (later reused for F2)
-  float* sP = dsm + 49 * 256;      // [256][64] then [64][256]
-  float* sF = sP + 256 * 64;       // [49][64]
+  extern __shared__ __align__(16) float dsm[];
+  float* sX = dsm;                    // [49][256]   (later reused for F2)
+  float* sPin = sX + 49 * 256;        // [256][64]
+  float* sPout = sPin + 256 * 64;     // [64][256]
+  float* sF = sPout + 64 * 256;       // [49][64]
   const int r = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4* gx = reinterpret_cast<const float4*>(X + static_cast<long long>(r) * 12544);
-  const float4* gp = reinterpret_cast<const float4*>(params + static_cast<long long>(r) * 32768);
-  for (int i = tid; i < 12544 / 4; i += 256) reinterpret_cast<float4*>(sX)[i] = gx[i];
-  for (int i = tid; i < 16384 / 4; i += 256) reinterpret_cast<float4*>(sP)[i] = gp[i];
+  const float* gx = X + static_cast<long long>(r) * 12544;
+  const float* gp = params + static_cast<long long>(r) * 32768;
+  for (int i = tid; i < 12544 / 4; i += 256) cp_async16(sX + i * 4, gx + i * 4);
+  for (int i = tid; i < 16384 / 4; i += 256) cp_async16(sPin + i * 4, gp + i * 4);
+  cp_async_commit();
+  for (int i = tid; i < 16384 / 4; i += 256) cp_async16(sPout + i * 4, gp + 16384 + i * 4);
+  cp_async_commit();
+  cp_async_wait<1>();
   __syncthreads();
-  {  // F1[p][f] : thread -> feature f = tid%64, positions p = tid/64 + 4*i
-    const int f = tid & 63, pg = tid >> 6;
-    float acc[13];
+  if (warp < 7) {  // F1[p][f], p = 7*warp + i, f = 2*lane + {0,1}
+    float acc[7][2];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 7; ++i) acc[i][0] = acc[i][1] = 0.f;
+    const float* xr = sX + warp * 7 * 256;
+#pragma unroll 4
     for (int k = 0; k < 256; ++k) {
-      const float w = sP[k * 64 + f];
+      const float2 w = *reinterpret_cast<const float2*>(sPin + k * 64 + lane * 2);
 #pragma unroll
-      for (int i = 0; i < 13; ++i) {
-        const int p = pg + 4 * i;
-        if (p < 49) acc[i] = fmaf(sX[p * 256 + k], w, acc[i]);
+      for (int i = 0; i < 7; ++i) {
+        const float x = xr[i * 256 + k];
+        acc[i][0] = fmaf(x, w.x, acc[i][0]);
+        acc[i][1] = fmaf(x, w.y, acc[i][1]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 13; ++i) {
-      const int p = pg + 4 * i;
-      if (p < 49) sF[p * 64 + f] = acc[i];
-    }
+    for (int i = 0; i < 7; ++i)
+      *reinterpret_cast<float2*>(sF + (warp * 7 + i) * 64 + lane * 2) = make_float2(acc[i][0], acc[i][1]);
   }
   __syncthreads();
-  // LN(64) + ReLU per position (one warp per position), and load Pout into sP
+  // LN(64) + ReLU per position (one warp per position)
   for (int p = warp; p < 49; p += 8) {
     float a = sF[p * 64 + lane], b = sF[p * 64 + 32 + lane];
     float s = a + b;
@@ -345,41 +381,46 @@ __global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ 
     sF[p * 64 + lane] = fmaxf((a - mean) * rstd * g_in[lane] + b_in[lane], 0.f);
     sF[p * 64 + 32 + lane] = fmaxf((b - mean) * rstd * g_in[32 + lane] + b_in[32 + lane], 0.f);
   }
-  for (int i = tid; i < 16384 / 4; i += 256) reinterpret_cast<float4*>(sP)[i] = gp[16384 / 4 + i];
+  cp_async_wait<0>();
   __syncthreads();
-  {  // F2[p][c] : thread -> channel c = tid, all 49 positions
-    const int c = tid;
-    float acc[49];
+  if (warp < 7) {  // F2[p][c], p = 7*warp + i, c = lane + 32*j
+    float acc[7][8];
 #pragma unroll
-    for (int p = 0; p < 49; ++p) acc[p] = 0.f;
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float* fr = sF + warp * 7 * 64;
+#pragma unroll 2
     for (int k = 0; k < 64; ++k) {
-      const float w = sP[k * 256 + c];
+      float w[8];
 #pragma unroll
-      for (int p = 0; p < 49; ++p) acc[p] = fmaf(sF[p * 64 + k], w, acc[p]);
+      for (int j = 0; j < 8; ++j) w[j] = sPout[k * 256 + lane + 32 * j];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const float x = fr[i * 64 + k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, w[j], acc[i][j]);
+      }
     }
+    // LN(256) + ReLU over the 8 x 32 channels this warp holds for each of its 7 positions
 #pragma unroll
-    for (int p = 0; p < 49; ++p) sX[p * 256 + c] = acc[p];
-  }
-  __syncthreads();
-  for (int p = warp; p < 49; p += 8) {
-    float v[8];
-    float s = 0.f;
+    for (int i = 0; i < 7; ++i) {
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = sX[p * 256 + j * 32 + lane];
-      s += v[j];
-    }
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / 256.f;
-    float q = 0.f;
+      for (int j = 0; j < 8; ++j) s += acc[i][j];
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / 256.f;
+      float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
-    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / 256.f + 1e-5f);
+      for (int j = 0; j < 8; ++j) q += (acc[i][j] - mean) * (acc[i][j] - mean);
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / 256.f + 1e-5f);
+      float* orow = out + static_cast<long long>(r) * 12544 + (warp * 7 + i) * 256;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = j * 32 + lane;
-      out[static_cast<long long>(r) * 12544 + p * 256 + c] = fmaxf((v[j] - mean) * rstd * g_out[c] + b_out[c], 0.f);
+      for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        orow[c] = fmaxf((acc[i][j] - mean) * rstd * g_out[c] + b_out[c], 0.f);
+      }
     }
   }
 }
@@ -441,6 +482,72 @@ __global__ void finalize_kernel(const float* __restrict__ gvec, const float* __r
       if (scale_factor) b /= scale_factor[n * 4 + j];
       out_boxes[(n * 3 + c) * 4 + j] = b;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Small fp32 Linear for the head's latency-bound layers (M = 3*frames rows, K = 256, N <= 768):
+// y[m, n] = act( sum_k x[m, k] * Wt[k, n] + b[n] (+ res[m, n]) ).  Weights are stored transposed
+// ([K, N]) so a warp reads 128 contiguous bytes per k; a CTA owns 8 rows x 64 columns and splits
+// K over its 4 warps-pairs (4 k-slices x 64 columns), which keeps >300 CTAs in flight for
+// M = 672 and the per-thread dependent-load chain at K/4.
+// ---------------------------------------------------------------------------------------
+constexpr int kSlRows = 8;
+
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, long long ldx,
+                                                           const float* __restrict__ wt /*[K,N]*/,
+                                                           const float* __restrict__ bias, const float* __restrict__ res,
+                                                           long long ldres, float* __restrict__ y, long long ldy,
+                                                           long long M, int N, int K, int relu) {
+  extern __shared__ __align__(16) float sl_smem[];
+  float* xs = sl_smem;                       // [8][K]
+  float* red = sl_smem + kSlRows * K;        // [4][8][64]
+  const int tid = threadIdx.x;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kSlRows;
+  const int col = tid & 63, kq = tid >> 6;
+  const int n = blockIdx.y * 64 + col;
+  for (int i = tid; i < kSlRows * K; i += 256) {
+    const int rr = i / K, k = i - rr * K;
+    xs[i] = (m0 + rr < M) ? x[(m0 + rr) * ldx + k] : 0.f;
+  }
+  __syncthreads();
+  float acc[kSlRows];
+#pragma unroll
+  for (int i = 0; i < kSlRows; ++i) acc[i] = 0.f;
+  const int kslice = (K + 3) / 4;
+  const int k0 = kq * kslice, k1 = min(K, k0 + kslice);
+  if (n < N) {
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = __ldg(wt + static_cast<long long>(k + j) * N + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k + j], w[j], acc[i]);
+    }
+    for (; k < k1; ++k) {
+      const float w = __ldg(wt + static_cast<long long>(k) * N + n);
+#pragma unroll
+      for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k], w, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSlRows; ++i) red[(kq * kSlRows + i) * 64 + col] = acc[i];
+  __syncthreads();
+  // 256 threads finish 8 rows x 64 columns: thread -> (row = tid / 32, two columns)
+  for (int o = tid; o < kSlRows * 64; o += 256) {
+    const int rr = o >> 6, c = o & 63;
+    const int nn = blockIdx.y * 64 + c;
+    const long long m = m0 + rr;
+    if (nn >= N || m >= M) continue;
+    float v = red[(0 * kSlRows + rr) * 64 + c] + red[(1 * kSlRows + rr) * 64 + c] + red[(2 * kSlRows + rr) * 64 + c] +
+              red[(3 * kSlRows + rr) * 64 + c];
+    if (bias) v += bias[nn];
+    if (res) v += res[m * ldres + nn];
+    if (relu) v = fmaxf(v, 0.f);
+    y[m * ldy + nn] = v;
   }
 }
 

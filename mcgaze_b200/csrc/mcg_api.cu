@@ -90,6 +90,7 @@ static inline __half h_from_float(float v) { return __float2half_rn(v); }
 struct GemmW {  // packed [N, K] weight (+ bias) on device
   int N = 0, K = 0;
   const float* w_f32 = nullptr;
+  const float* w_t = nullptr;  // [K, N] transposed copy for small_linear_kernel (small layers only)
   Planes w;
   const float* bias = nullptr;
 };
@@ -143,6 +144,7 @@ class Engine {
     load_weights();
     host_.clear();
     MCG_CUDA(cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+    MCG_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     if (precision != MCG_PRECISION_SIMT) umma_set_attrs();
   }
 
@@ -327,6 +329,12 @@ class Engine {
     g.w.hi = upload(keep_, hi);
     g.w.lo = upload(keep_, lo);
     if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
+    if (N <= 768 && K <= 2048) {
+      std::vector<float> t(w.size());
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) t[static_cast<size_t>(k) * N + n] = w[static_cast<size_t>(n) * K + k];
+      g.w_t = upload(keep_, t);
+    }
     return g;
   }
 
@@ -659,6 +667,14 @@ class Engine {
   // fp32 linear on (possibly strided) rows: y = x W^T + b (+res) (relu)
   void linear(const float* x, long long ldx, const GemmW& w, long long M, float* y, long long ldy, bool relu,
               const float* res, long long ldres, cudaStream_t st) {
+    if (w.w_t != nullptr) {
+      dim3 grid(static_cast<unsigned>((M + kSlRows - 1) / kSlRows), static_cast<unsigned>((w.N + 63) / 64));
+      const size_t smem = (static_cast<size_t>(kSlRows) * w.K + 4 * kSlRows * 64) * sizeof(float);
+      small_linear_kernel<<<grid, 256, smem, st>>>(x, ldx, w.w_t, w.bias, res, ldres, y, ldy, M, w.N, w.K, relu ? 1 : 0);
+      MCG_CUDA(cudaGetLastError());
+      count();
+      return;
+    }
     AGeom g;
     g.kind = 0;
     g.lda = ldx;
@@ -820,7 +836,7 @@ class Engine {
       float* boxes_out = boxes_[cur ^ 1];
       float* obj_in = obj_[cur];
       float* obj_out = obj_[cur ^ 1];
-      roi_align_kernel<<<R * 49, 256, 0, st>>>(fl, boxes_in, R, roi_);
+      roi_align_kernel<<<(R * 49 + 7) / 8, 256, 0, st>>>(fl, boxes_in, R, roi_);
       MCG_CUDA(cudaGetLastError());
       count();
       // spatial then temporal self-attention with the SAME weights (gaze_stqi_head.py:148-166)
