@@ -35,20 +35,28 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
   __syncthreads();
   const long long m0 = (static_cast<long long>(n) * P + p) * Q;
-  for (int i = threadIdx.x; i < Q * (kStemK / 8); i += blockDim.x) {
-    const int k8 = i % (kStemK / 8);
-    const int q = i / (kStemK / 8);
+  // 240 active threads = 10 pixels x 24 groups of 8 consecutive k: the 8 smem offsets of a group do
+  // not depend on the pixel, so the div/mod index math is done once per thread
+  if (threadIdx.x >= 240) return;
+  const int k8 = threadIdx.x % (kStemK / 8);
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k8 * 8 + j;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int r = tap / 7, sx = tap - r * 7;
+      off[j] = (c * 7 + r) * WP + sx;
+    } else {
+      off[j] = -1;
+    }
+  }
+  for (int q = threadIdx.x / (kStemK / 8); q < Q; q += 10) {
     __align__(16) __half hh[8];
     __align__(16) __half hl[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = k8 * 8 + j;
-      float v = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int r = tap / 7, s = tap - r * 7;
-        v = srow[(c * 7 + r) * WP + q * 2 + s];
-      }
+      const float v = off[j] >= 0 ? srow[off[j] + q * 2] : 0.f;
       const __half h = __float2half_rn(v);
       hh[j] = h;
       hl[j] = __float2half_rn(v - __half2float(h));
@@ -493,20 +501,30 @@ __global__ void finalize_kernel(const float* __restrict__ gvec, const float* __r
 // M = 672 and the per-thread dependent-load chain at K/4.
 // ---------------------------------------------------------------------------------------
 constexpr int kSlRows = 8;
+constexpr int kSlSlices = 8;
+constexpr int kSlThreads = 64 * kSlSlices;
 
-__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, long long ldx,
-                                                           const float* __restrict__ wt /*[K,N]*/,
-                                                           const float* __restrict__ bias, const float* __restrict__ res,
-                                                           long long ldres, float* __restrict__ y, long long ldy,
-                                                           long long M, int N, int K, int relu) {
+__global__ void __launch_bounds__(kSlThreads) small_linear_kernel(const float* __restrict__ x, long long ldx,
+                                                                 const float* __restrict__ wt /*[K,N]*/,
+                                                                 const float* __restrict__ bias,
+                                                                 const float* __restrict__ res, long long ldres,
+                                                                 float* __restrict__ y, long long ldy, long long M,
+                                                                 int N, int K, int relu) {
   extern __shared__ __align__(16) float sl_smem[];
   float* xs = sl_smem;                       // [8][K]
-  float* red = sl_smem + kSlRows * K;        // [4][8][64]
+  float* red = sl_smem + kSlRows * K;        // [slices][8][64]
   const int tid = threadIdx.x;
   const long long m0 = static_cast<long long>(blockIdx.x) * kSlRows;
   const int col = tid & 63, kq = tid >> 6;
   const int n = blockIdx.y * 64 + col;
-  for (int i = tid; i < kSlRows * K; i += 256) {
+  const int kslice = (K + kSlSlices - 1) / kSlSlices;
+  const int k0 = kq * kslice, k1 = min(K, k0 + kslice);
+  // first weight batch is independent of the activations: issue it before staging x
+  float w[8];
+  const bool act = n < N;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = (act && k0 + j < k1) ? __ldg(wt + static_cast<long long>(k0 + j) * N + n) : 0.f;
+  for (int i = tid; i < kSlRows * K; i += kSlThreads) {
     const int rr = i / K, k = i - rr * K;
     xs[i] = (m0 + rr < M) ? x[(m0 + rr) * ldx + k] : 0.f;
   }
@@ -514,40 +532,121 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   float acc[kSlRows];
 #pragma unroll
   for (int i = 0; i < kSlRows; ++i) acc[i] = 0.f;
-  const int kslice = (K + 3) / 4;
-  const int k0 = kq * kslice, k1 = min(K, k0 + kslice);
-  if (n < N) {
-    int k = k0;
-    for (; k + 8 <= k1; k += 8) {
-      float w[8];
+  for (int k = k0; k < k1; k += 8) {
+    float wn[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] = __ldg(wt + static_cast<long long>(k + j) * N + n);
+    for (int j = 0; j < 8; ++j)
+      wn[j] = (act && k + 8 + j < k1) ? __ldg(wt + static_cast<long long>(k + 8 + j) * N + n) : 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 8; ++j) {
+      if (k + j < k1) {
 #pragma unroll
         for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k + j], w[j], acc[i]);
+      }
     }
-    for (; k < k1; ++k) {
-      const float w = __ldg(wt + static_cast<long long>(k) * N + n);
 #pragma unroll
-      for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k], w, acc[i]);
-    }
+    for (int j = 0; j < 8; ++j) w[j] = wn[j];
   }
 #pragma unroll
   for (int i = 0; i < kSlRows; ++i) red[(kq * kSlRows + i) * 64 + col] = acc[i];
   __syncthreads();
-  // 256 threads finish 8 rows x 64 columns: thread -> (row = tid / 32, two columns)
-  for (int o = tid; o < kSlRows * 64; o += 256) {
-    const int rr = o >> 6, c = o & 63;
+  {  // 512 threads finish 8 rows x 64 columns
+    const int rr = tid >> 6, c = tid & 63;
     const int nn = blockIdx.y * 64 + c;
     const long long m = m0 + rr;
-    if (nn >= N || m >= M) continue;
-    float v = red[(0 * kSlRows + rr) * 64 + c] + red[(1 * kSlRows + rr) * 64 + c] + red[(2 * kSlRows + rr) * 64 + c] +
-              red[(3 * kSlRows + rr) * 64 + c];
-    if (bias) v += bias[nn];
-    if (res) v += res[m * ldres + nn];
-    if (relu) v = fmaxf(v, 0.f);
-    y[m * ldy + nn] = v;
+    if (nn < N && m < M) {
+      float v = 0.f;
+#pragma unroll
+      for (int sidx = 0; sidx < kSlSlices; ++sidx) v += red[(sidx * kSlRows + rr) * 64 + c];
+      if (bias) v += bias[nn];
+      if (res) v += res[m * ldres + nn];
+      if (relu) v = fmaxf(v, 0.f);
+      y[m * ldy + nn] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused  y = act( LN( x . Wt (+ b) (+ res) ) * gamma + beta )  for N = 256 (the head's
+// Linear -> LayerNorm(-> ReLU) pairs: attention out_proj + identity + attention_norm, cls / reg
+// towers, gaze towers).  A CTA owns 8 complete rows (256 columns x 4 k-slices = 1024 threads),
+// so the row statistics never leave the SM.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) linear256_ln_kernel(const float* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ wt /*[K,256]*/,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ res, long long ldres,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ y,
+                                                            long long ldy, long long M, int K, int relu) {
+  extern __shared__ __align__(16) float ll_smem[];
+  float* xs = ll_smem;                  // [8][K]
+  float* red = ll_smem + kSlRows * K;   // [4][8][256]
+  const int tid = threadIdx.x;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kSlRows;
+  const int n = tid & 255, kq = tid >> 8;
+  const int kslice = (K + 3) / 4;
+  const int k0 = kq * kslice, k1 = min(K, k0 + kslice);
+  float w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = (k0 + j < k1) ? __ldg(wt + static_cast<long long>(k0 + j) * 256 + n) : 0.f;
+  for (int i = tid; i < kSlRows * K; i += 1024) {
+    const int rr = i / K, k = i - rr * K;
+    xs[i] = (m0 + rr < M) ? x[(m0 + rr) * ldx + k] : 0.f;
+  }
+  __syncthreads();
+  float acc[kSlRows];
+#pragma unroll
+  for (int i = 0; i < kSlRows; ++i) acc[i] = 0.f;
+  for (int k = k0; k < k1; k += 8) {
+    float wn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wn[j] = (k + 8 + j < k1) ? __ldg(wt + static_cast<long long>(k + 8 + j) * 256 + n) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (k + j < k1) {
+#pragma unroll
+        for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k + j], w[j], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = wn[j];
+  }
+#pragma unroll
+  for (int i = 0; i < kSlRows; ++i) red[(kq * kSlRows + i) * 256 + n] = acc[i];
+  __syncthreads();
+  // warp r (of the first 8) finishes row r: 8 columns per lane, LayerNorm over the 256 columns
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < kSlRows) {
+    const long long m = m0 + warp;
+    if (m < M) {
+      float v[8];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = j * 32 + lane;
+        float t = red[(0 * kSlRows + warp) * 256 + c] + red[(1 * kSlRows + warp) * 256 + c] +
+                  red[(2 * kSlRows + warp) * 256 + c] + red[(3 * kSlRows + warp) * 256 + c];
+        if (bias) t += bias[c];
+        if (res) t += res[m * ldres + c];
+        v[j] = t;
+        s += t;
+      }
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / 256.f;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / 256.f + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = j * 32 + lane;
+        float t = (v[j] - mean) * rstd * gamma[c] + beta[c];
+        if (relu) t = fmaxf(t, 0.f);
+        y[m * ldy + c] = t;
+      }
+    }
   }
 }
 

@@ -145,6 +145,7 @@ class Engine {
     host_.clear();
     MCG_CUDA(cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
     MCG_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MCG_CUDA(cudaFuncSetAttribute(linear256_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     if (precision != MCG_PRECISION_SIMT) umma_set_attrs();
   }
 
@@ -669,8 +670,9 @@ class Engine {
               const float* res, long long ldres, cudaStream_t st) {
     if (w.w_t != nullptr) {
       dim3 grid(static_cast<unsigned>((M + kSlRows - 1) / kSlRows), static_cast<unsigned>((w.N + 63) / 64));
-      const size_t smem = (static_cast<size_t>(kSlRows) * w.K + 4 * kSlRows * 64) * sizeof(float);
-      small_linear_kernel<<<grid, 256, smem, st>>>(x, ldx, w.w_t, w.bias, res, ldres, y, ldy, M, w.N, w.K, relu ? 1 : 0);
+      const size_t smem = (static_cast<size_t>(kSlRows) * w.K + kSlSlices * kSlRows * 64) * sizeof(float);
+      small_linear_kernel<<<grid, kSlThreads, smem, st>>>(x, ldx, w.w_t, w.bias, res, ldres, y, ldy, M, w.N, w.K,
+                                                         relu ? 1 : 0);
       MCG_CUDA(cudaGetLastError());
       count();
       return;
@@ -689,6 +691,17 @@ class Engine {
       ep.ldr = ldres;
     }
     gemm("", nullptr, x, g, w, M, ep, st, 0);
+  }
+
+  // y = act(LN(x W^T + b (+res)))  for N == 256 Linears followed by a LayerNorm
+  void linear_ln(const float* x, long long ldx, const GemmW& w, const LnW& n, long long M, float* y, long long ldy,
+                 bool relu, const float* res, long long ldres, cudaStream_t st) {
+    MCG_CHECK(w.N == 256 && w.w_t != nullptr && n.C == 256, "linear_ln needs a 256-wide small Linear");
+    const size_t smem = (static_cast<size_t>(kSlRows) * w.K + 4 * kSlRows * 256) * sizeof(float);
+    linear256_ln_kernel<<<static_cast<unsigned>((M + kSlRows - 1) / kSlRows), 1024, smem, st>>>(
+        x, ldx, w.w_t, w.bias, res, ldres, n.g, n.b, y, ldy, M, w.K, relu ? 1 : 0);
+    MCG_CUDA(cudaGetLastError());
+    count();
   }
 
   // big head linears: split the fp32 activations into fp16 planes and run on tensor cores
@@ -847,8 +860,8 @@ class Engine {
         attention_kernel<<<(R * 8 * 32 + 255) / 256, 256, 0, st>>>(qkv_, att_, R, T, mode);
         MCG_CUDA(cudaGetLastError());
         count();
-        linear(att_, 256, sw.out_proj, R, xc_, 256, false, xin, 256, st);  // + identity (mmcv MHA)
-        ln(xc_, 256, nullptr, 0, sw.attn_norm, xout[mode], 256, R, false, st);
+        // out_proj + identity (mmcv MHA) + attention_norm in one kernel
+        linear_ln(att_, 256, sw.out_proj, sw.attn_norm, R, xout[mode], 256, false, xin, 256, st);
         xin = xout[mode];
       }
       const float* attn = xb_;
@@ -866,15 +879,13 @@ class Engine {
       linear_tc(sk + "ffn2", ffn_h_, 2048, hh_, sw.ffn2, R, xc_, false, xa_, st);
       ln(xc_, 256, nullptr, 0, sw.ffn_norm, obj_out, 256, R, false, st);
       // cls / reg towers + per-clue heads (gaze_stqi_head.py:185-201)
-      linear(obj_out, 256, sw.cls_fc, R, t256a_, 256, false, nullptr, 0, st);
-      ln(t256a_, 256, nullptr, 0, sw.cls_ln, t256a_, 256, R, true, st);
+      linear_ln(obj_out, 256, sw.cls_fc, sw.cls_ln, R, t256a_, 256, true, nullptr, 0, st);
       for (int c = 0; c < 3; ++c) linear(t256a_ + c * 256, 768, sw.fc_cls[c], NB, cls_logit_ + c, 3, false, nullptr, 0, st);
       const float* rin = obj_out;
       float* rbuf[2] = {t256b_, xc_};
       for (int j = 0; j < 3; ++j) {
         float* ro = rbuf[j & 1];
-        linear(rin, 256, sw.reg_fc[j], R, ro, 256, false, nullptr, 0, st);
-        ln(ro, 256, nullptr, 0, sw.reg_ln[j], ro, 256, R, true, st);
+        linear_ln(rin, 256, sw.reg_fc[j], sw.reg_ln[j], R, ro, 256, true, nullptr, 0, st);
         rin = ro;
       }
       for (int c = 0; c < 3; ++c) linear(rin + c * 256, 768, sw.fc_reg[c], NB, delta_ + c * 4, 12, false, nullptr, 0, st);
@@ -902,10 +913,8 @@ class Engine {
       for (int branch = 0; branch < 2; ++branch) {
         const GemmW* tw = branch == 0 ? gaze_.tower[c] : gaze_.ctower[c];
         const LnW* tl = branch == 0 ? gaze_.tower_ln[c] : gaze_.ctower_ln[c];
-        linear(obj + c * 256, 768, tw[0], NB, gz_a_, 256, false, nullptr, 0, st);
-        ln(gz_a_, 256, nullptr, 0, tl[0], gz_a_, 256, NB, true, st);
-        linear(gz_a_, 256, tw[1], NB, gz_b_, 256, false, nullptr, 0, st);
-        ln(gz_b_, 256, nullptr, 0, tl[1], gz_b_, 256, NB, true, st);
+        linear_ln(obj + c * 256, 768, tw[0], tl[0], NB, gz_a_, 256, true, nullptr, 0, st);
+        linear_ln(gz_a_, 256, tw[1], tl[1], NB, gz_b_, 256, true, nullptr, 0, st);
         const GemmW& head = branch == 0 ? gaze_.fc[c] : gaze_.fc_conf[c];
         float* dst = (branch == 0 ? gvec_ : conf_) + static_cast<size_t>(c) * NB * 3;
         linear(gz_b_, 256, head, NB, dst, 3, false, nullptr, 0, st);
