@@ -24,14 +24,16 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   const int WP = W + 6;
   const int p = blockIdx.x % P;
   const int n = blockIdx.x / P;
-  for (int i = threadIdx.x; i < 3 * 7 * WP; i += blockDim.x) {
-    const int wp = i % WP;
-    const int r = (i / WP) % 7;
-    const int c = i / (WP * 7);
-    const int h = p * 2 - 3 + r, w = wp - 3;
-    float v = 0.f;
-    if (h >= 0 && h < H && w >= 0 && w < W) v = img[((static_cast<long long>(n) * 3 + c) * H + h) * W + w];
-    srow[i] = v;
+#pragma unroll
+  for (int cr = 0; cr < 21; ++cr) {
+    const int c = cr / 7, r = cr % 7;
+    const int h = p * 2 - 3 + r;
+    const bool hok = h >= 0 && h < H;
+    const float* src = img + ((static_cast<long long>(n) * 3 + c) * H + (hok ? h : 0)) * W;
+    for (int wp = threadIdx.x; wp < WP; wp += blockDim.x) {
+      const int w = wp - 3;
+      srow[cr * WP + wp] = (hok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
+    }
   }
   __syncthreads();
   const long long m0 = (static_cast<long long>(n) * P + p) * Q;
@@ -537,12 +539,22 @@ __global__ void __launch_bounds__(kSlThreads) small_linear_kernel(const float* _
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       wn[j] = (act && k + 8 + j < k1) ? __ldg(wt + static_cast<long long>(k + 8 + j) * N + n) : 0.f;
+    // K % 32 == 0 (checked on the host): every slice is a whole number of 8-wide batches and the
+    // activations are read as two 16-byte broadcasts per row
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (k + j < k1) {
-#pragma unroll
-        for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k + j], w[j], acc[i]);
-      }
+    for (int i = 0; i < kSlRows; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + i * K + k);
+      const float4 x1 = *reinterpret_cast<const float4*>(xs + i * K + k + 4);
+      float a = acc[i];
+      a = fmaf(x0.x, w[0], a);
+      a = fmaf(x0.y, w[1], a);
+      a = fmaf(x0.z, w[2], a);
+      a = fmaf(x0.w, w[3], a);
+      a = fmaf(x1.x, w[4], a);
+      a = fmaf(x1.y, w[5], a);
+      a = fmaf(x1.z, w[6], a);
+      a = fmaf(x1.w, w[7], a);
+      acc[i] = a;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = wn[j];
@@ -602,12 +614,22 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const float* __restr
     float wn[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) wn[j] = (k + 8 + j < k1) ? __ldg(wt + static_cast<long long>(k + 8 + j) * 256 + n) : 0.f;
+    // K % 32 == 0 (checked on the host): every slice is a whole number of 8-wide batches and the
+    // activations are read as two 16-byte broadcasts per row
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (k + j < k1) {
-#pragma unroll
-        for (int i = 0; i < kSlRows; ++i) acc[i] = fmaf(xs[i * K + k + j], w[j], acc[i]);
-      }
+    for (int i = 0; i < kSlRows; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + i * K + k);
+      const float4 x1 = *reinterpret_cast<const float4*>(xs + i * K + k + 4);
+      float a = acc[i];
+      a = fmaf(x0.x, w[0], a);
+      a = fmaf(x0.y, w[1], a);
+      a = fmaf(x0.z, w[2], a);
+      a = fmaf(x0.w, w[3], a);
+      a = fmaf(x1.x, w[4], a);
+      a = fmaf(x1.y, w[5], a);
+      a = fmaf(x1.z, w[6], a);
+      a = fmaf(x1.w, w[7], a);
+      acc[i] = a;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = wn[j];

@@ -330,7 +330,7 @@ class Engine {
     g.w.hi = upload(keep_, hi);
     g.w.lo = upload(keep_, lo);
     if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
-    if (N <= 768 && K <= 2048) {
+    if (N <= 768 && K <= 2048 && K % 32 == 0) {
       std::vector<float> t(w.size());
       for (int n = 0; n < N; ++n)
         for (int k = 0; k < K; ++k) t[static_cast<size_t>(k) * N + n] = w[static_cast<size_t>(n) * K + k];
