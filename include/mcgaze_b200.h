@@ -71,6 +71,16 @@ int mcg_forward_host(mcg_handle h, const float* img_host, int B, int T, int H, i
                      const float* scale_factor, float* out_gaze_host, float* out_boxes_host,
                      float* out_scores_host);
 
+/* Pipelined form of mcg_forward_host (two slots): mcg_submit_host enqueues the host->device copy on a
+ * copy stream and the forward + device->host read-back on the compute stream and returns a ticket;
+ * mcg_wait_host blocks until that submission's results are on the host.  Submitting batch i+1 before
+ * waiting for batch i overlaps its H2D copy with batch i's forward (what a DataLoader-fed test loop,
+ * mmdet/apis/test.py:107-109, gets from pinned memory + non_blocking copies).  At most two
+ * submissions may be in flight; the host image buffer must stay valid until the matching wait. */
+int mcg_submit_host(mcg_handle h, const float* img_host, int B, int T, int H, int W, const float* img_hw,
+                    const float* scale_factor, int* ticket);
+int mcg_wait_host(mcg_handle h, int ticket, float* out_gaze_host, float* out_boxes_host, float* out_scores_host);
+
 /* Per-op parity support: copy a named intermediate of the LAST forward as dense fp32 into `dst`
  * (DEVICE).  Activations are returned NCHW like the reference's tensors.  Names: "stem", "pool",
  * "layer{1-4}.{i}", "fpn{0-3}", "stage{0-3}.roi_feat" ([R,49,256]), "stage{s}.attn",

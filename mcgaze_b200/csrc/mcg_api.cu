@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -150,9 +151,14 @@ class Engine {
   }
 
   ~Engine() {
-    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    drop_graph();
+    for (int i = 0; i < 2; ++i) {
+      if (slot_[i].h2d_done) cudaEventDestroy(slot_[i].h2d_done);
+      if (slot_[i].done) cudaEventDestroy(slot_[i].done);
+      if (slot_[i].pin_out) cudaFreeHost(slot_[i].pin_out);
+    }
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
-    if (pin_out_) cudaFreeHost(pin_out_);
     if (pin_meta_) cudaFreeHost(pin_meta_);
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (cap_stream_) cudaStreamDestroy(cap_stream_);
@@ -208,71 +214,96 @@ class Engine {
     }
     has_scale_ = scale_factor != nullptr;
 
-    const bool same_io = img == g_img_ && out_gaze == g_gaze_ && out_boxes == g_boxes_ && out_scores == g_scores_ &&
-                         has_scale_ == g_has_scale_;
-    if (graph_mode_ && graph_exec_ && same_io) {
-      MCG_CUDA(cudaGraphLaunch(graph_exec_, stream));
-      return;
-    }
     if (graph_mode_) {
-      drop_graph();
-      // capture on a private stream (the caller's may be the legacy default stream, which cannot
-      // be captured), then replay the instantiated graph on the caller's stream
-      if (!cap_stream_) MCG_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
-      MCG_CUDA(cudaStreamSynchronize(stream));
-      cudaGraph_t graph = nullptr;
-      MCG_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
-      try {
-        schedule(img, out_gaze, out_boxes, out_scores, cap_stream_);
-      } catch (...) {
-        cudaStreamEndCapture(cap_stream_, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
+      const GraphKey key{img, out_gaze, out_boxes, out_scores, has_scale_};
+      auto it = graphs_.find(key);
+      if (it == graphs_.end()) {
+        if (graphs_.size() >= 8) drop_graph();
+        // capture on a private stream (the caller's may be the legacy default stream, which cannot
+        // be captured), then replay the instantiated graph on the caller's stream
+        if (!cap_stream_) MCG_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+        MCG_CUDA(cudaStreamSynchronize(stream));
+        cudaGraph_t graph = nullptr;
+        MCG_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+        try {
+          schedule(img, out_gaze, out_boxes, out_scores, cap_stream_);
+        } catch (...) {
+          cudaStreamEndCapture(cap_stream_, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        MCG_CUDA(cudaStreamEndCapture(cap_stream_, &graph));
+        cudaGraphExec_t exec = nullptr;
+        MCG_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        MCG_CUDA(cudaGraphDestroy(graph));
+        it = graphs_.emplace(key, exec).first;
       }
-      MCG_CUDA(cudaStreamEndCapture(cap_stream_, &graph));
-      MCG_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
-      MCG_CUDA(cudaGraphDestroy(graph));
-      g_img_ = img;
-      g_gaze_ = out_gaze;
-      g_boxes_ = out_boxes;
-      g_scores_ = out_scores;
-      g_has_scale_ = has_scale_;
-      MCG_CUDA(cudaGraphLaunch(graph_exec_, stream));
+      MCG_CUDA(cudaGraphLaunch(it->second, stream));
       return;
     }
     schedule(img, out_gaze, out_boxes, out_scores, stream);
   }
 
-  void forward_host(const float* img_host, int B, int T, int H, int W, const float* img_hw,
-                    const float* scale_factor, float* out_gaze, float* out_boxes, float* out_scores) {
+  // Two-slot pipelined host entry: the H2D copy of submission i+1 (copy stream) overlaps the forward
+  // of submission i (compute stream); results come back through pinned slot buffers.
+  int submit_host(const float* img_host, int B, int T, int H, int W, const float* img_hw, const float* scale_factor) {
     MCG_CUDA(cudaSetDevice(device_));
     const int NB = B * T;
     const size_t in_bytes = static_cast<size_t>(NB) * 3 * H * W * sizeof(float);
-    const size_t out_floats = static_cast<size_t>(NB) * (12 + 12 + 3);
+    const size_t out_bytes = static_cast<size_t>(NB) * (12 + 12 + 3) * sizeof(float);
     if (!own_stream_) MCG_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
-    if (in_bytes > io_in_bytes_) {
-      io_in_.reset(new DeviceBlock(in_bytes));
-      io_in_bytes_ = in_bytes;
+    if (!copy_stream_) MCG_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    const int si = next_slot_;
+    HostSlot& sl = slot_[si];
+    MCG_CHECK(!sl.busy, "mcg_submit_host: both pipeline slots are in flight; call mcg_wait_host first");
+    if (in_bytes > sl.in_bytes || out_bytes > sl.out_bytes) {
+      MCG_CUDA(cudaDeviceSynchronize());
       drop_graph();
+      sl.d_in.reset(new DeviceBlock(in_bytes));
+      sl.d_out.reset(new DeviceBlock(out_bytes));
+      sl.in_bytes = in_bytes;
+      sl.out_bytes = out_bytes;
+      if (sl.pin_out) cudaFreeHost(sl.pin_out);
+      MCG_CUDA(cudaMallocHost(&sl.pin_out, out_bytes));
     }
-    if (out_floats * sizeof(float) > io_out_bytes_) {
-      io_out_.reset(new DeviceBlock(out_floats * sizeof(float)));
-      io_out_bytes_ = out_floats * sizeof(float);
-      if (pin_out_) cudaFreeHost(pin_out_);
-      MCG_CUDA(cudaMallocHost(&pin_out_, io_out_bytes_));
-      drop_graph();
+    if (!sl.h2d_done) {
+      MCG_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+      MCG_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    } else {
+      MCG_CUDA(cudaStreamWaitEvent(copy_stream_, sl.done, 0));  // previous forward on this slot has consumed d_in
     }
-    float* d_in = reinterpret_cast<float*>(io_in_->p);
-    float* d_out = reinterpret_cast<float*>(io_out_->p);
-    // async when the caller's buffer is pinned; otherwise the runtime stages it
-    MCG_CUDA(cudaMemcpyAsync(d_in, img_host, in_bytes, cudaMemcpyHostToDevice, own_stream_));
+    float* d_in = reinterpret_cast<float*>(sl.d_in->p);
+    float* d_out = reinterpret_cast<float*>(sl.d_out->p);
+    // asynchronous when the caller's buffer is pinned; otherwise the runtime stages it
+    MCG_CUDA(cudaMemcpyAsync(d_in, img_host, in_bytes, cudaMemcpyHostToDevice, copy_stream_));
+    MCG_CUDA(cudaEventRecord(sl.h2d_done, copy_stream_));
+    MCG_CUDA(cudaStreamWaitEvent(own_stream_, sl.h2d_done, 0));
     forward(d_in, B, T, H, W, img_hw, scale_factor, d_out, d_out + NB * 12, d_out + NB * 24, own_stream_);
-    MCG_CUDA(cudaMemcpyAsync(pin_out_, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, own_stream_));
-    MCG_CUDA(cudaStreamSynchronize(own_stream_));
-    const float* po = reinterpret_cast<const float*>(pin_out_);
+    MCG_CUDA(cudaMemcpyAsync(sl.pin_out, d_out, out_bytes, cudaMemcpyDeviceToHost, own_stream_));
+    MCG_CUDA(cudaEventRecord(sl.done, own_stream_));
+    sl.busy = true;
+    sl.NB = NB;
+    next_slot_ ^= 1;
+    return si;
+  }
+
+  void wait_host(int ticket, float* out_gaze, float* out_boxes, float* out_scores) {
+    MCG_CHECK(ticket == 0 || ticket == 1, "mcg_wait_host: bad ticket");
+    HostSlot& sl = slot_[ticket];
+    MCG_CHECK(sl.busy, "mcg_wait_host: nothing submitted on this ticket");
+    MCG_CUDA(cudaEventSynchronize(sl.done));
+    const int NB = sl.NB;
+    const float* po = reinterpret_cast<const float*>(sl.pin_out);
     std::memcpy(out_gaze, po, static_cast<size_t>(NB) * 12 * sizeof(float));
     std::memcpy(out_boxes, po + NB * 12, static_cast<size_t>(NB) * 12 * sizeof(float));
     std::memcpy(out_scores, po + NB * 24, static_cast<size_t>(NB) * 3 * sizeof(float));
+    sl.busy = false;
+  }
+
+  void forward_host(const float* img_host, int B, int T, int H, int W, const float* img_hw,
+                    const float* scale_factor, float* out_gaze, float* out_boxes, float* out_scores) {
+    const int t = submit_host(img_host, B, T, H, W, img_hw, scale_factor);
+    wait_host(t, out_gaze, out_boxes, out_scores);
   }
 
   int get_intermediate(const char* name, float* dst, int64_t capacity, int64_t shape_out[4]) {
@@ -570,11 +601,8 @@ class Engine {
   }
 
   void drop_graph() {
-    if (graph_exec_) {
-      cudaGraphExecDestroy(graph_exec_);
-      graph_exec_ = nullptr;
-    }
-    g_img_ = nullptr;
+    for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+    graphs_.clear();
   }
 
   // -------------------------------------------------------------------------- op helpers
@@ -972,16 +1000,29 @@ class Engine {
   int launches_ = 0;
 
   bool graph_mode_ = false;
-  cudaGraphExec_t graph_exec_ = nullptr;
-  const float* g_img_ = nullptr;
-  float *g_gaze_ = nullptr, *g_boxes_ = nullptr, *g_scores_ = nullptr;
-  bool g_has_scale_ = false;
+  struct GraphKey {
+    const float* img;
+    float *gaze, *boxes, *scores;
+    bool has_scale;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(img, gaze, boxes, scores, has_scale) < std::tie(o.img, o.gaze, o.boxes, o.scores, o.has_scale);
+    }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs_;
 
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t cap_stream_ = nullptr;
-  std::unique_ptr<DeviceBlock> io_in_, io_out_;
-  size_t io_in_bytes_ = 0, io_out_bytes_ = 0;
-  void* pin_out_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr;
+  struct HostSlot {
+    std::unique_ptr<DeviceBlock> d_in, d_out;
+    size_t in_bytes = 0, out_bytes = 0;
+    void* pin_out = nullptr;
+    cudaEvent_t h2d_done = nullptr, done = nullptr;
+    bool busy = false;
+    int NB = 0;
+  };
+  HostSlot slot_[2];
+  int next_slot_ = 0;
 };
 
 }  // namespace mcg
@@ -1063,6 +1104,29 @@ int mcg_forward_host(mcg_handle h, const float* img_host, int B, int T, int H, i
       return MCG_ERR_INVALID;
     }
     h->impl->forward_host(img_host, B, T, H, W, img_hw, scale_factor, out_gaze_host, out_boxes_host, out_scores_host);
+    return MCG_OK;
+  });
+}
+
+int mcg_submit_host(mcg_handle h, const float* img_host, int B, int T, int H, int W, const float* img_hw,
+                    const float* scale_factor, int* ticket) {
+  return guarded([&]() -> int {
+    if (!h || !img_host || !ticket) {
+      mcg::g_last_error = "mcg_submit_host: null argument";
+      return MCG_ERR_INVALID;
+    }
+    *ticket = h->impl->submit_host(img_host, B, T, H, W, img_hw, scale_factor);
+    return MCG_OK;
+  });
+}
+
+int mcg_wait_host(mcg_handle h, int ticket, float* out_gaze_host, float* out_boxes_host, float* out_scores_host) {
+  return guarded([&]() -> int {
+    if (!h || !out_gaze_host || !out_boxes_host || !out_scores_host) {
+      mcg::g_last_error = "mcg_wait_host: null argument";
+      return MCG_ERR_INVALID;
+    }
+    h->impl->wait_host(ticket, out_gaze_host, out_boxes_host, out_scores_host);
     return MCG_OK;
   });
 }

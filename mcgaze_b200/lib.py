@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, 'libmcgaze_b200.so')
 PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2}
 
 # every symbol include/mcgaze_b200.h declares
-EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_get_intermediate',
+EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
+           'mcg_get_intermediate',
            'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
            'mcg_last_error', 'mcg_version')
 
@@ -46,6 +47,8 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_destroy.argtypes = [vp]
     lib.mcg_forward.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.mcg_forward_host.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+    lib.mcg_submit_host.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, ctypes.POINTER(ci)]
+    lib.mcg_wait_host.argtypes = [vp, ci, vp, vp, vp]
     lib.mcg_get_intermediate.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     lib.mcg_last_launch_count.argtypes = [vp]
     lib.mcg_set_graph_mode.argtypes = [vp, ci]
@@ -193,6 +196,31 @@ class Engine:
         _check(self._lib.mcg_forward_host(self._h, img.data_ptr(), N // T, T, H, W, p1, p2, gaze.data_ptr(),
                                           boxes.data_ptr(), scores.data_ptr()), 'mcg_forward_host')
         del k1, k2
+        return {'gaze': gaze, 'boxes': boxes, 'scores': scores}
+
+    def submit_host(self, img, clip_length: Optional[int] = None, img_hw=None, scale_factor=None):
+        """Pipelined host entry: enqueue H2D copy + forward + read-back, return a ticket for wait_host().
+        Keep `img` (CPU fp32, ideally pinned) alive until the matching wait_host()."""
+        import torch
+        assert (not img.is_cuda) and img.dtype == torch.float32 and img.dim() == 4 and img.is_contiguous()
+        N, _, H, W = img.shape
+        T = N if clip_length is None else int(clip_length)
+        k1, p1 = self._meta(img_hw, N, 2)
+        k2, p2 = self._meta(scale_factor, N, 4)
+        ticket = ctypes.c_int(-1)
+        _check(self._lib.mcg_submit_host(self._h, img.data_ptr(), N // T, T, H, W, p1, p2, ctypes.byref(ticket)),
+               'mcg_submit_host')
+        del k1, k2
+        return (ticket.value, N, img)
+
+    def wait_host(self, ticket):
+        import torch
+        t, N, _keep = ticket
+        gaze = torch.empty(N, 4, 3, dtype=torch.float32)
+        boxes = torch.empty(N, 3, 4, dtype=torch.float32)
+        scores = torch.empty(N, 3, dtype=torch.float32)
+        _check(self._lib.mcg_wait_host(self._h, t, gaze.data_ptr(), boxes.data_ptr(), scores.data_ptr()),
+               'mcg_wait_host')
         return {'gaze': gaze, 'boxes': boxes, 'scores': scores}
 
     def intermediate(self, name: str, max_elems: int = 1 << 28):

@@ -127,6 +127,36 @@ def test_host_entry_and_graph_replay_match_eager(engines):
         eng.set_graph_mode(False)
 
 
+def test_pipelined_host_submissions(engines):
+    """mcg_submit_host / mcg_wait_host with two batches in flight return what the device entry returns."""
+    from mcgaze_b200 import lib
+    eng = engines('fp16x3')
+    clips = [O.make_clip(30 + i, 7).pin_memory() for i in range(5)]
+    want = []
+    for c in clips:
+        want.append({k: v.cpu() for k, v in eng.forward(c.cuda(), clip_length=7).items()})
+    for graph in (False, True):
+        eng.set_graph_mode(graph)
+        try:
+            got = []
+            t = eng.submit_host(clips[0], clip_length=7)
+            for i in range(1, len(clips)):
+                nxt = eng.submit_host(clips[i], clip_length=7)
+                got.append(eng.wait_host(t))
+                t = nxt
+            got.append(eng.wait_host(t))
+            for a, b in zip(want, got):
+                for k in a:
+                    assert torch.equal(a[k], b[k]), (graph, k)
+            t0 = eng.submit_host(clips[0], clip_length=7)
+            t1 = eng.submit_host(clips[1], clip_length=7)
+            with pytest.raises(lib.McgError):
+                eng.submit_host(clips[2], clip_length=7)           # both slots busy
+            eng.wait_host(t0), eng.wait_host(t1)
+        finally:
+            eng.set_graph_mode(False)
+
+
 @pytest.mark.parametrize('precision', ['fp16x3', 'fp16'])
 def test_full_batch_properties(engines, precision):
     """BASELINE configs[1] size (32 clips x 7 frames x 224^2): clips are independent units, so
