@@ -242,9 +242,11 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
 // norm and ReLU after it.  One warp per row; rows may be strided (per-clue views).
 // y[row] = act( LN(x[row] (+ res[row])) * gamma + beta )
 // ---------------------------------------------------------------------------------------
+// x may be `nsplit` split-K partial sums `split_stride` elements apart (+ `xbias`), reduced here.
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res,
                                  long long ldres, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float* __restrict__ y, long long ldy, long long rows, int C, int relu) {
+                                 float* __restrict__ y, long long ldy, long long rows, int C, int relu,
+                                 int nsplit = 1, long long split_stride = 0, const float* __restrict__ xbias = nullptr) {
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -254,6 +256,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
   for (int j = 0; j < per; ++j) {
     const int c = j * 32 + lane;
     float t = x[row * ldx + c];
+    for (int sp = 1; sp < nsplit; ++sp) t += x[sp * split_stride + row * ldx + c];
+    if (xbias) t += xbias[c];
     if (res) t += res[row * ldres + c];
     v[j] = t;
     s += t;

@@ -119,6 +119,8 @@ struct GazeW {
   const float* bg = nullptr;
 };
 
+constexpr int kFcSplit = 14;  // 196 k-blocks -> 14 per slice
+
 struct Interm {
   int kind = 0;  // 0 = fp32 dense, 1 = NHWC planes
   const float* f32 = nullptr;
@@ -581,6 +583,7 @@ class Engine {
     roi_ = arena_.alloc<float>(Rr * 12544);
     dynf_ = arena_.alloc<float>(Rr * 12544);
     fc_ = arena_.alloc<float>(Rr * 256);
+    fcp_ = arena_.alloc<float>(Rr * 256 * kFcSplit);
     ffn_h_ = arena_.alloc<float>(Rr * 2048);
     t256a_ = arena_.alloc<float>(Rr * 256);
     t256b_ = arena_.alloc<float>(Rr * 256);
@@ -614,13 +617,13 @@ class Engine {
     return precision_ == MCG_PRECISION_SIMT ? 0 : (precision_ == MCG_PRECISION_FP16X3 ? 3 : 1);
   }
   void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
-            long long M, const Epilogue& ep, cudaStream_t st, int terms) {
+            long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0) {
     const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
                         (terms == 1 || A->lo != nullptr);
     if (tensor) {
       auto it = plans_.find(key);
       if (it == plans_.end()) {
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_);
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -734,7 +737,7 @@ class Engine {
 
   // big head linears: split the fp32 activations into fp16 planes and run on tensor cores
   void linear_tc(const std::string& key, const float* x, int K, const Planes& stage, const GemmW& w, long long M,
-                 float* y, bool relu, const float* res, cudaStream_t st) {
+                 float* y, bool relu, const float* res, cudaStream_t st, int k_split = 1) {
     if (precision_ == MCG_PRECISION_SIMT || !head_tc_) {
       linear(x, K, w, M, y, w.N, relu, res, w.N, st);
       return;
@@ -755,15 +758,17 @@ class Engine {
       ep.res_mode = RES_SAME;
       ep.ldr = w.N;
     }
+    if (k_split > 1) ep.bias = nullptr;  // the split-K reduction (fused into the following LayerNorm) adds it
     // head GEMMs always use the 3-term split: the head is precision critical and only 2.5 % of the FLOPs
-    gemm(key, &stage, nullptr, g, w, M, ep, st, 3);
+    gemm(key, &stage, nullptr, g, w, M, ep, st, 3, k_split, static_cast<long long>(M) * w.N);
   }
 
   void ln(const float* x, long long ldx, const float* res, long long ldres, const LnW& w, float* y, long long ldy,
-          long long rows, bool relu, cudaStream_t st) {
+          long long rows, bool relu, cudaStream_t st, int nsplit = 1, long long split_stride = 0,
+          const float* xbias = nullptr) {
     const int wpb = 8;
-    layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, ldx, res, ldres, w.g, w.b, y,
-                                                                                       ldy, rows, w.C, relu ? 1 : 0);
+    layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        x, ldx, res, ldres, w.g, w.b, y, ldy, rows, w.C, relu ? 1 : 0, nsplit, split_stride, xbias);
     MCG_CUDA(cudaGetLastError());
     count();
   }
@@ -899,8 +904,15 @@ class Engine {
                                                     sw.norm_out.b, dynf_);
       MCG_CUDA(cudaGetLastError());
       count();
-      linear_tc(sk + "fc", dynf_, 12544, hf_, sw.fc, R, fc_, false, nullptr, st);
-      ln(fc_, 256, nullptr, 0, sw.fc_norm, fc_, 256, R, true, st);
+      {
+        // 12544 -> 256 over only 3*frames rows: split K so that >100 tiles exist; the partial sums are
+        // reduced (and the bias added) inside the fc_norm LayerNorm kernel
+        const bool tc = precision_ != MCG_PRECISION_SIMT && head_tc_;
+        const int ks = tc ? kFcSplit : 1;
+        linear_tc(sk + "fc", dynf_, 12544, hf_, sw.fc, R, fcp_, false, nullptr, st, ks);
+        ln(fcp_, 256, nullptr, 0, sw.fc_norm, fc_, 256, R, true, st, ks, static_cast<long long>(R) * 256,
+           ks > 1 ? sw.fc.bias : nullptr);
+      }
       ln(attn, 256, fc_, 256, sw.iic_norm, xa_, 256, R, false, st);  // obj = LN(attn + iic)
       // FFN with identity (gaze_stqi_head.py:179)
       linear_tc(sk + "ffn1", xa_, 256, hq_, sw.ffn1, R, ffn_h_, true, nullptr, st);
@@ -988,7 +1000,7 @@ class Engine {
   Act lat_[4], fpn_[4];
   float *boxes_[2] = {nullptr, nullptr}, *obj_[2] = {nullptr, nullptr};
   float *qkv_ = nullptr, *att_ = nullptr, *xa_ = nullptr, *xb_ = nullptr, *xc_ = nullptr, *params_ = nullptr,
-        *roi_ = nullptr, *dynf_ = nullptr, *fc_ = nullptr, *ffn_h_ = nullptr, *t256a_ = nullptr, *t256b_ = nullptr,
+        *roi_ = nullptr, *dynf_ = nullptr, *fc_ = nullptr, *fcp_ = nullptr, *ffn_h_ = nullptr, *t256a_ = nullptr, *t256b_ = nullptr,
         *cls_logit_ = nullptr, *delta_ = nullptr, *gz_a_ = nullptr, *gz_b_ = nullptr, *gvec_ = nullptr,
         *conf_ = nullptr, *d_meta_ = nullptr;
   Planes hq_, hh_, hf_;

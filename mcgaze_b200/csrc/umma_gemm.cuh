@@ -50,6 +50,10 @@ struct UmmaParams {
   int num_kb = 0;
   int m_tiles = 0, n_tiles = 0;
   int cblocks = 1;  // C / 64 for im2col
+  int k_split = 1;  // split-K factor: tile t covers k-blocks [ks*num_kb/k_split, (ks+1)*num_kb/k_split) and writes
+                    // its fp32 partial sums to out_f32 + ks * split_stride (bias / residual / ReLU only in slice 0
+                    // resp. never: the reduction kernel applies them)
+  long long split_stride = 0;
   int out_tma = 0;  // planes output through smem staging + TMA store
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
   AGeom a;
@@ -87,7 +91,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kPlanes * kEpiBufBytes : 0);  // [4][2 bufs][planes][2 KB]
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = mn_tiles * p.k_split;
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm.a_hi);
@@ -126,8 +131,12 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+        const int ks = tile / mn_tiles;
+        const int mn = tile - ks * mn_tiles;
+        const int m_tile = mn / p.n_tiles;
+        const int n_tile = mn - m_tile * p.n_tiles;
+        const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
+        const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
         const long long m0 = static_cast<long long>(m_tile) * kBlockM;
         int img_n = 0, base_h = 0, base_w = 0;
         if (p.a.kind == 1) {
@@ -139,7 +148,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           base_h = p0 * p.a.stride - p.a.pad;
           base_w = q0 * p.a.stride - p.a.pad;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* s = stage_base + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sA_hi = s;
@@ -182,7 +191,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int ks = tile / mn_tiles;
+      const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
+      const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (lane == 0) {
@@ -196,7 +208,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             const uint32_t koff = j * kUmmaK * 2;  // bytes inside the 128 B swizzle row
             const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(aA_hi + koff);
             const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(aW_hi + koff);
-            uint32_t accum = (kb > 0 || j > 0) ? 1u : 0u;
+            uint32_t accum = (kb > kb_begin || j > 0) ? 1u : 0u;
             if (kTerms == 3) {
               const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(aA_lo + koff);
               const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(aW_lo + koff);
@@ -207,7 +219,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             ptx::umma_f16(tmem_d, dA_hi, dW_hi, idesc, accum);
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == p.num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);
+          if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == p.num_stages) {
@@ -229,8 +241,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     const int nchunks = p.block_n / kEpiChunk;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
+      const int ks = tile / mn_tiles;
+      const int mn = tile - ks * mn_tiles;
+      const int m_tile = mn / p.n_tiles;
+      const int n_tile = mn - m_tile * p.n_tiles;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const long long m_warp = static_cast<long long>(m_tile) * kBlockM + quarter * 32;  // first row of this warp
@@ -251,8 +265,37 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       ptx::tc_fence_after();
       const long long rrow = (valid && ep.res_mode != RES_NONE && !p.res_tma) ? res_row(ep, m) : 0;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      // gathered residual (FPN nearest-2x top-down add): per-thread vector loads, software-pipelined
+      // one chunk ahead in registers so the L2 latency overlaps the previous chunk's math
+      const bool res_direct = valid && ep.res_mode != RES_NONE && !p.res_tma && ep.res_f32 == nullptr;
+      uint4 rpre[8];
+      if (res_direct) {
+        const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n_base);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rpre[j] = __ldg(rh + j);
+        if (ep.res_lo) {
+          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n_base);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
+        }
+      }
       for (int c = 0; c < nchunks; ++c) {
         const int n = n_base + c * kEpiChunk;
+        uint4 rnow[8];
+        if (res_direct) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rnow[j] = rpre[j];
+          if (c + 1 < nchunks) {
+            const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n + kEpiChunk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rpre[j] = __ldg(rh + j);
+            if (ep.res_lo) {
+              const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n + kEpiChunk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
+            }
+          }
+        }
         const uint8_t* rcur = nullptr;
         if (use_rtma) {
           const int b = rcnt & 1;
@@ -275,7 +318,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias) {
+        if (ep.bias && p.k_split == 1) {
           const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -313,20 +356,20 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               v[4 * j + 3] += f.w;
             }
           } else {
+            const int npl = ep.res_lo ? 2 : 1;
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
-              const __half* rp = pl == 0 ? ep.res_hi : ep.res_lo;
-              if (rp == nullptr) continue;
-              const uint4* rh = reinterpret_cast<const uint4*>(rp + rrow * ep.ldr + n);
+              if (pl < npl) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(rh + j);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 u = rnow[pl * 4 + j];
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float2 f = __half22float2(h2[t]);
-                  v[8 * j + 2 * t] += f.x;
-                  v[8 * j + 2 * t + 1] += f.y;
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 f = __half22float2(h2[t]);
+                    v[8 * j + 2 * t] += f.x;
+                    v[8 * j + 2 * t + 1] += f.y;
+                  }
                 }
               }
             }
@@ -369,7 +412,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           oset ^= 1;
         } else if (valid) {
           if (ep.out_f32) {
-            float4* o = reinterpret_cast<float4*>(ep.out_f32 + m * ep.ldo + n);
+            float4* o = reinterpret_cast<float4*>(ep.out_f32 + ks * p.split_stride + m * ep.ldo + n);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
@@ -491,7 +534,8 @@ inline bool umma_supported(long long M, int N, int K, const AGeom& a) {
 
 // A planes: for kind 0 the [M,K] matrix, for kind 1 the NHWC activation.  W planes: [N,K].
 inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
-                               const Epilogue& ep, int num_sms, int force_block_n = 0) {
+                               const Epilogue& ep, int num_sms, int force_block_n = 0, int k_split = 1,
+                               long long split_stride = 0) {
   MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
   MCG_CHECK(terms == 1 || (A.lo && W.lo), "3-term GEMM needs lo planes");
   UmmaPlan pl;
@@ -537,9 +581,15 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.cblocks = a.kind == 1 ? a.C / kBlockK : 1;
   if (a.kind == 1) MCG_CHECK(K == a.R * a.S * a.C, "im2col K mismatch");
   p.ep = ep;
+  if (k_split > 1) {
+    MCG_CHECK(ep.out_f32 != nullptr && ep.res_mode == RES_NONE && !ep.relu && k_split <= p.num_kb,
+              "split-K needs a plain fp32 output (bias / activation are applied by the reduction)");
+    p.k_split = k_split;
+    p.split_stride = split_stride;
+  }
   pl.smem = 1024 + kSmemBarrierBytes + p.num_stages * stage_bytes + epi_bytes;
   MCG_CHECK(pl.smem <= kMaxDynSmem, "shared memory plan exceeds the 227 KB limit");
-  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.k_split;
   pl.grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   UmmaMaps& tm = pl.tm;
   if (a.kind == 1) {
