@@ -34,7 +34,9 @@ typedef struct {
 enum {
   MCG_PRECISION_FP16X3 = 0, /* tcgen05, split-fp16 operands (hi+lo), 3 MMAs/k-step: fp32-equivalent; parity mode */
   MCG_PRECISION_FP16 = 1,   /* tcgen05, single fp16 operands, fp32 accumulate: fast mode */
-  MCG_PRECISION_SIMT = 2    /* fp32 CUDA-core kernels only (cross-check / bring-up) */
+  MCG_PRECISION_SIMT = 2,   /* fp32 CUDA-core kernels only (cross-check / bring-up) */
+  MCG_PRECISION_FP16LO8 = 3 /* tcgen05, activations = fp16 hi + e4m3 low part (3 B/element): hi*hi + hi*lo_w in fp16 and
+                               lo8_a*hi8_w as an fp8 MMA into a second accumulator; ~3e-5 rad vs the fp32 reference */
 };
 
 enum {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -10,12 +11,28 @@
 
 namespace mcg {
 
-// Split-fp16 tensor: value = hi + lo.  `lo == nullptr` means single-fp16 ("fast") storage.
+// Split tensor: value = hi + lo.  hi is fp16.  The low part is stored either as fp16 (`lo`, mode
+// fp16x3) or as e4m3 fp8 of (value - hi) * 2^kLo8Shift (`lo8`, mode fp16lo8: 3 bytes / element and an
+// fp8 tensor-core correction term); both null means single-fp16 ("fast") storage.
 // Layout of every activation is NHWC (channels innermost), i.e. a row-major [pixels, C] matrix.
 struct Planes {
   __half* hi = nullptr;
   __half* lo = nullptr;
+  uint8_t* lo8 = nullptr;
 };
+
+// |value - hi| <= 2^-11 |value|; 2^13 maps the residue of |value| in [2^-8, 32] into e4m3's normal range
+constexpr int kLo8Shift = 13;
+constexpr float kLo8Scale = 8192.f;          // 2^13
+constexpr float kLo8InvScale = 1.f / 8192.f;
+
+__host__ __device__ inline uint8_t float_to_e4m3(float v) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
+}
+__host__ __device__ inline float e4m3_to_float(uint8_t b) {
+  const __half_raw hr = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(b), __NV_E4M3);
+  return __half2float(__half(hr));
+}
 
 enum ResMode : int { RES_NONE = 0, RES_SAME = 1, RES_UP2X = 2 };
 
@@ -27,11 +44,13 @@ struct Epilogue {
   const float* bias = nullptr;   // [N] or null
   const __half* res_hi = nullptr;
   const __half* res_lo = nullptr;
+  const uint8_t* res_lo8 = nullptr;
   const float* res_f32 = nullptr;  // fp32 residual (head); used instead of res_hi/res_lo when set
   int res_mode = RES_NONE;
   int relu = 0;
   __half* out_hi = nullptr;
   __half* out_lo = nullptr;
+  uint8_t* out_lo8 = nullptr;
   float* out_f32 = nullptr;      // if non-null, fp32 output instead of planes
   long long ldo = 0;             // output row stride (elements)
   long long ldr = 0;             // residual row stride (elements)
@@ -55,10 +74,32 @@ __host__ __device__ inline long long res_row(const Epilogue& e, long long m) {
   return (n * (e.P / 2) + (p >> 1)) * (e.Q / 2) + (q >> 1);
 }
 
-__device__ __forceinline__ void split_store(float v, __half* hi, __half* lo, long long idx) {
+__device__ __forceinline__ void split_store(float v, __half* hi, __half* lo, long long idx, uint8_t* lo8 = nullptr) {
   __half h = __float2half_rn(v);
   hi[idx] = h;
   if (lo) lo[idx] = __float2half_rn(v - __half2float(h));
+  if (lo8) lo8[idx] = float_to_e4m3((v - __half2float(h)) * kLo8Scale);
+}
+
+// 8 consecutive e4m3 values (one uint2) -> 8 floats (unscaled)
+__device__ __forceinline__ void e4m3x8_to_float(const uint2& u, float (&f)[8]) {
+  const uint16_t* p = reinterpret_cast<const uint16_t*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(p[t]), __NV_E4M3);
+    const float2 v = __half22float2(__half2(hr));
+    f[2 * t] = v.x;
+    f[2 * t + 1] = v.y;
+  }
+}
+// 8 floats -> 8 e4m3 (saturating), packed in a uint2
+__device__ __forceinline__ uint2 float8_to_e4m3x8(const float (&f)[8]) {
+  uint2 u;
+  uint16_t* p = reinterpret_cast<uint16_t*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    p[t] = static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(f[2 * t], f[2 * t + 1]), __NV_SATFINITE, __NV_E4M3));
+  return u;
 }
 
 struct CudaError : std::runtime_error {

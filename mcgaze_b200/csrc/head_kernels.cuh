@@ -19,7 +19,7 @@ constexpr int kStemK = 192;
 // (consecutive threads -> consecutive addresses: rows of A are contiguous in memory).
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, int NB, int H, int W, int P,
                                                           int Q, __half* __restrict__ a_hi,
-                                                          __half* __restrict__ a_lo) {
+                                                          __half* __restrict__ a_lo, uint8_t* __restrict__ a_lo8) {
   extern __shared__ float srow[];  // [3][7][W + 6], zero padded
   const int WP = W + 6;
   const int p = blockIdx.x % P;
@@ -56,25 +56,30 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   for (int q = threadIdx.x / (kStemK / 8); q < Q; q += 10) {
     __align__(16) __half hh[8];
     __align__(16) __half hl[8];
+    float rs[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float v = off[j] >= 0 ? srow[off[j] + q * 2] : 0.f;
       const __half h = __float2half_rn(v);
       hh[j] = h;
-      hl[j] = __float2half_rn(v - __half2float(h));
+      rs[j] = v - __half2float(h);
+      hl[j] = __float2half_rn(rs[j]);
+      rs[j] *= kLo8Scale;
     }
     const long long o = (m0 + q) * kStemK + k8 * 8;
     *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hh);
     if (a_lo) *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(hl);
+    if (a_lo8) *reinterpret_cast<uint2*>(a_lo8 + o) = float8_to_e4m3x8(rs);
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // max-pool 3x3 stride 2 pad 1 over NHWC split-fp16 planes (resnet.py:611,639)
 // ---------------------------------------------------------------------------------------
-__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int NB,
-                                    int H, int W, int C, int P, int Q, __half* __restrict__ out_hi,
-                                    __half* __restrict__ out_lo) {
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                    const uint8_t* __restrict__ in_lo8, int NB, int H, int W, int C, int P, int Q,
+                                    __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                    uint8_t* __restrict__ out_lo8) {
   const int c8n = C / 8;
   const long long total = static_cast<long long>(NB) * P * Q * c8n;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -100,21 +105,28 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __ha
         uint4 ul = make_uint4(0, 0, 0, 0);
         if (in_lo) ul = *reinterpret_cast<const uint4*>(in_lo + idx);
         const __half* pl = reinterpret_cast<const __half*>(&ul);
+        float l8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (in_lo8) e4m3x8_to_float(*reinterpret_cast<const uint2*>(in_lo8 + idx), l8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], __half2float(ph[j]) + __half2float(pl[j]));
+        for (int j = 0; j < 8; ++j)
+          best[j] = fmaxf(best[j], __half2float(ph[j]) + __half2float(pl[j]) + l8[j] * kLo8InvScale);
       }
     }
     __align__(16) __half hh[8];
     __align__(16) __half hl[8];
+    float rs[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const __half h = __float2half_rn(best[j]);
       hh[j] = h;
-      hl[j] = __float2half_rn(best[j] - __half2float(h));
+      rs[j] = best[j] - __half2float(h);
+      hl[j] = __float2half_rn(rs[j]);
+      rs[j] *= kLo8Scale;
     }
     const long long o = ((static_cast<long long>(n) * P + p) * Q + q) * C + c8 * 8;
     *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
     if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(hl);
+    if (out_lo8) *reinterpret_cast<uint2*>(out_lo8 + o) = float8_to_e4m3x8(rs);
   }
 }
 
@@ -148,6 +160,7 @@ __global__ void init_proposals_kernel(const float* __restrict__ init_boxes /*[3,
 struct FpnLevels {
   const __half* hi[4];
   const __half* lo[4];
+  const uint8_t* lo8[4];
   int H[4];
   int W[4];
 };
@@ -186,6 +199,7 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
   const int H = f.H[lvl], W = f.W[lvl];
   const __half* fhi = f.hi[lvl];
   const __half* flo = f.lo[lvl];
+  const uint8_t* flo8 = f.lo8[lvl];
   const float x1 = bx1 * scale - 0.5f, y1 = by1 * scale - 0.5f;
   const float bw = (bx2 * scale - 0.5f - x1) / 7.f;
   const float bh = (by2 * scale - 0.5f - y1) / 7.f;
@@ -229,6 +243,17 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
         acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i01)), hy * lx);
         acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i10)), ly * hx);
         acc8(acc, __ldg(reinterpret_cast<const uint4*>(flo + i11)), ly * lx);
+      }
+      if (flo8) {
+        const long long ii[4] = {i00, i01, i10, i11};
+        const float ww[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float l8[8];
+          e4m3x8_to_float(__ldg(reinterpret_cast<const uint2*>(flo8 + ii[t])), l8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww[t] * kLo8InvScale, l8[j], acc[j]);
+        }
       }
     }
   }
@@ -678,27 +703,28 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const float* __restr
 
 // fp32 [rows, C] (row stride ld) -> split-fp16 planes [rows, C] (dense)
 __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, long long rows, int C,
-                                    __half* __restrict__ hi, __half* __restrict__ lo) {
+                                    __half* __restrict__ hi, __half* __restrict__ lo, uint8_t* __restrict__ lo8 = nullptr) {
   const long long total = rows * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C;
     const int c = static_cast<int>(i - r * C);
-    split_store(x[r * ld + c], hi, lo, i);
+    split_store(x[r * ld + c], hi, lo, i, lo8);
   }
 }
 
 // split-fp16 planes -> dense fp32, same layout (debug only)
-__global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n,
-                                     float* __restrict__ out) {
+__global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                     const uint8_t* __restrict__ lo8, long long n, float* __restrict__ out) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = __half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f);
+    out[i] = __half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f) + (lo8 ? e4m3_to_float(lo8[i]) * kLo8InvScale : 0.f);
 }
 
 // split-fp16 NHWC planes -> fp32 NCHW (debug / intermediate export only)
-__global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int NB, int H,
-                                      int W, int C, float* __restrict__ out) {
+__global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                      const uint8_t* __restrict__ lo8, int NB, int H, int W, int C,
+                                      float* __restrict__ out) {
   const long long total = static_cast<long long>(NB) * H * W * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -710,6 +736,7 @@ __global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, const __hal
     const int n = static_cast<int>(t / H);
     float v = __half2float(hi[i]);
     if (lo) v += __half2float(lo[i]);
+    if (lo8) v += e4m3_to_float(lo8[i]) * kLo8InvScale;
     out[((static_cast<long long>(n) * C + c) * H + h) * W + w] = v;
   }
 }

@@ -3,6 +3,7 @@
 // Host-side runtime for the MCGaze per-clip forward: checkpoint ingestion (BN folding, K-major
 // repack, split-fp16), workspace arena, launch schedule of the trunk (ResNet-50 + FPN) and of the
 // 4-stage query head, intermediates registry for per-op parity tests, optional CUDA-graph replay.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -92,7 +93,8 @@ struct GemmW {  // packed [N, K] weight (+ bias) on device
   int N = 0, K = 0;
   const float* w_f32 = nullptr;
   const float* w_t = nullptr;  // [K, N] transposed copy for small_linear_kernel (small layers only)
-  Planes w;
+  Planes w;                    // hi / lo fp16 planes; w.lo8 = e4m3(hi * 2^w_shift) for the fp16lo8 mode
+  int w_shift = 0;
   const float* bias = nullptr;
 };
 struct LnW {
@@ -322,7 +324,7 @@ class Engine {
     } else {
       const int NB = static_cast<int>(t.shape[0]), H = static_cast<int>(t.shape[1]), W = static_cast<int>(t.shape[2]),
                 C = static_cast<int>(t.shape[3]);
-      planes_to_nchw_kernel<<<1024, 256>>>(t.pl.hi, t.pl.lo, NB, H, W, C, dst);
+      planes_to_nchw_kernel<<<1024, 256>>>(t.pl.hi, t.pl.lo, t.pl.lo8, NB, H, W, C, dst);
       MCG_CUDA(cudaGetLastError());
       MCG_CUDA(cudaDeviceSynchronize());
       shape_out[0] = NB;
@@ -362,6 +364,15 @@ class Engine {
     }
     g.w.hi = upload(keep_, hi);
     g.w.lo = upload(keep_, lo);
+    if (precision_ == MCG_PRECISION_FP16LO8) {
+      float mx = 0.f;
+      for (size_t i = 0; i < w.size(); ++i) mx = std::max(mx, std::fabs(__half2float(hi[i])));
+      g.w_shift = mx > 0.f ? static_cast<int>(std::floor(std::log2(256.0f / mx))) : 0;  // max |w| -> [128, 256)
+      const float sc = std::ldexp(1.0f, g.w_shift);
+      std::vector<uint8_t> h8(w.size());
+      for (size_t i = 0; i < w.size(); ++i) h8[i] = float_to_e4m3(__half2float(hi[i]) * sc);
+      g.w.lo8 = upload(keep_, h8);
+    }
     if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
     if (N <= 768 && K <= 2048 && K % 32 == 0) {
       std::vector<float> t(w.size());
@@ -516,11 +527,19 @@ class Engine {
     a.W = W;
     a.C = C;
     const size_t n = static_cast<size_t>(NB) * H * W * C;
-    a.pl.hi = arena_.alloc<__half>(n);
-    a.pl.lo = two_planes() ? arena_.alloc<__half>(n) : nullptr;
+    a.pl = alloc_planes(n);
     return a;
   }
-  bool two_planes() const { return precision_ != MCG_PRECISION_FP16; }
+  // low-part storage of the trunk's activations: fp16 (fp16x3 / simt), e4m3 (fp16lo8) or none (fp16)
+  bool lo_fp16() const { return precision_ == MCG_PRECISION_FP16X3 || precision_ == MCG_PRECISION_SIMT; }
+  bool lo_fp8() const { return precision_ == MCG_PRECISION_FP16LO8; }
+  Planes alloc_planes(size_t n) {
+    Planes pl;
+    pl.hi = arena_.alloc<__half>(n);
+    pl.lo = lo_fp16() ? arena_.alloc<__half>(n) : nullptr;
+    pl.lo8 = lo_fp8() ? arena_.alloc<uint8_t>(n) : nullptr;
+    return pl;
+  }
 
   void ensure_workspace(int NB, int T, int H, int W) {
     if (NB == ws_NB_ && T == ws_T_ && H == ws_H_ && W == ws_W_) return;
@@ -545,8 +564,7 @@ class Engine {
 
   void layout_workspace(int NB, int H, int W) {
     const int P1 = H / 2, Q1 = W / 2, P2 = H / 4, Q2 = W / 4;
-    stemA_.hi = arena_.alloc<__half>(static_cast<size_t>(NB) * P1 * Q1 * kStemK);
-    stemA_.lo = two_planes() ? arena_.alloc<__half>(static_cast<size_t>(NB) * P1 * Q1 * kStemK) : nullptr;
+    stemA_ = alloc_planes(static_cast<size_t>(NB) * P1 * Q1 * kStemK);
     stem_out_ = new_act(NB, P1, Q1, 64);
     pool_out_ = new_act(NB, P2, Q2, 64);
     int h = P2, w = Q2;
@@ -614,16 +632,21 @@ class Engine {
   // generic GEMM dispatch.  A: planes (kind 0/1) or fp32 (kind 0).
   // terms: 0 = CUDA-core fp32 kernel, 1 / 3 = tcgen05 kernel with 1 / 3 MMAs per k-step
   int trunk_terms() const {
-    return precision_ == MCG_PRECISION_SIMT ? 0 : (precision_ == MCG_PRECISION_FP16X3 ? 3 : 1);
+    switch (precision_) {
+      case MCG_PRECISION_SIMT: return 0;
+      case MCG_PRECISION_FP16X3: return 3;
+      case MCG_PRECISION_FP16LO8: return 2;
+      default: return 1;
+    }
   }
   void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
             long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0) {
     const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
-                        (terms == 1 || A->lo != nullptr);
+                        (terms == 1 || (terms == 3 && A->lo != nullptr) || (terms == 2 && A->lo8 != nullptr));
     if (tensor) {
       auto it = plans_.find(key);
       if (it == plans_.end()) {
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride);
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, w.w_shift);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -652,6 +675,7 @@ class Engine {
       if (A) {
         p.a_hi = A->hi;
         p.a_lo = A->lo;
+        p.a_lo8 = A->lo8;
       } else {
         p.a_f32 = A_f32;
       }
@@ -684,10 +708,12 @@ class Engine {
     ep.relu = relu ? 1 : 0;
     ep.out_hi = y.pl.hi;
     ep.out_lo = y.pl.lo;
+    ep.out_lo8 = y.pl.lo8;
     ep.ldo = y.C;
     if (res) {
       ep.res_hi = res->pl.hi;
       ep.res_lo = res->pl.lo;
+      ep.res_lo8 = res->pl.lo8;
       ep.res_mode = res_mode;
       ep.ldr = res->C;
       ep.P = y.H;
@@ -810,7 +836,7 @@ class Engine {
     const int ew_grid = num_sms_ * 8;
     // ---- stem (resnet.py:636-639)
     stem_im2col_kernel<<<NB * (H / 2), 256, 3 * 7 * (W + 6) * sizeof(float), st>>>(img, NB, H, W, H / 2, W / 2,
-                                                                                   stemA_.hi, stemA_.lo);
+                                                                                   stemA_.hi, stemA_.lo, stemA_.lo8);
     MCG_CUDA(cudaGetLastError());
     count();
     {
@@ -822,11 +848,12 @@ class Engine {
       ep.relu = 1;
       ep.out_hi = stem_out_.pl.hi;
       ep.out_lo = stem_out_.pl.lo;
+      ep.out_lo8 = stem_out_.pl.lo8;
       ep.ldo = 64;
       gemm("stem", &stemA_, nullptr, g, stem_.g, stem_out_.rows(), ep, st, trunk_terms());
     }
-    maxpool3x3s2_kernel<<<ew_grid, 256, 0, st>>>(stem_out_.pl.hi, stem_out_.pl.lo, NB, H / 2, W / 2, 64, H / 4, W / 4,
-                                                 pool_out_.pl.hi, pool_out_.pl.lo);
+    maxpool3x3s2_kernel<<<ew_grid, 256, 0, st>>>(stem_out_.pl.hi, stem_out_.pl.lo, stem_out_.pl.lo8, NB, H / 2, W / 2, 64,
+                                                 H / 4, W / 4, pool_out_.pl.hi, pool_out_.pl.lo, pool_out_.pl.lo8);
     MCG_CUDA(cudaGetLastError());
     count();
     reg_act("stem", stem_out_);
@@ -871,6 +898,7 @@ class Engine {
     for (int i = 0; i < 4; ++i) {
       fl.hi[i] = fpn_[i].pl.hi;
       fl.lo[i] = fpn_[i].pl.lo;
+      fl.lo8[i] = fpn_[i].pl.lo8;
       fl.H[i] = fpn_[i].H;
       fl.W[i] = fpn_[i].W;
     }
@@ -1072,7 +1100,7 @@ const char* mcg_version(void) { return "mcgaze_b200 0.1 (sm_100a)"; }
 
 int mcg_create(mcg_handle* out, int device, const mcg_tensor* weights, int n_weights, int precision) {
   return guarded([&]() -> int {
-    if (!out || !weights || n_weights <= 0 || precision < 0 || precision > 2) {
+    if (!out || !weights || n_weights <= 0 || precision < 0 || precision > 3) {
       mcg::g_last_error = "mcg_create: invalid argument";
       return MCG_ERR_INVALID;
     }
@@ -1195,14 +1223,41 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
       RW = Q / 2;
     }
     const size_t nr = res ? static_cast<size_t>(NB) * RH * RW * Cout : 0;
-    DeviceBlock bx(nx * 4), bw(nw * 4), br(nr * 4 + 16);
-    Planes px{reinterpret_cast<__half*>(bx.p), reinterpret_cast<__half*>(bx.p) + nx};
-    Planes pw{reinterpret_cast<__half*>(bw.p), reinterpret_cast<__half*>(bw.p) + nw};
-    Planes pr{reinterpret_cast<__half*>(br.p), reinterpret_cast<__half*>(br.p) + nr};
-    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, px.lo);
+    const bool lo8 = engine == MCG_PRECISION_FP16LO8;
+    DeviceBlock bx(nx * 5), bw(nw * 5), br(nr * 5 + 16);
+    Planes px{reinterpret_cast<__half*>(bx.p), reinterpret_cast<__half*>(bx.p) + nx, nullptr};
+    Planes pw{reinterpret_cast<__half*>(bw.p), reinterpret_cast<__half*>(bw.p) + nw, nullptr};
+    Planes pr{reinterpret_cast<__half*>(br.p), reinterpret_cast<__half*>(br.p) + nr, nullptr};
+    int w_shift = 0;
+    if (lo8) {  // activations / residual carry an e4m3 low part instead of the fp16 one
+      px.lo8 = reinterpret_cast<uint8_t*>(bx.p) + nx * 4;
+      pr.lo8 = reinterpret_cast<uint8_t*>(br.p) + nr * 4;
+      pw.lo8 = reinterpret_cast<uint8_t*>(bw.p) + nw * 4;
+    }
+    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, lo8 ? nullptr : px.lo,
+                                              px.lo8);
     split_planes_kernel<<<1024, 256, 0, st>>>(w, K, Cout, K, pw.hi, pw.lo);
-    if (res) split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi, pr.lo);
+    if (res)
+      split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi,
+                                                lo8 ? nullptr : pr.lo, pr.lo8);
     MCG_CUDA(cudaGetLastError());
+    if (lo8) {  // e4m3(W_hi * 2^shift) packed on the host exactly like Engine::pack_gemm
+      std::vector<float> hw(nw);
+      MCG_CUDA(cudaMemcpyAsync(hw.data(), w, nw * 4, cudaMemcpyDeviceToHost, st));
+      MCG_CUDA(cudaStreamSynchronize(st));
+      float mx = 0.f;
+      for (size_t i = 0; i < nw; ++i) mx = std::max(mx, std::fabs(__half2float(__float2half_rn(hw[i]))));
+      w_shift = mx > 0.f ? static_cast<int>(std::floor(std::log2(256.0f / mx))) : 0;
+      std::vector<uint8_t> h8(nw);
+      for (size_t i = 0; i < nw; ++i)
+        h8[i] = float_to_e4m3(__half2float(__float2half_rn(hw[i])) * std::ldexp(1.0f, w_shift));
+      MCG_CUDA(cudaMemcpyAsync(pw.lo8, h8.data(), nw, cudaMemcpyHostToDevice, st));
+      MCG_CUDA(cudaStreamSynchronize(st));
+    }
+    if (lo8) {
+      px.lo = nullptr;
+      pr.lo = nullptr;
+    }
     AGeom g;
     const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col;
     g.kind = plain ? 0 : 1;
@@ -1228,6 +1283,7 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     if (planes_out) {
       ep.out_hi = po.hi;
       ep.out_lo = engine == MCG_PRECISION_FP16X3 ? po.lo : nullptr;
+      ep.out_lo8 = lo8 ? reinterpret_cast<uint8_t*>(po.lo) : nullptr;
     } else {
       ep.out_f32 = out;
     }
@@ -1235,6 +1291,7 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     if (res) {
       ep.res_hi = pr.hi;
       ep.res_lo = pr.lo;
+      ep.res_lo8 = pr.lo8;
       ep.res_mode = res_mode;
       ep.ldr = Cout;
       ep.P = P;
@@ -1248,6 +1305,7 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
       p.a = g;
       p.a_hi = px.hi;
       p.a_lo = px.lo;
+      p.a_lo8 = px.lo8;
       p.w_hi = pw.hi;
       p.w_lo = pw.lo;
       p.ep = ep;
@@ -1261,10 +1319,11 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
         return MCG_ERR_UNSUPPORTED;
       }
       if (engine == MCG_PRECISION_FP16 && res) ep.res_lo = nullptr;
-      UmmaPlan pl = make_umma_plan(engine == MCG_PRECISION_FP16X3 ? 3 : 1, px, g, pw, M, Cout, K, ep, sms, force_block_n);
+      const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : (lo8 ? 2 : 1);
+      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n, 1, 0, w_shift);
       launch_umma(pl, st);
       if (planes_out) {
-        planes_to_f32_kernel<<<1024, 256, 0, st>>>(po.hi, ep.out_lo, static_cast<long long>(ny), out);
+        planes_to_f32_kernel<<<1024, 256, 0, st>>>(po.hi, ep.out_lo, ep.out_lo8, static_cast<long long>(ny), out);
         MCG_CUDA(cudaGetLastError());
       }
     }

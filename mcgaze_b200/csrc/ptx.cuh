@@ -130,6 +130,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, e4m3 x e4m3 operands (kind::f8f6f4, K = 32 per instruction, twice the fp16 rate)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -159,7 +171,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
   return d;
 }
-// instruction descriptor: A,B = fp16 (K-major), D = fp32, M x N tile
+// K-major, 64-byte-swizzled descriptor (rows of 64 B: 64 fp8 elements; 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                    // SBO = 512 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                           // SWIZZLE_64B
+  return d;
+}
+// instruction descriptor: A,B = fp16 (K-major), D = fp32, M x N tile.  The same bit pattern describes
+// e4m3 x e4m3 -> fp32 for kind::f8f6f4 (format code 0 = F16 resp. E4M3).
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);

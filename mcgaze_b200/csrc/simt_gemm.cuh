@@ -15,6 +15,7 @@ struct SimtParams {
   const float* a_f32 = nullptr;
   const __half* a_hi = nullptr;
   const __half* a_lo = nullptr;
+  const uint8_t* a_lo8 = nullptr;
   // W operand [N, K] row-major: fp32, or split-fp16 planes
   const float* w_f32 = nullptr;
   const __half* w_hi = nullptr;
@@ -33,6 +34,7 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, long long m, 
     } else {
       v += __half2float(ep.res_hi[ri]);
       if (ep.res_lo) v += __half2float(ep.res_lo[ri]);
+      if (ep.res_lo8) v += e4m3_to_float(ep.res_lo8[ri]) * kLo8InvScale;
     }
   }
   if (ep.relu) v = fmaxf(v, 0.f);
@@ -40,7 +42,7 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, long long m, 
   if (ep.out_f32)
     ep.out_f32[oi] = v;
   else
-    split_store(v, ep.out_hi, ep.out_lo, oi);
+    split_store(v, ep.out_hi, ep.out_lo, oi, ep.out_lo8);
 }
 
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtParams p) {
@@ -93,7 +95,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtParams p) {
             if (p.a_f32)
               av[j] = p.a_f32[idx + j];
             else
-              av[j] = __half2float(p.a_hi[idx + j]) + (p.a_lo ? __half2float(p.a_lo[idx + j]) : 0.f);
+              av[j] = __half2float(p.a_hi[idx + j]) + (p.a_lo ? __half2float(p.a_lo[idx + j]) : 0.f) +
+                      (p.a_lo8 ? e4m3_to_float(p.a_lo8[idx + j]) * kLo8InvScale : 0.f);
           }
         }
       }

@@ -9,7 +9,10 @@
 // Precision: operands are split-fp16 (value = hi + lo).  kTerms == 1 issues one MMA per k-step
 // (hi*hi, "fast" mode); kTerms == 3 issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM
 // accumulator (~22-bit operand mantissa: fp32-equivalent products, the mode that meets the
-// 1e-3 (yaw,pitch) parity bar against the fp32 oracle).
+// 1e-3 (yaw,pitch) parity bar against the fp32 oracle).  kTerms == 2 ("fp16lo8") keeps hi*hi and
+// hi*lo_w in fp16 but stores the activations' low part as e4m3 (x 2^13) and adds lo8_a * hi8_w as an
+// fp8 MMA (kind::f8f6f4, half the cycles) into a SECOND TMEM accumulator that the epilogue scales
+// and adds: 3 bytes per activation element instead of 4 and 2.5 instead of 3 MMA units per k-step.
 //
 // Structure (persistent, one CTA per SM, 256 threads):
 //   warp 0   : TMA producer  (one elected lane; A tile 128 x 64, W tile block_n x 64, SWIZZLE_128B)
@@ -26,6 +29,8 @@
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), per-warp
 // residual mbarriers, so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
+#include <cmath>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -56,13 +61,22 @@ struct UmmaParams {
   long long split_stride = 0;
   int out_tma = 0;  // planes output through smem staging + TMA store
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
+  float corr_scale = 0.f;  // fp16lo8: factor of the fp8 correction accumulator = 2^-(13 + weight shift)
   AGeom a;
   Epilogue ep;
 };
 
 struct UmmaMaps {
   CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, r_hi, r_lo;
+  CUtensorMap a_lo8, w_hi8, o_lo8, r_lo8;  // fp16lo8 mode (uint8 tensors)
 };
+
+// shared-memory bytes of one pipeline stage / one epilogue staging set for a precision mode
+__host__ __device__ constexpr int a_stage_bytes(int terms) { return terms == 3 ? 2 * kATileBytes : (terms == 2 ? kATileBytes + kATileBytes / 2 : kATileBytes); }
+__host__ __device__ constexpr int w_stage_bytes(int terms, int bn) {
+  return terms == 3 ? 2 * bn * kBlockK * 2 : (terms == 2 ? 2 * bn * kBlockK * 2 + bn * kBlockK : bn * kBlockK * 2);
+}
+__host__ __device__ constexpr int epi_set_bytes(int terms) { return terms == 1 ? kEpiBufBytes : 2 * kEpiBufBytes; }
 
 // byte offset of logical 16-byte chunk j of row `row` in a 64B-swizzled [32][64 B] tile
 __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
@@ -72,7 +86,7 @@ __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
 template <int kTerms>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
-  constexpr int kPlanes = (kTerms == 3) ? 2 : 1;
+  constexpr int kSet = epi_set_bytes(kTerms);  // bytes of one epilogue staging set (hi tile [+ lo / lo8 tile])
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -86,9 +100,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   const int w_tile_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kPlanes * (kATileBytes + w_tile_bytes);
-  uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;  // [4][2 sets][planes][2 KB]
-  uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kPlanes * kEpiBufBytes : 0);  // [4][2 bufs][planes][2 KB]
+  const int a_bytes = a_stage_bytes(kTerms);
+  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n);
+  uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;  // [4 warps][2 sets][kSet]
+  uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kSet : 0);                    // [4 warps][2 bufs][kSet]
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int mn_tiles = p.m_tiles * p.n_tiles;
@@ -100,6 +115,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     if (kTerms == 3) {
       ptx::prefetch_tmap(&tm.a_lo);
       ptx::prefetch_tmap(&tm.w_lo);
+    }
+    if (kTerms == 2) {
+      ptx::prefetch_tmap(&tm.a_lo8);
+      ptx::prefetch_tmap(&tm.w_lo);
+      ptx::prefetch_tmap(&tm.w_hi8);
     }
     if (p.out_tma) ptx::prefetch_tmap(&tm.o_hi);
     if (p.res_tma) ptx::prefetch_tmap(&tm.r_hi);
@@ -152,9 +172,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* s = stage_base + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sA_hi = s;
-          uint8_t* sA_lo = s + kATileBytes;
-          uint8_t* sW_hi = s + kPlanes * kATileBytes;
+          uint8_t* sA_lo = s + kATileBytes;  // fp16 lo tile (x3) or e4m3 lo8 tile (fp16lo8)
+          uint8_t* sW_hi = s + a_bytes;
           uint8_t* sW_lo = sW_hi + w_tile_bytes;
+          uint8_t* sW_hi8 = sW_lo + w_tile_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
           if (p.a.kind == 1) {
             const int tap = kb / p.cblocks;
@@ -166,12 +187,17 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             if (kTerms == 3)
               ptx::tma_load_im2col_4d(sA_lo, &tm.a_lo, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
                                       static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+            if (kTerms == 2)
+              ptx::tma_load_im2col_4d(sA_lo, &tm.a_lo8, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
+                                      static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
           } else {
             ptx::tma_load_2d(sA_hi, &tm.a_hi, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
             if (kTerms == 3) ptx::tma_load_2d(sA_lo, &tm.a_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+            if (kTerms == 2) ptx::tma_load_2d(sA_lo, &tm.a_lo8, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
           }
           ptx::tma_load_2d(sW_hi, &tm.w_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-          if (kTerms == 3) ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (kTerms >= 2) ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (kTerms == 2) ptx::tma_load_2d(sW_hi8, &tm.w_hi8, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
@@ -201,8 +227,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           const uint32_t s = ptx::smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t aA_hi = s;
           const uint32_t aA_lo = s + kATileBytes;
-          const uint32_t aW_hi = s + kPlanes * kATileBytes;
+          const uint32_t aW_hi = s + a_bytes;
           const uint32_t aW_lo = aW_hi + w_tile_bytes;
+          const uint32_t aW_hi8 = aW_lo + w_tile_bytes;
 #pragma unroll
           for (int j = 0; j < kBlockK / kUmmaK; ++j) {
             const uint32_t koff = j * kUmmaK * 2;  // bytes inside the 128 B swizzle row
@@ -216,7 +243,21 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               ptx::umma_f16(tmem_d, dA_hi, dW_lo, idesc, 1u);
               accum = 1u;
             }
+            if (kTerms == 2) {
+              const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(aW_lo + koff);
+              ptx::umma_f16(tmem_d, dA_hi, dW_lo, idesc, accum);
+              accum = 1u;
+            }
             ptx::umma_f16(tmem_d, dA_hi, dW_hi, idesc, accum);
+          }
+          if (kTerms == 2) {
+            // fp8 correction lo8_a * hi8_w into the second accumulator (columns +128), K = 32 per MMA
+#pragma unroll
+            for (int j = 0; j < kBlockK / 32; ++j) {
+              const uint64_t dA8 = ptx::make_sw64_kmajor_desc(aA_lo + j * 32);
+              const uint64_t dW8 = ptx::make_sw64_kmajor_desc(aW_hi8 + j * 32);
+              ptx::umma_f8(tmem_d + 128u, dA8, dW8, idesc, (kb > kb_begin || j > 0) ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
@@ -232,8 +273,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     // ===================== epilogue =====================
     const int quarter = warp_idx & 3;
     const Epilogue& ep = p.ep;
-    uint8_t* obuf = obuf_base + quarter * (2 * kPlanes * kEpiBufBytes);
-    uint8_t* rbuf = rbuf_base + quarter * (2 * kPlanes * kEpiBufBytes);
+    uint8_t* obuf = obuf_base + quarter * (2 * kSet);
+    uint8_t* rbuf = rbuf_base + quarter * (2 * kSet);
+    // bytes one residual chunk brings in: fp16 hi tile (+ fp16 lo tile | + e4m3 lo8 tile)
+    constexpr uint32_t kResTx = kTerms == 3 ? 2 * kEpiBufBytes : (kTerms == 2 ? kEpiBufBytes + kEpiBufBytes / 2 : kEpiBufBytes);
     uint64_t* rbar = res_bar + quarter * 2;
     uint32_t rphase0 = 0, rphase1 = 0;
     int oset = 0;   // staging set used by the next chunk
@@ -255,11 +298,12 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const bool use_rtma = p.res_tma && warp_live;
       // the residual does not depend on the MMA: fetch the first chunk before waiting for the accumulator
       if (use_rtma && lane == 0) {
-        uint8_t* dst = rbuf + (rcnt & 1) * (kPlanes * kEpiBufBytes);
+        uint8_t* dst = rbuf + (rcnt & 1) * kSet;
         ptx::fence_proxy_async();
-        ptx::mbar_arrive_expect_tx(&rbar[rcnt & 1], kPlanes * kEpiBufBytes);
+        ptx::mbar_arrive_expect_tx(&rbar[rcnt & 1], kResTx);
         ptx::tma_load_2d(dst, &tm.r_hi, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
         if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
+        if (kTerms == 2) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo8, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -278,6 +322,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
         }
+        if (ep.res_lo8) {
+          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n_base);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) rpre[4 + j] = __ldg(rl + j);
+        }
       }
       for (int c = 0; c < nchunks; ++c) {
         const int n = n_base + c * kEpiChunk;
@@ -294,6 +343,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
             }
+            if (ep.res_lo8) {
+              const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n + kEpiChunk);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) rpre[4 + j] = __ldg(rl + j);
+            }
           }
         }
         const uint8_t* rcur = nullptr;
@@ -301,23 +355,32 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           const int b = rcnt & 1;
           if (c + 1 < nchunks && lane == 0) {  // prefetch the next chunk's residual into the other buffer
             const int nb = b ^ 1;
-            uint8_t* dst = rbuf + nb * (kPlanes * kEpiBufBytes);
+            uint8_t* dst = rbuf + nb * kSet;
             ptx::fence_proxy_async();
-            ptx::mbar_arrive_expect_tx(&rbar[nb], kPlanes * kEpiBufBytes);
+            ptx::mbar_arrive_expect_tx(&rbar[nb], kResTx);
             ptx::tma_load_2d(dst, &tm.r_hi, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
             if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
+            if (kTerms == 2) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo8, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
           }
           ptx::mbar_wait(&rbar[b], b ? rphase1 : rphase0);
           if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
-          rcur = rbuf + b * (kPlanes * kEpiBufBytes);
+          rcur = rbuf + b * kSet;
           ++rcnt;
         }
         uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
-        ptx::tmem_ld_wait();
         float v[32];
+        ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
+        if (kTerms == 2) {
+          uint32_t r2[32];
+          ptx::tmem_ld_32x32(taddr0 + 128u + static_cast<uint32_t>(c * kEpiChunk), r2);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r2[j]), p.corr_scale, __uint_as_float(r[j]));
+        } else {
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
         if (ep.bias && p.k_split == 1) {
           const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
 #pragma unroll
@@ -330,8 +393,21 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           }
         }
         if (rcur) {
+          if (kTerms == 2) {  // e4m3 low part: 32 bytes per row, unswizzled
 #pragma unroll
-          for (int pl = 0; pl < kPlanes; ++pl) {
+            for (int j = 0; j < 2; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rcur + kEpiBufBytes + lane * 32 + j * 16);
+              float l8[8];
+              e4m3x8_to_float(make_uint2(u.x, u.y), l8);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[16 * j + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + t]);
+              e4m3x8_to_float(make_uint2(u.z, u.w), l8);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[16 * j + 8 + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + 8 + t]);
+            }
+          }
+#pragma unroll
+          for (int pl = 0; pl < (kTerms == 3 ? 2 : 1); ++pl) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiBufBytes + sw64_off(lane, j));
@@ -356,6 +432,19 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               v[4 * j + 3] += f.w;
             }
           } else {
+            if (ep.res_lo8) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 u = rnow[4 + j];
+                float l8[8];
+                e4m3x8_to_float(make_uint2(u.x, u.y), l8);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[16 * j + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + t]);
+                e4m3x8_to_float(make_uint2(u.z, u.w), l8);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[16 * j + 8 + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + 8 + t]);
+              }
+            }
             const int npl = ep.res_lo ? 2 : 1;
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
@@ -380,7 +469,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.out_tma) {
-          uint8_t* ob = obuf + oset * (kPlanes * kEpiBufBytes);
+          uint8_t* ob = obuf + oset * kSet;
           // the set was handed to TMA two chunks ago: wait until that store has finished reading it
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
@@ -399,6 +488,16 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             }
             *reinterpret_cast<uint4*>(ob + sw64_off(lane, j)) = uh;
             if (kTerms == 3) *reinterpret_cast<uint4*>(ob + kEpiBufBytes + sw64_off(lane, j)) = ul;
+            if (kTerms == 2) {  // low part as e4m3 of (v - hi) * 2^13: 8 bytes per 8 columns
+              float rs[8];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 hf = __half22float2(hh[t]);
+                rs[2 * t] = (v[8 * j + 2 * t] - hf.x) * kLo8Scale;
+                rs[2 * t + 1] = (v[8 * j + 2 * t + 1] - hf.y) * kLo8Scale;
+              }
+              *reinterpret_cast<uint2*>(ob + kEpiBufBytes + lane * 32 + j * 8) = float8_to_e4m3x8(rs);
+            }
           }
           ptx::fence_proxy_async();
           __syncwarp();
@@ -406,6 +505,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             if (warp_live) {
               ptx::tma_store_2d(&tm.o_hi, ob, n, static_cast<int>(m_warp));
               if (kTerms == 3) ptx::tma_store_2d(&tm.o_lo, ob + kEpiBufBytes, n, static_cast<int>(m_warp));
+              if (kTerms == 2) ptx::tma_store_2d(&tm.o_lo8, ob + kEpiBufBytes, n, static_cast<int>(m_warp));
             }
             ptx::tma_store_commit();  // one (possibly empty) group per chunk keeps wait_group counting uniform
           }
@@ -500,6 +600,38 @@ inline CUtensorMap make_tmap_2d(const __half* base, long long rows, long long co
   return m;
 }
 
+// uint8 (e4m3) variants: one byte per element
+inline CUtensorMap make_tmap_2d_u8(const uint8_t* base, long long rows, long long cols, long long ld, int box_rows,
+                                   int box_cols, CUtensorMapSwizzle swz) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = DriverApi::get().encodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims,
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(u8) failed, code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+inline CUtensorMap make_tmap_im2col_u8(const uint8_t* base, const AGeom& g) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H),
+                        static_cast<cuuint64_t>(g.NB)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W) * g.C,
+                           static_cast<cuuint64_t>(g.H) * g.W * g.C};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.S - 1), g.pad - (g.R - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
+  CUresult r = DriverApi::get().encodeIm2col(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(base), dims,
+                                             strides, lower, upper, kBlockK, kBlockM, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col(u8) failed, code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
 inline CUtensorMap make_tmap_im2col(const __half* base, const AGeom& g) {
   CUtensorMap m;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H),
@@ -528,31 +660,36 @@ struct UmmaPlan {
 inline bool umma_supported(long long M, int N, int K, const AGeom& a) {
   if (N % 64 != 0 || K % kBlockK != 0 || M <= 0) return false;
   if (a.kind == 1 && (a.C % kBlockK != 0)) return false;
-  if (a.kind == 0 && (a.lda % 8 != 0)) return false;
+  if (a.kind == 0 && (a.lda % 16 != 0)) return false;
   return true;
 }
 
 // A planes: for kind 0 the [M,K] matrix, for kind 1 the NHWC activation.  W planes: [N,K].
+// W.lo8 (terms == 2) holds e4m3(W_hi * 2^w_shift); the fp8 accumulator is scaled by 2^-(13 + w_shift).
 inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
                                const Epilogue& ep, int num_sms, int force_block_n = 0, int k_split = 1,
-                               long long split_stride = 0) {
+                               long long split_stride = 0, int w_shift = 0) {
   MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
-  MCG_CHECK(terms == 1 || (A.lo && W.lo), "3-term GEMM needs lo planes");
+  MCG_CHECK(terms != 3 || (A.lo && W.lo), "3-term GEMM needs lo planes");
+  MCG_CHECK(terms != 2 || (A.lo8 && W.lo && W.lo8), "fp16lo8 GEMM needs an e4m3 activation low plane and fp16 lo + e4m3 hi weights");
   UmmaPlan pl;
   pl.terms = terms;
   UmmaParams& p = pl.p;
   p.M = static_cast<int>(M);
   p.N = N;
   p.K = K;
-  const int planes = terms == 3 ? 2 : 1;
   // epilogue staging (per CTA): TMA-store staging when the output is fp16 planes, plus residual
   // prefetch buffers for the same-shape residual
-  p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 8 == 0 && (terms == 1 || ep.out_lo != nullptr)) ? 1 : 0;
-  p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 8 == 0 &&
-               (terms == 1 || ep.res_lo != nullptr))
+  const bool out_lo_ok = terms == 1 || (terms == 3 && ep.out_lo != nullptr) || (terms == 2 && ep.out_lo8 != nullptr);
+  const bool res_lo_ok = terms == 1 || (terms == 3 && ep.res_lo != nullptr) || (terms == 2 && ep.res_lo8 != nullptr);
+  p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 16 == 0 && out_lo_ok) ? 1 : 0;
+  MCG_CHECK(ep.out_f32 != nullptr || terms != 2 || p.out_tma, "fp16lo8 planes output needs the TMA-store epilogue");
+  p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0 &&
+               res_lo_ok)
                   ? 1
                   : 0;
-  const int epi_bytes = (p.out_tma ? 4 * 2 * planes * kEpiBufBytes : 0) + (p.res_tma ? 4 * 2 * planes * kEpiBufBytes : 0);
+  const int epi_bytes = (p.out_tma ? 4 * 2 * epi_set_bytes(terms) : 0) + (p.res_tma ? 4 * 2 * epi_set_bytes(terms) : 0);
+  if (terms == 2) p.corr_scale = std::ldexp(1.0f, -(kLo8Shift + w_shift));
   const int ring_budget = kMaxDynSmem - 1024 - kSmemBarrierBytes - epi_bytes;
   int bn = force_block_n;
   if (bn == 0) {
@@ -560,7 +697,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (N % c) continue;
-      const int sb = planes * (kATileBytes + c * kBlockK * 2);
+      if (terms == 2 && c > 128) continue;  // two accumulators (main + fp8 correction) share a 256-column buffer
+      const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, c);
       // residual (bottleneck conv3) layers are HBM-bound with short K loops: 2 stages are enough there
       if (ring_budget / sb >= (p.res_tma ? 2 : 3) || c == 64) {
         bn = c;
@@ -570,7 +708,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   }
   MCG_CHECK(bn > 0 && N % bn == 0, "bad block_n");
   p.block_n = bn;
-  const int stage_bytes = planes * (kATileBytes + bn * kBlockK * 2);
+  MCG_CHECK(terms != 2 || bn <= 128, "fp16lo8 needs block_n <= 128");
+  const int stage_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, bn);
   p.num_stages = ring_budget / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   MCG_CHECK(p.num_stages >= 2, "not enough shared memory for 2 stages");
@@ -602,6 +741,15 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   tm.w_hi = make_tmap_2d(W.hi, N, K, K, bn);
   tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : tm.w_hi;
   tm.o_hi = tm.o_lo = tm.r_hi = tm.r_lo = tm.w_hi;  // placeholders when unused
+  tm.a_lo8 = tm.w_hi8 = tm.o_lo8 = tm.r_lo8 = tm.w_hi;
+  if (terms == 2) {
+    tm.a_lo8 = a.kind == 1 ? make_tmap_im2col_u8(A.lo8, a)
+                           : make_tmap_2d_u8(A.lo8, M, K, a.lda, kBlockM, kBlockK, CU_TENSOR_MAP_SWIZZLE_64B);
+    tm.w_lo = make_tmap_2d(W.lo, N, K, K, bn);
+    tm.w_hi8 = make_tmap_2d_u8(W.lo8, N, K, K, bn, kBlockK, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (p.out_tma) tm.o_lo8 = make_tmap_2d_u8(ep.out_lo8, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (p.res_tma) tm.r_lo8 = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
   if (p.out_tma) {
     tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
     tm.o_lo = terms == 3 ? make_tmap_2d(ep.out_lo, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.o_hi;
@@ -618,6 +766,7 @@ inline void umma_set_attrs() {
   if (done) return;
   MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   done = true;
 }
 
@@ -625,6 +774,8 @@ inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   umma_set_attrs();
   if (pl.terms == 3)
     umma_gemm_kernel<3><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
+  else if (pl.terms == 2)
+    umma_gemm_kernel<2><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   else
     umma_gemm_kernel<1><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   MCG_CUDA(cudaGetLastError());

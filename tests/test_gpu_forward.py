@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 # north_star: "within 1e-3 on the regressed (yaw, pitch)" -> the parity mode (fp16x3) and the fp32
 # CUDA-core mode must meet it; the single-fp16 fast mode is documented as ~3e-3 and only bounded.
-YAW_PITCH_TOL = {'fp16x3': 1e-3, 'simt': 1e-3, 'fp16': 2e-2}
+YAW_PITCH_TOL = {'fp16x3': 1e-3, 'fp16lo8': 1e-3, 'simt': 1e-3, 'fp16': 2e-2}
 KEYS = ('gaze_score', 'face_gaze_score', 'eyes_gaze_score', 'head_gaze_score')
 
 
@@ -37,7 +37,7 @@ def engines(synthetic_sd):
         e.close()
 
 
-@pytest.mark.parametrize('precision', ['fp16x3', 'simt', 'fp16'])
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16lo8', 'simt', 'fp16'])
 def test_single_clip_vs_oracle(engines, synthetic_sd, precision):
     """BASELINE configs[0]: one 7-frame 224x224 clip, random weights, (yaw,pitch) vs the fp32 reference path."""
     img = O.make_clip(0, 7)
@@ -52,15 +52,16 @@ def test_single_clip_vs_oracle(engines, synthetic_sd, precision):
         assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16lo8'])
 @pytest.mark.parametrize('name', ['t7_224', 't3_192x224_rescale', 't1_224'])
-def test_vs_reference_fixtures(engines, golden_dir, name):
+def test_vs_reference_fixtures(engines, golden_dir, name, precision):
     """Outputs of the reference's own MultiClueGaze.forward (oracle/gen_golden.py) on the same inputs."""
     g = np.load(os.path.join(golden_dir, f'golden_forward_{name}.npz'))
     T, H, W = int(g['T']), int(g['H']), int(g['W'])
     img = O.make_clip(int(g['seed']), T, H, W).cuda()
     img_hw = np.array([[g['img_hw'][0], g['img_hw'][1]]] * T, dtype=np.float32)
     scale = np.tile(g['scale'][None], (T, 1))
-    out = engines('fp16x3').forward(img, clip_length=T, img_hw=img_hw, scale_factor=scale)
+    out = engines(precision).forward(img, clip_length=T, img_hw=img_hw, scale_factor=scale)
     gz = out['gaze'].cpu()
     for i, k in enumerate(KEYS):
         assert yaw_pitch_err(gz[:, i], torch.from_numpy(g[k])) < 1e-3, k
@@ -157,7 +158,7 @@ def test_pipelined_host_submissions(engines):
             eng.set_graph_mode(False)
 
 
-@pytest.mark.parametrize('precision', ['fp16x3', 'fp16'])
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16lo8', 'fp16'])
 def test_full_batch_properties(engines, precision):
     """BASELINE configs[1] size (32 clips x 7 frames x 224^2): clips are independent units, so
     (a) a clip's result must not depend on its batch neighbours (bit-exact), (b) permuting clips
