@@ -47,6 +47,7 @@ constexpr int kSmemBarrierBytes = 1024;
 constexpr int kMaxDynSmem = 232448;  // 227 KB: the sm_100 opt-in limit per block
 constexpr int kEpiChunk = 32;        // columns per epilogue chunk (64 B of fp16 per row)
 constexpr int kEpiBufBytes = 32 * kEpiChunk * 2;  // one warp's [32 rows x 32 cols] fp16 staging tile = 2 KB
+constexpr int kResBufs = 4;          // residual chunks in flight per epilogue warp (covers the ~1.5 us HBM latency)
 
 struct UmmaParams {
   int M = 0, N = 0, K = 0;
@@ -95,15 +96,15 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;  // [4 warps][2 buffers]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint64_t* res_bar = tempty_bar + 2;  // [4 warps][kResBufs]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4 * kResBufs);
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   const int w_tile_bytes = p.block_n * kBlockK * 2;
   const int a_bytes = a_stage_bytes(kTerms);
   const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n);
   uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;  // [4 warps][2 sets][kSet]
-  uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kSet : 0);                    // [4 warps][2 bufs][kSet]
+  uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kSet : 0);                    // [4 warps][kResBufs][kSet]
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int mn_tiles = p.m_tiles * p.n_tiles;
@@ -133,7 +134,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 4 * kResBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -274,14 +275,48 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     const int quarter = warp_idx & 3;
     const Epilogue& ep = p.ep;
     uint8_t* obuf = obuf_base + quarter * (2 * kSet);
-    uint8_t* rbuf = rbuf_base + quarter * (2 * kSet);
+    uint8_t* rbuf = rbuf_base + quarter * (kResBufs * kSet);
     // bytes one residual chunk brings in: fp16 hi tile (+ fp16 lo tile | + e4m3 lo8 tile)
     constexpr uint32_t kResTx = kTerms == 3 ? 2 * kEpiBufBytes : (kTerms == 2 ? kEpiBufBytes + kEpiBufBytes / 2 : kEpiBufBytes);
-    uint64_t* rbar = res_bar + quarter * 2;
-    uint32_t rphase0 = 0, rphase1 = 0;
+    uint64_t* rbar = res_bar + quarter * kResBufs;
     int oset = 0;   // staging set used by the next chunk
-    int rcnt = 0;   // residual chunks consumed so far (buffer = rcnt & 1)
     const int nchunks = p.block_n / kEpiChunk;
+    // Residual chunk stream: the same-shape residual of every (tile, chunk) this warp will process is
+    // TMA-prefetched kResBufs chunks ahead, across tile boundaries, into a ring of per-warp buffers.
+    int ri_tile = blockIdx.x, ri_c = 0;
+    uint32_t r_issued = 0, r_consumed = 0;
+    auto res_issue = [&]() {
+      while (ri_tile < num_tiles) {  // tiles whose 32 rows of this warp are all out of range carry no residual
+        const int mt = (ri_tile % mn_tiles) / p.n_tiles;
+        if (static_cast<long long>(mt) * kBlockM + quarter * 32 < p.M) break;
+        ri_tile += gridDim.x;
+        ri_c = 0;
+      }
+      if (ri_tile >= num_tiles) return;
+      const int mn_i = ri_tile % mn_tiles;
+      const int mt = mn_i / p.n_tiles;
+      const int nt = mn_i - mt * p.n_tiles;
+      const int row0 = mt * kBlockM + quarter * 32;
+      const int col0 = nt * p.block_n + ri_c * kEpiChunk;
+      const uint32_t b = r_issued % kResBufs;
+      if (lane == 0) {
+        uint8_t* dst = rbuf + b * kSet;
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive_expect_tx(&rbar[b], kResTx);
+        ptx::tma_load_2d(dst, &tm.r_hi, &rbar[b], col0, row0);
+        if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[b], col0, row0);
+        if (kTerms == 2) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo8, &rbar[b], col0, row0);
+      }
+      ++r_issued;
+      if (++ri_c == nchunks) {
+        ri_c = 0;
+        ri_tile += gridDim.x;
+      }
+    };
+    if (p.res_tma) {
+#pragma unroll
+      for (int i = 0; i < kResBufs; ++i) res_issue();
+    }
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int ks = tile / mn_tiles;
@@ -296,15 +331,6 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const bool warp_live = m_warp < p.M;  // warp-uniform: at least one valid row
       const int n_base = n_tile * p.block_n;
       const bool use_rtma = p.res_tma && warp_live;
-      // the residual does not depend on the MMA: fetch the first chunk before waiting for the accumulator
-      if (use_rtma && lane == 0) {
-        uint8_t* dst = rbuf + (rcnt & 1) * kSet;
-        ptx::fence_proxy_async();
-        ptx::mbar_arrive_expect_tx(&rbar[rcnt & 1], kResTx);
-        ptx::tma_load_2d(dst, &tm.r_hi, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
-        if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
-        if (kTerms == 2) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo8, &rbar[rcnt & 1], n_base, static_cast<int>(m_warp));
-      }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const long long rrow = (valid && ep.res_mode != RES_NONE && !p.res_tma) ? res_row(ep, m) : 0;
@@ -352,20 +378,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         }
         const uint8_t* rcur = nullptr;
         if (use_rtma) {
-          const int b = rcnt & 1;
-          if (c + 1 < nchunks && lane == 0) {  // prefetch the next chunk's residual into the other buffer
-            const int nb = b ^ 1;
-            uint8_t* dst = rbuf + nb * kSet;
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive_expect_tx(&rbar[nb], kResTx);
-            ptx::tma_load_2d(dst, &tm.r_hi, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
-            if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
-            if (kTerms == 2) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo8, &rbar[nb], n + kEpiChunk, static_cast<int>(m_warp));
-          }
-          ptx::mbar_wait(&rbar[b], b ? rphase1 : rphase0);
-          if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
+          const uint32_t b = r_consumed % kResBufs;
+          ptx::mbar_wait(&rbar[b], (r_consumed / kResBufs) & 1u);
           rcur = rbuf + b * kSet;
-          ++rcnt;
+          ++r_consumed;
         }
         uint32_t r[32];
         float v[32];
@@ -420,6 +436,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               }
             }
           }
+          __syncwarp();   // every lane has read its residual row: the buffer can be refilled
+          res_issue();
         } else if (valid && ep.res_mode != RES_NONE && !p.res_tma) {
           if (ep.res_f32) {
             const float4* rf = reinterpret_cast<const float4*>(ep.res_f32 + rrow * ep.ldr + n);
@@ -688,7 +706,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
                res_lo_ok)
                   ? 1
                   : 0;
-  const int epi_bytes = (p.out_tma ? 4 * 2 * epi_set_bytes(terms) : 0) + (p.res_tma ? 4 * 2 * epi_set_bytes(terms) : 0);
+  const int epi_bytes =
+      (p.out_tma ? 4 * 2 * epi_set_bytes(terms) : 0) + (p.res_tma ? 4 * kResBufs * epi_set_bytes(terms) : 0);
   if (terms == 2) p.corr_scale = std::ldexp(1.0f, -(kLo8Shift + w_shift));
   const int ring_budget = kMaxDynSmem - 1024 - kSmemBarrierBytes - epi_bytes;
   int bn = force_block_n;
