@@ -45,9 +45,9 @@ constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSmemBarrierBytes = 1024;
 constexpr int kMaxDynSmem = 232448;  // 227 KB: the sm_100 opt-in limit per block
-constexpr int kEpiChunk = 32;        // columns per epilogue chunk (64 B of fp16 per row)
-constexpr int kEpiBufBytes = 32 * kEpiChunk * 2;  // one warp's [32 rows x 32 cols] fp16 staging tile = 2 KB
-constexpr int kResBufs = 4;          // residual chunks in flight per epilogue warp (covers the ~1.5 us HBM latency)
+constexpr int kEpiChunk = 64;        // columns per epilogue chunk (128 B of fp16 per row)
+constexpr int kEpiHiBytes = kBlockM * kEpiChunk * 2;  // [128 rows x 64 cols] fp16 staging tile = 16 KB
+constexpr int kResBufs = 2;          // residual chunks (128 x 64) in flight, prefetched across tile boundaries
 
 struct UmmaParams {
   int M = 0, N = 0, K = 0;
@@ -61,6 +61,7 @@ struct UmmaParams {
                     // resp. never: the reduction kernel applies them)
   long long split_stride = 0;
   int out_tma = 0;  // planes output through smem staging + TMA store
+  int out_sets = 1; // staging sets for the TMA-store epilogue (2 = double buffered)
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
   float corr_scale = 0.f;  // fp16lo8: factor of the fp8 correction accumulator = 2^-(13 + weight shift)
   AGeom a;
@@ -77,11 +78,18 @@ __host__ __device__ constexpr int a_stage_bytes(int terms) { return terms == 3 ?
 __host__ __device__ constexpr int w_stage_bytes(int terms, int bn) {
   return terms == 3 ? 2 * bn * kBlockK * 2 : (terms == 2 ? 2 * bn * kBlockK * 2 + bn * kBlockK : bn * kBlockK * 2);
 }
-__host__ __device__ constexpr int epi_set_bytes(int terms) { return terms == 1 ? kEpiBufBytes : 2 * kEpiBufBytes; }
+// one epilogue staging set / residual slot: fp16 hi tile (+ fp16 lo tile | + e4m3 lo8 tile of half the size)
+__host__ __device__ constexpr int epi_set_bytes(int terms) {
+  return terms == 3 ? 2 * kEpiHiBytes : (terms == 2 ? kEpiHiBytes + kEpiHiBytes / 2 : kEpiHiBytes);
+}
 
-// byte offset of logical 16-byte chunk j of row `row` in a 64B-swizzled [32][64 B] tile
+// byte offset of logical 16-byte chunk j of row `row` in a 64B-swizzled [rows][64 B] tile
 __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
   return static_cast<uint32_t>(row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+}
+// same for a 128B-swizzled [rows][128 B] tile (8 chunks per row)
+__device__ __forceinline__ uint32_t sw128_off(int row, int j) {
+  return static_cast<uint32_t>(row * 128 + ((j ^ (row & 7)) << 4));
 }
 
 template <int kTerms>
@@ -96,15 +104,15 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;  // [4 warps][kResBufs]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4 * kResBufs);
+  uint64_t* res_bar = tempty_bar + 2;  // [kResBufs]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + kResBufs);
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   const int w_tile_bytes = p.block_n * kBlockK * 2;
   const int a_bytes = a_stage_bytes(kTerms);
   const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n);
-  uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;  // [4 warps][2 sets][kSet]
-  uint8_t* rbuf_base = obuf_base + (p.out_tma ? 4 * 2 * kSet : 0);                    // [4 warps][kResBufs][kSet]
+  uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;  // [out_sets][kSet]
+  uint8_t* rbuf_base = obuf_base + (p.out_tma ? p.out_sets * kSet : 0);               // [kResBufs][kSet]
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int mn_tiles = p.m_tiles * p.n_tiles;
@@ -134,7 +142,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
-    for (int i = 0; i < 4 * kResBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kResBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -272,40 +280,31 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
+    // The four warps work in lock step on one 64-column chunk of the 128-row tile at a time so that
+    // ONE thread can move the whole [128 x 64] chunk with a single TMA op per plane (the per-SM TMA
+    // unit is shared with the main loop's loads: many small boxes starve it).
     const int quarter = warp_idx & 3;
+    const int row = quarter * 32 + lane;  // row of the tile == TMEM lane
+    const bool leader = threadIdx.x == 128;
     const Epilogue& ep = p.ep;
-    uint8_t* obuf = obuf_base + quarter * (2 * kSet);
-    uint8_t* rbuf = rbuf_base + quarter * (kResBufs * kSet);
-    // bytes one residual chunk brings in: fp16 hi tile (+ fp16 lo tile | + e4m3 lo8 tile)
-    constexpr uint32_t kResTx = kTerms == 3 ? 2 * kEpiBufBytes : (kTerms == 2 ? kEpiBufBytes + kEpiBufBytes / 2 : kEpiBufBytes);
-    uint64_t* rbar = res_bar + quarter * kResBufs;
-    int oset = 0;   // staging set used by the next chunk
     const int nchunks = p.block_n / kEpiChunk;
-    // Residual chunk stream: the same-shape residual of every (tile, chunk) this warp will process is
-    // TMA-prefetched kResBufs chunks ahead, across tile boundaries, into a ring of per-warp buffers.
+    constexpr uint32_t kResTx = kTerms == 3 ? 2 * kEpiHiBytes : (kTerms == 2 ? kEpiHiBytes + kEpiHiBytes / 2 : kEpiHiBytes);
+    // residual chunk stream, prefetched kResBufs chunks ahead across tile boundaries by the leader
     int ri_tile = blockIdx.x, ri_c = 0;
     uint32_t r_issued = 0, r_consumed = 0;
     auto res_issue = [&]() {
-      while (ri_tile < num_tiles) {  // tiles whose 32 rows of this warp are all out of range carry no residual
-        const int mt = (ri_tile % mn_tiles) / p.n_tiles;
-        if (static_cast<long long>(mt) * kBlockM + quarter * 32 < p.M) break;
-        ri_tile += gridDim.x;
-        ri_c = 0;
-      }
       if (ri_tile >= num_tiles) return;
       const int mn_i = ri_tile % mn_tiles;
       const int mt = mn_i / p.n_tiles;
       const int nt = mn_i - mt * p.n_tiles;
-      const int row0 = mt * kBlockM + quarter * 32;
-      const int col0 = nt * p.block_n + ri_c * kEpiChunk;
       const uint32_t b = r_issued % kResBufs;
-      if (lane == 0) {
-        uint8_t* dst = rbuf + b * kSet;
+      if (leader) {
+        uint8_t* dst = rbuf_base + b * kSet;
         ptx::fence_proxy_async();
-        ptx::mbar_arrive_expect_tx(&rbar[b], kResTx);
-        ptx::tma_load_2d(dst, &tm.r_hi, &rbar[b], col0, row0);
-        if (kTerms == 3) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo, &rbar[b], col0, row0);
-        if (kTerms == 2) ptx::tma_load_2d(dst + kEpiBufBytes, &tm.r_lo8, &rbar[b], col0, row0);
+        ptx::mbar_arrive_expect_tx(&res_bar[b], kResTx);
+        ptx::tma_load_2d(dst, &tm.r_hi, &res_bar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
+        if (kTerms == 3) ptx::tma_load_2d(dst + kEpiHiBytes, &tm.r_lo, &res_bar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
+        if (kTerms == 2) ptx::tma_load_2d(dst + kEpiHiBytes, &tm.r_lo8, &res_bar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
       }
       ++r_issued;
       if (++ri_c == nchunks) {
@@ -317,6 +316,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
 #pragma unroll
       for (int i = 0; i < kResBufs; ++i) res_issue();
     }
+    uint32_t ostores = 0;  // chunks handed to TMA so far (staging set = ostores % osets)
+    const uint32_t osets = static_cast<uint32_t>(p.out_sets);
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int ks = tile / mn_tiles;
@@ -325,135 +326,88 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const int n_tile = mn - m_tile * p.n_tiles;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const long long m_warp = static_cast<long long>(m_tile) * kBlockM + quarter * 32;  // first row of this warp
-      const long long m = m_warp + lane;
+      const long long m = static_cast<long long>(m_tile) * kBlockM + row;
       const bool valid = m < p.M;
-      const bool warp_live = m_warp < p.M;  // warp-uniform: at least one valid row
       const int n_base = n_tile * p.block_n;
-      const bool use_rtma = p.res_tma && warp_live;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const long long rrow = (valid && ep.res_mode != RES_NONE && !p.res_tma) ? res_row(ep, m) : 0;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
       // gathered residual (FPN nearest-2x top-down add): per-thread vector loads, software-pipelined
-      // one chunk ahead in registers so the L2 latency overlaps the previous chunk's math
+      // one 32-column half ahead in registers so the L2 latency overlaps the previous half's math
       const bool res_direct = valid && ep.res_mode != RES_NONE && !p.res_tma && ep.res_f32 == nullptr;
       uint4 rpre[8];
-      if (res_direct) {
-        const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n_base);
+      auto load_direct = [&](int n) {
+        const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rpre[j] = __ldg(rh + j);
         if (ep.res_lo) {
-          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n_base);
+          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
         }
         if (ep.res_lo8) {
-          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n_base);
+          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n);
 #pragma unroll
           for (int j = 0; j < 2; ++j) rpre[4 + j] = __ldg(rl + j);
         }
-      }
+      };
+      if (res_direct) load_direct(n_base);
       for (int c = 0; c < nchunks; ++c) {
-        const int n = n_base + c * kEpiChunk;
-        uint4 rnow[8];
-        if (res_direct) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rnow[j] = rpre[j];
-          if (c + 1 < nchunks) {
-            const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n + kEpiChunk);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rpre[j] = __ldg(rh + j);
-            if (ep.res_lo) {
-              const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n + kEpiChunk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
-            }
-            if (ep.res_lo8) {
-              const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n + kEpiChunk);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) rpre[4 + j] = __ldg(rl + j);
-            }
-          }
-        }
         const uint8_t* rcur = nullptr;
-        if (use_rtma) {
+        if (p.res_tma) {
           const uint32_t b = r_consumed % kResBufs;
-          ptx::mbar_wait(&rbar[b], (r_consumed / kResBufs) & 1u);
-          rcur = rbuf + b * kSet;
+          ptx::mbar_wait(&res_bar[b], (r_consumed / kResBufs) & 1u);
+          rcur = rbuf_base + b * kSet;
           ++r_consumed;
         }
-        uint32_t r[32];
-        float v[32];
-        ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
-        if (kTerms == 2) {
-          uint32_t r2[32];
-          ptx::tmem_ld_32x32(taddr0 + 128u + static_cast<uint32_t>(c * kEpiChunk), r2);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r2[j]), p.corr_scale, __uint_as_float(r[j]));
-        } else {
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        uint8_t* ob = obuf_base + (ostores % osets) * kSet;
+        if (p.out_tma) {
+          // the staging set was handed to TMA `osets` chunks ago: wait until that store has read it
+          if (leader) {
+            if (osets == 2) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>();
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        if (ep.bias && p.k_split == 1) {
-          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          const int n = n_base + c * kEpiChunk + hf * 32;
+          uint4 rnow[8];
+          if (res_direct) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x;
-            v[4 * j + 1] += b.y;
-            v[4 * j + 2] += b.z;
-            v[4 * j + 3] += b.w;
+            for (int j = 0; j < 8; ++j) rnow[j] = rpre[j];
+            if (hf == 0 || c + 1 < nchunks) load_direct(n + 32);
           }
-        }
-        if (rcur) {
-          if (kTerms == 2) {  // e4m3 low part: 32 bytes per row, unswizzled
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk + hf * 32), r);
+          if (kTerms == 2) {
+            uint32_t r2[32];
+            ptx::tmem_ld_32x32(taddr0 + 128u + static_cast<uint32_t>(c * kEpiChunk + hf * 32), r2);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rcur + kEpiBufBytes + lane * 32 + j * 16);
-              float l8[8];
-              e4m3x8_to_float(make_uint2(u.x, u.y), l8);
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r2[j]), p.corr_scale, __uint_as_float(r[j]));
+          } else {
+            ptx::tmem_ld_wait();
 #pragma unroll
-              for (int t = 0; t < 8; ++t) v[16 * j + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + t]);
-              e4m3x8_to_float(make_uint2(u.z, u.w), l8);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[16 * j + 8 + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + 8 + t]);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
-#pragma unroll
-          for (int pl = 0; pl < (kTerms == 3 ? 2 : 1); ++pl) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiBufBytes + sw64_off(lane, j));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = __half22float2(h2[t]);
-                v[8 * j + 2 * t] += f.x;
-                v[8 * j + 2 * t + 1] += f.y;
-              }
-            }
-          }
-          __syncwarp();   // every lane has read its residual row: the buffer can be refilled
-          res_issue();
-        } else if (valid && ep.res_mode != RES_NONE && !p.res_tma) {
-          if (ep.res_f32) {
-            const float4* rf = reinterpret_cast<const float4*>(ep.res_f32 + rrow * ep.ldr + n);
+          if (ep.bias && p.k_split == 1) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 f = __ldg(rf + j);
-              v[4 * j + 0] += f.x;
-              v[4 * j + 1] += f.y;
-              v[4 * j + 2] += f.z;
-              v[4 * j + 3] += f.w;
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
             }
-          } else {
-            if (ep.res_lo8) {
+          }
+          if (rcur) {
+            if (kTerms == 2) {  // e4m3 low part: [128 rows][64 B], 64B swizzle; this half = 16-byte chunks 2hf, 2hf+1
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint4 u = rnow[4 + j];
+                const uint4 u = *reinterpret_cast<const uint4*>(rcur + kEpiHiBytes + sw64_off(row, hf * 2 + j));
                 float l8[8];
                 e4m3x8_to_float(make_uint2(u.x, u.y), l8);
 #pragma unroll
@@ -463,95 +417,133 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
                 for (int t = 0; t < 8; ++t) v[16 * j + 8 + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + 8 + t]);
               }
             }
-            const int npl = ep.res_lo ? 2 : 1;
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl) {
-              if (pl < npl) {
+            for (int pl = 0; pl < (kTerms == 3 ? 2 : 1); ++pl) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 u = rnow[pl * 4 + j];
-                  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiHiBytes + sw128_off(row, hf * 4 + j));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 f = __half22float2(h2[t]);
-                    v[8 * j + 2 * t] += f.x;
-                    v[8 * j + 2 * t + 1] += f.y;
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(h2[t]);
+                  v[8 * j + 2 * t] += f.x;
+                  v[8 * j + 2 * t + 1] += f.y;
+                }
+              }
+            }
+          } else if (valid && ep.res_mode != RES_NONE && !p.res_tma) {
+            if (ep.res_f32) {
+              const float4* rf = reinterpret_cast<const float4*>(ep.res_f32 + rrow * ep.ldr + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 f = __ldg(rf + j);
+                v[4 * j + 0] += f.x;
+                v[4 * j + 1] += f.y;
+                v[4 * j + 2] += f.z;
+                v[4 * j + 3] += f.w;
+              }
+            } else {
+              if (ep.res_lo8) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint4 u = rnow[4 + j];
+                  float l8[8];
+                  e4m3x8_to_float(make_uint2(u.x, u.y), l8);
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[16 * j + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + t]);
+                  e4m3x8_to_float(make_uint2(u.z, u.w), l8);
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[16 * j + 8 + t] = fmaf(l8[t], kLo8InvScale, v[16 * j + 8 + t]);
+                }
+              }
+              const int npl = ep.res_lo ? 2 : 1;
+#pragma unroll
+              for (int pl = 0; pl < 2; ++pl) {
+                if (pl < npl) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint4 u = rnow[pl * 4 + j];
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                      const float2 f = __half22float2(h2[t]);
+                      v[8 * j + 2 * t] += f.x;
+                      v[8 * j + 2 * t + 1] += f.y;
+                    }
                   }
                 }
               }
             }
           }
-        }
-        if (ep.relu) {
+          if (ep.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.out_tma) {
-          uint8_t* ob = obuf + oset * kSet;
-          // the set was handed to TMA two chunks ago: wait until that store has finished reading it
-          if (lane == 0) ptx::tma_store_wait_read<1>();
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 uh, ul;
-            __half2* hh = reinterpret_cast<__half2*>(&uh);
-            __half2* hl = reinterpret_cast<__half2*>(&ul);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float a = v[8 * j + 2 * t], b = v[8 * j + 2 * t + 1];
-              const __half2 h = __floats2half2_rn(a, b);
-              const float2 hf = __half22float2(h);
-              hh[t] = h;
-              hl[t] = __floats2half2_rn(a - hf.x, b - hf.y);
-            }
-            *reinterpret_cast<uint4*>(ob + sw64_off(lane, j)) = uh;
-            if (kTerms == 3) *reinterpret_cast<uint4*>(ob + kEpiBufBytes + sw64_off(lane, j)) = ul;
-            if (kTerms == 2) {  // low part as e4m3 of (v - hi) * 2^13: 8 bytes per 8 columns
-              float rs[8];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 hf = __half22float2(hh[t]);
-                rs[2 * t] = (v[8 * j + 2 * t] - hf.x) * kLo8Scale;
-                rs[2 * t + 1] = (v[8 * j + 2 * t + 1] - hf.y) * kLo8Scale;
-              }
-              *reinterpret_cast<uint2*>(ob + kEpiBufBytes + lane * 32 + j * 8) = float8_to_e4m3x8(rs);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (warp_live) {
-              ptx::tma_store_2d(&tm.o_hi, ob, n, static_cast<int>(m_warp));
-              if (kTerms == 3) ptx::tma_store_2d(&tm.o_lo, ob + kEpiBufBytes, n, static_cast<int>(m_warp));
-              if (kTerms == 2) ptx::tma_store_2d(&tm.o_lo8, ob + kEpiBufBytes, n, static_cast<int>(m_warp));
-            }
-            ptx::tma_store_commit();  // one (possibly empty) group per chunk keeps wait_group counting uniform
-          }
-          oset ^= 1;
-        } else if (valid) {
-          if (ep.out_f32) {
-            float4* o = reinterpret_cast<float4*>(ep.out_f32 + ks * p.split_stride + m * ep.ldo + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* oh = reinterpret_cast<uint4*>(ep.out_hi + m * ep.ldo + n);
-            uint4* ol = ep.out_lo ? reinterpret_cast<uint4*>(ep.out_lo + m * ep.ldo + n) : nullptr;
+          if (p.out_tma) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 uh, ul;
               __half2* hh = reinterpret_cast<__half2*>(&uh);
               __half2* hl = reinterpret_cast<__half2*>(&ul);
+              float rs[8];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float a = v[8 * j + 2 * t], b = v[8 * j + 2 * t + 1];
                 const __half2 h = __floats2half2_rn(a, b);
-                const float2 hf = __half22float2(h);
+                const float2 hfv = __half22float2(h);
                 hh[t] = h;
-                hl[t] = __floats2half2_rn(a - hf.x, b - hf.y);
+                hl[t] = __floats2half2_rn(a - hfv.x, b - hfv.y);
+                rs[2 * t] = (a - hfv.x) * kLo8Scale;
+                rs[2 * t + 1] = (b - hfv.y) * kLo8Scale;
               }
-              oh[j] = uh;
-              if (ol) ol[j] = ul;
+              *reinterpret_cast<uint4*>(ob + sw128_off(row, hf * 4 + j)) = uh;
+              if (kTerms == 3) *reinterpret_cast<uint4*>(ob + kEpiHiBytes + sw128_off(row, hf * 4 + j)) = ul;
+              if (kTerms == 2)  // low part as e4m3 of (v - hi) * 2^13: 8 bytes per 8 columns
+                *reinterpret_cast<uint2*>(ob + kEpiHiBytes + sw64_off(row, hf * 2 + (j >> 1)) + (j & 1) * 8) =
+                    float8_to_e4m3x8(rs);
             }
+          } else if (valid) {
+            if (ep.out_f32) {
+              float4* o = reinterpret_cast<float4*>(ep.out_f32 + ks * p.split_stride + m * ep.ldo + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* oh = reinterpret_cast<uint4*>(ep.out_hi + m * ep.ldo + n);
+              uint4* ol = ep.out_lo ? reinterpret_cast<uint4*>(ep.out_lo + m * ep.ldo + n) : nullptr;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 uh, ul;
+                __half2* hh = reinterpret_cast<__half2*>(&uh);
+                __half2* hl = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float a = v[8 * j + 2 * t], b = v[8 * j + 2 * t + 1];
+                  const __half2 h = __floats2half2_rn(a, b);
+                  const float2 hfv = __half22float2(h);
+                  hh[t] = h;
+                  hl[t] = __floats2half2_rn(a - hfv.x, b - hfv.y);
+                }
+                oh[j] = uh;
+                if (ol) ol[j] = ul;
+              }
+            }
+          }
+        }
+        if (p.res_tma || p.out_tma) {
+          // all 128 threads have consumed the residual slot and filled the staging set
+          ptx::fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (p.res_tma) res_issue();
+          if (p.out_tma) {
+            if (leader) {
+              const int n = n_base + c * kEpiChunk;
+              const int m0 = m_tile * kBlockM;
+              ptx::tma_store_2d(&tm.o_hi, ob, n, m0);
+              if (kTerms == 3) ptx::tma_store_2d(&tm.o_lo, ob + kEpiHiBytes, n, m0);
+              if (kTerms == 2) ptx::tma_store_2d(&tm.o_lo8, ob + kEpiHiBytes, n, m0);
+              ptx::tma_store_commit();
+            }
+            ++ostores;
           }
         }
       }
@@ -559,8 +551,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
     }
-    // smem must stay valid until every bulk store of this warp has been read out
-    if (p.out_tma && lane == 0) ptx::tma_store_wait_all<0>();
+    // smem must stay valid until every bulk store has been read out
+    if (p.out_tma && leader) ptx::tma_store_wait_all<0>();
   }
 
   ptx::tc_fence_before();
@@ -706,8 +698,13 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
                res_lo_ok)
                   ? 1
                   : 0;
-  const int epi_bytes =
-      (p.out_tma ? 4 * 2 * epi_set_bytes(terms) : 0) + (p.res_tma ? 4 * kResBufs * epi_set_bytes(terms) : 0);
+  // staging: double buffered when two ring stages still fit beside it (the HBM-bound layers), else single
+  const int set_bytes = epi_set_bytes(terms);
+  const int res_bytes = p.res_tma ? kResBufs * set_bytes : 0;
+  const int min_ring = 2 * (a_stage_bytes(terms) + w_stage_bytes(terms, 128 < N ? 128 : 64));
+  p.out_sets = 1;
+  if (p.out_tma && p.res_tma && kMaxDynSmem - 1024 - kSmemBarrierBytes - res_bytes - 2 * set_bytes >= min_ring) p.out_sets = 2;
+  const int epi_bytes = (p.out_tma ? p.out_sets * set_bytes : 0) + res_bytes;
   if (terms == 2) p.corr_scale = std::ldexp(1.0f, -(kLo8Shift + w_shift));
   const int ring_budget = kMaxDynSmem - 1024 - kSmemBarrierBytes - epi_bytes;
   int bn = force_block_n;
@@ -766,16 +763,16 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
                            : make_tmap_2d_u8(A.lo8, M, K, a.lda, kBlockM, kBlockK, CU_TENSOR_MAP_SWIZZLE_64B);
     tm.w_lo = make_tmap_2d(W.lo, N, K, K, bn);
     tm.w_hi8 = make_tmap_2d_u8(W.lo8, N, K, K, bn, kBlockK, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (p.out_tma) tm.o_lo8 = make_tmap_2d_u8(ep.out_lo8, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (p.res_tma) tm.r_lo8 = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (p.out_tma) tm.o_lo8 = make_tmap_2d_u8(ep.out_lo8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (p.res_tma) tm.r_lo8 = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
   }
   if (p.out_tma) {
-    tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
-    tm.o_lo = terms == 3 ? make_tmap_2d(ep.out_lo, M, N, ep.ldo, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.o_hi;
+    tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_128B);
+    tm.o_lo = terms == 3 ? make_tmap_2d(ep.out_lo, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_128B) : tm.o_hi;
   }
   if (p.res_tma) {
-    tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
-    tm.r_lo = terms == 3 ? make_tmap_2d(ep.res_lo, M, N, ep.ldr, 32, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.r_hi;
+    tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_128B);
+    tm.r_lo = terms == 3 ? make_tmap_2d(ep.res_lo, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_128B) : tm.r_hi;
   }
   return pl;
 }
