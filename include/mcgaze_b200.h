@@ -98,6 +98,10 @@ int mcg_last_launch_count(mcg_handle h);
  * CUDA events around each launch (needs option "time_kernels" = 1; synchronises). */
 int mcg_last_umma_stats(mcg_handle h, double out[3]);
 
+/* Per-launch device times (ms, launch order) of the tcgen05 GEMMs of the last EAGER forward (needs "time_kernels");
+ * returns the number of entries written (<= capacity) or a negative error code. */
+int mcg_last_umma_times(mcg_handle h, double* out_ms, int capacity);
+
 /* Capture the forward for the current shape in a CUDA graph and replay it on later calls
  * (on = 1) or launch kernels eagerly (on = 0, default). */
 int mcg_set_graph_mode(mcg_handle h, int on);

@@ -310,6 +310,18 @@ class Engine {
     wait_host(t, out_gaze, out_boxes, out_scores);
   }
 
+  // per-launch device times (ms) of the tcgen05 GEMMs of the last eager forward (option time_kernels)
+  int umma_times(double* out, int cap) {
+    int n = 0;
+    if (ev_used_) MCG_CUDA(cudaEventSynchronize(ev_pool_[ev_used_ - 1]));
+    for (size_t i = 0; i + 1 < ev_used_ && n < cap; i += 2, ++n) {
+      float t = 0.f;
+      MCG_CUDA(cudaEventElapsedTime(&t, ev_pool_[i], ev_pool_[i + 1]));
+      out[n] = t;
+    }
+    return n;
+  }
+
   int get_intermediate(const char* name, float* dst, int64_t capacity, int64_t shape_out[4]) {
     auto it = interm_.find(name);
     if (it == interm_.end()) return MCG_ERR_INVALID;
@@ -1188,6 +1200,16 @@ int mcg_last_umma_stats(mcg_handle h, double out[3]) {
     h->impl->umma_stats(out);
     return MCG_OK;
   });
+}
+
+int mcg_last_umma_times(mcg_handle h, double* out_ms, int capacity) {
+  int n = -1;
+  const int rc = guarded([&]() -> int {
+    if (!h || !out_ms || capacity <= 0) return MCG_ERR_INVALID;
+    n = h->impl->umma_times(out_ms, capacity);
+    return MCG_OK;
+  });
+  return rc == MCG_OK ? n : rc;
 }
 
 int mcg_set_graph_mode(mcg_handle h, int on) {

@@ -30,6 +30,7 @@
 // residual mbarriers, so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -64,6 +65,8 @@ struct UmmaParams {
   int out_sets = 1; // staging sets for the TMA-store epilogue (2 = double buffered)
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
   float corr_scale = 0.f;  // fp16lo8: factor of the fp8 correction accumulator = 2^-(13 + weight shift)
+  int dbg = 0;             // attribution experiments only (env MCG_DEBUG_FLAGS): 1 no stores, 2 no epilogue math,
+                           // 4 no A loads, 8 no W loads, 16 no MMA issue, 32 no residual loads.  Results are garbage.
   AGeom a;
   Epilogue ep;
 };
@@ -185,8 +188,16 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           uint8_t* sW_hi = s + a_bytes;
           uint8_t* sW_lo = sW_hi + w_tile_bytes;
           uint8_t* sW_hi8 = sW_lo + w_tile_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          if (p.a.kind == 1) {
+          uint32_t tx = static_cast<uint32_t>(stage_bytes);
+          if (p.dbg & 4) tx -= static_cast<uint32_t>(a_bytes);
+          if (p.dbg & 8) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
+          if (tx == 0) {
+            ptx::mbar_arrive(&full_bar[stage]);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
+          }
+          if (p.dbg & 4) {
+          } else if (p.a.kind == 1) {
             const int tap = kb / p.cblocks;
             const int cb = kb - tap * p.cblocks;
             const int r = tap / p.a.S;
@@ -204,9 +215,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             if (kTerms == 3) ptx::tma_load_2d(sA_lo, &tm.a_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
             if (kTerms == 2) ptx::tma_load_2d(sA_lo, &tm.a_lo8, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
           }
-          ptx::tma_load_2d(sW_hi, &tm.w_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-          if (kTerms >= 2) ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-          if (kTerms == 2) ptx::tma_load_2d(sW_hi8, &tm.w_hi8, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (!(p.dbg & 8)) {
+            ptx::tma_load_2d(sW_hi, &tm.w_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+            if (kTerms >= 2) ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+            if (kTerms == 2) ptx::tma_load_2d(sW_hi8, &tm.w_hi8, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          }
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
@@ -232,7 +245,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (lane == 0 && (p.dbg & 16)) {
+          ptx::umma_commit(&empty_bar[stage]);
+          if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
+        } else if (lane == 0) {
           const uint32_t s = ptx::smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t aA_hi = s;
           const uint32_t aA_lo = s + kATileBytes;
@@ -298,7 +314,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const int mt = mn_i / p.n_tiles;
       const int nt = mn_i - mt * p.n_tiles;
       const uint32_t b = r_issued % kResBufs;
-      if (leader) {
+      if (leader && (p.dbg & 32)) {
+        ptx::mbar_arrive(&res_bar[b]);
+      } else if (leader) {
         uint8_t* dst = rbuf_base + b * kSet;
         ptx::fence_proxy_async();
         ptx::mbar_arrive_expect_tx(&res_bar[b], kResTx);
@@ -370,7 +388,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
 #pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int hf = 0; hf < ((p.dbg & 2) ? 0 : 2); ++hf) {
           const int n = n_base + c * kEpiChunk + hf * 32;
           uint4 rnow[8];
           if (res_direct) {
@@ -535,12 +553,14 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (p.res_tma) res_issue();
           if (p.out_tma) {
-            if (leader) {
+            if (leader && !(p.dbg & 1)) {
               const int n = n_base + c * kEpiChunk;
               const int m0 = m_tile * kBlockM;
               ptx::tma_store_2d(&tm.o_hi, ob, n, m0);
               if (kTerms == 3) ptx::tma_store_2d(&tm.o_lo, ob + kEpiHiBytes, n, m0);
               if (kTerms == 2) ptx::tma_store_2d(&tm.o_lo8, ob + kEpiHiBytes, n, m0);
+              ptx::tma_store_commit();
+            } else if (leader) {
               ptx::tma_store_commit();
             }
             ++ostores;
@@ -736,6 +756,13 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.cblocks = a.kind == 1 ? a.C / kBlockK : 1;
   if (a.kind == 1) MCG_CHECK(K == a.R * a.S * a.C, "im2col K mismatch");
   p.ep = ep;
+  {
+    static const int dbg_flags = [] {
+      const char* e = std::getenv("MCG_DEBUG_FLAGS");
+      return e ? std::atoi(e) : 0;
+    }();
+    p.dbg = dbg_flags;
+  }
   if (k_split > 1) {
     MCG_CHECK(ep.out_f32 != nullptr && ep.res_mode == RES_NONE && !ep.relu && k_split <= p.num_kb,
               "split-K needs a plain fp32 output (bias / activation are applied by the reduction)");

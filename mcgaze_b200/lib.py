@@ -17,7 +17,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16lo8': 3}
 # every symbol include/mcgaze_b200.h declares
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
-           'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
+           'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
            'mcg_last_error', 'mcg_version')
 
 
@@ -53,6 +53,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_last_launch_count.argtypes = [vp]
     lib.mcg_set_graph_mode.argtypes = [vp, ci]
     lib.mcg_last_umma_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.mcg_last_umma_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ci]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
@@ -137,6 +138,14 @@ class Engine:
         out = (ctypes.c_double * 3)()
         _check(self._lib.mcg_last_umma_stats(self._h, out), 'mcg_last_umma_stats')
         return int(out[0]), float(out[1]), float(out[2])
+
+    def umma_times(self):
+        """Per-launch device times (ms) of the tcgen05 GEMMs of the last eager forward (option time_kernels)."""
+        buf = (ctypes.c_double * 256)()
+        n = self._lib.mcg_last_umma_times(self._h, buf, 256)
+        if n < 0:
+            _check(n, 'mcg_last_umma_times')
+        return [float(buf[i]) for i in range(n)]
 
     # ------------------------------------------------------------------ forward
     @staticmethod
