@@ -153,7 +153,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='mcgaze_b200', choices=['mcgaze_b200', 'reference'])
-    ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16lo8', 'fp16', 'simt'])
+    ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16', 'simt'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU work for cpu_baseline')
     ap.add_argument('--skip-extras', action='store_true', help='skip fast-mode / cpu_baseline side measurements')

@@ -35,8 +35,7 @@ enum {
   MCG_PRECISION_FP16X3 = 0, /* tcgen05, split-fp16 operands (hi+lo), 3 MMAs/k-step: fp32-equivalent; parity mode */
   MCG_PRECISION_FP16 = 1,   /* tcgen05, single fp16 operands, fp32 accumulate: fast mode */
   MCG_PRECISION_SIMT = 2,   /* fp32 CUDA-core kernels only (cross-check / bring-up) */
-  MCG_PRECISION_FP16LO8 = 3 /* tcgen05, activations = fp16 hi + e4m3 low part (3 B/element): hi*hi + hi*lo_w in fp16 and
-                               lo8_a*hi8_w as an fp8 MMA into a second accumulator; ~3e-5 rad vs the fp32 reference */
+  MCG_PRECISION_FP16LO8 = 3 /* reserved: removed experimental mode (e4m3 low plane); mcg_create rejects it */
 };
 
 enum {
@@ -101,6 +100,11 @@ int mcg_last_umma_stats(mcg_handle h, double out[3]);
 /* Per-launch device times (ms, launch order) of the tcgen05 GEMMs of the last EAGER forward (needs "time_kernels");
  * returns the number of entries written (<= capacity) or a negative error code. */
 int mcg_last_umma_times(mcg_handle h, double* out_ms, int capacity);
+
+/* Device time of EVERY kernel launch of the last EAGER forward (needs "time_kernels"), as text lines
+ * "kernel-name<TAB>milliseconds\n" in launch order (tcgen05 GEMMs are named "umma:<layer>").  Returns the number of
+ * bytes needed including the terminating NUL (call again with a larger buffer if > capacity) or a negative error. */
+int mcg_last_kernel_profile(mcg_handle h, char* buf, int capacity);
 
 /* Capture the forward for the current shape in a CUDA graph and replay it on later calls
  * (on = 1) or launch kernels eagerly (on = 0, default). */

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmcgaze_b200.so')
 SOURCES = ['mcg_api.cu']
-HEADERS = ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'simt_gemm.cuh', 'head_kernels.cuh',
+HEADERS = ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh',
            os.path.join('..', '..', 'include', 'mcgaze_b200.h')]
 
 

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res,
                                  long long ldres, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ y, long long ldy, long long rows, int C, int relu,
-                                 int nsplit = 1, long long split_stride = 0, const float* __restrict__ xbias = nullptr) {
+                                 int nsplit = 1, long long split_stride = 0, const float* __restrict__ xbias = nullptr,
+                                 __half* __restrict__ yh = nullptr, __half* __restrict__ yl = nullptr) {
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -301,6 +302,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
     float t = (v[j] - mean) * rstd * gamma[c] + beta[c];
     if (relu) t = fmaxf(t, 0.f);
     y[row * ldy + c] = t;
+    if (yh) split_store(t, yh, yl, row * C + c);  // dense [rows, C] planes for a following tensor-core Linear
   }
 }
 
@@ -371,7 +373,9 @@ __global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ 
                                                       const float* __restrict__ params /*[R,32768]*/,
                                                       const float* __restrict__ g_in, const float* __restrict__ b_in,
                                                       const float* __restrict__ g_out, const float* __restrict__ b_out,
-                                                      float* __restrict__ out /*[R,12544]*/) {
+                                                      float* __restrict__ out /*[R,12544]*/,
+                                                      __half* __restrict__ out_hi = nullptr,
+                                                      __half* __restrict__ out_lo = nullptr) {
   extern __shared__ __align__(16) float dsm[];
   float* sX = dsm;                    // [49][256]   (later reused for F2)
   float* sPin = sX + 49 * 256;        // [256][64]
@@ -454,11 +458,15 @@ __global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ 
       for (int j = 0; j < 8; ++j) q += (acc[i][j] - mean) * (acc[i][j] - mean);
       for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
       const float rstd = rsqrtf(q / 256.f + 1e-5f);
-      float* orow = out + static_cast<long long>(r) * 12544 + (warp * 7 + i) * 256;
+      const long long o = static_cast<long long>(r) * 12544 + (warp * 7 + i) * 256;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = lane + 32 * j;
-        orow[c] = fmaxf((acc[i][j] - mean) * rstd * g_out[c] + b_out[c], 0.f);
+        const float t = fmaxf((acc[i][j] - mean) * rstd * g_out[c] + b_out[c], 0.f);
+        if (out_hi)
+          split_store(t, out_hi, out_lo, o + c);  // feeds the 12544 -> 256 tensor-core Linear directly
+        else
+          out[o + c] = t;
       }
     }
   }
@@ -534,13 +542,26 @@ __global__ void finalize_kernel(const float* __restrict__ gvec, const float* __r
 constexpr int kSlRows = 8;
 constexpr int kSlSlices = 8;
 constexpr int kSlThreads = 64 * kSlSlices;
+constexpr int kMaxLinGroups = 6;
 
-__global__ void __launch_bounds__(kSlThreads) small_linear_kernel(const float* __restrict__ x, long long ldx,
-                                                                 const float* __restrict__ wt /*[K,N]*/,
-                                                                 const float* __restrict__ bias,
+// Up to six independent Linears of the same shape in one launch (blockIdx.z = group): the per-clue
+// cls / reg heads and the gaze head's 3 clues x {gaze, confidence} branches.
+struct LinGroups {
+  const float* x[kMaxLinGroups];
+  const float* wt[kMaxLinGroups];
+  const float* bias[kMaxLinGroups];
+  const float* gamma[kMaxLinGroups];  // linear256_ln_kernel only
+  const float* beta[kMaxLinGroups];
+  float* y[kMaxLinGroups];
+};
+
+__global__ void __launch_bounds__(kSlThreads) small_linear_kernel(const LinGroups grp, long long ldx,
                                                                  const float* __restrict__ res, long long ldres,
-                                                                 float* __restrict__ y, long long ldy, long long M,
-                                                                 int N, int K, int relu) {
+                                                                 long long ldy, long long M, int N, int K, int relu) {
+  const float* __restrict__ x = grp.x[blockIdx.z];
+  const float* __restrict__ wt = grp.wt[blockIdx.z];  // [K, N]
+  const float* __restrict__ bias = grp.bias[blockIdx.z];
+  float* __restrict__ y = grp.y[blockIdx.z];
   extern __shared__ __align__(16) float sl_smem[];
   float* xs = sl_smem;                       // [8][K]
   float* red = sl_smem + kSlRows * K;        // [slices][8][64]
@@ -613,13 +634,16 @@ __global__ void __launch_bounds__(kSlThreads) small_linear_kernel(const float* _
 // towers, gaze towers).  A CTA owns 8 complete rows (256 columns x 4 k-slices = 1024 threads),
 // so the row statistics never leave the SM.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) linear256_ln_kernel(const float* __restrict__ x, long long ldx,
-                                                            const float* __restrict__ wt /*[K,256]*/,
-                                                            const float* __restrict__ bias,
+__global__ void __launch_bounds__(1024) linear256_ln_kernel(const LinGroups grp, long long ldx,
                                                             const float* __restrict__ res, long long ldres,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float* __restrict__ y,
-                                                            long long ldy, long long M, int K, int relu) {
+                                                            long long ldy, long long M, int K, int relu,
+                                                            __half* __restrict__ yh, __half* __restrict__ yl) {
+  const float* __restrict__ x = grp.x[blockIdx.y];
+  const float* __restrict__ wt = grp.wt[blockIdx.y];  // [K, 256]
+  const float* __restrict__ bias = grp.bias[blockIdx.y];
+  const float* __restrict__ gamma = grp.gamma[blockIdx.y];
+  const float* __restrict__ beta = grp.beta[blockIdx.y];
+  float* __restrict__ y = grp.y[blockIdx.y];
   extern __shared__ __align__(16) float ll_smem[];
   float* xs = ll_smem;                  // [8][K]
   float* red = ll_smem + kSlRows * K;   // [4][8][256]
@@ -696,6 +720,7 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const float* __restr
         float t = (v[j] - mean) * rstd * gamma[c] + beta[c];
         if (relu) t = fmaxf(t, 0.f);
         y[m * ldy + c] = t;
+        if (yh) split_store(t, yh, yl, m * 256 + c);  // dense planes for a following tensor-core Linear
       }
     }
   }

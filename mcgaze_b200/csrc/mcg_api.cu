@@ -19,6 +19,7 @@
 #include "head_kernels.cuh"
 #include "simt_gemm.cuh"
 #include "umma_gemm.cuh"
+#include "stem_fused.cuh"
 
 namespace mcg {
 
@@ -138,6 +139,8 @@ class Engine {
     cudaDeviceProp prop;
     MCG_CUDA(cudaGetDeviceProperties(&prop, device));
     num_sms_ = prop.multiProcessorCount;
+    MCG_CHECK(precision != MCG_PRECISION_FP16LO8,
+              "precision fp16lo8 was removed (superseded; use fp16x3 for parity or fp16 for speed)");
     if (precision != MCG_PRECISION_SIMT)
       MCG_CHECK(prop.major == 10, "tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major) +
                                       std::to_string(prop.minor));
@@ -163,6 +166,7 @@ class Engine {
     }
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
+    for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
     if (pin_meta_) cudaFreeHost(pin_meta_);
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (cap_stream_) cudaStreamDestroy(cap_stream_);
@@ -170,7 +174,8 @@ class Engine {
   void set_option(const std::string& k, int v) {
     if (k == "keep_intermediates") keep_stage_interm_ = v != 0;
     else if (k == "time_kernels") time_kernels_ = v != 0;
-    else if (k == "head_tensor_cores") { head_tc_ = v != 0; plans_.clear(); drop_graph(); }
+    else if (k == "head_tensor_cores") { head_tc_ = v != 0; plans_.clear(); stem_plan_valid_ = false; drop_graph(); }
+    else if (k == "fused_stem") { fused_stem_ = v != 0; drop_graph(); }
     else throw CudaError("check failed: unknown option " + k);
   }
 
@@ -322,6 +327,19 @@ class Engine {
     return n;
   }
 
+  // "name<TAB>ms" lines, one per kernel launch of the last eager forward (option time_kernels)
+  std::string kernel_profile() {
+    std::string out;
+    if (prof_used_ < 2) return out;
+    MCG_CUDA(cudaEventSynchronize(prof_ev_[prof_used_ - 1]));
+    for (size_t i = 1; i < prof_used_; ++i) {
+      float t = 0.f;
+      MCG_CUDA(cudaEventElapsedTime(&t, prof_ev_[i - 1], prof_ev_[i]));
+      out += prof_names_[i] + "\t" + std::to_string(t) + "\n";
+    }
+    return out;
+  }
+
   int get_intermediate(const char* name, float* dst, int64_t capacity, int64_t shape_out[4]) {
     auto it = interm_.find(name);
     if (it == interm_.end()) return MCG_ERR_INVALID;
@@ -376,15 +394,6 @@ class Engine {
     }
     g.w.hi = upload(keep_, hi);
     g.w.lo = upload(keep_, lo);
-    if (precision_ == MCG_PRECISION_FP16LO8) {
-      float mx = 0.f;
-      for (size_t i = 0; i < w.size(); ++i) mx = std::max(mx, std::fabs(__half2float(hi[i])));
-      g.w_shift = mx > 0.f ? static_cast<int>(std::floor(std::log2(256.0f / mx))) : 0;  // max |w| -> [128, 256)
-      const float sc = std::ldexp(1.0f, g.w_shift);
-      std::vector<uint8_t> h8(w.size());
-      for (size_t i = 0; i < w.size(); ++i) h8[i] = float_to_e4m3(__half2float(hi[i]) * sc);
-      g.w.lo8 = upload(keep_, h8);
-    }
     if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
     if (N <= 768 && K <= 2048 && K % 32 == 0) {
       std::vector<float> t(w.size());
@@ -558,6 +567,7 @@ class Engine {
     MCG_CUDA(cudaDeviceSynchronize());
     drop_graph();
     plans_.clear();
+    stem_plan_valid_ = false;
     interm_.clear();
     dbg_.clear();
     arena_.begin_measure();
@@ -619,8 +629,8 @@ class Engine {
     t256b_ = arena_.alloc<float>(Rr * 256);
     cls_logit_ = arena_.alloc<float>(Rr);
     delta_ = arena_.alloc<float>(Rr * 4);
-    gz_a_ = arena_.alloc<float>(static_cast<size_t>(NB) * 256);
-    gz_b_ = arena_.alloc<float>(static_cast<size_t>(NB) * 256);
+    gz_a_ = arena_.alloc<float>(static_cast<size_t>(NB) * 256 * 6);  // six gaze-head branches side by side
+    gz_b_ = arena_.alloc<float>(static_cast<size_t>(NB) * 256 * 6);
     gvec_ = arena_.alloc<float>(static_cast<size_t>(NB) * 9);
     conf_ = arena_.alloc<float>(static_cast<size_t>(NB) * 9);
     d_meta_ = arena_.alloc<float>(static_cast<size_t>(NB) * 6);
@@ -639,7 +649,19 @@ class Engine {
   }
 
   // -------------------------------------------------------------------------- op helpers
-  void count() { ++launches_; }
+  // every kernel launch of the forward passes through here; with option "time_kernels" (eager mode) an event
+  // is recorded after it, so consecutive events bracket each kernel on the (serial) stream
+  void count(const char* name) {
+    ++launches_;
+    if (time_kernels_ && !graph_mode_) {
+      if (prof_used_ >= prof_ev_.size()) {
+        prof_ev_.push_back(nullptr);
+        MCG_CUDA(cudaEventCreate(&prof_ev_.back()));
+      }
+      MCG_CUDA(cudaEventRecord(prof_ev_[prof_used_++], cur_stream_));
+      prof_names_.push_back(name);
+    }
+  }
 
   // generic GEMM dispatch.  A: planes (kind 0/1) or fp32 (kind 0).
   // terms: 0 = CUDA-core fp32 kernel, 1 / 3 = tcgen05 kernel with 1 / 3 MMAs per k-step
@@ -647,18 +669,17 @@ class Engine {
     switch (precision_) {
       case MCG_PRECISION_SIMT: return 0;
       case MCG_PRECISION_FP16X3: return 3;
-      case MCG_PRECISION_FP16LO8: return 2;
       default: return 1;
     }
   }
   void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
             long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0) {
     const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
-                        (terms == 1 || (terms == 3 && A->lo != nullptr) || (terms == 2 && A->lo8 != nullptr));
+                        (terms == 1 || (terms == 3 && A->lo != nullptr));
     if (tensor) {
       auto it = plans_.find(key);
       if (it == plans_.end()) {
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, w.w_shift);
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -695,7 +716,7 @@ class Engine {
       p.ep = ep;
       launch_simt_gemm(p, st);
     }
-    count();
+    count(tensor ? ("umma:" + key).c_str() : "simt_gemm_kernel");
   }
 
   // convolution over NHWC planes -> NHWC planes
@@ -738,12 +759,10 @@ class Engine {
   void linear(const float* x, long long ldx, const GemmW& w, long long M, float* y, long long ldy, bool relu,
               const float* res, long long ldres, cudaStream_t st) {
     if (w.w_t != nullptr) {
-      dim3 grid(static_cast<unsigned>((M + kSlRows - 1) / kSlRows), static_cast<unsigned>((w.N + 63) / 64));
-      const size_t smem = (static_cast<size_t>(kSlRows) * w.K + kSlSlices * kSlRows * 64) * sizeof(float);
-      small_linear_kernel<<<grid, kSlThreads, smem, st>>>(x, ldx, w.w_t, w.bias, res, ldres, y, ldy, M, w.N, w.K,
-                                                         relu ? 1 : 0);
-      MCG_CUDA(cudaGetLastError());
-      count();
+      const GemmW* ws[1] = {&w};
+      const float* xs[1] = {x};
+      float* ys[1] = {y};
+      linear_grouped(1, xs, ldx, ws, M, ys, ldy, relu, res, ldres, st);
       return;
     }
     AGeom g;
@@ -762,34 +781,87 @@ class Engine {
     gemm("", nullptr, x, g, w, M, ep, st, 0);
   }
 
-  // y = act(LN(x W^T + b (+res)))  for N == 256 Linears followed by a LayerNorm
-  void linear_ln(const float* x, long long ldx, const GemmW& w, const LnW& n, long long M, float* y, long long ldy,
-                 bool relu, const float* res, long long ldres, cudaStream_t st) {
-    MCG_CHECK(w.N == 256 && w.w_t != nullptr && n.C == 256, "linear_ln needs a 256-wide small Linear");
-    const size_t smem = (static_cast<size_t>(kSlRows) * w.K + 4 * kSlRows * 256) * sizeof(float);
-    linear256_ln_kernel<<<static_cast<unsigned>((M + kSlRows - 1) / kSlRows), 1024, smem, st>>>(
-        x, ldx, w.w_t, w.bias, res, ldres, n.g, n.b, y, ldy, M, w.K, relu ? 1 : 0);
+  // n (<= 6) independent small Linears of one shape in a single launch (per-clue heads, gaze branches)
+  void linear_grouped(int n, const float* const* x, long long ldx, const GemmW* const* w, long long M, float* const* y,
+                      long long ldy, bool relu, const float* res, long long ldres, cudaStream_t st) {
+    MCG_CHECK(n >= 1 && n <= kMaxLinGroups && (res == nullptr || n == 1), "bad Linear group");
+    LinGroups g = {};
+    for (int i = 0; i < n; ++i) {
+      MCG_CHECK(w[i]->w_t != nullptr && w[i]->N == w[0]->N && w[i]->K == w[0]->K, "grouped Linears must share a shape");
+      g.x[i] = x[i];
+      g.wt[i] = w[i]->w_t;
+      g.bias[i] = w[i]->bias;
+      g.y[i] = y[i];
+    }
+    const int N = w[0]->N, K = w[0]->K;
+    dim3 grid(static_cast<unsigned>((M + kSlRows - 1) / kSlRows), static_cast<unsigned>((N + 63) / 64), n);
+    const size_t smem = (static_cast<size_t>(kSlRows) * K + kSlSlices * kSlRows * 64) * sizeof(float);
+    small_linear_kernel<<<grid, kSlThreads, smem, st>>>(g, ldx, res, ldres, ldy, M, N, K, relu ? 1 : 0);
     MCG_CUDA(cudaGetLastError());
-    count();
+    count("small_linear_kernel");
   }
 
-  // big head linears: split the fp32 activations into fp16 planes and run on tensor cores
-  void linear_tc(const std::string& key, const float* x, int K, const Planes& stage, const GemmW& w, long long M,
-                 float* y, bool relu, const float* res, cudaStream_t st, int k_split = 1) {
-    if (precision_ == MCG_PRECISION_SIMT || !head_tc_) {
+  // y = act(LN(x W^T + b (+res)))  for N == 256 Linears followed by a LayerNorm; optionally also written as
+  // split-fp16 planes (input of a following tensor-core Linear)
+  void linear_ln(const float* x, long long ldx, const GemmW& w, const LnW& n, long long M, float* y, long long ldy,
+                 bool relu, const float* res, long long ldres, cudaStream_t st, const Planes* planes = nullptr) {
+    const GemmW* ws[1] = {&w};
+    const LnW* ns[1] = {&n};
+    const float* xs[1] = {x};
+    float* ys[1] = {y};
+    linear_ln_grouped(1, xs, ldx, ws, ns, M, ys, ldy, relu, res, ldres, st, planes);
+  }
+  void linear_ln_grouped(int cnt, const float* const* x, long long ldx, const GemmW* const* w, const LnW* const* n,
+                         long long M, float* const* y, long long ldy, bool relu, const float* res, long long ldres,
+                         cudaStream_t st, const Planes* planes = nullptr) {
+    MCG_CHECK(cnt >= 1 && cnt <= kMaxLinGroups && ((res == nullptr && planes == nullptr) || cnt == 1), "bad Linear+LN group");
+    LinGroups g = {};
+    for (int i = 0; i < cnt; ++i) {
+      MCG_CHECK(w[i]->N == 256 && w[i]->w_t != nullptr && n[i]->C == 256 && w[i]->K == w[0]->K,
+                "linear_ln needs 256-wide small Linears of one shape");
+      g.x[i] = x[i];
+      g.wt[i] = w[i]->w_t;
+      g.bias[i] = w[i]->bias;
+      g.gamma[i] = n[i]->g;
+      g.beta[i] = n[i]->b;
+      g.y[i] = y[i];
+    }
+    const int K = w[0]->K;
+    const size_t smem = (static_cast<size_t>(kSlRows) * K + 4 * kSlRows * 256) * sizeof(float);
+    dim3 grid(static_cast<unsigned>((M + kSlRows - 1) / kSlRows), cnt);
+    linear256_ln_kernel<<<grid, 1024, smem, st>>>(g, ldx, res, ldres, ldy, M, K, relu ? 1 : 0,
+                                                  planes ? planes->hi : nullptr, planes ? planes->lo : nullptr);
+    MCG_CUDA(cudaGetLastError());
+    count("linear256_ln_kernel");
+  }
+
+  // big head linears on tensor cores.  The producer of x normally writes the split-fp16 planes `stage`
+  // itself (staged == true); otherwise the fp32 activations are split here.  With out_planes the result
+  // goes out as planes (input of the next tensor-core Linear) instead of fp32.
+  void linear_tc(const std::string& key, const float* x, int K, const Planes& stage, bool staged, const GemmW& w,
+                 long long M, float* y, bool relu, const float* res, cudaStream_t st, int k_split = 1,
+                 const Planes* out_planes = nullptr) {
+    if (!head_on_tc()) {
       linear(x, K, w, M, y, w.N, relu, res, w.N, st);
       return;
     }
-    split_planes_kernel<<<num_sms_ * 4, 256, 0, st>>>(x, K, M, K, stage.hi, stage.lo);
-    MCG_CUDA(cudaGetLastError());
-    count();
+    if (!staged) {
+      split_planes_kernel<<<num_sms_ * 4, 256, 0, st>>>(x, K, M, K, stage.hi, stage.lo);
+      MCG_CUDA(cudaGetLastError());
+      count("split_planes_kernel");
+    }
     AGeom g;
     g.kind = 0;
     g.lda = K;
     Epilogue ep;
     ep.bias = w.bias;
     ep.relu = relu ? 1 : 0;
-    ep.out_f32 = y;
+    if (out_planes) {
+      ep.out_hi = out_planes->hi;
+      ep.out_lo = out_planes->lo;
+    } else {
+      ep.out_f32 = y;
+    }
     ep.ldo = w.N;
     if (res) {
       ep.res_f32 = res;
@@ -800,15 +872,17 @@ class Engine {
     // head GEMMs always use the 3-term split: the head is precision critical and only 2.5 % of the FLOPs
     gemm(key, &stage, nullptr, g, w, M, ep, st, 3, k_split, static_cast<long long>(M) * w.N);
   }
+  bool head_on_tc() const { return precision_ != MCG_PRECISION_SIMT && head_tc_; }
 
   void ln(const float* x, long long ldx, const float* res, long long ldres, const LnW& w, float* y, long long ldy,
           long long rows, bool relu, cudaStream_t st, int nsplit = 1, long long split_stride = 0,
-          const float* xbias = nullptr) {
+          const float* xbias = nullptr, const Planes* planes = nullptr) {
     const int wpb = 8;
     layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-        x, ldx, res, ldres, w.g, w.b, y, ldy, rows, w.C, relu ? 1 : 0, nsplit, split_stride, xbias);
+        x, ldx, res, ldres, w.g, w.b, y, ldy, rows, w.C, relu ? 1 : 0, nsplit, split_stride, xbias,
+        planes ? planes->hi : nullptr, planes ? planes->lo : nullptr);
     MCG_CUDA(cudaGetLastError());
-    count();
+    count("layernorm_kernel");
   }
 
   const float* snapshot(const float* src, size_t n, cudaStream_t st) {
@@ -843,32 +917,52 @@ class Engine {
     umma_launches_ = 0;
     umma_flops_ = 0.0;
     ev_used_ = 0;
+    cur_stream_ = st;
+    prof_used_ = 0;
+    prof_names_.clear();
+    count("(start)");
+    --launches_;
     if (!graph_mode_) dbg_.clear();
     const int NB = ws_NB_, T = ws_T_, H = ws_H_, W = ws_W_;
     const int ew_grid = num_sms_ * 8;
-    // ---- stem (resnet.py:636-639)
-    stem_im2col_kernel<<<NB * (H / 2), 256, 3 * 7 * (W + 6) * sizeof(float), st>>>(img, NB, H, W, H / 2, W / 2,
-                                                                                   stemA_.hi, stemA_.lo, stemA_.lo8);
-    MCG_CUDA(cudaGetLastError());
-    count();
-    {
-      AGeom g;
-      g.kind = 0;
-      g.lda = kStemK;
-      Epilogue ep;
-      ep.bias = stem_.g.bias;
-      ep.relu = 1;
-      ep.out_hi = stem_out_.pl.hi;
-      ep.out_lo = stem_out_.pl.lo;
-      ep.out_lo8 = stem_out_.pl.lo8;
-      ep.ldo = 64;
-      gemm("stem", &stemA_, nullptr, g, stem_.g, stem_out_.rows(), ep, st, trunk_terms());
+    // ---- stem (resnet.py:636-639): one fused tcgen05 kernel (conv 7x7/2 + BN + ReLU + max-pool), or the
+    // unfused im2col -> GEMM -> max-pool chain (CUDA-core mode, "fused_stem" = 0: keeps the 112^2 stem map
+    // addressable for per-layer parity tests)
+    const bool fused_stem = fused_stem_ && precision_ != MCG_PRECISION_SIMT && stem_fused_supported(H, W);
+    if (fused_stem) {
+      if (!stem_plan_valid_) {
+        stem_plan_ = make_stem_fused_plan(trunk_terms(), img, NB, H, W, stem_.g.w, stem_.g.bias, pool_out_.pl, num_sms_);
+        stem_plan_valid_ = true;
+      }
+      stem_plan_.p.img = img;
+      launch_stem_fused(stem_plan_, st);
+      count("stem_fused_kernel");
+      // algorithmic work of the stem convolution (K = 147), as the GEMM path counts it
+      umma_flops_ += 2.0 * static_cast<double>(stem_out_.rows()) * 64 * 147;
+    } else {
+      stem_im2col_kernel<<<NB * (H / 2), 256, 3 * 7 * (W + 6) * sizeof(float), st>>>(img, NB, H, W, H / 2, W / 2,
+                                                                                     stemA_.hi, stemA_.lo, stemA_.lo8);
+      MCG_CUDA(cudaGetLastError());
+      count("stem_im2col_kernel");
+      {
+        AGeom g;
+        g.kind = 0;
+        g.lda = kStemK;
+        Epilogue ep;
+        ep.bias = stem_.g.bias;
+        ep.relu = 1;
+        ep.out_hi = stem_out_.pl.hi;
+        ep.out_lo = stem_out_.pl.lo;
+        ep.out_lo8 = stem_out_.pl.lo8;
+        ep.ldo = 64;
+        gemm("stem", &stemA_, nullptr, g, stem_.g, stem_out_.rows(), ep, st, trunk_terms());
+      }
+      maxpool3x3s2_kernel<<<ew_grid, 256, 0, st>>>(stem_out_.pl.hi, stem_out_.pl.lo, stem_out_.pl.lo8, NB, H / 2, W / 2, 64,
+                                                   H / 4, W / 4, pool_out_.pl.hi, pool_out_.pl.lo, pool_out_.pl.lo8);
+      MCG_CUDA(cudaGetLastError());
+      count("maxpool3x3s2_kernel");
+      reg_act("stem", stem_out_);
     }
-    maxpool3x3s2_kernel<<<ew_grid, 256, 0, st>>>(stem_out_.pl.hi, stem_out_.pl.lo, stem_out_.pl.lo8, NB, H / 2, W / 2, 64,
-                                                 H / 4, W / 4, pool_out_.pl.hi, pool_out_.pl.lo, pool_out_.pl.lo8);
-    MCG_CUDA(cudaGetLastError());
-    count();
-    reg_act("stem", stem_out_);
     reg_act("pool", pool_out_);
     // ---- layer1..4 (resnet.py:263-302)
     const Act* x = &pool_out_;
@@ -905,7 +999,7 @@ class Engine {
     float* scale = d_meta_ + NB * 2;
     init_proposals_kernel<<<NB, 256, 0, st>>>(init_boxes_, init_feats_, img_hw, NB, boxes_[0], obj_[0]);
     MCG_CUDA(cudaGetLastError());
-    count();
+    count("init_proposals_kernel");
     FpnLevels fl;
     for (int i = 0; i < 4; ++i) {
       fl.hi[i] = fpn_[i].pl.hi;
@@ -915,6 +1009,7 @@ class Engine {
       fl.W[i] = fpn_[i].W;
     }
     int cur = 0;
+    const bool tc = head_on_tc();
     for (int s = 0; s < 4; ++s) {
       const StageW& sw = stage_[s];
       const std::string sk = "s" + std::to_string(s);
@@ -924,7 +1019,7 @@ class Engine {
       float* obj_out = obj_[cur ^ 1];
       roi_align_kernel<<<(R * 49 + 7) / 8, 256, 0, st>>>(fl, boxes_in, R, roi_);
       MCG_CUDA(cudaGetLastError());
-      count();
+      count("roi_align_kernel");
       // spatial then temporal self-attention with the SAME weights (gaze_stqi_head.py:148-166)
       const float* xin = obj_in;
       float* xout[2] = {xa_, xb_};
@@ -932,46 +1027,59 @@ class Engine {
         linear(xin, 256, sw.in_proj, R, qkv_, 768, false, nullptr, 0, st);
         attention_kernel<<<(R * 8 * 32 + 255) / 256, 256, 0, st>>>(qkv_, att_, R, T, mode);
         MCG_CUDA(cudaGetLastError());
-        count();
-        // out_proj + identity (mmcv MHA) + attention_norm in one kernel
-        linear_ln(att_, 256, sw.out_proj, sw.attn_norm, R, xout[mode], 256, false, xin, 256, st);
+        count("attention_kernel");
+        // out_proj + identity (mmcv MHA) + attention_norm in one kernel; the temporal pass also emits the
+        // split-fp16 planes the dynamic_layer GEMM reads
+        linear_ln(att_, 256, sw.out_proj, sw.attn_norm, R, xout[mode], 256, false, xin, 256, st,
+                  (mode == 1 && tc) ? &hq_ : nullptr);
         xin = xout[mode];
       }
       const float* attn = xb_;
       // DynamicConv (transformer.py:1116-1164)
-      linear_tc(sk + "dyn", attn, 256, hq_, sw.dyn, R, params_, false, nullptr, st);
+      linear_tc(sk + "dyn", attn, 256, hq_, tc, sw.dyn, R, params_, false, nullptr, st);
       dynconv_kernel<<<R, 256, kDynSmemBytes, st>>>(roi_, params_, sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
-                                                    sw.norm_out.b, dynf_);
+                                                    sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr, tc ? hf_.lo : nullptr);
       MCG_CUDA(cudaGetLastError());
-      count();
+      count("dynconv_kernel");
       {
         // 12544 -> 256 over only 3*frames rows: split K so that >100 tiles exist; the partial sums are
         // reduced (and the bias added) inside the fc_norm LayerNorm kernel
-        const bool tc = precision_ != MCG_PRECISION_SIMT && head_tc_;
         const int ks = tc ? kFcSplit : 1;
-        linear_tc(sk + "fc", dynf_, 12544, hf_, sw.fc, R, fcp_, false, nullptr, st, ks);
+        linear_tc(sk + "fc", dynf_, 12544, hf_, tc, sw.fc, R, fcp_, false, nullptr, st, ks);
         ln(fcp_, 256, nullptr, 0, sw.fc_norm, fc_, 256, R, true, st, ks, static_cast<long long>(R) * 256,
            ks > 1 ? sw.fc.bias : nullptr);
       }
-      ln(attn, 256, fc_, 256, sw.iic_norm, xa_, 256, R, false, st);  // obj = LN(attn + iic)
-      // FFN with identity (gaze_stqi_head.py:179)
-      linear_tc(sk + "ffn1", xa_, 256, hq_, sw.ffn1, R, ffn_h_, true, nullptr, st);
-      linear_tc(sk + "ffn2", ffn_h_, 2048, hh_, sw.ffn2, R, xc_, false, xa_, st);
+      ln(attn, 256, fc_, 256, sw.iic_norm, xa_, 256, R, false, st, 1, 0, nullptr, tc ? &hq_ : nullptr);  // obj = LN(attn + iic)
+      // FFN with identity (gaze_stqi_head.py:179): the hidden activations stay split-fp16 planes
+      linear_tc(sk + "ffn1", xa_, 256, hq_, tc, sw.ffn1, R, ffn_h_, true, nullptr, st, 1, tc ? &hh_ : nullptr);
+      linear_tc(sk + "ffn2", ffn_h_, 2048, hh_, tc, sw.ffn2, R, xc_, false, xa_, st);
       ln(xc_, 256, nullptr, 0, sw.ffn_norm, obj_out, 256, R, false, st);
-      // cls / reg towers + per-clue heads (gaze_stqi_head.py:185-201)
-      linear_ln(obj_out, 256, sw.cls_fc, sw.cls_ln, R, t256a_, 256, true, nullptr, 0, st);
-      for (int c = 0; c < 3; ++c) linear(t256a_ + c * 256, 768, sw.fc_cls[c], NB, cls_logit_ + c, 3, false, nullptr, 0, st);
-      const float* rin = obj_out;
-      float* rbuf[2] = {t256b_, xc_};
-      for (int j = 0; j < 3; ++j) {
-        float* ro = rbuf[j & 1];
-        linear_ln(rin, 256, sw.reg_fc[j], sw.reg_ln[j], R, ro, 256, true, nullptr, 0, st);
-        rin = ro;
+      // cls / reg towers + per-clue heads (gaze_stqi_head.py:185-201); the cls tower and the first reg layer
+      // read the same input and run as one grouped launch, as do the three per-clue heads of each kind
+      {
+        const float* xs[2] = {obj_out, obj_out};
+        const GemmW* ws[2] = {&sw.cls_fc, &sw.reg_fc[0]};
+        const LnW* ns[2] = {&sw.cls_ln, &sw.reg_ln[0]};
+        float* ys[2] = {t256a_, t256b_};
+        linear_ln_grouped(2, xs, 256, ws, ns, R, ys, 256, true, nullptr, 0, st);
       }
-      for (int c = 0; c < 3; ++c) linear(rin + c * 256, 768, sw.fc_reg[c], NB, delta_ + c * 4, 12, false, nullptr, 0, st);
+      {
+        const float* xs[3] = {t256a_, t256a_ + 256, t256a_ + 512};
+        const GemmW* ws[3] = {&sw.fc_cls[0], &sw.fc_cls[1], &sw.fc_cls[2]};
+        float* ys[3] = {cls_logit_, cls_logit_ + 1, cls_logit_ + 2};
+        linear_grouped(3, xs, 768, ws, NB, ys, 3, false, nullptr, 0, st);
+      }
+      linear_ln(t256b_, 256, sw.reg_fc[1], sw.reg_ln[1], R, xc_, 256, true, nullptr, 0, st);
+      linear_ln(xc_, 256, sw.reg_fc[2], sw.reg_ln[2], R, t256b_, 256, true, nullptr, 0, st);
+      {
+        const float* xs[3] = {t256b_, t256b_ + 256, t256b_ + 512};
+        const GemmW* ws[3] = {&sw.fc_reg[0], &sw.fc_reg[1], &sw.fc_reg[2]};
+        float* ys[3] = {delta_, delta_ + 4, delta_ + 8};
+        linear_grouped(3, xs, 768, ws, NB, ys, 12, false, nullptr, 0, st);
+      }
       box_decode_kernel<<<(R + 127) / 128, 128, 0, st>>>(boxes_in, delta_, R, boxes_out);
       MCG_CUDA(cudaGetLastError());
-      count();
+      count("box_decode_kernel");
       if (keep_stage_interm_ && !graph_mode_) {
         // head buffers are reused by every stage: snapshot them for per-op parity tests
         const std::string nm = "stage" + std::to_string(s);
@@ -988,22 +1096,46 @@ class Engine {
     reg_f32("boxes", boxes_[cur], NB, 3, 4);
     reg_f32("cls", cls_logit_, NB, 3);
     // ---- gaze head on the last stage's object features (gaze_head.py:138-202)
+    // the 3 clues x {gaze, confidence} branches are six independent tower chains: three grouped launches
     const float* obj = obj_[cur];
-    for (int c = 0; c < 3; ++c) {
-      for (int branch = 0; branch < 2; ++branch) {
-        const GemmW* tw = branch == 0 ? gaze_.tower[c] : gaze_.ctower[c];
-        const LnW* tl = branch == 0 ? gaze_.tower_ln[c] : gaze_.ctower_ln[c];
-        linear_ln(obj + c * 256, 768, tw[0], tl[0], NB, gz_a_, 256, true, nullptr, 0, st);
-        linear_ln(gz_a_, 256, tw[1], tl[1], NB, gz_b_, 256, true, nullptr, 0, st);
-        const GemmW& head = branch == 0 ? gaze_.fc[c] : gaze_.fc_conf[c];
-        float* dst = (branch == 0 ? gvec_ : conf_) + static_cast<size_t>(c) * NB * 3;
-        linear(gz_b_, 256, head, NB, dst, 3, false, nullptr, 0, st);
+    {
+      const float* x0[6];
+      const float* x1[6];
+      const float* x2[6];
+      float* y0[6];
+      float* y1[6];
+      float* y2[6];
+      const GemmW* w0[6];
+      const GemmW* w1[6];
+      const GemmW* w2[6];
+      const LnW* n0[6];
+      const LnW* n1[6];
+      for (int c = 0; c < 3; ++c) {
+        for (int branch = 0; branch < 2; ++branch) {
+          const int g = c * 2 + branch;
+          const GemmW* tw = branch == 0 ? gaze_.tower[c] : gaze_.ctower[c];
+          const LnW* tl = branch == 0 ? gaze_.tower_ln[c] : gaze_.ctower_ln[c];
+          x0[g] = obj + c * 256;
+          y0[g] = gz_a_ + static_cast<size_t>(g) * NB * 256;
+          x1[g] = y0[g];
+          y1[g] = gz_b_ + static_cast<size_t>(g) * NB * 256;
+          x2[g] = y1[g];
+          y2[g] = (branch == 0 ? gvec_ : conf_) + static_cast<size_t>(c) * NB * 3;
+          w0[g] = &tw[0];
+          w1[g] = &tw[1];
+          n0[g] = &tl[0];
+          n1[g] = &tl[1];
+          w2[g] = branch == 0 ? &gaze_.fc[c] : &gaze_.fc_conf[c];
+        }
       }
+      linear_ln_grouped(6, x0, 768, w0, n0, NB, y0, 256, true, nullptr, 0, st);
+      linear_ln_grouped(6, x1, 256, w1, n1, NB, y1, 256, true, nullptr, 0, st);
+      linear_grouped(6, x2, 256, w2, NB, y2, 3, false, nullptr, 0, st);
     }
     finalize_kernel<<<(NB + 127) / 128, 128, 0, st>>>(gvec_, conf_, gaze_.wg, gaze_.bg, cls_logit_, boxes_[cur],
                                                       has_scale_ ? scale : nullptr, NB, out_gaze, out_boxes, out_scores);
     MCG_CUDA(cudaGetLastError());
-    count();
+    count("finalize_kernel");
   }
 
   // -------------------------------------------------------------------------- state
@@ -1011,8 +1143,15 @@ class Engine {
   int precision_ = 0;
   int num_sms_ = 148;
   bool head_tc_ = true;
+  bool fused_stem_ = true;
+  StemFusedPlan stem_plan_;
+  bool stem_plan_valid_ = false;
   bool keep_stage_interm_ = false;
   bool time_kernels_ = false;
+  std::vector<cudaEvent_t> prof_ev_;
+  size_t prof_used_ = 0;
+  std::vector<std::string> prof_names_;
+  cudaStream_t cur_stream_ = nullptr;
   std::vector<cudaEvent_t> ev_pool_;
   size_t ev_used_ = 0;
   int umma_launches_ = 0;
@@ -1212,6 +1351,18 @@ int mcg_last_umma_times(mcg_handle h, double* out_ms, int capacity) {
   return rc == MCG_OK ? n : rc;
 }
 
+int mcg_last_kernel_profile(mcg_handle h, char* buf, int capacity) {
+  int n = -1;
+  const int rc = guarded([&]() -> int {
+    if (!h || (capacity > 0 && !buf)) return MCG_ERR_INVALID;
+    const std::string s = h->impl->kernel_profile();
+    n = static_cast<int>(s.size()) + 1;
+    if (capacity >= n) std::memcpy(buf, s.c_str(), static_cast<size_t>(n));
+    return MCG_OK;
+  });
+  return rc == MCG_OK ? n : rc;
+}
+
 int mcg_set_graph_mode(mcg_handle h, int on) {
   return guarded([&]() -> int {
     if (!h) return MCG_ERR_INVALID;
@@ -1245,41 +1396,19 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
       RW = Q / 2;
     }
     const size_t nr = res ? static_cast<size_t>(NB) * RH * RW * Cout : 0;
-    const bool lo8 = engine == MCG_PRECISION_FP16LO8;
-    DeviceBlock bx(nx * 5), bw(nw * 5), br(nr * 5 + 16);
+    if (engine == MCG_PRECISION_FP16LO8) {
+      g_last_error = "mcg_debug_conv: precision fp16lo8 was removed";
+      return MCG_ERR_UNSUPPORTED;
+    }
+    DeviceBlock bx(nx * 4), bw(nw * 4), br(nr * 4 + 16);
     Planes px{reinterpret_cast<__half*>(bx.p), reinterpret_cast<__half*>(bx.p) + nx, nullptr};
     Planes pw{reinterpret_cast<__half*>(bw.p), reinterpret_cast<__half*>(bw.p) + nw, nullptr};
     Planes pr{reinterpret_cast<__half*>(br.p), reinterpret_cast<__half*>(br.p) + nr, nullptr};
-    int w_shift = 0;
-    if (lo8) {  // activations / residual carry an e4m3 low part instead of the fp16 one
-      px.lo8 = reinterpret_cast<uint8_t*>(bx.p) + nx * 4;
-      pr.lo8 = reinterpret_cast<uint8_t*>(br.p) + nr * 4;
-      pw.lo8 = reinterpret_cast<uint8_t*>(bw.p) + nw * 4;
-    }
-    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, lo8 ? nullptr : px.lo,
-                                              px.lo8);
+    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, px.lo);
     split_planes_kernel<<<1024, 256, 0, st>>>(w, K, Cout, K, pw.hi, pw.lo);
     if (res)
-      split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi,
-                                                lo8 ? nullptr : pr.lo, pr.lo8);
+      split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi, pr.lo);
     MCG_CUDA(cudaGetLastError());
-    if (lo8) {  // e4m3(W_hi * 2^shift) packed on the host exactly like Engine::pack_gemm
-      std::vector<float> hw(nw);
-      MCG_CUDA(cudaMemcpyAsync(hw.data(), w, nw * 4, cudaMemcpyDeviceToHost, st));
-      MCG_CUDA(cudaStreamSynchronize(st));
-      float mx = 0.f;
-      for (size_t i = 0; i < nw; ++i) mx = std::max(mx, std::fabs(__half2float(__float2half_rn(hw[i]))));
-      w_shift = mx > 0.f ? static_cast<int>(std::floor(std::log2(256.0f / mx))) : 0;
-      std::vector<uint8_t> h8(nw);
-      for (size_t i = 0; i < nw; ++i)
-        h8[i] = float_to_e4m3(__half2float(__float2half_rn(hw[i])) * std::ldexp(1.0f, w_shift));
-      MCG_CUDA(cudaMemcpyAsync(pw.lo8, h8.data(), nw, cudaMemcpyHostToDevice, st));
-      MCG_CUDA(cudaStreamSynchronize(st));
-    }
-    if (lo8) {
-      px.lo = nullptr;
-      pr.lo = nullptr;
-    }
     AGeom g;
     const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col;
     g.kind = plain ? 0 : 1;
@@ -1305,7 +1434,6 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     if (planes_out) {
       ep.out_hi = po.hi;
       ep.out_lo = engine == MCG_PRECISION_FP16X3 ? po.lo : nullptr;
-      ep.out_lo8 = lo8 ? reinterpret_cast<uint8_t*>(po.lo) : nullptr;
     } else {
       ep.out_f32 = out;
     }
@@ -1313,7 +1441,6 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     if (res) {
       ep.res_hi = pr.hi;
       ep.res_lo = pr.lo;
-      ep.res_lo8 = pr.lo8;
       ep.res_mode = res_mode;
       ep.ldr = Cout;
       ep.P = P;
@@ -1341,8 +1468,8 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
         return MCG_ERR_UNSUPPORTED;
       }
       if (engine == MCG_PRECISION_FP16 && res) ep.res_lo = nullptr;
-      const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : (lo8 ? 2 : 1);
-      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n, 1, 0, w_shift);
+      const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : 1;
+      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n);
       launch_umma(pl, st);
       if (planes_out) {
         planes_to_f32_kernel<<<1024, 256, 0, st>>>(po.hi, ep.out_lo, ep.out_lo8, static_cast<long long>(ny), out);

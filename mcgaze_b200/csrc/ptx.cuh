@@ -100,6 +100,42 @@ __device__ __forceinline__ void tma_store_wait_all() {
 // make generic-proxy smem writes visible to the async proxy (TMA) and vice versa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------ packed fp16 <-> fp32 epilogue arithmetic
+// sm_100 mixed-precision add (SASS FHADD): one instruction per element adds a packed-fp16 operand
+// to an fp32 value without a separate conversion.
+// a += low half of h2, b += high half
+__device__ __forceinline__ void add_half2(float& a, float& b, uint32_t h2) {
+  asm("{\n"
+      ".reg .b16 l, h;\n"
+      "mov.b32 {l, h}, %2;\n"
+      "add.rn.f32.f16 %0, l, %0;\n"
+      "add.rn.f32.f16 %1, h, %1;\n"
+      "}\n"
+      : "+f"(a), "+f"(b)
+      : "r"(h2));
+}
+// fp16x2 {low = rn(a), high = rn(b)}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// fp16x2 of the rounding residue {a - low(h2), b - high(h2)} (the `lo` plane of a split value)
+__device__ __forceinline__ uint32_t residue_half2(float a, float b, uint32_t h2) {
+  float da, db;
+  asm("{\n"
+      ".reg .b16 l, h;\n"
+      "mov.b32 {l, h}, %2;\n"
+      "neg.f16 l, l;\n"
+      "neg.f16 h, h;\n"
+      "add.rn.f32.f16 %0, l, %3;\n"
+      "add.rn.f32.f16 %1, h, %4;\n"
+      "}\n"
+      : "=f"(da), "=f"(db)
+      : "r"(h2), "f"(a), "f"(b));
+  return pack_half2(da, db);
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

@@ -12,12 +12,12 @@ from typing import Dict, Optional, Sequence
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libmcgaze_b200.so')
 
-PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16lo8': 3}
+PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2}   # 3 (fp16lo8) was removed
 
 # every symbol include/mcgaze_b200.h declares
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
-           'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
+           'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
            'mcg_last_error', 'mcg_version')
 
 
@@ -54,6 +54,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_set_graph_mode.argtypes = [vp, ci]
     lib.mcg_last_umma_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.mcg_last_umma_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ci]
+    lib.mcg_last_kernel_profile.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
@@ -146,6 +147,15 @@ class Engine:
         if n < 0:
             _check(n, 'mcg_last_umma_times')
         return [float(buf[i]) for i in range(n)]
+
+    def kernel_profile(self):
+        """[(kernel name, ms)] for every launch of the last eager forward (option time_kernels)."""
+        n = self._lib.mcg_last_kernel_profile(self._h, None, 0)
+        if n < 0:
+            _check(n, 'mcg_last_kernel_profile')
+        buf = ctypes.create_string_buffer(n)
+        _check(min(self._lib.mcg_last_kernel_profile(self._h, buf, n), 0), 'mcg_last_kernel_profile')
+        return [(l.split('\t')[0], float(l.split('\t')[1])) for l in buf.value.decode().splitlines() if l]
 
     # ------------------------------------------------------------------ forward
     @staticmethod

@@ -24,10 +24,18 @@ CASES = [
     ('block_n64', 2, 256, 28, 28, 256, 1, 1, 0, 0, 0, 0, 64),
     ('block_n128', 2, 256, 28, 28, 256, 1, 1, 0, 0, 0, 0, 128),
     ('bigK', 1, 2048, 7, 7, 512, 1, 1, 0, 0, 1, 0, 0),
+    # several tiles per persistent CTA: both epilogue groups, all TMEM accumulator buffers and the
+    # residual prefetch ring wrap around
+    ('multi_1x1_residual', 8, 64, 56, 56, 256, 1, 1, 0, 1, 1, 0, 0),
+    ('multi_1x1_residual_bn64', 8, 64, 56, 56, 256, 1, 1, 0, 1, 1, 0, 64),
+    ('multi_1x1_plain_k128', 6, 128, 56, 56, 256, 1, 1, 0, 0, 1, 0, 0),
+    ('multi_3x3_c64', 8, 64, 56, 56, 64, 3, 1, 1, 0, 1, 0, 0),
+    ('multi_fpn_topdown', 8, 256, 28, 28, 256, 1, 1, 0, 2, 0, 0, 0),
+    ('multi_3x3_c128_bn128', 8, 128, 28, 28, 256, 3, 1, 1, 0, 0, 0, 128),
 ]
 # max |err| relative to max |ref|: split-fp16 x3 and the fp32 CUDA-core kernel are fp32-class,
 # single fp16 carries 2^-11 operand rounding
-TOL = {'simt': 5e-6, 'fp16x3': 2e-5, 'fp16lo8': 2e-4, 'fp16': 1e-3}
+TOL = {'simt': 5e-6, 'fp16x3': 2e-5, 'fp16': 1e-3}
 
 
 def _run(engine, case, out_mode=0):
@@ -57,13 +65,13 @@ def _run(engine, case, out_mode=0):
     return (out.double() - ref).abs().max().item() / ref.abs().max().item()
 
 
-@pytest.mark.parametrize('engine', ['simt', 'fp16x3', 'fp16lo8', 'fp16'])
+@pytest.mark.parametrize('engine', ['simt', 'fp16x3', 'fp16'])
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_conv_parity(engine, case):
     assert _run(engine, case) < TOL[engine]
 
 
-@pytest.mark.parametrize('engine', ['fp16x3', 'fp16lo8', 'fp16'])
+@pytest.mark.parametrize('engine', ['fp16x3', 'fp16'])
 @pytest.mark.parametrize('case', [CASES[0], CASES[1], CASES[3], CASES[4], CASES[9]], ids=lambda c: c[0])
 def test_conv_parity_fp32_epilogue(engine, case):
     """out_mode=1: the direct fp32 store epilogue the head's Linear layers use."""

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 # north_star: "within 1e-3 on the regressed (yaw, pitch)" -> the parity mode (fp16x3) and the fp32
 # CUDA-core mode must meet it; the single-fp16 fast mode is documented as ~3e-3 and only bounded.
-YAW_PITCH_TOL = {'fp16x3': 1e-3, 'fp16lo8': 1e-3, 'simt': 1e-3, 'fp16': 2e-2}
+YAW_PITCH_TOL = {'fp16x3': 1e-3, 'simt': 1e-3, 'fp16': 2e-2}
 KEYS = ('gaze_score', 'face_gaze_score', 'eyes_gaze_score', 'head_gaze_score')
 
 
@@ -37,7 +37,7 @@ def engines(synthetic_sd):
         e.close()
 
 
-@pytest.mark.parametrize('precision', ['fp16x3', 'fp16lo8', 'simt', 'fp16'])
+@pytest.mark.parametrize('precision', ['fp16x3', 'simt', 'fp16'])
 def test_single_clip_vs_oracle(engines, synthetic_sd, precision):
     """BASELINE configs[0]: one 7-frame 224x224 clip, random weights, (yaw,pitch) vs the fp32 reference path."""
     img = O.make_clip(0, 7)
@@ -52,7 +52,7 @@ def test_single_clip_vs_oracle(engines, synthetic_sd, precision):
         assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
 
 
-@pytest.mark.parametrize('precision', ['fp16x3', 'fp16lo8'])
+@pytest.mark.parametrize('precision', ['fp16x3'])
 @pytest.mark.parametrize('name', ['t7_224', 't3_192x224_rescale', 't1_224'])
 def test_vs_reference_fixtures(engines, golden_dir, name, precision):
     """Outputs of the reference's own MultiClueGaze.forward (oracle/gen_golden.py) on the same inputs."""
@@ -92,7 +92,7 @@ def test_intermediates_per_layer(engines, synthetic_sd):
     eng.set_option('keep_intermediates', 1)
     eng.forward(img.cuda())
     torch.cuda.synchronize()
-    for n in ['stem', 'pool', 'layer1.2', 'layer2.3', 'layer3.5', 'layer4.2', 'fpn0', 'fpn1', 'fpn2', 'fpn3']:
+    for n in ['pool', 'layer1.2', 'layer2.3', 'layer3.5', 'layer4.2', 'fpn0', 'fpn1', 'fpn2', 'fpn3']:
         got, r = eng.intermediate(n).cpu(), taps[n]
         assert got.shape == r.shape
         assert (got - r).abs().max() < 1e-4 * r.abs().max(), n
@@ -105,6 +105,39 @@ def test_intermediates_per_layer(engines, synthetic_sd):
             got, r = eng.intermediate(mine).cpu(), taps[theirs]
             assert (got - r).abs().max() < 5e-4 * max(r.abs().max().item(), 1.0), mine
     eng.set_option('keep_intermediates', 0)
+
+
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16'])
+@pytest.mark.parametrize('shape', [(2, 224, 224), (1, 96, 128), (1, 320, 320), (1, 256, 448), (3, 64, 64)],
+                         ids=lambda s: 'x'.join(map(str, s)))
+def test_fused_stem_matches_unfused_chain_and_oracle(engines, synthetic_sd, precision, shape):
+    """The fused conv7x7/2 + BN + ReLU + max-pool kernel against the oracle's pooled stem map and against the
+    unfused im2col -> GEMM -> max-pool chain (which also exposes the 112^2 stem map), over image sizes that
+    need one, two (W/4 > 60) or partially filled column groups."""
+    T, H, W = shape
+    img = O.make_clip(11, T, H, W)
+    taps = {}
+    O.forward(synthetic_sd, img, clip_length=T, hk=O.Hooks(tap=lambda n, t: taps.__setitem__(n, t.clone())))
+    eng = engines(precision)
+    tol = 1e-5 if precision == 'fp16x3' else 2e-3
+    eng.set_option('keep_intermediates', 1)
+    try:
+        eng.forward(img.cuda(), clip_length=T)
+        fused = eng.intermediate('pool').cpu()
+        eng.set_option('fused_stem', 0)
+        eng.forward(img.cuda(), clip_length=T)
+        chain = eng.intermediate('pool').cpu()
+        stem = eng.intermediate('stem').cpu()
+    finally:
+        eng.set_option('fused_stem', 1)
+        eng.set_option('keep_intermediates', 0)
+    scale = taps['pool'].abs().max()
+    assert fused.shape == taps['pool'].shape
+    assert (stem - taps['stem']).abs().max() < tol * taps['stem'].abs().max()
+    assert (chain - taps['pool']).abs().max() < tol * scale
+    assert (fused - taps['pool']).abs().max() < tol * scale
+    if precision == 'fp16x3':
+        assert (fused - chain).abs().max() < 2e-6 * scale
 
 
 def test_host_entry_and_graph_replay_match_eager(engines):
@@ -158,7 +191,7 @@ def test_pipelined_host_submissions(engines):
             eng.set_graph_mode(False)
 
 
-@pytest.mark.parametrize('precision', ['fp16x3', 'fp16lo8', 'fp16'])
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16'])
 def test_full_batch_properties(engines, precision):
     """BASELINE configs[1] size (32 clips x 7 frames x 224^2): clips are independent units, so
     (a) a clip's result must not depend on its batch neighbours (bit-exact), (b) permuting clips

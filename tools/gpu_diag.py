@@ -159,9 +159,6 @@ GROUPS = {
     'conv_simt': lambda: group_conv('simt'),
     'conv_fp16x3': lambda: group_conv('fp16x3'),
     'conv_fp16': lambda: group_conv('fp16'),
-    'conv_fp16lo8': lambda: group_conv('fp16lo8'),
-    'forward_fp16lo8': lambda: group_forward('fp16lo8'),
-    'bench_fp16lo8_graph': lambda: group_bench('fp16lo8', graph=1),
     'forward_simt': lambda: group_forward('simt'),
     'forward_fp16x3': lambda: group_forward('fp16x3'),
     'forward_fp16': lambda: group_forward('fp16'),

@@ -1,5 +1,5 @@
-"""Per-layer device times of the tcgen05 GEMM launches (CUDA events, warm, eager).
-usage: python tools/layer_times.py <precision> [B]      (env MCG_DEBUG_FLAGS for attribution experiments)"""
+"""Device time of every kernel of the forward (CUDA events after each launch, warm, eager mode).
+usage: python tools/layer_times.py <precision> [B] [detail]      (env MCG_* tuning / attribution flags apply)"""
 import collections
 import json
 import os
@@ -12,27 +12,28 @@ import torch  # noqa: E402
 from mcgaze_b200 import lib  # noqa: E402
 from oracle import mcgaze_oracle as O  # noqa: E402
 
-precision = sys.argv[1] if len(sys.argv) > 1 else 'fp16lo8'
+precision = sys.argv[1] if len(sys.argv) > 1 else 'fp16x3'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-names = ['stem']
-for l, n in enumerate((3, 4, 6, 3)):
-    for b in range(n):
-        names += [f'l{l+1}b{b}c1', f'l{l+1}b{b}c2'] + ([f'l{l+1}b{b}ds'] if b == 0 else []) + [f'l{l+1}b{b}c3']
-names += ['lat3', 'lat2', 'lat1', 'lat0', 'fpn0', 'fpn1', 'fpn2', 'fpn3']
-for s in range(4):
-    names += [f's{s}dyn', f's{s}fc', f's{s}ffn1', f's{s}ffn2']
+detail = len(sys.argv) > 3
 eng = lib.Engine(O.make_state_dict(0), 0, precision)
 img = torch.randn(B * 7, 3, 224, 224, device='cuda')
 out = eng.forward(img, clip_length=7)
 eng.set_option('time_kernels', 1)
 acc = collections.OrderedDict()
+cnt = collections.Counter()
 reps = 3
 for _ in range(reps):
     eng.forward_into(img, 7, out)
     torch.cuda.synchronize()
-    for nm, t in zip(names, eng.umma_times()):
-        key = re.sub(r'b\d', '', nm)
-        key = re.sub(r'^s\d', 'head_', key)
-        acc[key] = acc.get(key, 0.0) + t * 1e3 / reps
-print(json.dumps({'precision': precision, 'flags': os.environ.get('MCG_DEBUG_FLAGS', '0'),
-                  'total_us': round(sum(acc.values())), 'layers_us': {k: round(v, 1) for k, v in acc.items()}}))
+    for nm, ms in eng.kernel_profile():
+        key = nm
+        if not detail:
+            key = re.sub(r'^umma:l(\d)b\d+', r'umma:l\1', key)
+            key = re.sub(r'^umma:s\d', 'umma:head_', key)
+        acc[key] = acc.get(key, 0.0) + ms * 1e3 / reps
+        cnt[key] += 1
+env = {k: v for k, v in os.environ.items() if k.startswith('MCG_')}
+gemm = sum(v for k, v in acc.items() if k.startswith('umma:'))
+print(json.dumps({'precision': precision, 'env': env, 'total_us': round(sum(acc.values())), 'gemm_us': round(gemm),
+                  'other_us': round(sum(acc.values()) - gemm),
+                  'kernels_us': {k: [round(v, 1), cnt[k] // reps] for k, v in acc.items()}}))
