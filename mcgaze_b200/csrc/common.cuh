@@ -12,13 +12,14 @@
 namespace mcg {
 
 // Split tensor: value = hi + lo.  hi is fp16.  The low part is stored either as fp16 (`lo`, mode
-// fp16x3) or as e4m3 fp8 of (value - hi) * 2^kLo8Shift (`lo8`, mode fp16lo8: 3 bytes / element and an
-// fp8 tensor-core correction term); both null means single-fp16 ("fast") storage.
+// fp16x3) or as e4m3 fp8 of (value - hi) * 2^kLo8Shift (`lo8`, mode fp16c8: 3 bytes / element and
+// fp8 tensor-core correction terms); both null means single-fp16 ("fast") storage.
 // Layout of every activation is NHWC (channels innermost), i.e. a row-major [pixels, C] matrix.
 struct Planes {
   __half* hi = nullptr;
   __half* lo = nullptr;
   uint8_t* lo8 = nullptr;
+  uint8_t* hi8 = nullptr;  // e4m3(hi): second fp8 operand of "T" layers (fp16c8 mode)
 };
 
 // |value - hi| <= 2^-11 |value|; 2^13 maps the residue of |value| in [2^-8, 32] into e4m3's normal range
@@ -51,6 +52,7 @@ struct Epilogue {
   __half* out_hi = nullptr;
   __half* out_lo = nullptr;
   uint8_t* out_lo8 = nullptr;
+  uint8_t* out_hi8 = nullptr;    // optional e4m3 copy of out_hi (fp16c8: input of a tensor-bound consumer)
   float* out_f32 = nullptr;      // if non-null, fp32 output instead of planes
   long long ldo = 0;             // output row stride (elements)
   long long ldr = 0;             // residual row stride (elements)
@@ -74,11 +76,13 @@ __host__ __device__ inline long long res_row(const Epilogue& e, long long m) {
   return (n * (e.P / 2) + (p >> 1)) * (e.Q / 2) + (q >> 1);
 }
 
-__device__ __forceinline__ void split_store(float v, __half* hi, __half* lo, long long idx, uint8_t* lo8 = nullptr) {
+__device__ __forceinline__ void split_store(float v, __half* hi, __half* lo, long long idx, uint8_t* lo8 = nullptr,
+                                            uint8_t* hi8 = nullptr) {
   __half h = __float2half_rn(v);
   hi[idx] = h;
   if (lo) lo[idx] = __float2half_rn(v - __half2float(h));
   if (lo8) lo8[idx] = float_to_e4m3((v - __half2float(h)) * kLo8Scale);
+  if (hi8) hi8[idx] = float_to_e4m3(__half2float(h));
 }
 
 // 8 consecutive e4m3 values (one uint2) -> 8 floats (unscaled)

@@ -728,14 +728,22 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const LinGroups grp,
 
 // fp32 [rows, C] (row stride ld) -> split-fp16 planes [rows, C] (dense)
 __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, long long rows, int C,
-                                    __half* __restrict__ hi, __half* __restrict__ lo, uint8_t* __restrict__ lo8 = nullptr) {
+                                    __half* __restrict__ hi, __half* __restrict__ lo, uint8_t* __restrict__ lo8 = nullptr,
+                                    uint8_t* __restrict__ hi8 = nullptr) {
   const long long total = rows * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C;
     const int c = static_cast<int>(i - r * C);
-    split_store(x[r * ld + c], hi, lo, i, lo8);
+    split_store(x[r * ld + c], hi, lo, i, lo8, hi8);
   }
+}
+
+// e4m3 plane -> fp32 (unscaled; debug only)
+__global__ void e4m3_to_f32_kernel(const uint8_t* __restrict__ p8, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = e4m3_to_float(p8[i]);
 }
 
 // split-fp16 planes -> dense fp32, same layout (debug only)

@@ -94,8 +94,9 @@ struct GemmW {  // packed [N, K] weight (+ bias) on device
   int N = 0, K = 0;
   const float* w_f32 = nullptr;
   const float* w_t = nullptr;  // [K, N] transposed copy for small_linear_kernel (small layers only)
-  Planes w;                    // hi / lo fp16 planes; w.lo8 = e4m3(hi * 2^w_shift) for the fp16lo8 mode
-  int w_shift = 0;
+  Planes w;                    // hi / lo fp16 planes; fp16c8 conv weights also carry w.hi8 = e4m3(hi 2^s_n),
+                               // w.lo8 = e4m3(lo 2^(13+s_n)) with a per-output-channel shift s_n
+  const float* cscale = nullptr;  // [N] 2^-(13+s_n): factor of the fp8 correction accumulator
   const float* bias = nullptr;
 };
 struct LnW {
@@ -139,8 +140,6 @@ class Engine {
     cudaDeviceProp prop;
     MCG_CUDA(cudaGetDeviceProperties(&prop, device));
     num_sms_ = prop.multiProcessorCount;
-    MCG_CHECK(precision != MCG_PRECISION_FP16LO8,
-              "precision fp16lo8 was removed (superseded; use fp16x3 for parity or fp16 for speed)");
     if (precision != MCG_PRECISION_SIMT)
       MCG_CHECK(prop.major == 10, "tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major) +
                                       std::to_string(prop.minor));
@@ -381,7 +380,31 @@ class Engine {
   }
   bool has(const std::string& k) const { return host_.count(k) != 0; }
 
-  GemmW pack_gemm(const std::vector<float>& w, int N, int K, const float* bias) {
+  // e4m3 operand planes of the fp16c8 correction MMAs.  Per output channel n the shift s_n puts the largest
+  // |W[n,:]| into (56, 112]: hi8 <= 112 and lo8 = lo 2^(13+s_n) <= 2^-11 2^13 112 = 448 (the e4m3 maximum).
+  void pack_c8(GemmW& g, const std::vector<float>& w, const std::vector<__half>& hi, int N, int K) {
+    std::vector<uint8_t> hi8(w.size()), lo8(w.size());
+    std::vector<float> cs(N);
+    for (int n = 0; n < N; ++n) {
+      float mx = 0.f;
+      for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(w[static_cast<size_t>(n) * K + k]));
+      int sh = mx > 0.f ? static_cast<int>(std::floor(std::log2(112.0 / mx))) : 0;
+      sh = std::max(-40, std::min(40, sh));
+      const float s1 = std::ldexp(1.f, sh), s2 = std::ldexp(1.f, sh + kLo8Shift);
+      for (int k = 0; k < K; ++k) {
+        const size_t i = static_cast<size_t>(n) * K + k;
+        const float h = __half2float(hi[i]);
+        hi8[i] = float_to_e4m3(h * s1);
+        lo8[i] = float_to_e4m3((w[i] - h) * s2);
+      }
+      cs[n] = std::ldexp(1.f, -(sh + kLo8Shift));
+    }
+    g.w.hi8 = upload(keep_, hi8);
+    g.w.lo8 = upload(keep_, lo8);
+    g.cscale = upload(keep_, cs);
+  }
+
+  GemmW pack_gemm(const std::vector<float>& w, int N, int K, const float* bias, bool c8 = false) {
     GemmW g;
     g.N = N;
     g.K = K;
@@ -394,6 +417,7 @@ class Engine {
     }
     g.w.hi = upload(keep_, hi);
     g.w.lo = upload(keep_, lo);
+    if (c8) pack_c8(g, w, hi, N, K);
     if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
     if (N <= 768 && K <= 2048 && K % 32 == 0) {
       std::vector<float> t(w.size());
@@ -435,7 +459,7 @@ class Engine {
             packed[static_cast<size_t>(o) * Kp + (r * S + s) * Cin + c] =
                 w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s] * scale[o];
     ConvW cw;
-    cw.g = pack_gemm(packed, Cout, Kp, shift.data());
+    cw.g = pack_gemm(packed, Cout, Kp, shift.data(), precision_ == MCG_PRECISION_FP16C8);
     cw.Cin = Cin;
     cw.Cout = Cout;
     cw.R = R;
@@ -541,24 +565,26 @@ class Engine {
     int NB = 0, H = 0, W = 0, C = 0;
     long long rows() const { return static_cast<long long>(NB) * H * W; }
   };
-  Act new_act(int NB, int H, int W, int C) {
+  // hi8: the tensor is read by a tensor-bound ("T") layer of the fp16c8 mode and carries an e4m3 copy of hi
+  Act new_act(int NB, int H, int W, int C, bool hi8 = false) {
     Act a;
     a.NB = NB;
     a.H = H;
     a.W = W;
     a.C = C;
     const size_t n = static_cast<size_t>(NB) * H * W * C;
-    a.pl = alloc_planes(n);
+    a.pl = alloc_planes(n, hi8);
     return a;
   }
-  // low-part storage of the trunk's activations: fp16 (fp16x3 / simt), e4m3 (fp16lo8) or none (fp16)
+  // low-part storage of the trunk's activations: fp16 (fp16x3 / simt), e4m3 (fp16c8) or none (fp16)
   bool lo_fp16() const { return precision_ == MCG_PRECISION_FP16X3 || precision_ == MCG_PRECISION_SIMT; }
-  bool lo_fp8() const { return precision_ == MCG_PRECISION_FP16LO8; }
-  Planes alloc_planes(size_t n) {
+  bool lo_fp8() const { return precision_ == MCG_PRECISION_FP16C8; }
+  Planes alloc_planes(size_t n, bool hi8 = false) {
     Planes pl;
     pl.hi = arena_.alloc<__half>(n);
     pl.lo = lo_fp16() ? arena_.alloc<__half>(n) : nullptr;
     pl.lo8 = lo_fp8() ? arena_.alloc<uint8_t>(n) : nullptr;
+    pl.hi8 = (lo_fp8() && hi8) ? arena_.alloc<uint8_t>(n) : nullptr;
     return pl;
   }
 
@@ -591,22 +617,28 @@ class Engine {
     pool_out_ = new_act(NB, P2, Q2, 64);
     int h = P2, w = Q2;
     const int planes_c[4] = {64, 128, 256, 512};
+    // fp16c8: tensors read by tensor-bound layers carry the hi8 plane (SURVEY App. D arithmetic intensities):
+    // bit 0: inputs of the 3x3 convolutions (t1, FPN laterals); bit 1: layer4's 1x1 inputs and the output of
+    // layer3 (-> layer4.0.conv1 / downsample, lateral 2: K >= 1024)
+    static const int tune_t = tune_env("MCG_TUNE_TMODE");
+    const int tmask = tune_t > 0 ? tune_t - 1 : 3;
     for (int l = 0; l < 4; ++l) {
       blk_act_[l].clear();
       for (size_t b = 0; b < blocks_[l].size(); ++b) {
         const int stride = blocks_[l][b].c2.stride;
+        const bool last = b + 1 == blocks_[l].size();
         BlkAct ba;
-        ba.t1 = new_act(NB, h, w, planes_c[l]);
-        ba.t2 = new_act(NB, h / stride, w / stride, planes_c[l]);
+        ba.t1 = new_act(NB, h, w, planes_c[l], (tmask & 1) != 0);
+        ba.t2 = new_act(NB, h / stride, w / stride, planes_c[l], (tmask & 2) && l == 3);
         if (blocks_[l][b].has_ds) ba.ds = new_act(NB, h / stride, w / stride, planes_c[l] * 4);
-        ba.out = new_act(NB, h / stride, w / stride, planes_c[l] * 4);
+        ba.out = new_act(NB, h / stride, w / stride, planes_c[l] * 4, (tmask & 2) && (l == 3 || (l == 2 && last)));
         h /= stride;
         w /= stride;
         blk_act_[l].push_back(ba);
       }
     }
     for (int i = 0; i < 4; ++i) {
-      lat_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256);
+      lat_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256, (tmask & 1) != 0);
       fpn_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256);
     }
     const size_t Rr = static_cast<size_t>(NB) * 3;
@@ -669,17 +701,18 @@ class Engine {
     switch (precision_) {
       case MCG_PRECISION_SIMT: return 0;
       case MCG_PRECISION_FP16X3: return 3;
+      case MCG_PRECISION_FP16C8: return 2;
       default: return 1;
     }
   }
   void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
             long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0) {
     const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
-                        (terms == 1 || (terms == 3 && A->lo != nullptr));
+                        (terms == 1 || (terms == 3 && A->lo != nullptr) || (terms == 2 && A->lo8 != nullptr && w.cscale != nullptr));
     if (tensor) {
       auto it = plans_.find(key);
       if (it == plans_.end()) {
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride);
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, w.cscale);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -742,6 +775,7 @@ class Engine {
     ep.out_hi = y.pl.hi;
     ep.out_lo = y.pl.lo;
     ep.out_lo8 = y.pl.lo8;
+    ep.out_hi8 = y.pl.hi8;
     ep.ldo = y.C;
     if (res) {
       ep.res_hi = res->pl.hi;
@@ -931,7 +965,9 @@ class Engine {
     const bool fused_stem = fused_stem_ && precision_ != MCG_PRECISION_SIMT && stem_fused_supported(H, W);
     if (fused_stem) {
       if (!stem_plan_valid_) {
-        stem_plan_ = make_stem_fused_plan(trunk_terms(), img, NB, H, W, stem_.g.w, stem_.g.bias, pool_out_.pl, num_sms_);
+        // fp16c8: the stem (2 % of the FLOPs, builder-bound) keeps the 3-term fp16 products and writes hi + lo8
+        stem_plan_ = make_stem_fused_plan(trunk_terms() == 1 ? 1 : 3, img, NB, H, W, stem_.g.w, stem_.g.bias, pool_out_.pl,
+                                          num_sms_);
         stem_plan_valid_ = true;
       }
       stem_plan_.p.img = img;
@@ -1251,7 +1287,7 @@ const char* mcg_version(void) { return "mcgaze_b200 0.1 (sm_100a)"; }
 
 int mcg_create(mcg_handle* out, int device, const mcg_tensor* weights, int n_weights, int precision) {
   return guarded([&]() -> int {
-    if (!out || !weights || n_weights <= 0 || precision < 0 || precision > 3) {
+    if (!out || !weights || n_weights <= 0 || precision < 0 || precision > MCG_PRECISION_FP16C8) {
       mcg::g_last_error = "mcg_create: invalid argument";
       return MCG_ERR_INVALID;
     }
@@ -1396,19 +1432,55 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
       RW = Q / 2;
     }
     const size_t nr = res ? static_cast<size_t>(NB) * RH * RW * Cout : 0;
-    if (engine == MCG_PRECISION_FP16LO8) {
-      g_last_error = "mcg_debug_conv: precision fp16lo8 was removed";
-      return MCG_ERR_UNSUPPORTED;
-    }
+    // fp16c8: out_mode bit 1 = "T" layer (A carries the hi8 plane, both corrections in e4m3), bit 2 = return the
+    // emitted hi8 output plane (as fp32) instead of hi + lo8
+    const bool c8 = engine == MCG_PRECISION_FP16C8;
+    const bool c8_t = c8 && (out_mode & 2);
+    const bool c8_hi8_out = c8 && (out_mode & 4);
+    out_mode &= 1;
     DeviceBlock bx(nx * 4), bw(nw * 4), br(nr * 4 + 16);
+    DeviceBlock bx8(c8 ? nx * 2 : 16), bw8(c8 ? nw * 2 : 16), br8(c8 ? nr + 16 : 16), bcs(c8 ? Cout * 4 : 16);
     Planes px{reinterpret_cast<__half*>(bx.p), reinterpret_cast<__half*>(bx.p) + nx, nullptr};
     Planes pw{reinterpret_cast<__half*>(bw.p), reinterpret_cast<__half*>(bw.p) + nw, nullptr};
     Planes pr{reinterpret_cast<__half*>(br.p), reinterpret_cast<__half*>(br.p) + nr, nullptr};
-    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, px.lo);
+    if (c8) {
+      px.lo8 = reinterpret_cast<uint8_t*>(bx8.p);
+      if (c8_t) px.hi8 = px.lo8 + nx;
+      pr.lo8 = reinterpret_cast<uint8_t*>(br8.p);
+    }
+    split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, px.lo, px.lo8, px.hi8);
     split_planes_kernel<<<1024, 256, 0, st>>>(w, K, Cout, K, pw.hi, pw.lo);
     if (res)
-      split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi, pr.lo);
+      split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi, pr.lo, pr.lo8);
     MCG_CUDA(cudaGetLastError());
+    const float* cscale = nullptr;
+    if (c8) {
+      // same per-channel e4m3 packing as Engine::pack_c8, on the host
+      std::vector<float> hw(nw), cs(Cout);
+      std::vector<uint8_t> hi8(nw), lo8(nw);
+      MCG_CUDA(cudaMemcpyAsync(hw.data(), w, nw * 4, cudaMemcpyDeviceToHost, st));
+      MCG_CUDA(cudaStreamSynchronize(st));
+      for (int n = 0; n < Cout; ++n) {
+        float mx = 0.f;
+        for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(hw[static_cast<size_t>(n) * K + k]));
+        int sh = mx > 0.f ? static_cast<int>(std::floor(std::log2(112.0 / mx))) : 0;
+        sh = std::max(-40, std::min(40, sh));
+        const float s1 = std::ldexp(1.f, sh), s2 = std::ldexp(1.f, sh + kLo8Shift);
+        for (int k = 0; k < K; ++k) {
+          const size_t i = static_cast<size_t>(n) * K + k;
+          const float h = __half2float(__float2half_rn(hw[i]));
+          hi8[i] = float_to_e4m3(h * s1);
+          lo8[i] = float_to_e4m3((hw[i] - h) * s2);
+        }
+        cs[n] = std::ldexp(1.f, -(sh + kLo8Shift));
+      }
+      pw.hi8 = reinterpret_cast<uint8_t*>(bw8.p);
+      pw.lo8 = pw.hi8 + nw;
+      MCG_CUDA(cudaMemcpy(pw.hi8, hi8.data(), nw, cudaMemcpyHostToDevice));
+      MCG_CUDA(cudaMemcpy(pw.lo8, lo8.data(), nw, cudaMemcpyHostToDevice));
+      MCG_CUDA(cudaMemcpy(bcs.p, cs.data(), Cout * 4, cudaMemcpyHostToDevice));
+      cscale = reinterpret_cast<const float*>(bcs.p);
+    }
     AGeom g;
     const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col;
     g.kind = plain ? 0 : 1;
@@ -1434,13 +1506,18 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     if (planes_out) {
       ep.out_hi = po.hi;
       ep.out_lo = engine == MCG_PRECISION_FP16X3 ? po.lo : nullptr;
+      if (c8) {
+        ep.out_lo8 = reinterpret_cast<uint8_t*>(po.lo);
+        ep.out_hi8 = c8_hi8_out ? ep.out_lo8 + ny : nullptr;
+      }
     } else {
       ep.out_f32 = out;
     }
     ep.ldo = Cout;
     if (res) {
       ep.res_hi = pr.hi;
-      ep.res_lo = pr.lo;
+      ep.res_lo = c8 ? nullptr : pr.lo;
+      ep.res_lo8 = pr.lo8;
       ep.res_mode = res_mode;
       ep.ldr = Cout;
       ep.P = P;
@@ -1468,11 +1545,14 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
         return MCG_ERR_UNSUPPORTED;
       }
       if (engine == MCG_PRECISION_FP16 && res) ep.res_lo = nullptr;
-      const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : 1;
-      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n);
+      const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : c8 ? 2 : 1;
+      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n, 1, 0, cscale);
       launch_umma(pl, st);
       if (planes_out) {
-        planes_to_f32_kernel<<<1024, 256, 0, st>>>(po.hi, ep.out_lo, ep.out_lo8, static_cast<long long>(ny), out);
+        if (c8_hi8_out)
+          e4m3_to_f32_kernel<<<1024, 256, 0, st>>>(ep.out_hi8, static_cast<long long>(ny), out);
+        else
+          planes_to_f32_kernel<<<1024, 256, 0, st>>>(po.hi, ep.out_lo, ep.out_lo8, static_cast<long long>(ny), out);
         MCG_CUDA(cudaGetLastError());
       }
     }

@@ -42,7 +42,7 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, long long m, 
   if (ep.out_f32)
     ep.out_f32[oi] = v;
   else
-    split_store(v, ep.out_hi, ep.out_lo, oi, ep.out_lo8);
+    split_store(v, ep.out_hi, ep.out_lo, oi, ep.out_lo8, ep.out_hi8);
 }
 
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtParams p) {

@@ -44,6 +44,7 @@ struct StemFusedParams {
   const float* bias = nullptr; // [64] folded BN shift
   __half* out_hi = nullptr;    // [NB, H/4, W/4, 64]
   __half* out_lo = nullptr;
+  uint8_t* out_lo8 = nullptr;  // fp16c8 storage: e4m3((v - hi) 2^13) instead of the fp16 lo plane
   int NB = 0, H = 0, W = 0;
   int P = 0, Q = 0;            // stem map
   int PP = 0, QQ = 0;          // pooled map
@@ -135,30 +136,29 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
         for (int kt = 0; kt < 3; ++kt) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          {
+            // warp-uniform: descriptors live in uniform registers, umma_* elect the issuing lane
             const uint32_t aA_hi = ptx::smem_u32(a_ring + stage * sf_a_stage_bytes(kTerms));
             const uint32_t aA_lo = aA_hi + kATileBytes;
             const uint32_t aW_hi = ptx::smem_u32(w_smem + kt * kSfWTileBytes);
             const uint32_t aW_lo = aW_hi + 3 * kSfWTileBytes;
+            const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(aA_hi);
+            const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(aW_hi);
+            const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(aA_lo);
+            const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(aW_lo);
             const int ksteps = kt == 2 ? (kSfK - 128) / kUmmaK : 4;
             for (int j = 0; j < ksteps; ++j) {
-              const uint32_t koff = j * kUmmaK * 2;
-              const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(aA_hi + koff);
-              const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(aW_hi + koff);
               uint32_t accum = (kt > 0 || j > 0) ? 1u : 0u;
               if (kTerms == 3) {
-                const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(aA_lo + koff);
-                const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(aW_lo + koff);
-                ptx::umma_f16(tmem_d, dA_lo, dW_hi, idesc, accum);
-                ptx::umma_f16(tmem_d, dA_hi, dW_lo, idesc, 1u);
+                ptx::umma_f16(tmem_d, dA_lo + 2 * j, dW_hi + 2 * j, idesc, accum);
+                ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, 1u);
                 accum = 1u;
               }
-              ptx::umma_f16(tmem_d, dA_hi, dW_hi, idesc, accum);
+              ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_hi + 2 * j, idesc, accum);
             }
             ptx::umma_commit(&empty_bar[stage]);
             if (d == 2 && kt == 2) ptx::umma_commit(&tfull_bar[ab]);
           }
-          __syncwarp();
           if (++stage == kSfStages) {
             stage = 0;
             phase ^= 1u;
@@ -330,6 +330,12 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
               ul.w = ptx::residue_half2(v[8 * c8 + 6], v[8 * c8 + 7], uh.w);
               ol[c8] = ul;
             }
+            if (p.out_lo8) {
+              uint2 l8;
+              l8.x = residue_e4m3x2(v[8 * c8 + 0], v[8 * c8 + 1], uh.x) | (residue_e4m3x2(v[8 * c8 + 2], v[8 * c8 + 3], uh.y) << 16);
+              l8.y = residue_e4m3x2(v[8 * c8 + 4], v[8 * c8 + 5], uh.z) | (residue_e4m3x2(v[8 * c8 + 6], v[8 * c8 + 7], uh.w) << 16);
+              *reinterpret_cast<uint2*>(p.out_lo8 + o + 8 * c8) = l8;
+            }
           }
         }
       }
@@ -361,7 +367,7 @@ inline bool stem_fused_supported(int H, int W) { return H % 4 == 0 && W % 8 == 0
 inline StemFusedPlan make_stem_fused_plan(int terms, const float* img, int NB, int H, int W, Planes Wt, const float* bias,
                                           Planes out, int num_sms) {
   MCG_CHECK(stem_fused_supported(H, W), "fused stem needs H % 4 == 0 and W % 8 == 0");
-  MCG_CHECK(terms == 1 || (terms == 3 && Wt.lo && out.lo), "fused stem: 3-term mode needs lo planes");
+  MCG_CHECK(terms == 1 || (terms == 3 && Wt.lo && (out.lo || out.lo8)), "fused stem: 3-term mode needs lo planes");
   StemFusedPlan pl;
   pl.terms = terms;
   StemFusedParams& p = pl.p;
@@ -369,6 +375,7 @@ inline StemFusedPlan make_stem_fused_plan(int terms, const float* img, int NB, i
   p.bias = bias;
   p.out_hi = out.hi;
   p.out_lo = terms == 3 ? out.lo : nullptr;
+  p.out_lo8 = terms == 3 ? out.lo8 : nullptr;
   p.NB = NB;
   p.H = H;
   p.W = W;

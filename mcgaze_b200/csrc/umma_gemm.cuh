@@ -10,6 +10,14 @@
 // (hi*hi, "fast" mode); kTerms == 3 issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM
 // accumulator (~22-bit operand mantissa: fp32-equivalent products, the mode that meets the
 // 1e-3 (yaw,pitch) parity bar against the fp32 oracle).
+// kTerms == 2 ("fp16c8") keeps hi*hi in fp16 and moves the two rounding corrections to e4m3 tensor-core
+// MMAs (kind::f8f6f4, K = 32 per instruction, twice the fp16 rate) that accumulate into a SECOND TMEM
+// accumulator which the epilogue scales per output channel and adds:
+//     A*W ~= A_hi*W_hi + [ e4m3(A_lo 2^13) * e4m3(W_hi 2^s_n) + e4m3(A_hi) * e4m3(W_lo 2^(13+s_n)) ] 2^-(13+s_n)
+// Activations are stored as fp16 hi + e4m3 lo8 (3 bytes / element instead of 4).  The e4m3 copy of A_hi
+// ("hi8" plane) is written by the producing layer only for consumers that are tensor-bound ("T" layers: 8
+// MMA units per 64-wide k-block instead of 12); HBM-bound consumers ("H" layers) read hi + lo8 only and run
+// the weight correction A_hi*W_lo as a second fp16 MMA (10 units).
 //
 // Structure (persistent, one CTA per SM, 384 threads):
 //   warp 0    : TMA producer  (one elected lane; A tile 128 x 64, W tile block_n x 64, SWIZZLE_128B)
@@ -28,6 +36,7 @@
 // residual mbarriers.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -66,21 +75,71 @@ struct UmmaParams {
   int out_tma = 0;  // planes output through smem staging + TMA store
   int out_sets = 1; // staging sets per epilogue group for the TMA-store epilogue (2 = double buffered)
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
+  int tmode = 0;    // kTerms == 2: A has an e4m3 copy of hi (hi8), both corrections run as fp8 MMAs
+  int out_hi8 = 0;  // kTerms == 2: also emit the e4m3 copy of the output's hi plane (TMA-store epilogue only)
+  const float* cscale = nullptr;  // kTerms == 2: [N] factor of the fp8 correction accumulator, 2^-(13 + s_n)
   int dbg = 0;      // attribution experiments only (env MCG_DEBUG_FLAGS): 1 no stores, 2 no epilogue math,
                     // 4 no A loads, 8 no W loads, 16 no MMA issue, 32 no residual loads.  Results are garbage.
   AGeom a;
   Epilogue ep;
 };
 
+// kTerms == 2 re-uses the *_lo slots for the e4m3 planes (a_lo = A lo8, o_lo = output lo8, r_lo = residual lo8,
+// w_lo = fp16 W_lo for H layers / e4m3 W_lo8 for T layers)
 struct UmmaMaps {
   CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, r_hi, r_lo;
+  CUtensorMap a_hi8, w_hi8, o_hi8;
 };
 
 // shared-memory bytes of one pipeline stage / one epilogue staging set for a precision mode
-__host__ __device__ constexpr int a_stage_bytes(int terms) { return terms == 3 ? 2 * kATileBytes : kATileBytes; }
-__host__ __device__ constexpr int w_stage_bytes(int terms, int bn) { return (terms == 3 ? 2 : 1) * bn * kBlockK * 2; }
-// one epilogue staging set / residual slot: fp16 hi chunk (+ fp16 lo chunk)
-__host__ __device__ constexpr int epi_set_bytes(int terms) { return (terms == 3 ? 2 : 1) * kEpiPlaneBytes; }
+// kTerms == 2: A = fp16 hi tile + e4m3 lo8 tile (+ e4m3 hi8 tile, T layers);
+//              W = fp16 hi + fp16 lo + e4m3 hi8 (H layers)  or  fp16 hi + e4m3 hi8 + e4m3 lo8 (T layers)
+__host__ __device__ constexpr int a_stage_bytes(int terms, int tmode = 0) {
+  return terms == 3 ? 2 * kATileBytes : terms == 2 ? kATileBytes + (tmode ? 2 : 1) * (kATileBytes / 2) : kATileBytes;
+}
+__host__ __device__ constexpr int w_stage_bytes(int terms, int bn, int tmode = 0) {
+  return terms == 3 ? 2 * bn * kBlockK * 2 : terms == 2 ? bn * kBlockK * (tmode ? 4 : 5) : bn * kBlockK * 2;
+}
+// one epilogue staging set / residual slot: fp16 hi chunk (+ fp16 lo chunk | + e4m3 lo8 chunk + e4m3 hi8 chunk)
+__host__ __device__ constexpr int epi_set_bytes(int terms) { return (terms == 1 ? 1 : 2) * kEpiPlaneBytes; }
+constexpr int kEpiLo8Off = kEpiPlaneBytes;                       // kTerms == 2: [128 x 32 B] e4m3 lo8 chunk
+constexpr int kEpiHi8Off = kEpiPlaneBytes + kEpiPlaneBytes / 2;  //              [128 x 32 B] e4m3 hi8 chunk
+
+// v[0..15] += e4m3x16(u) * 2^-13   (the lo8 plane of a residual)
+__device__ __forceinline__ void add_lo8x16(float* v, const uint4& u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const __half2 k = __float2half2_rn(kLo8InvScale);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>((w[t] >> (16 * h)) & 0xffffu), __NV_E4M3);
+      const __half2 s2 = __hmul2(__half2(hr), k);
+      ptx::add_half2(v[4 * t + 2 * h], v[4 * t + 2 * h + 1], *reinterpret_cast<const uint32_t*>(&s2));
+    }
+  }
+}
+// e4m3x2 of the rounding residue {(a - low(h2)) 2^13, (b - high(h2)) 2^13}
+__device__ __forceinline__ uint32_t residue_e4m3x2(float a, float b, uint32_t h2) {
+  float da, db;
+  asm("{\n"
+      ".reg .b16 l, h;\n"
+      "mov.b32 {l, h}, %2;\n"
+      "neg.f16 l, l;\n"
+      "neg.f16 h, h;\n"
+      "add.rn.f32.f16 %0, l, %3;\n"
+      "add.rn.f32.f16 %1, h, %4;\n"
+      "}\n"
+      : "=f"(da), "=f"(db)
+      : "r"(h2), "f"(a), "f"(b));
+  return static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(da * kLo8Scale, db * kLo8Scale), __NV_SATFINITE, __NV_E4M3));
+}
+__device__ __forceinline__ uint32_t half2_to_e4m3x2(uint32_t h2) {
+  __half2_raw hr;
+  hr.x = static_cast<unsigned short>(h2 & 0xffffu);
+  hr.y = static_cast<unsigned short>(h2 >> 16);
+  return static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(hr, __NV_SATFINITE, __NV_E4M3));
+}
 
 // byte offset of logical 16-byte chunk j of row `row` in a 64B-swizzled [rows][64 B] tile
 __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
@@ -104,8 +163,14 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   const int w_tile_bytes = p.block_n * kBlockK * 2;
-  const int a_bytes = a_stage_bytes(kTerms);
-  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n);
+  const int a_bytes = a_stage_bytes(kTerms, p.tmode);
+  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n, p.tmode);
+  // kTerms == 2 stage layout: [A_hi 16K | A_lo8 8K | (A_hi8 8K)] [W_hi | W_lo (fp16) | W_hi8]   (H layers)
+  //                                                              [W_hi | W_hi8 | W_lo8]          (T layers)
+  const int w8_tile_bytes = p.block_n * kBlockK;
+  const int off_a_hi8 = kATileBytes + kATileBytes / 2;
+  const int off_w_hi8 = a_bytes + w_tile_bytes + (p.tmode ? 0 : w_tile_bytes);
+  const int off_w_lo8 = off_w_hi8 + w8_tile_bytes;  // T layers only
   uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;        // [groups][out_sets][kSet]
   uint8_t* rbuf_base = obuf_base + (p.out_tma ? kEpiGroups * p.out_sets * kSet : 0);       // [groups][kResBufs][kSet]
   const int warp_idx = threadIdx.x >> 5;
@@ -116,9 +181,13 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm.a_hi);
     ptx::prefetch_tmap(&tm.w_hi);
-    if (kTerms == 3) {
+    if (kTerms != 1) {
       ptx::prefetch_tmap(&tm.a_lo);
       ptx::prefetch_tmap(&tm.w_lo);
+    }
+    if (kTerms == 2) {
+      ptx::prefetch_tmap(&tm.w_hi8);
+      if (p.tmode) ptx::prefetch_tmap(&tm.a_hi8);
     }
     if (p.out_tma) ptx::prefetch_tmap(&tm.o_hi);
     if (p.res_tma) ptx::prefetch_tmap(&tm.r_hi);
@@ -146,29 +215,33 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ks = tile / mn_tiles;
-        const int mn = tile - ks * mn_tiles;
-        const int m_tile = mn / p.n_tiles;
-        const int n_tile = mn - m_tile * p.n_tiles;
-        const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
-        const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
-        const long long m0 = static_cast<long long>(m_tile) * kBlockM;
-        int img_n = 0, base_h = 0, base_w = 0;
-        if (p.a.kind == 1) {
-          const long long pq = static_cast<long long>(p.a.P) * p.a.Q;
-          img_n = static_cast<int>(m0 / pq);
-          const int rem = static_cast<int>(m0 - img_n * pq);
-          const int p0 = rem / p.a.Q;
-          const int q0 = rem - p0 * p.a.Q;
-          base_h = p0 * p.a.stride - p.a.pad;
-          base_w = q0 * p.a.stride - p.a.pad;
-        }
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // The whole warp runs the loop (warp-uniform control flow keeps coordinates and smem addresses in
+    // uniform registers, which the TMA instructions read directly); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ks = tile / mn_tiles;
+      const int mn = tile - ks * mn_tiles;
+      const int m_tile = mn / p.n_tiles;
+      const int n_tile = mn - m_tile * p.n_tiles;
+      const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
+      const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
+      const long long m0 = static_cast<long long>(m_tile) * kBlockM;
+      int img_n = 0, base_h = 0, base_w = 0;
+      if (p.a.kind == 1) {
+        const long long pq = static_cast<long long>(p.a.P) * p.a.Q;
+        img_n = static_cast<int>(m0 / pq);
+        const int rem = static_cast<int>(m0 - img_n * pq);
+        const int p0 = rem / p.a.Q;
+        const int q0 = rem - p0 * p.a.Q;
+        base_h = p0 * p.a.stride - p.a.pad;
+        base_w = q0 * p.a.stride - p.a.pad;
+      }
+      int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
+      int tr = tap / p.a.S, tsx = tap - tr * p.a.S;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
           uint8_t* s = stage_base + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sA_hi = s;
           uint8_t* sA_lo = s + kATileBytes;
@@ -184,81 +257,131 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           }
           if (p.dbg & 4) {
           } else if (p.a.kind == 1) {
-            const int tap = kb / p.cblocks;
-            const int cb = kb - tap * p.cblocks;
-            const int r = tap / p.a.S;
-            const int sx = tap - r * p.a.S;
             ptx::tma_load_im2col_4d(sA_hi, &tm.a_hi, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
-                                    static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
-            if (kTerms == 3)
+                                    static_cast<uint16_t>(tsx), static_cast<uint16_t>(tr));
+            if (kTerms != 1)  // fp16 lo tile (x3) or e4m3 lo8 tile (c8), both right behind the hi tile
               ptx::tma_load_im2col_4d(sA_lo, &tm.a_lo, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
-                                      static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                                      static_cast<uint16_t>(tsx), static_cast<uint16_t>(tr));
+            if (kTerms == 2 && p.tmode)
+              ptx::tma_load_im2col_4d(s + off_a_hi8, &tm.a_hi8, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
+                                      static_cast<uint16_t>(tsx), static_cast<uint16_t>(tr));
           } else {
             ptx::tma_load_2d(sA_hi, &tm.a_hi, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
-            if (kTerms == 3) ptx::tma_load_2d(sA_lo, &tm.a_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+            if (kTerms != 1) ptx::tma_load_2d(sA_lo, &tm.a_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
+            if (kTerms == 2 && p.tmode)
+              ptx::tma_load_2d(s + off_a_hi8, &tm.a_hi8, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
           }
           if (!(p.dbg & 8)) {
             ptx::tma_load_2d(sW_hi, &tm.w_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-            if (kTerms == 3) ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+            if (kTerms == 3 || (kTerms == 2 && !p.tmode))
+              ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+            if (kTerms == 2) {
+              ptx::tma_load_2d(s + off_w_hi8, &tm.w_hi8, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+              if (p.tmode) ptx::tma_load_2d(s + off_w_lo8, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+            }
           }
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1u;
+        }
+        __syncwarp();
+        // next filter tap / channel block (im2col view: kb = tap * cblocks + cb, tap = r * S + s)
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++tsx == p.a.S) {
+            tsx = 0;
+            ++tr;
           }
+        }
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
+    // Warp-uniform loop, one elected lane issues each tcgen05.mma / commit (the shared-memory descriptors are
+    // then computed on the uniform datapath; a lane-0-only loop costs ~5 R2UR moves per MMA and made the issue
+    // rate, not the tensor pipe, the limit).
     const uint32_t idesc = ptx::make_idesc_f16_f32(kBlockM, p.block_n);
+    const uint32_t stage_base_u32 = ptx::smem_u32(stage_base);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
+    long long dbg_c0 = 0;
+    unsigned long long dbg_t0 = 0;
+    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
+      dbg_c0 = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local % p.num_acc;
       const uint32_t acc_phase = static_cast<uint32_t>(local / p.num_acc) & 1u;
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
+      const uint32_t tmem_c = tmem_d + static_cast<uint32_t>(p.block_n);  // kTerms == 2: e4m3 correction accumulator
       const int ks = tile / mn_tiles;
       const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
       const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        if (lane == 0 && (p.dbg & 16)) {
-          ptx::umma_commit(&empty_bar[stage]);
-          if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
-        } else if (lane == 0) {
-          const uint32_t s = ptx::smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t aA_hi = s;
-          const uint32_t aA_lo = s + kATileBytes;
-          const uint32_t aW_hi = s + a_bytes;
-          const uint32_t aW_lo = aW_hi + w_tile_bytes;
+        if (!(p.dbg & 16)) {
+          const uint32_t s = stage_base_u32 + static_cast<uint32_t>(stage * stage_bytes);
+          // descriptors of the k = 0 slice; the slice j advances the 16-byte-granular start address by 2 (32 B)
+          const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(s);
+          const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(s + kATileBytes);
+          const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(s + a_bytes);
+          const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(s + a_bytes + w_tile_bytes);
+          const uint32_t first = kb > kb_begin ? 1u : 0u;
+          auto issue_f8 = [&]() {
+            if constexpr (kTerms == 2) {
+              // e4m3 corrections into the second accumulator (columns + block_n), K = 32 per MMA:
+              // lo8_a * hi8_w  (+ hi8_a * lo8_w on T layers)
+              const uint64_t dA8 = ptx::make_sw64_kmajor_desc(s + kATileBytes);
+              const uint64_t dW8 = ptx::make_sw64_kmajor_desc(s + off_w_hi8);
+              const uint64_t dAh8 = ptx::make_sw64_kmajor_desc(s + off_a_hi8);
+              const uint64_t dWl8 = ptx::make_sw64_kmajor_desc(s + off_w_lo8);
+#pragma unroll
+              for (int j = 0; j < kBlockK / 32; ++j) {
+                ptx::umma_f8(tmem_c, dA8 + 2 * j, dW8 + 2 * j, idesc, (first || j > 0) ? 1u : 0u);
+                if (p.tmode) ptx::umma_f8(tmem_c, dAh8 + 2 * j, dWl8 + 2 * j, idesc, 1u);
+              }
+            }
+          };
+          // alternate the order of the fp16 and e4m3 groups between k-blocks: one kind switch per stage
+          const bool f8_first = kTerms == 2 && ((kb - kb_begin) & 1);
+          if (f8_first) issue_f8();
 #pragma unroll
           for (int j = 0; j < kBlockK / kUmmaK; ++j) {
-            const uint32_t koff = j * kUmmaK * 2;  // bytes inside the 128 B swizzle row
-            const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(aA_hi + koff);
-            const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(aW_hi + koff);
-            uint32_t accum = (kb > kb_begin || j > 0) ? 1u : 0u;
+            uint32_t accum = (first || j > 0) ? 1u : 0u;
             if (kTerms == 3) {
-              const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(aA_lo + koff);
-              const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(aW_lo + koff);
-              ptx::umma_f16(tmem_d, dA_lo, dW_hi, idesc, accum);
-              ptx::umma_f16(tmem_d, dA_hi, dW_lo, idesc, 1u);
+              ptx::umma_f16(tmem_d, dA_lo + 2 * j, dW_hi + 2 * j, idesc, accum);
+              ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, 1u);
               accum = 1u;
             }
-            ptx::umma_f16(tmem_d, dA_hi, dW_hi, idesc, accum);
+            if (kTerms == 2 && !p.tmode) {  // H layers: weight correction as a second fp16 MMA
+              ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, accum);
+              accum = 1u;
+            }
+            ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_hi + 2 * j, idesc, accum);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
+          if (kTerms == 2 && !f8_first) issue_f8();
         }
-        __syncwarp();
+        ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+        if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
         if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
+    }
+    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
+      // effective SM clock while this launch ran (attribution experiments only)
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      const long long c1 = clock64();
+      printf("umma M=%d N=%d K=%d terms=%d tmode=%d: %lld cycles in %llu ns = %.0f MHz\n", p.M, p.N, p.K, kTerms, p.tmode,
+             c1 - dbg_c0, t1 - dbg_t0, 1e3 * double(c1 - dbg_c0) / double(t1 - dbg_t0));
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue (two groups of four warps) =====================
@@ -289,9 +412,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         const int nt = mn_i - mt * p.n_tiles;
         uint8_t* dst = rbuf + b * kSet;
         ptx::fence_proxy_async();
-        ptx::mbar_arrive_expect_tx(&rbar[b], static_cast<uint32_t>(kSet));
+        ptx::mbar_arrive_expect_tx(&rbar[b], static_cast<uint32_t>(kTerms == 2 ? kEpiPlaneBytes + kEpiPlaneBytes / 2 : kSet));
         ptx::tma_load_2d(dst, &tm.r_hi, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
-        if (kTerms == 3)
+        if (kTerms != 1)  // fp16 lo chunk (x3) or e4m3 lo8 chunk (c8)
           ptx::tma_load_2d(dst + kEpiPlaneBytes, &tm.r_lo, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
       }
       ++r_issued;
@@ -335,6 +458,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
         }
+        if (kTerms == 2 && ep.res_lo8) {
+          const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) rpre[4 + j] = __ldg(rl + j);
+        }
       };
       if (res_direct) load_direct(n_base);
 #pragma unroll 1
@@ -342,6 +470,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         const int n = n_base + c * kEpiChunk;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
+        uint32_t r2[kTerms == 2 ? 32 : 1];
+        if constexpr (kTerms == 2) ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(p.block_n + c * kEpiChunk), r2);
         uint4 rnow[8];
         if (res_direct) {
 #pragma unroll
@@ -359,6 +489,18 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if constexpr (kTerms == 2) {
+          // + fp8 correction accumulator x 2^-(13 + s_n)
+          const float4* c4 = reinterpret_cast<const float4*>(p.cscale + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 cs = __ldg(c4 + j);
+            v[4 * j + 0] = fmaf(__uint_as_float(r2[4 * j + 0]), cs.x, v[4 * j + 0]);
+            v[4 * j + 1] = fmaf(__uint_as_float(r2[4 * j + 1]), cs.y, v[4 * j + 1]);
+            v[4 * j + 2] = fmaf(__uint_as_float(r2[4 * j + 2]), cs.z, v[4 * j + 2]);
+            v[4 * j + 3] = fmaf(__uint_as_float(r2[4 * j + 3]), cs.w, v[4 * j + 3]);
+          }
+        }
         if (!(p.dbg & 2)) {
           if (ep.bias && p.k_split == 1) {
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
@@ -372,6 +514,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             }
           }
           if (rcur) {
+            if constexpr (kTerms == 2) {
+              const uint8_t* r8 = rcur + kEpiLo8Off + row * 32;
+              add_lo8x16(v, *reinterpret_cast<const uint4*>(r8));
+              add_lo8x16(v + 16, *reinterpret_cast<const uint4*>(r8 + 16));
+            }
 #pragma unroll
             for (int pl = 0; pl < (kTerms == 3 ? 2 : 1); ++pl) {
 #pragma unroll
@@ -395,6 +542,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
                 v[4 * j + 3] += f.w;
               }
             } else {
+              if (kTerms == 2 && ep.res_lo8) {
+                add_lo8x16(v, rnow[4]);
+                add_lo8x16(v + 16, rnow[5]);
+              }
               const int npl = (kTerms == 3 && ep.res_lo) ? 2 : 1;
 #pragma unroll
               for (int pl = 0; pl < 2; ++pl) {
@@ -439,6 +590,18 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
                 ul.w = ptx::residue_half2(v[8 * j + 6], v[8 * j + 7], uh.w);
                 *reinterpret_cast<uint4*>(ob + kEpiPlaneBytes + sw64_off(row, j)) = ul;
               }
+              if (kTerms == 2) {
+                uint2 l8;
+                l8.x = residue_e4m3x2(v[8 * j + 0], v[8 * j + 1], uh.x) | (residue_e4m3x2(v[8 * j + 2], v[8 * j + 3], uh.y) << 16);
+                l8.y = residue_e4m3x2(v[8 * j + 4], v[8 * j + 5], uh.z) | (residue_e4m3x2(v[8 * j + 6], v[8 * j + 7], uh.w) << 16);
+                *reinterpret_cast<uint2*>(ob + kEpiLo8Off + row * 32 + j * 8) = l8;
+                if (p.out_hi8) {
+                  uint2 h8;
+                  h8.x = half2_to_e4m3x2(uh.x) | (half2_to_e4m3x2(uh.y) << 16);
+                  h8.y = half2_to_e4m3x2(uh.z) | (half2_to_e4m3x2(uh.w) << 16);
+                  *reinterpret_cast<uint2*>(ob + kEpiHi8Off + row * 32 + j * 8) = h8;
+                }
+              }
             }
           }
           // all 128 threads have consumed the residual slot and filled the staging set; with two sets the
@@ -451,7 +614,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             if (!(p.dbg & 1)) {
               const int m0 = m_tile * kBlockM;
               ptx::tma_store_2d(&tm.o_hi, ob, n, m0);
-              if (kTerms == 3) ptx::tma_store_2d(&tm.o_lo, ob + kEpiPlaneBytes, n, m0);
+              if (kTerms != 1) ptx::tma_store_2d(&tm.o_lo, ob + kEpiPlaneBytes, n, m0);  // fp16 lo / e4m3 lo8
+              if (kTerms == 2 && p.out_hi8) ptx::tma_store_2d(&tm.o_hi8, ob + kEpiHi8Off, n, m0);
             }
             ptx::tma_store_commit();
           }
@@ -478,6 +642,18 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
                 ul.z = ptx::residue_half2(v[8 * j + 4], v[8 * j + 5], uh.z);
                 ul.w = ptx::residue_half2(v[8 * j + 6], v[8 * j + 7], uh.w);
                 ol[j] = ul;
+              }
+              if (kTerms == 2 && ep.out_lo8) {
+                uint2 l8;
+                l8.x = residue_e4m3x2(v[8 * j + 0], v[8 * j + 1], uh.x) | (residue_e4m3x2(v[8 * j + 2], v[8 * j + 3], uh.y) << 16);
+                l8.y = residue_e4m3x2(v[8 * j + 4], v[8 * j + 5], uh.z) | (residue_e4m3x2(v[8 * j + 6], v[8 * j + 7], uh.w) << 16);
+                *reinterpret_cast<uint2*>(ep.out_lo8 + m * ep.ldo + n + 8 * j) = l8;
+              }
+              if (kTerms == 2 && ep.out_hi8) {
+                uint2 h8;
+                h8.x = half2_to_e4m3x2(uh.x) | (half2_to_e4m3x2(uh.y) << 16);
+                h8.y = half2_to_e4m3x2(uh.z) | (half2_to_e4m3x2(uh.w) << 16);
+                *reinterpret_cast<uint2*>(ep.out_hi8 + m * ep.ldo + n + 8 * j) = h8;
               }
             }
           }
@@ -546,6 +722,38 @@ inline CUtensorMap make_tmap_2d(const __half* base, long long rows, long long co
   return m;
 }
 
+// uint8 (e4m3) variants: one byte per element
+inline CUtensorMap make_tmap_2d_u8(const uint8_t* base, long long rows, long long cols, long long ld, int box_rows,
+                                   int box_cols, CUtensorMapSwizzle swz) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = DriverApi::get().encodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims,
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(u8) failed, code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+inline CUtensorMap make_tmap_im2col_u8(const uint8_t* base, const AGeom& g) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H),
+                        static_cast<cuuint64_t>(g.NB)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W) * g.C,
+                           static_cast<cuuint64_t>(g.H) * g.W * g.C};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.S - 1), g.pad - (g.R - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(g.stride), static_cast<cuuint32_t>(g.stride), 1};
+  CUresult r = DriverApi::get().encodeIm2col(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(base), dims,
+                                             strides, lower, upper, kBlockK, kBlockM, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col(u8) failed, code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
 inline CUtensorMap make_tmap_im2col(const __half* base, const AGeom& g) {
   CUtensorMap m;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H),
@@ -586,12 +794,14 @@ inline int tune_env(const char* name) {
 }
 
 // A planes: for kind 0 the [M,K] matrix, for kind 1 the NHWC activation.  W planes: [N,K].
+// terms == 2 (fp16c8): A = hi + lo8 (+ hi8 -> T layer), W = hi + lo + hi8 (+ lo8 for T layers), cscale[N].
 inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
                                const Epilogue& ep, int num_sms, int force_block_n = 0, int k_split = 1,
-                               long long split_stride = 0) {
+                               long long split_stride = 0, const float* cscale = nullptr) {
   MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
-  MCG_CHECK(terms == 1 || terms == 3, "the tcgen05 GEMM runs 1 or 3 MMA terms per k-step");
+  MCG_CHECK(terms >= 1 && terms <= 3, "the tcgen05 GEMM runs 1, 2 (fp16 + e4m3 corrections) or 3 MMA terms per k-step");
   MCG_CHECK(terms != 3 || (A.lo && W.lo), "3-term GEMM needs lo planes");
+  MCG_CHECK(terms != 2 || (A.lo8 && W.lo && W.hi8 && cscale), "fp16c8 GEMM needs an e4m3 activation low plane, fp16 lo + e4m3 hi weights and channel scales");
   static const int tune_res_bn = tune_env("MCG_TUNE_RES_BN");
   static const int tune_out_sets = tune_env("MCG_TUNE_OUT_SETS");
   static const int dbg_flags = tune_env("MCG_DEBUG_FLAGS");
@@ -602,10 +812,12 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.N = N;
   p.K = K;
   p.dbg = dbg_flags;
+  p.tmode = (terms == 2 && A.hi8 != nullptr && W.lo8 != nullptr) ? 1 : 0;
+  p.cscale = cscale;
   // epilogue staging (per epilogue group): TMA-store staging when the output is fp16 planes, plus residual
   // prefetch buffers for the same-shape residual
-  const bool out_lo_ok = terms == 1 || ep.out_lo != nullptr;
-  const bool res_lo_ok = terms == 1 || ep.res_lo != nullptr;
+  const bool out_lo_ok = terms == 1 || (terms == 3 && ep.out_lo != nullptr) || (terms == 2 && ep.out_lo8 != nullptr);
+  const bool res_lo_ok = terms == 1 || (terms == 3 && ep.res_lo != nullptr) || (terms == 2 && ep.res_lo8 != nullptr);
   p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 16 == 0 && out_lo_ok) ? 1 : 0;
   p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0 &&
                res_lo_ok)
@@ -624,7 +836,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (N % c) continue;
-      const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, c);
+      if (terms == 2 && c > 128) continue;  // main + correction accumulator: 2 x block_n TMEM columns per tile
+      const int sb = a_stage_bytes(terms, p.tmode) + w_stage_bytes(terms, c, p.tmode);
       if (ring_budget(1) / sb >= min_stages || c == 64) {
         bn = c;
         break;
@@ -632,16 +845,21 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     }
   }
   MCG_CHECK(bn > 0 && N % bn == 0 && bn % 64 == 0 && bn <= 256, "bad block_n");
+  MCG_CHECK(terms != 2 || bn <= 128, "fp16c8 needs block_n <= 128");
   p.block_n = bn;
-  const int stage_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, bn);
+  const int stage_bytes = a_stage_bytes(terms, p.tmode) + w_stage_bytes(terms, bn, p.tmode);
   // double-buffer the staging when that does not cost a needed pipeline stage
   p.out_sets = 1;
   if (p.out_tma && ring_budget(2) / stage_bytes >= min_stages) p.out_sets = 2;
   if (p.out_tma && tune_out_sets > 0 && ring_budget(tune_out_sets) / stage_bytes >= 2) p.out_sets = tune_out_sets > 2 ? 2 : tune_out_sets;
   p.num_stages = ring_budget(p.out_sets) / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  static const int tune_stages = tune_env("MCG_TUNE_STAGES");
+  if (tune_stages >= 2 && p.num_stages > tune_stages) p.num_stages = tune_stages;
   MCG_CHECK(p.num_stages >= 2, "not enough shared memory for 2 stages");
-  p.acc_cols = bn > 128 ? 256 : 128;
+  p.acc_cols = terms == 2 ? 2 * bn : (bn > 128 ? 256 : 128);
+  p.out_hi8 = (terms == 2 && p.out_tma && ep.out_hi8 != nullptr) ? 1 : 0;
+  MCG_CHECK(terms != 2 || ep.out_hi8 == nullptr || p.out_tma || ep.out_f32 == nullptr, "hi8 output needs a planes epilogue");
   p.num_acc = kTmemCols / p.acc_cols;
   p.num_kb = K / kBlockK;
   p.m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
@@ -671,13 +889,25 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   tm.w_hi = make_tmap_2d(W.hi, N, K, K, bn);
   tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : tm.w_hi;
   tm.o_hi = tm.o_lo = tm.r_hi = tm.r_lo = tm.w_hi;  // placeholders when unused
+  tm.a_hi8 = tm.w_hi8 = tm.o_hi8 = tm.w_hi;
+  if (terms == 2) {
+    const CUtensorMapSwizzle sw64 = CU_TENSOR_MAP_SWIZZLE_64B;
+    tm.a_lo = a.kind == 1 ? make_tmap_im2col_u8(A.lo8, a) : make_tmap_2d_u8(A.lo8, M, K, a.lda, kBlockM, kBlockK, sw64);
+    if (p.tmode)
+      tm.a_hi8 = a.kind == 1 ? make_tmap_im2col_u8(A.hi8, a) : make_tmap_2d_u8(A.hi8, M, K, a.lda, kBlockM, kBlockK, sw64);
+    tm.w_hi8 = make_tmap_2d_u8(W.hi8, N, K, K, bn, kBlockK, sw64);
+    tm.w_lo = p.tmode ? make_tmap_2d_u8(W.lo8, N, K, K, bn, kBlockK, sw64) : make_tmap_2d(W.lo, N, K, K, bn);
+  }
   if (p.out_tma) {
     tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
     tm.o_lo = terms == 3 ? make_tmap_2d(ep.out_lo, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.o_hi;
+    if (terms == 2) tm.o_lo = make_tmap_2d_u8(ep.out_lo8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (p.out_hi8) tm.o_hi8 = make_tmap_2d_u8(ep.out_hi8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   if (p.res_tma) {
     tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
     tm.r_lo = terms == 3 ? make_tmap_2d(ep.res_lo, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.r_hi;
+    if (terms == 2) tm.r_lo = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   return pl;
 }
@@ -686,6 +916,7 @@ inline void umma_set_attrs() {
   static bool done = false;
   if (done) return;
   MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   done = true;
 }
@@ -694,6 +925,8 @@ inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   umma_set_attrs();
   if (pl.terms == 3)
     umma_gemm_kernel<3><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
+  else if (pl.terms == 2)
+    umma_gemm_kernel<2><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   else
     umma_gemm_kernel<1><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   MCG_CUDA(cudaGetLastError());

@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libmcgaze_b200.so')
 
-PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2}   # 3 (fp16lo8) was removed
+PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 
 # every symbol include/mcgaze_b200.h declares
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
