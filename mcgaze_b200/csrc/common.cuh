@@ -22,10 +22,16 @@ struct Planes {
   uint8_t* hi8 = nullptr;  // e4m3(hi): second fp8 operand of "T" layers (fp16c8 mode)
 };
 
-// |value - hi| <= 2^-11 |value|; 2^13 maps the residue of |value| in [2^-8, 32] into e4m3's normal range
-constexpr int kLo8Shift = 13;
-constexpr float kLo8Scale = 8192.f;          // 2^13
-constexpr float kLo8InvScale = 1.f / 8192.f;
+// fp16c8 scales (all powers of two, global constants).  |value - hi| <= 2^-11 |value|, so lo8 = e4m3(lo 2^11)
+// stays below the e4m3 maximum (448) wherever hi8 = e4m3(hi) does, and is a normal e4m3 number for |value| >= 2^-6.
+// Weights: hi8 = e4m3(W_hi 2^4), lo8 = e4m3(W_lo 2^15) (normal for |W| >= 2^-10, saturating at |W| >= 28).
+// Both correction products then carry 2^15 = 2^kC8AccShift, the largest factor tcgen05.mma's scale-input-d removes.
+constexpr int kLo8Shift = 11;
+constexpr float kLo8Scale = 2048.f;          // 2^11
+constexpr float kLo8InvScale = 1.f / 2048.f;
+constexpr int kC8AccShift = 15;
+constexpr int kW8HiShift = kC8AccShift - kLo8Shift;  // 4
+constexpr int kW8LoShift = kC8AccShift;              // 15 (the activation's hi8 plane is unscaled)
 
 __host__ __device__ inline uint8_t float_to_e4m3(float v) {
   return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                                     const uint8_t* __restrict__ in_lo8, int NB, int H, int W, int C, int P, int Q,
                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                    uint8_t* __restrict__ out_lo8) {
+                                    uint8_t* __restrict__ out_lo8, uint8_t* __restrict__ out_hi8 = nullptr) {
   const int c8n = C / 8;
   const long long total = static_cast<long long>(NB) * P * Q * c8n;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -114,12 +114,13 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __ha
     }
     __align__(16) __half hh[8];
     __align__(16) __half hl[8];
-    float rs[8];
+    float rs[8], h8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const __half h = __float2half_rn(best[j]);
       hh[j] = h;
-      rs[j] = best[j] - __half2float(h);
+      h8[j] = __half2float(h);
+      rs[j] = best[j] - h8[j];
       hl[j] = __float2half_rn(rs[j]);
       rs[j] *= kLo8Scale;
     }
@@ -127,6 +128,7 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __ha
     *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<const uint4*>(hh);
     if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(hl);
     if (out_lo8) *reinterpret_cast<uint2*>(out_lo8 + o) = float8_to_e4m3x8(rs);
+    if (out_hi8) *reinterpret_cast<uint2*>(out_hi8 + o) = float8_to_e4m3x8(h8);
   }
 }
 

@@ -89,14 +89,23 @@ static T* upload(std::vector<std::unique_ptr<DeviceBlock>>& keep, const std::vec
 
 static inline __half h_from_float(float v) { return __float2half_rn(v); }
 
+// e4m3 weight planes of the fp16c8 mode: hi8 = e4m3(hi 2^kW8HiShift), lo8 = e4m3((w - hi) 2^kW8LoShift)
+static void pack_w8_host(const float* w, const __half* hi, size_t n, uint8_t* hi8, uint8_t* lo8) {
+  const float s1 = std::ldexp(1.f, kW8HiShift), s2 = std::ldexp(1.f, kW8LoShift);
+  for (size_t i = 0; i < n; ++i) {
+    const float h = __half2float(hi[i]);
+    hi8[i] = float_to_e4m3(h * s1);
+    lo8[i] = float_to_e4m3((w[i] - h) * s2);
+  }
+}
+
 // ------------------------------------------------------------------------------------ weights
 struct GemmW {  // packed [N, K] weight (+ bias) on device
   int N = 0, K = 0;
   const float* w_f32 = nullptr;
   const float* w_t = nullptr;  // [K, N] transposed copy for small_linear_kernel (small layers only)
-  Planes w;                    // hi / lo fp16 planes; fp16c8 conv weights also carry w.hi8 = e4m3(hi 2^s_n),
-                               // w.lo8 = e4m3(lo 2^(13+s_n)) with a per-output-channel shift s_n
-  const float* cscale = nullptr;  // [N] 2^-(13+s_n): factor of the fp8 correction accumulator
+  Planes w;                    // hi / lo fp16 planes; fp16c8 conv weights also carry w.hi8 = e4m3(hi 2^4),
+                               // w.lo8 = e4m3(lo 2^15)
   const float* bias = nullptr;
 };
 struct LnW {
@@ -380,28 +389,12 @@ class Engine {
   }
   bool has(const std::string& k) const { return host_.count(k) != 0; }
 
-  // e4m3 operand planes of the fp16c8 correction MMAs.  Per output channel n the shift s_n puts the largest
-  // |W[n,:]| into (56, 112]: hi8 <= 112 and lo8 = lo 2^(13+s_n) <= 2^-11 2^13 112 = 448 (the e4m3 maximum).
-  void pack_c8(GemmW& g, const std::vector<float>& w, const std::vector<__half>& hi, int N, int K) {
+  // e4m3 operand planes of the fp16c8 correction MMAs (fixed power-of-two scales, common.cuh)
+  void pack_c8(GemmW& g, const std::vector<float>& w, const std::vector<__half>& hi) {
     std::vector<uint8_t> hi8(w.size()), lo8(w.size());
-    std::vector<float> cs(N);
-    for (int n = 0; n < N; ++n) {
-      float mx = 0.f;
-      for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(w[static_cast<size_t>(n) * K + k]));
-      int sh = mx > 0.f ? static_cast<int>(std::floor(std::log2(112.0 / mx))) : 0;
-      sh = std::max(-40, std::min(40, sh));
-      const float s1 = std::ldexp(1.f, sh), s2 = std::ldexp(1.f, sh + kLo8Shift);
-      for (int k = 0; k < K; ++k) {
-        const size_t i = static_cast<size_t>(n) * K + k;
-        const float h = __half2float(hi[i]);
-        hi8[i] = float_to_e4m3(h * s1);
-        lo8[i] = float_to_e4m3((w[i] - h) * s2);
-      }
-      cs[n] = std::ldexp(1.f, -(sh + kLo8Shift));
-    }
+    pack_w8_host(w.data(), hi.data(), w.size(), hi8.data(), lo8.data());
     g.w.hi8 = upload(keep_, hi8);
     g.w.lo8 = upload(keep_, lo8);
-    g.cscale = upload(keep_, cs);
   }
 
   GemmW pack_gemm(const std::vector<float>& w, int N, int K, const float* bias, bool c8 = false) {
@@ -417,7 +410,7 @@ class Engine {
     }
     g.w.hi = upload(keep_, hi);
     g.w.lo = upload(keep_, lo);
-    if (c8) pack_c8(g, w, hi, N, K);
+    if (c8) pack_c8(g, w, hi);
     if (bias) g.bias = upload(keep_, std::vector<float>(bias, bias + N));
     if (N <= 768 && K <= 2048 && K % 32 == 0) {
       std::vector<float> t(w.size());
@@ -565,7 +558,7 @@ class Engine {
     int NB = 0, H = 0, W = 0, C = 0;
     long long rows() const { return static_cast<long long>(NB) * H * W; }
   };
-  // hi8: the tensor is read by a tensor-bound ("T") layer of the fp16c8 mode and carries an e4m3 copy of hi
+  // hi8: the tensor is the input of a convolution in the fp16c8 mode and carries the e4m3 copy of hi
   Act new_act(int NB, int H, int W, int C, bool hi8 = false) {
     Act a;
     a.NB = NB;
@@ -614,31 +607,25 @@ class Engine {
     const int P1 = H / 2, Q1 = W / 2, P2 = H / 4, Q2 = W / 4;
     stemA_ = alloc_planes(static_cast<size_t>(NB) * P1 * Q1 * kStemK);
     stem_out_ = new_act(NB, P1, Q1, 64);
-    pool_out_ = new_act(NB, P2, Q2, 64);
+    pool_out_ = new_act(NB, P2, Q2, 64, true);
     int h = P2, w = Q2;
     const int planes_c[4] = {64, 128, 256, 512};
-    // fp16c8: tensors read by tensor-bound layers carry the hi8 plane (SURVEY App. D arithmetic intensities):
-    // bit 0: inputs of the 3x3 convolutions (t1, FPN laterals); bit 1: layer4's 1x1 inputs and the output of
-    // layer3 (-> layer4.0.conv1 / downsample, lateral 2: K >= 1024)
-    static const int tune_t = tune_env("MCG_TUNE_TMODE");
-    const int tmask = tune_t > 0 ? tune_t - 1 : 3;
     for (int l = 0; l < 4; ++l) {
       blk_act_[l].clear();
       for (size_t b = 0; b < blocks_[l].size(); ++b) {
         const int stride = blocks_[l][b].c2.stride;
-        const bool last = b + 1 == blocks_[l].size();
         BlkAct ba;
-        ba.t1 = new_act(NB, h, w, planes_c[l], (tmask & 1) != 0);
-        ba.t2 = new_act(NB, h / stride, w / stride, planes_c[l], (tmask & 2) && l == 3);
-        if (blocks_[l][b].has_ds) ba.ds = new_act(NB, h / stride, w / stride, planes_c[l] * 4);
-        ba.out = new_act(NB, h / stride, w / stride, planes_c[l] * 4, (tmask & 2) && (l == 3 || (l == 2 && last)));
+        ba.t1 = new_act(NB, h, w, planes_c[l], true);
+        ba.t2 = new_act(NB, h / stride, w / stride, planes_c[l], true);
+        if (blocks_[l][b].has_ds) ba.ds = new_act(NB, h / stride, w / stride, planes_c[l] * 4);  // residual only
+        ba.out = new_act(NB, h / stride, w / stride, planes_c[l] * 4, true);
         h /= stride;
         w /= stride;
         blk_act_[l].push_back(ba);
       }
     }
     for (int i = 0; i < 4; ++i) {
-      lat_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256, (tmask & 1) != 0);
+      lat_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256, true);
       fpn_[i] = new_act(NB, H / (4 << i), W / (4 << i), 256);
     }
     const size_t Rr = static_cast<size_t>(NB) * 3;
@@ -708,11 +695,11 @@ class Engine {
   void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
             long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0) {
     const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
-                        (terms == 1 || (terms == 3 && A->lo != nullptr) || (terms == 2 && A->lo8 != nullptr && w.cscale != nullptr));
+                        (terms == 1 || (terms == 3 && A->lo != nullptr) || (terms == 2 && A->lo8 != nullptr && A->hi8 != nullptr && w.w.hi8 != nullptr));
     if (tensor) {
       auto it = plans_.find(key);
       if (it == plans_.end()) {
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, w.cscale);
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -994,7 +981,7 @@ class Engine {
         gemm("stem", &stemA_, nullptr, g, stem_.g, stem_out_.rows(), ep, st, trunk_terms());
       }
       maxpool3x3s2_kernel<<<ew_grid, 256, 0, st>>>(stem_out_.pl.hi, stem_out_.pl.lo, stem_out_.pl.lo8, NB, H / 2, W / 2, 64,
-                                                   H / 4, W / 4, pool_out_.pl.hi, pool_out_.pl.lo, pool_out_.pl.lo8);
+                                                   H / 4, W / 4, pool_out_.pl.hi, pool_out_.pl.lo, pool_out_.pl.lo8, pool_out_.pl.hi8);
       MCG_CUDA(cudaGetLastError());
       count("maxpool3x3s2_kernel");
       reg_act("stem", stem_out_);
@@ -1432,20 +1419,18 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
       RW = Q / 2;
     }
     const size_t nr = res ? static_cast<size_t>(NB) * RH * RW * Cout : 0;
-    // fp16c8: out_mode bit 1 = "T" layer (A carries the hi8 plane, both corrections in e4m3), bit 2 = return the
-    // emitted hi8 output plane (as fp32) instead of hi + lo8
+    // fp16c8: out_mode bit 2 = return the emitted hi8 output plane (as fp32) instead of hi + lo8
     const bool c8 = engine == MCG_PRECISION_FP16C8;
-    const bool c8_t = c8 && (out_mode & 2);
     const bool c8_hi8_out = c8 && (out_mode & 4);
     out_mode &= 1;
     DeviceBlock bx(nx * 4), bw(nw * 4), br(nr * 4 + 16);
-    DeviceBlock bx8(c8 ? nx * 2 : 16), bw8(c8 ? nw * 2 : 16), br8(c8 ? nr + 16 : 16), bcs(c8 ? Cout * 4 : 16);
+    DeviceBlock bx8(c8 ? nx * 2 : 16), bw8(c8 ? nw * 2 : 16), br8(c8 ? nr + 16 : 16);
     Planes px{reinterpret_cast<__half*>(bx.p), reinterpret_cast<__half*>(bx.p) + nx, nullptr};
     Planes pw{reinterpret_cast<__half*>(bw.p), reinterpret_cast<__half*>(bw.p) + nw, nullptr};
     Planes pr{reinterpret_cast<__half*>(br.p), reinterpret_cast<__half*>(br.p) + nr, nullptr};
     if (c8) {
       px.lo8 = reinterpret_cast<uint8_t*>(bx8.p);
-      if (c8_t) px.hi8 = px.lo8 + nx;
+      px.hi8 = px.lo8 + nx;
       pr.lo8 = reinterpret_cast<uint8_t*>(br8.p);
     }
     split_planes_kernel<<<1024, 256, 0, st>>>(x, C, static_cast<long long>(NB) * H * W, C, px.hi, px.lo, px.lo8, px.hi8);
@@ -1453,33 +1438,19 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     if (res)
       split_planes_kernel<<<1024, 256, 0, st>>>(res, Cout, static_cast<long long>(NB) * RH * RW, Cout, pr.hi, pr.lo, pr.lo8);
     MCG_CUDA(cudaGetLastError());
-    const float* cscale = nullptr;
     if (c8) {
-      // same per-channel e4m3 packing as Engine::pack_c8, on the host
-      std::vector<float> hw(nw), cs(Cout);
+      // same e4m3 weight packing as the engine (host side)
+      std::vector<float> hw(nw);
+      std::vector<__half> hh(nw);
       std::vector<uint8_t> hi8(nw), lo8(nw);
       MCG_CUDA(cudaMemcpyAsync(hw.data(), w, nw * 4, cudaMemcpyDeviceToHost, st));
       MCG_CUDA(cudaStreamSynchronize(st));
-      for (int n = 0; n < Cout; ++n) {
-        float mx = 0.f;
-        for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(hw[static_cast<size_t>(n) * K + k]));
-        int sh = mx > 0.f ? static_cast<int>(std::floor(std::log2(112.0 / mx))) : 0;
-        sh = std::max(-40, std::min(40, sh));
-        const float s1 = std::ldexp(1.f, sh), s2 = std::ldexp(1.f, sh + kLo8Shift);
-        for (int k = 0; k < K; ++k) {
-          const size_t i = static_cast<size_t>(n) * K + k;
-          const float h = __half2float(__float2half_rn(hw[i]));
-          hi8[i] = float_to_e4m3(h * s1);
-          lo8[i] = float_to_e4m3((hw[i] - h) * s2);
-        }
-        cs[n] = std::ldexp(1.f, -(sh + kLo8Shift));
-      }
+      for (size_t i = 0; i < nw; ++i) hh[i] = __float2half_rn(hw[i]);
+      pack_w8_host(hw.data(), hh.data(), nw, hi8.data(), lo8.data());
       pw.hi8 = reinterpret_cast<uint8_t*>(bw8.p);
       pw.lo8 = pw.hi8 + nw;
       MCG_CUDA(cudaMemcpy(pw.hi8, hi8.data(), nw, cudaMemcpyHostToDevice));
       MCG_CUDA(cudaMemcpy(pw.lo8, lo8.data(), nw, cudaMemcpyHostToDevice));
-      MCG_CUDA(cudaMemcpy(bcs.p, cs.data(), Cout * 4, cudaMemcpyHostToDevice));
-      cscale = reinterpret_cast<const float*>(bcs.p);
     }
     AGeom g;
     const bool plain = R == 1 && S == 1 && stride == 1 && pad == 0 && !force_im2col;
@@ -1516,7 +1487,7 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
     ep.ldo = Cout;
     if (res) {
       ep.res_hi = pr.hi;
-      ep.res_lo = c8 ? nullptr : pr.lo;
+      ep.res_lo = (c8 || engine == MCG_PRECISION_FP16) ? nullptr : pr.lo;
       ep.res_lo8 = pr.lo8;
       ep.res_mode = res_mode;
       ep.ldr = Cout;
@@ -1544,9 +1515,8 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
         g_last_error = "mcg_debug_conv: shape not supported by the tcgen05 kernel";
         return MCG_ERR_UNSUPPORTED;
       }
-      if (engine == MCG_PRECISION_FP16 && res) ep.res_lo = nullptr;
       const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : c8 ? 2 : 1;
-      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n, 1, 0, cscale);
+      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n);
       launch_umma(pl, st);
       if (planes_out) {
         if (c8_hi8_out)

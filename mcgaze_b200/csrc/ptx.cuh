@@ -58,6 +58,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// variants on 32-bit shared-window addresses (computed once outside the hot loops: the generic -> shared
+// conversion of a pointer costs a special-register read per use)
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -79,6 +98,22 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
       " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
       "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w,
+                                                     int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 
@@ -120,19 +155,22 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
 }
-// fp16x2 of the rounding residue {a - low(h2), b - high(h2)} (the `lo` plane of a split value)
-__device__ __forceinline__ uint32_t residue_half2(float a, float b, uint32_t h2) {
-  float da, db;
+// exact rounding residues da = a - low(h2), db = b - high(h2): one mixed-precision FMA each (h * -1 + a)
+__device__ __forceinline__ void residue2(float a, float b, uint32_t h2, float& da, float& db) {
   asm("{\n"
-      ".reg .b16 l, h;\n"
+      ".reg .b16 l, h, m;\n"
       "mov.b32 {l, h}, %2;\n"
-      "neg.f16 l, l;\n"
-      "neg.f16 h, h;\n"
-      "add.rn.f32.f16 %0, l, %3;\n"
-      "add.rn.f32.f16 %1, h, %4;\n"
+      "mov.b16 m, 0xBC00;\n"
+      "fma.rn.f32.f16 %0, l, m, %3;\n"
+      "fma.rn.f32.f16 %1, h, m, %4;\n"
       "}\n"
       : "=f"(da), "=f"(db)
       : "r"(h2), "f"(a), "f"(b));
+}
+// fp16x2 of the rounding residue {a - low(h2), b - high(h2)} (the `lo` plane of a split value)
+__device__ __forceinline__ uint32_t residue_half2(float a, float b, uint32_t h2) {
+  float da, db;
+  residue2(a, b, h2, da, db);
   return pack_half2(da, db);
 }
 
@@ -171,6 +209,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         : "memory");
   }
 }
+// D = A*B + D * 2^-kShift (scale-input-d, kind::f16 only): rescales what the accumulator holds so far
+template <int kShift>
+__device__ __forceinline__ void umma_f16_rescale_d(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  static_assert(kShift >= 0 && kShift <= 15, "scale-input-d is a 4-bit immediate");
+  if (elect_one()) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(kShift)
+        : "memory");
+  }
+}
 // same, e4m3 x e4m3 operands (kind::f8f6f4, K = 32 per instruction, twice the fp16 rate)
 __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -191,6 +244,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   if (elect_one()) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  if (elect_one()) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
   }
 }
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i <-> lane base+i)

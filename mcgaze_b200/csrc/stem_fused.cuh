@@ -44,7 +44,8 @@ struct StemFusedParams {
   const float* bias = nullptr; // [64] folded BN shift
   __half* out_hi = nullptr;    // [NB, H/4, W/4, 64]
   __half* out_lo = nullptr;
-  uint8_t* out_lo8 = nullptr;  // fp16c8 storage: e4m3((v - hi) 2^13) instead of the fp16 lo plane
+  uint8_t* out_lo8 = nullptr;  // fp16c8 storage: e4m3((v - hi) 2^11) instead of the fp16 lo plane ...
+  uint8_t* out_hi8 = nullptr;  // ... and the e4m3 copy of hi
   int NB = 0, H = 0, W = 0;
   int P = 0, Q = 0;            // stem map
   int PP = 0, QQ = 0;          // pooled map
@@ -336,6 +337,12 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
               l8.y = residue_e4m3x2(v[8 * c8 + 4], v[8 * c8 + 5], uh.z) | (residue_e4m3x2(v[8 * c8 + 6], v[8 * c8 + 7], uh.w) << 16);
               *reinterpret_cast<uint2*>(p.out_lo8 + o + 8 * c8) = l8;
             }
+            if (p.out_hi8) {
+              uint2 h8;
+              h8.x = half2_to_e4m3x2(uh.x) | (half2_to_e4m3x2(uh.y) << 16);
+              h8.y = half2_to_e4m3x2(uh.z) | (half2_to_e4m3x2(uh.w) << 16);
+              *reinterpret_cast<uint2*>(p.out_hi8 + o + 8 * c8) = h8;
+            }
           }
         }
       }
@@ -376,6 +383,7 @@ inline StemFusedPlan make_stem_fused_plan(int terms, const float* img, int NB, i
   p.out_hi = out.hi;
   p.out_lo = terms == 3 ? out.lo : nullptr;
   p.out_lo8 = terms == 3 ? out.lo8 : nullptr;
+  p.out_hi8 = terms == 3 ? out.hi8 : nullptr;
   p.NB = NB;
   p.H = H;
   p.W = W;

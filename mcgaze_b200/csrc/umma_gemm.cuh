@@ -11,13 +11,14 @@
 // accumulator (~22-bit operand mantissa: fp32-equivalent products, the mode that meets the
 // 1e-3 (yaw,pitch) parity bar against the fp32 oracle).
 // kTerms == 2 ("fp16c8") keeps hi*hi in fp16 and moves the two rounding corrections to e4m3 tensor-core
-// MMAs (kind::f8f6f4, K = 32 per instruction, twice the fp16 rate) that accumulate into a SECOND TMEM
-// accumulator which the epilogue scales per output channel and adds:
-//     A*W ~= A_hi*W_hi + [ e4m3(A_lo 2^13) * e4m3(W_hi 2^s_n) + e4m3(A_hi) * e4m3(W_lo 2^(13+s_n)) ] 2^-(13+s_n)
-// Activations are stored as fp16 hi + e4m3 lo8 (3 bytes / element instead of 4).  The e4m3 copy of A_hi
-// ("hi8" plane) is written by the producing layer only for consumers that are tensor-bound ("T" layers: 8
-// MMA units per 64-wide k-block instead of 12); HBM-bound consumers ("H" layers) read hi + lo8 only and run
-// the weight correction A_hi*W_lo as a second fp16 MMA (10 units).
+// MMAs (kind::f8f6f4, K = 32 per instruction: twice the fp16 rate), all into ONE accumulator:
+//     A*W ~= A_hi*W_hi + 2^-15 [ e4m3(A_lo 2^11) * e4m3(W_hi 2^4) + e4m3(A_hi) * e4m3(W_lo 2^15) ]
+// Each tile runs two passes over K through the same smem ring: pass 1 streams the e4m3 tiles (A lo8 | A hi8,
+// W hi8 | W lo8; same bytes per stage as the fp16 tiles) and accumulates the corrections scaled by 2^15; the
+// first fp16 MMA of pass 2 rescales the accumulator (tcgen05.mma scale-input-d = 15: D = A*B + D 2^-15) and
+// pass 2 adds hi*hi.  8 MMA units per 64-wide k-block instead of 12, a single accumulator (block_n up to 256,
+// double buffered), the plain epilogue.  Activations are stored as fp16 hi + e4m3 lo8 + e4m3 hi8 (e4m3(hi), the
+// operand of the weight-rounding correction).
 //
 // Structure (persistent, one CTA per SM, 384 threads):
 //   warp 0    : TMA producer  (one elected lane; A tile 128 x 64, W tile block_n x 64, SWIZZLE_128B)
@@ -75,34 +76,29 @@ struct UmmaParams {
   int out_tma = 0;  // planes output through smem staging + TMA store
   int out_sets = 1; // staging sets per epilogue group for the TMA-store epilogue (2 = double buffered)
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
-  int tmode = 0;    // kTerms == 2: A has an e4m3 copy of hi (hi8), both corrections run as fp8 MMAs
-  int out_hi8 = 0;  // kTerms == 2: also emit the e4m3 copy of the output's hi plane (TMA-store epilogue only)
-  const float* cscale = nullptr;  // kTerms == 2: [N] factor of the fp8 correction accumulator, 2^-(13 + s_n)
+  int out_fmt = 0;  // planes written by the epilogue: 0 hi, 1 hi + fp16 lo, 2 hi + e4m3 lo8 (+ e4m3 hi8 if out_hi8)
+  int out_hi8 = 0;
+  int res_fmt = 0;  // planes of the residual: 0 hi, 1 hi + fp16 lo, 2 hi + e4m3 lo8
   int dbg = 0;      // attribution experiments only (env MCG_DEBUG_FLAGS): 1 no stores, 2 no epilogue math,
                     // 4 no A loads, 8 no W loads, 16 no MMA issue, 32 no residual loads.  Results are garbage.
   AGeom a;
   Epilogue ep;
 };
 
-// kTerms == 2 re-uses the *_lo slots for the e4m3 planes (a_lo = A lo8, o_lo = output lo8, r_lo = residual lo8,
-// w_lo = fp16 W_lo for H layers / e4m3 W_lo8 for T layers)
+// kTerms == 2: a_lo = A lo8, w_lo = W lo8 (e4m3 maps).  o_lo / r_lo are fp16 or e4m3 maps by out_fmt / res_fmt.
 struct UmmaMaps {
   CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, r_hi, r_lo;
   CUtensorMap a_hi8, w_hi8, o_hi8;
 };
 
 // shared-memory bytes of one pipeline stage / one epilogue staging set for a precision mode
-// kTerms == 2: A = fp16 hi tile + e4m3 lo8 tile (+ e4m3 hi8 tile, T layers);
-//              W = fp16 hi + fp16 lo + e4m3 hi8 (H layers)  or  fp16 hi + e4m3 hi8 + e4m3 lo8 (T layers)
-__host__ __device__ constexpr int a_stage_bytes(int terms, int tmode = 0) {
-  return terms == 3 ? 2 * kATileBytes : terms == 2 ? kATileBytes + (tmode ? 2 : 1) * (kATileBytes / 2) : kATileBytes;
-}
-__host__ __device__ constexpr int w_stage_bytes(int terms, int bn, int tmode = 0) {
-  return terms == 3 ? 2 * bn * kBlockK * 2 : terms == 2 ? bn * kBlockK * (tmode ? 4 : 5) : bn * kBlockK * 2;
-}
+// kTerms == 2: one stage holds EITHER the fp16 tiles of a k-block (pass 2: A_hi 16K, W_hi) OR its e4m3 tiles
+// (pass 1: A_lo8 8K | A_hi8 8K, W_hi8 | W_lo8) - the same bytes as in single-fp16 mode
+__host__ __device__ constexpr int a_stage_bytes(int terms) { return terms == 3 ? 2 * kATileBytes : kATileBytes; }
+__host__ __device__ constexpr int w_stage_bytes(int terms, int bn) { return (terms == 3 ? 2 : 1) * bn * kBlockK * 2; }
 // one epilogue staging set / residual slot: fp16 hi chunk (+ fp16 lo chunk | + e4m3 lo8 chunk + e4m3 hi8 chunk)
-__host__ __device__ constexpr int epi_set_bytes(int terms) { return (terms == 1 ? 1 : 2) * kEpiPlaneBytes; }
-constexpr int kEpiLo8Off = kEpiPlaneBytes;                       // kTerms == 2: [128 x 32 B] e4m3 lo8 chunk
+__host__ __device__ constexpr int epi_set_bytes(int fmt) { return (fmt == 0 ? 1 : 2) * kEpiPlaneBytes; }
+constexpr int kEpiLo8Off = kEpiPlaneBytes;                       // format 2: [128 x 32 B] e4m3 lo8 chunk
 constexpr int kEpiHi8Off = kEpiPlaneBytes + kEpiPlaneBytes / 2;  //              [128 x 32 B] e4m3 hi8 chunk
 
 // v[0..15] += e4m3x16(u) * 2^-13   (the lo8 plane of a residual)
@@ -122,16 +118,7 @@ __device__ __forceinline__ void add_lo8x16(float* v, const uint4& u) {
 // e4m3x2 of the rounding residue {(a - low(h2)) 2^13, (b - high(h2)) 2^13}
 __device__ __forceinline__ uint32_t residue_e4m3x2(float a, float b, uint32_t h2) {
   float da, db;
-  asm("{\n"
-      ".reg .b16 l, h;\n"
-      "mov.b32 {l, h}, %2;\n"
-      "neg.f16 l, l;\n"
-      "neg.f16 h, h;\n"
-      "add.rn.f32.f16 %0, l, %3;\n"
-      "add.rn.f32.f16 %1, h, %4;\n"
-      "}\n"
-      : "=f"(da), "=f"(db)
-      : "r"(h2), "f"(a), "f"(b));
+  ptx::residue2(a, b, h2, da, db);
   return static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(da * kLo8Scale, db * kLo8Scale), __NV_SATFINITE, __NV_E4M3));
 }
 __device__ __forceinline__ uint32_t half2_to_e4m3x2(uint32_t h2) {
@@ -141,6 +128,10 @@ __device__ __forceinline__ uint32_t half2_to_e4m3x2(uint32_t h2) {
   return static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(hr, __NV_SATFINITE, __NV_E4M3));
 }
 
+// byte offset of logical 16-byte chunk j (0/1) of row `row` in a 32B-swizzled [rows][32 B] tile (e4m3 chunks)
+__device__ __forceinline__ uint32_t sw32_off(int row, int j) {
+  return static_cast<uint32_t>(row * 32 + ((j ^ ((row >> 2) & 1)) << 4));
+}
 // byte offset of logical 16-byte chunk j of row `row` in a 64B-swizzled [rows][64 B] tile
 __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
   return static_cast<uint32_t>(row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
@@ -149,7 +140,11 @@ __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
 template <int kTerms>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
-  constexpr int kSet = epi_set_bytes(kTerms);  // bytes of one epilogue staging set (hi chunk [+ lo chunk])
+  // storage format of the activation planes this instantiation reads / writes: 0 hi, 1 hi + fp16 lo,
+  // 2 hi + e4m3 lo8 (+ e4m3 hi8)
+  constexpr int kFmt = kTerms == 1 ? 0 : kTerms == 3 ? 1 : 2;
+  constexpr int kSet = epi_set_bytes(kFmt);   // bytes of one epilogue staging set (hi chunk [+ lo / lo8 + hi8 chunk])
+  constexpr int kRSet = kSet;                 // bytes of one residual prefetch slot
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -163,14 +158,14 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   const int w_tile_bytes = p.block_n * kBlockK * 2;
-  const int a_bytes = a_stage_bytes(kTerms, p.tmode);
-  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n, p.tmode);
-  // kTerms == 2 stage layout: [A_hi 16K | A_lo8 8K | (A_hi8 8K)] [W_hi | W_lo (fp16) | W_hi8]   (H layers)
-  //                                                              [W_hi | W_hi8 | W_lo8]          (T layers)
+  const int a_bytes = a_stage_bytes(kTerms);
+  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n);
+  // kTerms == 2, pass 1 (e4m3 tiles) re-uses the stage: [A_lo8 8K | A_hi8 8K] [W_hi8 | W_lo8]
   const int w8_tile_bytes = p.block_n * kBlockK;
-  const int off_a_hi8 = kATileBytes + kATileBytes / 2;
-  const int off_w_hi8 = a_bytes + w_tile_bytes + (p.tmode ? 0 : w_tile_bytes);
-  const int off_w_lo8 = off_w_hi8 + w8_tile_bytes;  // T layers only
+  const int off_a_hi8 = kATileBytes / 2;
+  const int off_w_lo8 = a_bytes + w8_tile_bytes;
+  // k-block iterations per tile: kTerms == 2 runs the K range twice (e4m3 pass, then fp16 pass)
+  const int passes = kTerms == 2 ? 2 : 1;
   uint8_t* obuf_base = stage_base + static_cast<size_t>(p.num_stages) * stage_bytes;        // [groups][out_sets][kSet]
   uint8_t* rbuf_base = obuf_base + (p.out_tma ? kEpiGroups * p.out_sets * kSet : 0);       // [groups][kResBufs][kSet]
   const int warp_idx = threadIdx.x >> 5;
@@ -187,7 +182,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     }
     if (kTerms == 2) {
       ptx::prefetch_tmap(&tm.w_hi8);
-      if (p.tmode) ptx::prefetch_tmap(&tm.a_hi8);
+      ptx::prefetch_tmap(&tm.a_hi8);
     }
     if (p.out_tma) ptx::prefetch_tmap(&tm.o_hi);
     if (p.res_tma) ptx::prefetch_tmap(&tm.r_hi);
@@ -219,6 +214,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     // uniform registers, which the TMA instructions read directly); one elected lane issues.
     int stage = 0;
     uint32_t phase = 0;
+    long long dbg_wait = 0;
+    const long long dbg_p0 = clock64();
+    const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
+    const uint32_t ring_a = ptx::smem_u32(stage_base);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ks = tile / mn_tiles;
       const int mn = tile - ks * mn_tiles;
@@ -227,6 +226,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
       const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
       const long long m0 = static_cast<long long>(m_tile) * kBlockM;
+      const int n0 = n_tile * p.block_n;
       int img_n = 0, base_h = 0, base_w = 0;
       if (p.a.kind == 1) {
         const long long pq = static_cast<long long>(p.a.P) * p.a.Q;
@@ -237,65 +237,74 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         base_h = p0 * p.a.stride - p.a.pad;
         base_w = q0 * p.a.stride - p.a.pad;
       }
-      int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
-      int tr = tap / p.a.S, tsx = tap - tr * p.a.S;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (ptx::elect_one()) {
-          uint8_t* s = stage_base + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sA_hi = s;
-          uint8_t* sA_lo = s + kATileBytes;
-          uint8_t* sW_hi = s + a_bytes;
-          uint8_t* sW_lo = sW_hi + w_tile_bytes;
-          uint32_t tx = static_cast<uint32_t>(stage_bytes);
-          if (p.dbg & 4) tx -= static_cast<uint32_t>(a_bytes);
-          if (p.dbg & 8) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
-          if (tx == 0) {
-            ptx::mbar_arrive(&full_bar[stage]);
+      for (int pass = 0; pass < passes; ++pass) {
+        const bool f8 = kTerms == 2 && pass == 0;
+        int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
+        int tr = tap / p.a.S, tsx = tap - tr * p.a.S;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (p.dbg & 128) {
+            const long long w0 = clock64();
+            ptx::mbar_wait_a(empty_a + stage * 8, phase ^ 1u);
+            dbg_wait += clock64() - w0;
           } else {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
+            ptx::mbar_wait_a(empty_a + stage * 8, phase ^ 1u);
           }
-          if (p.dbg & 4) {
-          } else if (p.a.kind == 1) {
-            ptx::tma_load_im2col_4d(sA_hi, &tm.a_hi, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
-                                    static_cast<uint16_t>(tsx), static_cast<uint16_t>(tr));
-            if (kTerms != 1)  // fp16 lo tile (x3) or e4m3 lo8 tile (c8), both right behind the hi tile
-              ptx::tma_load_im2col_4d(sA_lo, &tm.a_lo, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
-                                      static_cast<uint16_t>(tsx), static_cast<uint16_t>(tr));
-            if (kTerms == 2 && p.tmode)
-              ptx::tma_load_im2col_4d(s + off_a_hi8, &tm.a_hi8, &full_bar[stage], cb * kBlockK, base_w, base_h, img_n,
-                                      static_cast<uint16_t>(tsx), static_cast<uint16_t>(tr));
-          } else {
-            ptx::tma_load_2d(sA_hi, &tm.a_hi, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
-            if (kTerms != 1) ptx::tma_load_2d(sA_lo, &tm.a_lo, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
-            if (kTerms == 2 && p.tmode)
-              ptx::tma_load_2d(s + off_a_hi8, &tm.a_hi8, &full_bar[stage], kb * kBlockK, static_cast<int>(m0));
-          }
-          if (!(p.dbg & 8)) {
-            ptx::tma_load_2d(sW_hi, &tm.w_hi, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-            if (kTerms == 3 || (kTerms == 2 && !p.tmode))
-              ptx::tma_load_2d(sW_lo, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-            if (kTerms == 2) {
-              ptx::tma_load_2d(s + off_w_hi8, &tm.w_hi8, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
-              if (p.tmode) ptx::tma_load_2d(s + off_w_lo8, &tm.w_lo, &full_bar[stage], kb * kBlockK, n_tile * p.block_n);
+          if (ptx::elect_one()) {
+            const uint32_t s = ring_a + static_cast<uint32_t>(stage * stage_bytes);
+            const uint32_t sW = s + a_bytes;
+            const uint32_t fb = full_a + stage * 8;
+            uint32_t tx = static_cast<uint32_t>(stage_bytes);
+            if (p.dbg & 4) tx -= static_cast<uint32_t>(a_bytes);
+            if (p.dbg & 8) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
+            if (tx == 0) {
+              ptx::mbar_arrive_a(fb);
+            } else {
+              ptx::mbar_arrive_expect_tx_a(fb, tx);
+            }
+            // first / second A tile of the stage: (hi, lo) fp16 planes, or the (lo8, hi8) e4m3 planes in pass 1
+            const CUtensorMap* ma0 = f8 ? &tm.a_lo : &tm.a_hi;
+            const CUtensorMap* ma1 = f8 ? &tm.a_hi8 : &tm.a_lo;
+            const uint32_t sA1 = s + (f8 ? off_a_hi8 : kATileBytes);
+            const bool two_a = kTerms == 3 || f8;
+            if (p.dbg & 4) {
+            } else if (p.a.kind == 1) {
+              ptx::tma_load_im2col_4d_a(s, ma0, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
+                                        static_cast<uint16_t>(tr));
+              if (two_a)
+                ptx::tma_load_im2col_4d_a(sA1, ma1, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
+                                          static_cast<uint16_t>(tr));
+            } else {
+              ptx::tma_load_2d_a(s, ma0, fb, kb * kBlockK, static_cast<int>(m0));
+              if (two_a) ptx::tma_load_2d_a(sA1, ma1, fb, kb * kBlockK, static_cast<int>(m0));
+            }
+            if (!(p.dbg & 8)) {
+              if (f8) {
+                ptx::tma_load_2d_a(sW, &tm.w_hi8, fb, kb * kBlockK, n0);
+                ptx::tma_load_2d_a(s + off_w_lo8, &tm.w_lo, fb, kb * kBlockK, n0);
+              } else {
+                ptx::tma_load_2d_a(sW, &tm.w_hi, fb, kb * kBlockK, n0);
+                if (kTerms == 3) ptx::tma_load_2d_a(sW + w_tile_bytes, &tm.w_lo, fb, kb * kBlockK, n0);
+              }
             }
           }
-        }
-        __syncwarp();
-        // next filter tap / channel block (im2col view: kb = tap * cblocks + cb, tap = r * S + s)
-        if (++cb == p.cblocks) {
-          cb = 0;
-          if (++tsx == p.a.S) {
-            tsx = 0;
-            ++tr;
+          __syncwarp();
+          // next filter tap / channel block (im2col view: kb = tap * cblocks + cb, tap = r * S + s)
+          if (++cb == p.cblocks) {
+            cb = 0;
+            if (++tsx == p.a.S) {
+              tsx = 0;
+              ++tr;
+            }
           }
-        }
-        if (++stage == p.num_stages) {
-          stage = 0;
-          phase ^= 1u;
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
+    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0)
+      printf("prod M=%d N=%d K=%d: %lld cycles, %lld waiting for a free stage\n", p.M, p.N, p.K, clock64() - dbg_p0, dbg_wait);
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     // Warp-uniform loop, one elected lane issues each tcgen05.mma / commit (the shared-memory descriptors are
@@ -303,10 +312,12 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     // rate, not the tensor pipe, the limit).
     const uint32_t idesc = ptx::make_idesc_f16_f32(kBlockM, p.block_n);
     const uint32_t stage_base_u32 = ptx::smem_u32(stage_base);
+    const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
+    const uint32_t tfull_a = ptx::smem_u32(tfull_bar), tempty_a = ptx::smem_u32(tempty_bar);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    long long dbg_c0 = 0;
+    long long dbg_c0 = 0, dbg_wfull = 0, dbg_wacc = 0;
     unsigned long long dbg_t0 = 0;
     if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
       dbg_c0 = clock64();
@@ -315,63 +326,72 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local % p.num_acc;
       const uint32_t acc_phase = static_cast<uint32_t>(local / p.num_acc) & 1u;
-      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      if (p.dbg & 128) {
+        const long long w0 = clock64();
+        ptx::mbar_wait_a(tempty_a + acc * 8, acc_phase ^ 1u);
+        dbg_wacc += clock64() - w0;
+      } else {
+        ptx::mbar_wait_a(tempty_a + acc * 8, acc_phase ^ 1u);
+      }
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
-      const uint32_t tmem_c = tmem_d + static_cast<uint32_t>(p.block_n);  // kTerms == 2: e4m3 correction accumulator
       const int ks = tile / mn_tiles;
       const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
       const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after();
-        if (!(p.dbg & 16)) {
-          const uint32_t s = stage_base_u32 + static_cast<uint32_t>(stage * stage_bytes);
-          // descriptors of the k = 0 slice; the slice j advances the 16-byte-granular start address by 2 (32 B)
-          const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(s);
-          const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(s + kATileBytes);
-          const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(s + a_bytes);
-          const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(s + a_bytes + w_tile_bytes);
-          const uint32_t first = kb > kb_begin ? 1u : 0u;
-          auto issue_f8 = [&]() {
-            if constexpr (kTerms == 2) {
-              // e4m3 corrections into the second accumulator (columns + block_n), K = 32 per MMA:
-              // lo8_a * hi8_w  (+ hi8_a * lo8_w on T layers)
-              const uint64_t dA8 = ptx::make_sw64_kmajor_desc(s + kATileBytes);
-              const uint64_t dW8 = ptx::make_sw64_kmajor_desc(s + off_w_hi8);
-              const uint64_t dAh8 = ptx::make_sw64_kmajor_desc(s + off_a_hi8);
-              const uint64_t dWl8 = ptx::make_sw64_kmajor_desc(s + off_w_lo8);
+      for (int pass = 0; pass < passes; ++pass) {
+        const bool f8 = kTerms == 2 && pass == 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (p.dbg & 128) {
+            const long long w0 = clock64();
+            ptx::mbar_wait_a(full_a + stage * 8, phase);
+            dbg_wfull += clock64() - w0;
+          } else {
+            ptx::mbar_wait_a(full_a + stage * 8, phase);
+          }
+          ptx::tc_fence_after();
+          if (!(p.dbg & 16)) {
+            const uint32_t s = stage_base_u32 + static_cast<uint32_t>(stage * stage_bytes);
+            const uint32_t first = kb > kb_begin ? 1u : 0u;
+            // descriptors of the k = 0 slice; slice j advances the 16-byte-granular start address by 2 (32 B)
+            if (f8) {
+              // pass 1, e4m3 corrections x 2^15 (K = 32 per MMA): lo8_a * hi8_w + hi8_a * lo8_w
+              const uint64_t dA_lo8 = ptx::make_sw64_kmajor_desc(s);
+              const uint64_t dA_hi8 = ptx::make_sw64_kmajor_desc(s + off_a_hi8);
+              const uint64_t dW_hi8 = ptx::make_sw64_kmajor_desc(s + a_bytes);
+              const uint64_t dW_lo8 = ptx::make_sw64_kmajor_desc(s + off_w_lo8);
 #pragma unroll
               for (int j = 0; j < kBlockK / 32; ++j) {
-                ptx::umma_f8(tmem_c, dA8 + 2 * j, dW8 + 2 * j, idesc, (first || j > 0) ? 1u : 0u);
-                if (p.tmode) ptx::umma_f8(tmem_c, dAh8 + 2 * j, dWl8 + 2 * j, idesc, 1u);
+                ptx::umma_f8(tmem_d, dA_lo8 + 2 * j, dW_hi8 + 2 * j, idesc, (first || j > 0) ? 1u : 0u);
+                ptx::umma_f8(tmem_d, dA_hi8 + 2 * j, dW_lo8 + 2 * j, idesc, 1u);
+              }
+            } else {
+              const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(s);
+              const uint64_t dA_lo = ptx::make_sw128_kmajor_desc(s + kATileBytes);
+              const uint64_t dW_hi = ptx::make_sw128_kmajor_desc(s + a_bytes);
+              const uint64_t dW_lo = ptx::make_sw128_kmajor_desc(s + a_bytes + w_tile_bytes);
+#pragma unroll
+              for (int j = 0; j < kBlockK / kUmmaK; ++j) {
+                uint32_t accum = (first || j > 0) ? 1u : 0u;
+                if (kTerms == 3) {
+                  ptx::umma_f16(tmem_d, dA_lo + 2 * j, dW_hi + 2 * j, idesc, accum);
+                  ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, 1u);
+                  accum = 1u;
+                }
+                if (kTerms == 2 && j == 0 && !first) {
+                  // first fp16 MMA of the tile: D = A*B + D 2^-15 brings the e4m3 corrections to scale
+                  ptx::umma_f16_rescale_d<kC8AccShift>(tmem_d, dA_hi, dW_hi, idesc);
+                } else {
+                  ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_hi + 2 * j, idesc, accum);
+                }
               }
             }
-          };
-          // alternate the order of the fp16 and e4m3 groups between k-blocks: one kind switch per stage
-          const bool f8_first = kTerms == 2 && ((kb - kb_begin) & 1);
-          if (f8_first) issue_f8();
-#pragma unroll
-          for (int j = 0; j < kBlockK / kUmmaK; ++j) {
-            uint32_t accum = (first || j > 0) ? 1u : 0u;
-            if (kTerms == 3) {
-              ptx::umma_f16(tmem_d, dA_lo + 2 * j, dW_hi + 2 * j, idesc, accum);
-              ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, 1u);
-              accum = 1u;
-            }
-            if (kTerms == 2 && !p.tmode) {  // H layers: weight correction as a second fp16 MMA
-              ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, accum);
-              accum = 1u;
-            }
-            ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_hi + 2 * j, idesc, accum);
           }
-          if (kTerms == 2 && !f8_first) issue_f8();
-        }
-        ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-        if (kb == kb_end - 1) ptx::umma_commit(&tfull_bar[acc]);
-        if (++stage == p.num_stages) {
-          stage = 0;
-          phase ^= 1u;
+          ptx::umma_commit_a(empty_a + stage * 8);  // smem slot reusable once these MMAs retire
+          if (kb == kb_end - 1 && pass == passes - 1) ptx::umma_commit_a(tfull_a + acc * 8);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -380,8 +400,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       const long long c1 = clock64();
-      printf("umma M=%d N=%d K=%d terms=%d tmode=%d: %lld cycles in %llu ns = %.0f MHz\n", p.M, p.N, p.K, kTerms, p.tmode,
-             c1 - dbg_c0, t1 - dbg_t0, 1e3 * double(c1 - dbg_c0) / double(t1 - dbg_t0));
+      printf("umma M=%d N=%d K=%d terms=%d bn=%d stages=%d: %lld cycles in %llu ns = %.0f MHz; MMA warp waited %lld for operands, %lld for an accumulator\n",
+             p.M, p.N, p.K, kTerms, p.block_n, p.num_stages, c1 - dbg_c0, t1 - dbg_t0, 1e3 * double(c1 - dbg_c0) / double(t1 - dbg_t0),
+             dbg_wfull, dbg_wacc);
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue (two groups of four warps) =====================
@@ -395,7 +416,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     const int nchunks = p.block_n / kEpiChunk;
     const uint32_t osets = static_cast<uint32_t>(p.out_sets);
     uint8_t* obuf = obuf_base + grp * p.out_sets * kSet;
-    uint8_t* rbuf = rbuf_base + grp * kResBufs * kSet;
+    uint8_t* rbuf = rbuf_base + grp * kResBufs * kRSet;
     uint64_t* rbar = res_bar + grp * kResBufs;
     // residual chunk stream of this group's tiles, prefetched kResBufs chunks ahead across tile boundaries
     int ri_local = grp, ri_c = 0;
@@ -410,11 +431,13 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         const int mn_i = t % mn_tiles;
         const int mt = mn_i / p.n_tiles;
         const int nt = mn_i - mt * p.n_tiles;
-        uint8_t* dst = rbuf + b * kSet;
+        uint8_t* dst = rbuf + b * kRSet;
         ptx::fence_proxy_async();
-        ptx::mbar_arrive_expect_tx(&rbar[b], static_cast<uint32_t>(kTerms == 2 ? kEpiPlaneBytes + kEpiPlaneBytes / 2 : kSet));
+        ptx::mbar_arrive_expect_tx(&rbar[b], static_cast<uint32_t>(kFmt == 2   ? kEpiPlaneBytes + kEpiPlaneBytes / 2
+                                                                   : kFmt == 1 ? 2 * kEpiPlaneBytes
+                                                                                    : kEpiPlaneBytes));
         ptx::tma_load_2d(dst, &tm.r_hi, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
-        if (kTerms != 1)  // fp16 lo chunk (x3) or e4m3 lo8 chunk (c8)
+        if (kFmt != 0)  // fp16 lo chunk or e4m3 lo8 chunk
           ptx::tma_load_2d(dst + kEpiPlaneBytes, &tm.r_lo, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
       }
       ++r_issued;
@@ -453,12 +476,12 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         const uint4* rh = reinterpret_cast<const uint4*>(ep.res_hi + rrow * ep.ldr + n);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rpre[j] = __ldg(rh + j);
-        if (kTerms == 3 && ep.res_lo) {
+        if (kFmt == 1) {
           const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo + rrow * ep.ldr + n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rpre[4 + j] = __ldg(rl + j);
         }
-        if (kTerms == 2 && ep.res_lo8) {
+        if (kFmt == 2) {
           const uint4* rl = reinterpret_cast<const uint4*>(ep.res_lo8 + rrow * ep.ldr + n);
 #pragma unroll
           for (int j = 0; j < 2; ++j) rpre[4 + j] = __ldg(rl + j);
@@ -470,8 +493,6 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         const int n = n_base + c * kEpiChunk;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
-        uint32_t r2[kTerms == 2 ? 32 : 1];
-        if constexpr (kTerms == 2) ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(p.block_n + c * kEpiChunk), r2);
         uint4 rnow[8];
         if (res_direct) {
 #pragma unroll
@@ -482,25 +503,13 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         if (p.res_tma) {
           const uint32_t b = r_consumed % kResBufs;
           ptx::mbar_wait(&rbar[b], (r_consumed / kResBufs) & 1u);
-          rcur = rbuf + b * kSet;
+          rcur = rbuf + b * kRSet;
           ++r_consumed;
         }
         ptx::tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if constexpr (kTerms == 2) {
-          // + fp8 correction accumulator x 2^-(13 + s_n)
-          const float4* c4 = reinterpret_cast<const float4*>(p.cscale + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 cs = __ldg(c4 + j);
-            v[4 * j + 0] = fmaf(__uint_as_float(r2[4 * j + 0]), cs.x, v[4 * j + 0]);
-            v[4 * j + 1] = fmaf(__uint_as_float(r2[4 * j + 1]), cs.y, v[4 * j + 1]);
-            v[4 * j + 2] = fmaf(__uint_as_float(r2[4 * j + 2]), cs.z, v[4 * j + 2]);
-            v[4 * j + 3] = fmaf(__uint_as_float(r2[4 * j + 3]), cs.w, v[4 * j + 3]);
-          }
-        }
         if (!(p.dbg & 2)) {
           if (ep.bias && p.k_split == 1) {
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
@@ -514,13 +523,14 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             }
           }
           if (rcur) {
-            if constexpr (kTerms == 2) {
-              const uint8_t* r8 = rcur + kEpiLo8Off + row * 32;
-              add_lo8x16(v, *reinterpret_cast<const uint4*>(r8));
-              add_lo8x16(v + 16, *reinterpret_cast<const uint4*>(r8 + 16));
+            if (kFmt == 2) {
+              const uint8_t* r8 = rcur + kEpiLo8Off;
+              add_lo8x16(v, *reinterpret_cast<const uint4*>(r8 + sw32_off(row, 0)));
+              add_lo8x16(v + 16, *reinterpret_cast<const uint4*>(r8 + sw32_off(row, 1)));
             }
 #pragma unroll
-            for (int pl = 0; pl < (kTerms == 3 ? 2 : 1); ++pl) {
+            for (int pl = 0; pl < 2; ++pl) {
+              if (pl == 1 && kFmt != 1) break;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiPlaneBytes + sw64_off(row, j));
@@ -542,11 +552,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
                 v[4 * j + 3] += f.w;
               }
             } else {
-              if (kTerms == 2 && ep.res_lo8) {
+              if (kFmt == 2) {
                 add_lo8x16(v, rnow[4]);
                 add_lo8x16(v + 16, rnow[5]);
               }
-              const int npl = (kTerms == 3 && ep.res_lo) ? 2 : 1;
+              const int npl = kFmt == 1 ? 2 : 1;
 #pragma unroll
               for (int pl = 0; pl < 2; ++pl) {
                 if (pl < npl) {
@@ -575,6 +585,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           }
           if (!(p.dbg & 2)) {
+            uint2 l8[4], h8[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 uh, ul;
@@ -583,24 +594,31 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               uh.z = ptx::pack_half2(v[8 * j + 4], v[8 * j + 5]);
               uh.w = ptx::pack_half2(v[8 * j + 6], v[8 * j + 7]);
               *reinterpret_cast<uint4*>(ob + sw64_off(row, j)) = uh;
-              if (kTerms == 3) {
+              if (kFmt == 1) {
                 ul.x = ptx::residue_half2(v[8 * j + 0], v[8 * j + 1], uh.x);
                 ul.y = ptx::residue_half2(v[8 * j + 2], v[8 * j + 3], uh.y);
                 ul.z = ptx::residue_half2(v[8 * j + 4], v[8 * j + 5], uh.z);
                 ul.w = ptx::residue_half2(v[8 * j + 6], v[8 * j + 7], uh.w);
                 *reinterpret_cast<uint4*>(ob + kEpiPlaneBytes + sw64_off(row, j)) = ul;
               }
-              if (kTerms == 2) {
-                uint2 l8;
-                l8.x = residue_e4m3x2(v[8 * j + 0], v[8 * j + 1], uh.x) | (residue_e4m3x2(v[8 * j + 2], v[8 * j + 3], uh.y) << 16);
-                l8.y = residue_e4m3x2(v[8 * j + 4], v[8 * j + 5], uh.z) | (residue_e4m3x2(v[8 * j + 6], v[8 * j + 7], uh.w) << 16);
-                *reinterpret_cast<uint2*>(ob + kEpiLo8Off + row * 32 + j * 8) = l8;
+              if (kFmt == 2) {
+                l8[j].x = residue_e4m3x2(v[8 * j + 0], v[8 * j + 1], uh.x) | (residue_e4m3x2(v[8 * j + 2], v[8 * j + 3], uh.y) << 16);
+                l8[j].y = residue_e4m3x2(v[8 * j + 4], v[8 * j + 5], uh.z) | (residue_e4m3x2(v[8 * j + 6], v[8 * j + 7], uh.w) << 16);
                 if (p.out_hi8) {
-                  uint2 h8;
-                  h8.x = half2_to_e4m3x2(uh.x) | (half2_to_e4m3x2(uh.y) << 16);
-                  h8.y = half2_to_e4m3x2(uh.z) | (half2_to_e4m3x2(uh.w) << 16);
-                  *reinterpret_cast<uint2*>(ob + kEpiHi8Off + row * 32 + j * 8) = h8;
+                  h8[j].x = half2_to_e4m3x2(uh.x) | (half2_to_e4m3x2(uh.y) << 16);
+                  h8[j].y = half2_to_e4m3x2(uh.z) | (half2_to_e4m3x2(uh.w) << 16);
                 }
+              }
+            }
+            if (kFmt == 2) {
+              // e4m3 chunks: [128 rows x 32 B], 32B-swizzled (16-byte writes of consecutive rows hit distinct banks)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                *reinterpret_cast<uint4*>(ob + kEpiLo8Off + sw32_off(row, j)) =
+                    make_uint4(l8[2 * j].x, l8[2 * j].y, l8[2 * j + 1].x, l8[2 * j + 1].y);
+                if (p.out_hi8)
+                  *reinterpret_cast<uint4*>(ob + kEpiHi8Off + sw32_off(row, j)) =
+                      make_uint4(h8[2 * j].x, h8[2 * j].y, h8[2 * j + 1].x, h8[2 * j + 1].y);
               }
             }
           }
@@ -614,8 +632,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             if (!(p.dbg & 1)) {
               const int m0 = m_tile * kBlockM;
               ptx::tma_store_2d(&tm.o_hi, ob, n, m0);
-              if (kTerms != 1) ptx::tma_store_2d(&tm.o_lo, ob + kEpiPlaneBytes, n, m0);  // fp16 lo / e4m3 lo8
-              if (kTerms == 2 && p.out_hi8) ptx::tma_store_2d(&tm.o_hi8, ob + kEpiHi8Off, n, m0);
+              if (kFmt != 0) ptx::tma_store_2d(&tm.o_lo, ob + kEpiPlaneBytes, n, m0);  // fp16 lo / e4m3 lo8
+              if (p.out_hi8) ptx::tma_store_2d(&tm.o_hi8, ob + kEpiHi8Off, n, m0);
             }
             ptx::tma_store_commit();
           }
@@ -643,13 +661,13 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
                 ul.w = ptx::residue_half2(v[8 * j + 6], v[8 * j + 7], uh.w);
                 ol[j] = ul;
               }
-              if (kTerms == 2 && ep.out_lo8) {
+              if (ep.out_lo8) {
                 uint2 l8;
                 l8.x = residue_e4m3x2(v[8 * j + 0], v[8 * j + 1], uh.x) | (residue_e4m3x2(v[8 * j + 2], v[8 * j + 3], uh.y) << 16);
                 l8.y = residue_e4m3x2(v[8 * j + 4], v[8 * j + 5], uh.z) | (residue_e4m3x2(v[8 * j + 6], v[8 * j + 7], uh.w) << 16);
                 *reinterpret_cast<uint2*>(ep.out_lo8 + m * ep.ldo + n + 8 * j) = l8;
               }
-              if (kTerms == 2 && ep.out_hi8) {
+              if (ep.out_hi8) {
                 uint2 h8;
                 h8.x = half2_to_e4m3x2(uh.x) | (half2_to_e4m3x2(uh.y) << 16);
                 h8.y = half2_to_e4m3x2(uh.z) | (half2_to_e4m3x2(uh.w) << 16);
@@ -794,16 +812,18 @@ inline int tune_env(const char* name) {
 }
 
 // A planes: for kind 0 the [M,K] matrix, for kind 1 the NHWC activation.  W planes: [N,K].
-// terms == 2 (fp16c8): A = hi + lo8 (+ hi8 -> T layer), W = hi + lo + hi8 (+ lo8 for T layers), cscale[N].
+// terms == 2 (fp16c8): A = hi + lo8 + hi8, W = hi + hi8 + lo8 (scales: common.cuh).
+// The planes the epilogue writes / the residual carries follow from the pointers set in `ep`.
 inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
                                const Epilogue& ep, int num_sms, int force_block_n = 0, int k_split = 1,
-                               long long split_stride = 0, const float* cscale = nullptr) {
+                               long long split_stride = 0) {
   MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
   MCG_CHECK(terms >= 1 && terms <= 3, "the tcgen05 GEMM runs 1, 2 (fp16 + e4m3 corrections) or 3 MMA terms per k-step");
   MCG_CHECK(terms != 3 || (A.lo && W.lo), "3-term GEMM needs lo planes");
-  MCG_CHECK(terms != 2 || (A.lo8 && W.lo && W.hi8 && cscale), "fp16c8 GEMM needs an e4m3 activation low plane, fp16 lo + e4m3 hi weights and channel scales");
+  MCG_CHECK(terms != 2 || (A.lo8 && A.hi8 && W.hi8 && W.lo8), "fp16c8 GEMM needs the e4m3 lo8 / hi8 planes of both operands");
   static const int tune_res_bn = tune_env("MCG_TUNE_RES_BN");
   static const int tune_out_sets = tune_env("MCG_TUNE_OUT_SETS");
+  static const int tune_bn = tune_env("MCG_TUNE_BN");
   static const int dbg_flags = tune_env("MCG_DEBUG_FLAGS");
   UmmaPlan pl;
   pl.terms = terms;
@@ -812,32 +832,35 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.N = N;
   p.K = K;
   p.dbg = dbg_flags;
-  p.tmode = (terms == 2 && A.hi8 != nullptr && W.lo8 != nullptr) ? 1 : 0;
-  p.cscale = cscale;
+  p.out_fmt = ep.out_lo ? 1 : ep.out_lo8 ? 2 : 0;
+  p.res_fmt = ep.res_lo ? 1 : ep.res_lo8 ? 2 : 0;
+  MCG_CHECK(!(ep.out_lo && ep.out_lo8) && !(ep.res_lo && ep.res_lo8), "a tensor has either an fp16 or an e4m3 low plane");
+  MCG_CHECK(ep.out_hi8 == nullptr || p.out_fmt == 2, "the hi8 plane belongs to the hi + lo8 storage format");
+  // the kernel instantiation fixes the storage format of the planes it reads and writes
+  const int fmt = terms == 1 ? 0 : terms == 3 ? 1 : 2;
+  MCG_CHECK(ep.out_f32 != nullptr || p.out_fmt == fmt, "output planes do not match the precision mode's storage format");
+  MCG_CHECK(ep.res_mode == RES_NONE || ep.res_f32 != nullptr || p.res_fmt == fmt,
+            "residual planes do not match the precision mode's storage format");
   // epilogue staging (per epilogue group): TMA-store staging when the output is fp16 planes, plus residual
   // prefetch buffers for the same-shape residual
-  const bool out_lo_ok = terms == 1 || (terms == 3 && ep.out_lo != nullptr) || (terms == 2 && ep.out_lo8 != nullptr);
-  const bool res_lo_ok = terms == 1 || (terms == 3 && ep.res_lo != nullptr) || (terms == 2 && ep.res_lo8 != nullptr);
-  p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 16 == 0 && out_lo_ok) ? 1 : 0;
-  p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0 &&
-               res_lo_ok)
-                  ? 1
-                  : 0;
-  const int set_bytes = epi_set_bytes(terms);
-  const int res_bytes = p.res_tma ? kEpiGroups * kResBufs * set_bytes : 0;
+  p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 16 == 0) ? 1 : 0;
+  p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0) ? 1 : 0;
+  p.out_hi8 = (p.out_tma && ep.out_hi8 != nullptr) ? 1 : 0;
+  const int set_bytes = epi_set_bytes(p.out_fmt);
+  const int res_bytes = p.res_tma ? kEpiGroups * kResBufs * epi_set_bytes(p.res_fmt) : 0;
   const int fixed = 1024 + kSmemBarrierBytes + res_bytes;
   auto ring_budget = [&](int out_sets) { return kMaxDynSmem - fixed - (p.out_tma ? kEpiGroups * out_sets * set_bytes : 0); };
   // residual (bottleneck conv3) layers are HBM-bound with short K loops: 2 stages are enough there
   const int min_stages = p.res_tma ? 2 : 3;
   int bn = force_block_n;
   if (bn == 0 && p.res_tma && tune_res_bn > 0 && N % tune_res_bn == 0) bn = tune_res_bn;
+  if (bn == 0 && tune_bn > 0 && N % tune_bn == 0) bn = tune_bn;
   if (bn == 0) {
     // largest tile that divides N and still leaves enough pipeline stages beside one staging set per group
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (N % c) continue;
-      if (terms == 2 && c > 128) continue;  // main + correction accumulator: 2 x block_n TMEM columns per tile
-      const int sb = a_stage_bytes(terms, p.tmode) + w_stage_bytes(terms, c, p.tmode);
+      const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, c);
       if (ring_budget(1) / sb >= min_stages || c == 64) {
         bn = c;
         break;
@@ -845,9 +868,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     }
   }
   MCG_CHECK(bn > 0 && N % bn == 0 && bn % 64 == 0 && bn <= 256, "bad block_n");
-  MCG_CHECK(terms != 2 || bn <= 128, "fp16c8 needs block_n <= 128");
   p.block_n = bn;
-  const int stage_bytes = a_stage_bytes(terms, p.tmode) + w_stage_bytes(terms, bn, p.tmode);
+  const int stage_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, bn);
   // double-buffer the staging when that does not cost a needed pipeline stage
   p.out_sets = 1;
   if (p.out_tma && ring_budget(2) / stage_bytes >= min_stages) p.out_sets = 2;
@@ -857,9 +879,7 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   static const int tune_stages = tune_env("MCG_TUNE_STAGES");
   if (tune_stages >= 2 && p.num_stages > tune_stages) p.num_stages = tune_stages;
   MCG_CHECK(p.num_stages >= 2, "not enough shared memory for 2 stages");
-  p.acc_cols = terms == 2 ? 2 * bn : (bn > 128 ? 256 : 128);
-  p.out_hi8 = (terms == 2 && p.out_tma && ep.out_hi8 != nullptr) ? 1 : 0;
-  MCG_CHECK(terms != 2 || ep.out_hi8 == nullptr || p.out_tma || ep.out_f32 == nullptr, "hi8 output needs a planes epilogue");
+  p.acc_cols = bn > 128 ? 256 : 128;
   p.num_acc = kTmemCols / p.acc_cols;
   p.num_kb = K / kBlockK;
   p.m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
@@ -869,7 +889,7 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   if (a.kind == 1) MCG_CHECK(K == a.R * a.S * a.C, "im2col K mismatch");
   p.ep = ep;
   if (k_split > 1) {
-    MCG_CHECK(ep.out_f32 != nullptr && ep.res_mode == RES_NONE && !ep.relu && k_split <= p.num_kb,
+    MCG_CHECK(ep.out_f32 != nullptr && ep.res_mode == RES_NONE && !ep.relu && k_split <= p.num_kb && terms != 2,
               "split-K needs a plain fp32 output (bias / activation are applied by the reduction)");
     p.k_split = k_split;
     p.split_stride = split_stride;
@@ -890,24 +910,23 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : tm.w_hi;
   tm.o_hi = tm.o_lo = tm.r_hi = tm.r_lo = tm.w_hi;  // placeholders when unused
   tm.a_hi8 = tm.w_hi8 = tm.o_hi8 = tm.w_hi;
+  const CUtensorMapSwizzle sw64 = CU_TENSOR_MAP_SWIZZLE_64B;
   if (terms == 2) {
-    const CUtensorMapSwizzle sw64 = CU_TENSOR_MAP_SWIZZLE_64B;
     tm.a_lo = a.kind == 1 ? make_tmap_im2col_u8(A.lo8, a) : make_tmap_2d_u8(A.lo8, M, K, a.lda, kBlockM, kBlockK, sw64);
-    if (p.tmode)
-      tm.a_hi8 = a.kind == 1 ? make_tmap_im2col_u8(A.hi8, a) : make_tmap_2d_u8(A.hi8, M, K, a.lda, kBlockM, kBlockK, sw64);
+    tm.a_hi8 = a.kind == 1 ? make_tmap_im2col_u8(A.hi8, a) : make_tmap_2d_u8(A.hi8, M, K, a.lda, kBlockM, kBlockK, sw64);
     tm.w_hi8 = make_tmap_2d_u8(W.hi8, N, K, K, bn, kBlockK, sw64);
-    tm.w_lo = p.tmode ? make_tmap_2d_u8(W.lo8, N, K, K, bn, kBlockK, sw64) : make_tmap_2d(W.lo, N, K, K, bn);
+    tm.w_lo = make_tmap_2d_u8(W.lo8, N, K, K, bn, kBlockK, sw64);
   }
   if (p.out_tma) {
-    tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
-    tm.o_lo = terms == 3 ? make_tmap_2d(ep.out_lo, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.o_hi;
-    if (terms == 2) tm.o_lo = make_tmap_2d_u8(ep.out_lo8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (p.out_hi8) tm.o_hi8 = make_tmap_2d_u8(ep.out_hi8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
+    tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, kBlockM, kEpiChunk, sw64);
+    if (p.out_fmt == 1) tm.o_lo = make_tmap_2d(ep.out_lo, M, N, ep.ldo, kBlockM, kEpiChunk, sw64);
+    if (p.out_fmt == 2) tm.o_lo = make_tmap_2d_u8(ep.out_lo8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (p.out_hi8) tm.o_hi8 = make_tmap_2d_u8(ep.out_hi8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_32B);
   }
   if (p.res_tma) {
-    tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B);
-    tm.r_lo = terms == 3 ? make_tmap_2d(ep.res_lo, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_64B) : tm.r_hi;
-    if (terms == 2) tm.r_lo = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_NONE);
+    tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, kBlockM, kEpiChunk, sw64);
+    if (p.res_fmt == 1) tm.r_lo = make_tmap_2d(ep.res_lo, M, N, ep.ldr, kBlockM, kEpiChunk, sw64);
+    if (p.res_fmt == 2) tm.r_lo = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_32B);
   }
   return pl;
 }

@@ -36,6 +36,7 @@ CASES = [
 # max |err| relative to max |ref|: split-fp16 x3 and the fp32 CUDA-core kernel are fp32-class,
 # single fp16 carries 2^-11 operand rounding
 # single fp16 carries 2^-11 operand rounding; fp16c8 corrects both roundings to ~4 more bits in e4m3
+# (largest |activation| in these cases ~5: e4m3 lo8 / hi8 stay in their normal range)
 TOL = {'simt': 5e-6, 'fp16x3': 2e-5, 'fp16c8': 2e-4, 'fp16': 1e-3}
 
 
@@ -76,17 +77,10 @@ def test_conv_parity(engine, case):
     assert _run(engine, case) < TOL[engine]
 
 
-@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
-def test_conv_parity_fp16c8_tensor_bound_layers(case):
-    """out_mode bit 1: the input carries the e4m3 hi8 plane, both corrections run as fp8 MMAs ("T" layers)."""
-    assert _run('fp16c8', case, out_mode=2) < TOL['fp16c8']
-
-
 @pytest.mark.parametrize('case', [CASES[0], CASES[3], CASES[4], CASES[8], CASES[15]], ids=lambda c: c[0])
 def test_conv_fp16c8_emits_hi8_plane(case):
-    """out_mode bit 2: the e4m3 copy of the output a tensor-bound consumer reads."""
+    """out_mode bit 2: the e4m3 copy of the output's hi plane (operand of the next layer's weight correction)."""
     assert _run('fp16c8', case, out_mode=4) <= 1.0
-    assert _run('fp16c8', case, out_mode=6) <= 1.0
 
 
 @pytest.mark.parametrize('engine', ['fp16x3', 'fp16c8', 'fp16'])

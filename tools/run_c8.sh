@@ -3,9 +3,7 @@ mkdir -p gpurun_out
 {
 timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -x -q 2>&1 | tail -5
 echo "=== layer times"
-timeout 300 python tools/layer_times.py fp16c8 32 detail
-timeout 300 python tools/layer_times.py fp16x3 32 detail
-timeout 300 python tools/layer_times.py fp16 32 detail
+for prec in ${PRECS:-fp16c8}; do timeout 300 python tools/layer_times.py $prec 32 detail; done
 } > gpurun_out/c8.log 2>&1
 python - <<'PY'
 import json
