@@ -699,7 +699,14 @@ class Engine {
     if (tensor) {
       auto it = plans_.find(key);
       if (it == plans_.end()) {
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride);
+        // CTA pairs (tcgen05 cta_group::2, 256-row tiles) where the W tile is worth sharing: env MCG_TUNE_PAIR
+        // 0 off, 1 the 3x3 / strided convolutions, 2 every trunk convolution with >= 1 tile per pair
+        // (measured, profiles/: fp16c8 gains on both, fp16x3 / fp16 only on the 3x3 layers)
+        static const int tune_pair = std::getenv("MCG_TUNE_PAIR") ? std::atoi(std::getenv("MCG_TUNE_PAIR")) : -1;
+        const int pair_mode = tune_pair >= 0 ? tune_pair : (terms == 2 ? 2 : 1);
+        const bool big = M >= 2 * kBlockM * (num_sms_ / 2) && k_split == 1 && ep.out_f32 == nullptr;
+        const int pair = (big && ((pair_mode == 1 && geom.kind == 1) || pair_mode == 2)) ? 1 : 0;
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, pair);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -1516,7 +1523,9 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
         return MCG_ERR_UNSUPPORTED;
       }
       const int terms = engine == MCG_PRECISION_FP16X3 ? 3 : c8 ? 2 : 1;
-      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n);
+      // force_block_n >= 1000: the CTA-pair (cta_group::2) variant with block_n = force_block_n - 1000 (0 = automatic)
+      const int pair = force_block_n >= 1000 ? 1 : 0;
+      UmmaPlan pl = make_umma_plan(terms, px, g, pw, M, Cout, K, ep, sms, force_block_n % 1000, 1, 0, pair);
       launch_umma(pl, st);
       if (planes_out) {
         if (c8_hi8_out)

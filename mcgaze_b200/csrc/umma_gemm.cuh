@@ -137,7 +137,11 @@ __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
   return static_cast<uint32_t>(row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int kTerms>
+// kPair: the kernel runs as clusters of two CTAs (one SM pair) that share each tile of 256 rows x block_n
+// columns through tcgen05 cta_group::2: every CTA loads its own 128 rows of A and HALF of the W rows, the leader
+// CTA issues one M = 256 MMA over both, each CTA drains its own 128 accumulator rows.  Halves the W bytes every
+// SM pulls from L2 per FLOP (the 3x3 convolutions are L2 -> shared-memory bound with 128 x 256 tiles).
+template <int kTerms, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   // storage format of the activation planes this instantiation reads / writes: 0 hi, 1 hi + fp16 lo,
@@ -157,11 +161,15 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiGroups * kResBufs);
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
-  const int w_tile_bytes = p.block_n * kBlockK * 2;
+  // rows of W this CTA keeps in shared memory (a CTA pair splits the block_n rows)
+  const int w_rows = kPair ? p.block_n / 2 : p.block_n;
+  const uint32_t cta_rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader_cta = cta_rank == 0;
+  const int w_tile_bytes = w_rows * kBlockK * 2;
   const int a_bytes = a_stage_bytes(kTerms);
-  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, p.block_n);
+  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, w_rows);
   // kTerms == 2, pass 1 (e4m3 tiles) re-uses the stage: [A_lo8 8K | A_hi8 8K] [W_hi8 | W_lo8]
-  const int w8_tile_bytes = p.block_n * kBlockK;
+  const int w8_tile_bytes = w_rows * kBlockK;
   const int off_a_hi8 = kATileBytes / 2;
   const int off_w_lo8 = a_bytes + w8_tile_bytes;
   // k-block iterations per tile: kTerms == 2 runs the K range twice (e4m3 pass, then fp16 pass)
@@ -189,24 +197,34 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&full_bar[i], kPair ? 2 : 1);  // pair: one arrive per CTA, on the leader's barrier
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per warp of the owning epilogue group
+      // one arrive per warp of the owning epilogue group (pair: of both CTAs, on the leader's barrier)
+      ptx::mbar_init(&tempty_bar[i], kPair ? 8 : 4);
     }
     for (int i = 0; i < kEpiGroups * kResBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp_idx == 2) {
-    ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
-    ptx::tmem_relinquish();
+    if (kPair) {
+      ptx::tmem_alloc_pair(tmem_ptr_smem, kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (kPair) ptx::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // persistent tile walk: a CTA pair walks the tile list together
+  const int walker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int walkers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -218,15 +236,16 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     const long long dbg_p0 = clock64();
     const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
     const uint32_t ring_a = ptx::smem_u32(stage_base);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = walker; tile < num_tiles; tile += walkers) {
       const int ks = tile / mn_tiles;
       const int mn = tile - ks * mn_tiles;
       const int m_tile = mn / p.n_tiles;
       const int n_tile = mn - m_tile * p.n_tiles;
       const int kb_begin = static_cast<int>(static_cast<long long>(ks) * p.num_kb / p.k_split);
       const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
-      const long long m0 = static_cast<long long>(m_tile) * kBlockM;
-      const int n0 = n_tile * p.block_n;
+      // pair: m_tile counts 256-row tiles, this CTA owns rows [128 rank, 128 rank + 128) and W rows [w_rows rank, ...)
+      const long long m0 = (static_cast<long long>(m_tile) * (kPair ? 2 : 1) + cta_rank) * kBlockM;
+      const int n0 = n_tile * p.block_n + static_cast<int>(cta_rank) * (kPair ? w_rows : 0);
       int img_n = 0, base_h = 0, base_w = 0;
       if (p.a.kind == 1) {
         const long long pq = static_cast<long long>(p.a.P) * p.a.Q;
@@ -252,15 +271,34 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           if (ptx::elect_one()) {
             const uint32_t s = ring_a + static_cast<uint32_t>(stage * stage_bytes);
             const uint32_t sW = s + a_bytes;
-            const uint32_t fb = full_a + stage * 8;
+            // pair: both CTAs' loads signal the LEADER's full barrier (it counts the bytes of both)
+            const uint32_t fb = kPair ? ptx::mapa(full_a + stage * 8, 0) : full_a + stage * 8;
             uint32_t tx = static_cast<uint32_t>(stage_bytes);
             if (p.dbg & 4) tx -= static_cast<uint32_t>(a_bytes);
             if (p.dbg & 8) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
-            if (tx == 0) {
+            if (kPair) {
+              if (leader_cta)
+                ptx::mbar_arrive_expect_tx_a(full_a + stage * 8, 2 * tx);
+              else
+                ptx::mbar_arrive_cluster_a(fb);
+            } else if (tx == 0) {
               ptx::mbar_arrive_a(fb);
             } else {
               ptx::mbar_arrive_expect_tx_a(fb, tx);
             }
+            auto tma_2d = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+              if (kPair)
+                ptx::tma_load_2d_pair_a(dst, m, bar, c0, c1);
+              else
+                ptx::tma_load_2d_a(dst, m, bar, c0, c1);
+            };
+            auto tma_im2col = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n, uint16_t ow,
+                                  uint16_t oh) {
+              if (kPair)
+                ptx::tma_load_im2col_4d_pair_a(dst, m, bar, c, w, h, n, ow, oh);
+              else
+                ptx::tma_load_im2col_4d_a(dst, m, bar, c, w, h, n, ow, oh);
+            };
             // first / second A tile of the stage: (hi, lo) fp16 planes, or the (lo8, hi8) e4m3 planes in pass 1
             const CUtensorMap* ma0 = f8 ? &tm.a_lo : &tm.a_hi;
             const CUtensorMap* ma1 = f8 ? &tm.a_hi8 : &tm.a_lo;
@@ -268,22 +306,22 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             const bool two_a = kTerms == 3 || f8;
             if (p.dbg & 4) {
             } else if (p.a.kind == 1) {
-              ptx::tma_load_im2col_4d_a(s, ma0, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
+              tma_im2col(s, ma0, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
                                         static_cast<uint16_t>(tr));
               if (two_a)
-                ptx::tma_load_im2col_4d_a(sA1, ma1, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
+                tma_im2col(sA1, ma1, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
                                           static_cast<uint16_t>(tr));
             } else {
-              ptx::tma_load_2d_a(s, ma0, fb, kb * kBlockK, static_cast<int>(m0));
-              if (two_a) ptx::tma_load_2d_a(sA1, ma1, fb, kb * kBlockK, static_cast<int>(m0));
+              tma_2d(s, ma0, fb, kb * kBlockK, static_cast<int>(m0));
+              if (two_a) tma_2d(sA1, ma1, fb, kb * kBlockK, static_cast<int>(m0));
             }
             if (!(p.dbg & 8)) {
               if (f8) {
-                ptx::tma_load_2d_a(sW, &tm.w_hi8, fb, kb * kBlockK, n0);
-                ptx::tma_load_2d_a(s + off_w_lo8, &tm.w_lo, fb, kb * kBlockK, n0);
+                tma_2d(sW, &tm.w_hi8, fb, kb * kBlockK, n0);
+                tma_2d(s + off_w_lo8, &tm.w_lo, fb, kb * kBlockK, n0);
               } else {
-                ptx::tma_load_2d_a(sW, &tm.w_hi, fb, kb * kBlockK, n0);
-                if (kTerms == 3) ptx::tma_load_2d_a(sW + w_tile_bytes, &tm.w_lo, fb, kb * kBlockK, n0);
+                tma_2d(sW, &tm.w_hi, fb, kb * kBlockK, n0);
+                if (kTerms == 3) tma_2d(sW + w_tile_bytes, &tm.w_lo, fb, kb * kBlockK, n0);
               }
             }
           }
@@ -310,8 +348,26 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     // Warp-uniform loop, one elected lane issues each tcgen05.mma / commit (the shared-memory descriptors are
     // then computed on the uniform datapath; a lane-0-only loop costs ~5 R2UR moves per MMA and made the issue
     // rate, not the tensor pipe, the limit).
-    const uint32_t idesc = ptx::make_idesc_f16_f32(kBlockM, p.block_n);
+    const uint32_t idesc = ptx::make_idesc_f16_f32(kPair ? 2 * kBlockM : kBlockM, p.block_n);
     const uint32_t stage_base_u32 = ptx::smem_u32(stage_base);
+    auto mma_f16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+      if (kPair)
+        ptx::umma_f16_pair(d, a, b, idesc, acc);
+      else
+        ptx::umma_f16(d, a, b, idesc, acc);
+    };
+    auto mma_f8 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+      if (kPair)
+        ptx::umma_f8_pair(d, a, b, idesc, acc);
+      else
+        ptx::umma_f8(d, a, b, idesc, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (kPair)
+        ptx::umma_commit_pair_a(bar);
+      else
+        ptx::umma_commit_a(bar);
+    };
     const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
     const uint32_t tfull_a = ptx::smem_u32(tfull_bar), tempty_a = ptx::smem_u32(tempty_bar);
     int stage = 0;
@@ -323,7 +379,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       dbg_c0 = clock64();
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = walker; tile < num_tiles && leader_cta; tile += walkers, ++local) {
       const int acc = local % p.num_acc;
       const uint32_t acc_phase = static_cast<uint32_t>(local / p.num_acc) & 1u;
       if (p.dbg & 128) {
@@ -361,8 +417,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               const uint64_t dW_lo8 = ptx::make_sw64_kmajor_desc(s + off_w_lo8);
 #pragma unroll
               for (int j = 0; j < kBlockK / 32; ++j) {
-                ptx::umma_f8(tmem_d, dA_lo8 + 2 * j, dW_hi8 + 2 * j, idesc, (first || j > 0) ? 1u : 0u);
-                ptx::umma_f8(tmem_d, dA_hi8 + 2 * j, dW_lo8 + 2 * j, idesc, 1u);
+                mma_f8(tmem_d, dA_lo8 + 2 * j, dW_hi8 + 2 * j, (first || j > 0) ? 1u : 0u);
+                mma_f8(tmem_d, dA_hi8 + 2 * j, dW_lo8 + 2 * j, 1u);
               }
             } else {
               const uint64_t dA_hi = ptx::make_sw128_kmajor_desc(s);
@@ -373,21 +429,24 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               for (int j = 0; j < kBlockK / kUmmaK; ++j) {
                 uint32_t accum = (first || j > 0) ? 1u : 0u;
                 if (kTerms == 3) {
-                  ptx::umma_f16(tmem_d, dA_lo + 2 * j, dW_hi + 2 * j, idesc, accum);
-                  ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, idesc, 1u);
+                  mma_f16(tmem_d, dA_lo + 2 * j, dW_hi + 2 * j, accum);
+                  mma_f16(tmem_d, dA_hi + 2 * j, dW_lo + 2 * j, 1u);
                   accum = 1u;
                 }
                 if (kTerms == 2 && j == 0 && !first) {
                   // first fp16 MMA of the tile: D = A*B + D 2^-15 brings the e4m3 corrections to scale
-                  ptx::umma_f16_rescale_d<kC8AccShift>(tmem_d, dA_hi, dW_hi, idesc);
+                  if (kPair)
+                    ptx::umma_f16_rescale_d_pair<kC8AccShift>(tmem_d, dA_hi, dW_hi, idesc);
+                  else
+                    ptx::umma_f16_rescale_d<kC8AccShift>(tmem_d, dA_hi, dW_hi, idesc);
                 } else {
-                  ptx::umma_f16(tmem_d, dA_hi + 2 * j, dW_hi + 2 * j, idesc, accum);
+                  mma_f16(tmem_d, dA_hi + 2 * j, dW_hi + 2 * j, accum);
                 }
               }
             }
           }
-          ptx::umma_commit_a(empty_a + stage * 8);  // smem slot reusable once these MMAs retire
-          if (kb == kb_end - 1 && pass == passes - 1) ptx::umma_commit_a(tfull_a + acc * 8);
+          commit(empty_a + stage * 8);  // smem slot reusable once these MMAs retire
+          if (kb == kb_end - 1 && pass == passes - 1) commit(tfull_a + acc * 8);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
@@ -422,15 +481,16 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     int ri_local = grp, ri_c = 0;
     uint32_t r_issued = 0, r_consumed = 0;
     auto res_issue = [&]() {
-      const int t = blockIdx.x + ri_local * static_cast<int>(gridDim.x);
+      const int t = walker + ri_local * walkers;
       if (t >= num_tiles) return;
       const uint32_t b = r_issued % kResBufs;
       if (leader && (p.dbg & 32)) {
         ptx::mbar_arrive(&rbar[b]);
       } else if (leader) {
         const int mn_i = t % mn_tiles;
-        const int mt = mn_i / p.n_tiles;
-        const int nt = mn_i - mt * p.n_tiles;
+        const int mtile = mn_i / p.n_tiles;
+        const int nt = mn_i - mtile * p.n_tiles;
+        const int mt = mtile * (kPair ? 2 : 1) + static_cast<int>(cta_rank);  // 128-row tile of this CTA
         uint8_t* dst = rbuf + b * kRSet;
         ptx::fence_proxy_async();
         ptx::mbar_arrive_expect_tx(&rbar[b], static_cast<uint32_t>(kFmt == 2   ? kEpiPlaneBytes + kEpiPlaneBytes / 2
@@ -452,7 +512,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     }
     uint32_t ostores = 0;  // chunks handed to TMA so far (staging set = ostores % osets)
     for (int local = grp;; local += kEpiGroups) {
-      const int tile = blockIdx.x + local * static_cast<int>(gridDim.x);
+      const int tile = walker + local * walkers;
       if (tile >= num_tiles) break;
       const int ks = tile / mn_tiles;
       const int mn = tile - ks * mn_tiles;
@@ -460,7 +520,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const int n_tile = mn - m_tile * p.n_tiles;
       const int acc = local % p.num_acc;
       const uint32_t acc_phase = static_cast<uint32_t>(local / p.num_acc) & 1u;
-      const long long m = static_cast<long long>(m_tile) * kBlockM + row;
+      const int m_tile_cta = m_tile * (kPair ? 2 : 1) + static_cast<int>(cta_rank);  // 128-row tile of this CTA
+      const long long m = static_cast<long long>(m_tile_cta) * kBlockM + row;
       const bool valid = m < p.M;
       const int n_base = n_tile * p.block_n;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -630,7 +691,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           if (p.res_tma) res_issue();
           if (leader) {
             if (!(p.dbg & 1)) {
-              const int m0 = m_tile * kBlockM;
+              const int m0 = m_tile_cta * kBlockM;
               ptx::tma_store_2d(&tm.o_hi, ob, n, m0);
               if (kFmt != 0) ptx::tma_store_2d(&tm.o_lo, ob + kEpiPlaneBytes, n, m0);  // fp16 lo / e4m3 lo8
               if (p.out_hi8) ptx::tma_store_2d(&tm.o_hi8, ob + kEpiHi8Off, n, m0);
@@ -679,7 +740,12 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kPair && !leader_cta)
+          ptx::mbar_arrive_cluster_a(ptx::mapa(ptx::smem_u32(&tempty_bar[acc]), 0));  // the leader's MMA warp waits
+        else
+          ptx::mbar_arrive(&tempty_bar[acc]);
+      }
     }
     // smem must stay valid until every bulk store has been read out
     if (p.out_tma && leader) ptx::tma_store_wait_all<0>();
@@ -687,9 +753,13 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (kPair) ptx::cluster_sync();  // no CTA leaves while its peer may still arrive on its barriers / read its smem
   if (warp_idx == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair)
+      ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else
+      ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -792,6 +862,7 @@ inline CUtensorMap make_tmap_im2col(const __half* base, const AGeom& g) {
 struct UmmaPlan {
   UmmaMaps tm;
   UmmaParams p;
+  int pair = 0;  // 1: clusters of two CTAs, tcgen05 cta_group::2 (tiles of 256 rows)
   int terms = 3;
   int grid = 0;
   int smem = 0;
@@ -816,8 +887,9 @@ inline int tune_env(const char* name) {
 // The planes the epilogue writes / the residual carries follow from the pointers set in `ep`.
 inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
                                const Epilogue& ep, int num_sms, int force_block_n = 0, int k_split = 1,
-                               long long split_stride = 0) {
+                               long long split_stride = 0, int pair = 0) {
   MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
+  MCG_CHECK(!pair || k_split == 1, "CTA-pair tiles do not combine with split-K");
   MCG_CHECK(terms >= 1 && terms <= 3, "the tcgen05 GEMM runs 1, 2 (fp16 + e4m3 corrections) or 3 MMA terms per k-step");
   MCG_CHECK(terms != 3 || (A.lo && W.lo), "3-term GEMM needs lo planes");
   MCG_CHECK(terms != 2 || (A.lo8 && A.hi8 && W.hi8 && W.lo8), "fp16c8 GEMM needs the e4m3 lo8 / hi8 planes of both operands");
@@ -827,6 +899,7 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   static const int dbg_flags = tune_env("MCG_DEBUG_FLAGS");
   UmmaPlan pl;
   pl.terms = terms;
+  pl.pair = pair ? 1 : 0;
   UmmaParams& p = pl.p;
   p.M = static_cast<int>(M);
   p.N = N;
@@ -860,7 +933,7 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (N % c) continue;
-      const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, c);
+      const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, pair ? c / 2 : c);
       if (ring_budget(1) / sb >= min_stages || c == 64) {
         bn = c;
         break;
@@ -869,7 +942,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   }
   MCG_CHECK(bn > 0 && N % bn == 0 && bn % 64 == 0 && bn <= 256, "bad block_n");
   p.block_n = bn;
-  const int stage_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, bn);
+  const int w_rows = pair ? bn / 2 : bn;  // W rows per CTA
+  const int stage_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, w_rows);
   // double-buffer the staging when that does not cost a needed pipeline stage
   p.out_sets = 1;
   if (p.out_tma && ring_budget(2) / stage_bytes >= min_stages) p.out_sets = 2;
@@ -882,7 +956,8 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.acc_cols = bn > 128 ? 256 : 128;
   p.num_acc = kTmemCols / p.acc_cols;
   p.num_kb = K / kBlockK;
-  p.m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+  const int tile_m = pair ? 2 * kBlockM : kBlockM;
+  p.m_tiles = static_cast<int>((M + tile_m - 1) / tile_m);
   p.n_tiles = N / bn;
   p.a = a;
   p.cblocks = a.kind == 1 ? a.C / kBlockK : 1;
@@ -897,7 +972,12 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   pl.smem = fixed + (p.out_tma ? kEpiGroups * p.out_sets * set_bytes : 0) + p.num_stages * stage_bytes;
   MCG_CHECK(pl.smem <= kMaxDynSmem, "shared memory plan exceeds the 227 KB limit");
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.k_split;
-  pl.grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  if (pair) {
+    const long long pairs = num_sms / 2;
+    pl.grid = 2 * static_cast<int>(tiles < pairs ? tiles : pairs);
+  } else {
+    pl.grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  }
   UmmaMaps& tm = pl.tm;
   if (a.kind == 1) {
     tm.a_hi = make_tmap_im2col(A.hi, a);
@@ -906,16 +986,16 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     tm.a_hi = make_tmap_2d(A.hi, M, K, a.lda, kBlockM);
     tm.a_lo = terms == 3 ? make_tmap_2d(A.lo, M, K, a.lda, kBlockM) : tm.a_hi;
   }
-  tm.w_hi = make_tmap_2d(W.hi, N, K, K, bn);
-  tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, bn) : tm.w_hi;
+  tm.w_hi = make_tmap_2d(W.hi, N, K, K, w_rows);
+  tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, w_rows) : tm.w_hi;
   tm.o_hi = tm.o_lo = tm.r_hi = tm.r_lo = tm.w_hi;  // placeholders when unused
   tm.a_hi8 = tm.w_hi8 = tm.o_hi8 = tm.w_hi;
   const CUtensorMapSwizzle sw64 = CU_TENSOR_MAP_SWIZZLE_64B;
   if (terms == 2) {
     tm.a_lo = a.kind == 1 ? make_tmap_im2col_u8(A.lo8, a) : make_tmap_2d_u8(A.lo8, M, K, a.lda, kBlockM, kBlockK, sw64);
     tm.a_hi8 = a.kind == 1 ? make_tmap_im2col_u8(A.hi8, a) : make_tmap_2d_u8(A.hi8, M, K, a.lda, kBlockM, kBlockK, sw64);
-    tm.w_hi8 = make_tmap_2d_u8(W.hi8, N, K, K, bn, kBlockK, sw64);
-    tm.w_lo = make_tmap_2d_u8(W.lo8, N, K, K, bn, kBlockK, sw64);
+    tm.w_hi8 = make_tmap_2d_u8(W.hi8, N, K, K, w_rows, kBlockK, sw64);
+    tm.w_lo = make_tmap_2d_u8(W.lo8, N, K, K, w_rows, kBlockK, sw64);
   }
   if (p.out_tma) {
     tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, kBlockM, kEpiChunk, sw64);
@@ -934,20 +1014,44 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
 inline void umma_set_attrs() {
   static bool done = false;
   if (done) return;
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   done = true;
 }
 
 inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   umma_set_attrs();
+  if (pl.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (pl.terms == 3)
+      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<3, true>, pl.tm, pl.p));
+    else if (pl.terms == 2)
+      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<2, true>, pl.tm, pl.p));
+    else
+      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1, true>, pl.tm, pl.p));
+    return;
+  }
   if (pl.terms == 3)
-    umma_gemm_kernel<3><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
+    umma_gemm_kernel<3, false><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   else if (pl.terms == 2)
-    umma_gemm_kernel<2><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
+    umma_gemm_kernel<2, false><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   else
-    umma_gemm_kernel<1><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
+    umma_gemm_kernel<1, false><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
   MCG_CUDA(cudaGetLastError());
 }
 

@@ -90,6 +90,27 @@ def test_conv_parity_fp32_epilogue(engine, case):
     assert _run(engine, case, out_mode=1) < TOL[engine]
 
 
+# CTA-pair variant (clusters of two CTAs, tcgen05 cta_group::2, 256-row tiles): block_n code 1000 + n
+PAIR_CASES = [
+    ('pair_3x3_c256', 4, 256, 28, 28, 256, 3, 1, 1, 0, 1, 0, 1000),          # M = 3136: 12.25 pair tiles (ragged)
+    ('pair_3x3_c64', 8, 64, 56, 56, 64, 3, 1, 1, 0, 1, 0, 1000),
+    ('pair_3x3_stride2', 2, 128, 56, 56, 128, 3, 2, 1, 0, 1, 0, 1000),
+    ('pair_1x1_residual', 8, 64, 56, 56, 256, 1, 1, 0, 1, 1, 0, 1000),
+    ('pair_1x1_residual_bn128', 8, 64, 56, 56, 256, 1, 1, 0, 1, 1, 0, 1128),
+    ('pair_fpn_topdown', 8, 256, 28, 28, 256, 1, 1, 0, 2, 0, 0, 1000),
+    ('pair_odd_tiles', 1, 256, 30, 30, 128, 1, 1, 0, 0, 1, 0, 1000),          # M = 900: 3.5 pair tiles, last half empty
+    ('pair_tiny_M', 1, 64, 3, 3, 64, 1, 1, 0, 0, 0, 0, 1000),                  # M = 9: the second CTA has no rows
+    ('pair_bigK', 2, 2048, 14, 14, 512, 1, 1, 0, 0, 1, 0, 1000),
+    ('pair_many_tiles', 16, 128, 56, 56, 128, 3, 1, 1, 0, 1, 0, 1000),         # > 2 tiles per pair, all buffers wrap
+]
+
+
+@pytest.mark.parametrize('engine', ['fp16x3', 'fp16c8', 'fp16'])
+@pytest.mark.parametrize('case', PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_conv_parity_cta_pairs(engine, case):
+    assert _run(engine, case) < TOL[engine]
+
+
 def test_tensor_core_and_cuda_core_kernels_agree():
     """x3 tcgen05 vs fp32 FFMA on identical split-fp16 operands: only summation order differs."""
     from mcgaze_b200 import lib
