@@ -9,10 +9,14 @@ namespace mcg {
 
 // ---------------------------------------------------------------------------------------
 // stem: explicit im2col of the fp32 NCHW input for the 7x7/2 pad-3 convolution
-// (mmdet/models/backbones/resnet.py:599-611, :636).  A[m, k], k = (r*7+s)*3 + c for k < 147,
-// zero for 147 <= k < 192, written as split-fp16 planes so the stem runs on the GEMM kernel.
+// (mmdet/models/backbones/resnet.py:599-611, :636).  The stem's K axis is ordered
+//     k = (r*3 + c)*8 + s    (filter row r, channel c, filter column s < 7; s = 7 and k >= 168 are zero weights)
+// so that 8 consecutive k (one 16-byte fp16 chunk of an A row) are 8 consecutive input columns of ONE input row:
+// the fused kernel builds a chunk from four aligned 8-byte shared-memory loads that are contiguous across the
+// lanes of a warp.  A[m, k] is written as split-fp16 planes so the stem can also run on the GEMM kernel.
 // ---------------------------------------------------------------------------------------
 constexpr int kStemK = 192;
+__host__ __device__ constexpr int stem_k_index(int r, int s, int c) { return (r * 3 + c) * 8 + s; }
 
 // One CTA per (frame, output row): the 7 input rows it needs are staged in shared memory with
 // coalesced reads along W, then the 112 x 192 im2col rows are written as 16-byte vectors
@@ -44,11 +48,10 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   int off[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int k = k8 * 8 + j;
-    if (k < 147) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int r = tap / 7, sx = tap - r * 7;
-      off[j] = (c * 7 + r) * WP + sx;
+    // chunk k8 = r*3 + c (21 of the 24 chunks carry data), element j = filter column s
+    if (k8 < 21 && j < 7) {
+      const int r = k8 / 3, c = k8 - r * 3;
+      off[j] = (c * 7 + r) * WP + j;
     } else {
       off[j] = -1;
     }

@@ -422,8 +422,9 @@ class Engine {
   }
 
   // conv weight [Cout,Cin,R,S] (+ optional BN, + optional conv bias) -> [Cout, (r,s,c)] scaled, bias folded
+  // stem_order: the 7x7 stem uses the K order of stem_k_index (head_kernels.cuh) instead of (r, s, c)
   ConvW pack_conv(const std::string& wkey, const std::string& bnkey, const std::string& biaskey, int Cout, int Cin,
-                  int R, int S, int stride, int pad, int Kpad = 0) {
+                  int R, int S, int stride, int pad, int Kpad = 0, bool stem_order = false) {
     const float* w = need(wkey, static_cast<size_t>(Cout) * Cin * R * S).p;
     std::vector<float> scale(Cout, 1.f), shift(Cout, 0.f);
     if (!bnkey.empty()) {
@@ -449,7 +450,7 @@ class Engine {
       for (int c = 0; c < Cin; ++c)
         for (int r = 0; r < R; ++r)
           for (int s = 0; s < S; ++s)
-            packed[static_cast<size_t>(o) * Kp + (r * S + s) * Cin + c] =
+            packed[static_cast<size_t>(o) * Kp + (stem_order ? stem_k_index(r, s, c) : (r * S + s) * Cin + c)] =
                 w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s] * scale[o];
     ConvW cw;
     cw.g = pack_gemm(packed, Cout, Kp, shift.data(), precision_ == MCG_PRECISION_FP16C8);
@@ -476,7 +477,7 @@ class Engine {
   }
 
   void load_weights() {
-    stem_ = pack_conv("backbone.conv1.weight", "backbone.bn1", "", 64, 3, 7, 7, 2, 3, kStemK);
+    stem_ = pack_conv("backbone.conv1.weight", "backbone.bn1", "", 64, 3, 7, 7, 2, 3, kStemK, true);
     const int nblk[4] = {3, 4, 6, 3};
     const int planes[4] = {64, 128, 256, 512};
     int cin = 64;

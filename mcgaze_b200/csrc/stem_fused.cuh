@@ -34,7 +34,7 @@ constexpr int kSfInRows = 11;         // input rows feeding three stem rows
 constexpr int kSfInCols = 256;        // staged input columns per unit (249 needed)
 constexpr int kSfInStride = 268;      // staging row pitch in floats: rows (c, r) that one warp instruction reads
                                       // land in different banks (pitch 256 -> 5-way conflicts, 268 -> 2-3-way)
-constexpr int kSfK = 160;             // 147 zero-padded to a multiple of 16 (the packed weight is padded to 192)
+constexpr int kSfK = 176;             // 21 chunks (r, c) x 8 columns = 168 (stem_k_index), rounded up to a multiple of 16
 constexpr int kSfPoolCols = 60;       // pooled columns per unit
 constexpr int kSfStageBufBytes = 3 * kSfInRows * kSfInStride * 4;  // 35376
 constexpr int kSfWTileBytes = 64 * 64 * 2;                       // one [64 x 64] weight k-tile plane
@@ -170,24 +170,7 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
   } else if (warp_idx < 10) {
     // ===================== builders =====================
     const int bt = threadIdx.x - 64;  // 0..255
-    const int chunk = bt & 7;         // 16-byte chunk (8 consecutive k) inside a k-tile row
-    const int rsub = bt >> 3;         // 0..31: row inside a 32-row slice
-    // staging offsets of the 8 k of this thread's chunk, per k-tile (-1: zero padding)
-    int off[3][8];
-#pragma unroll
-    for (int kt = 0; kt < 3; ++kt) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = kt * 64 + chunk * 8 + e;
-        if (k < 147) {
-          const int tap = k / 3, c = k - tap * 3;
-          const int r = tap / 7, s = tap - r * 7;
-          off[kt][e] = (c * kSfInRows + r) * kSfInStride + s + 5;
-        } else {
-          off[kt][e] = -1;
-        }
-      }
-    }
+    const int bw = bt >> 5;           // builder warp = 16-byte chunk (8 consecutive k) inside a k-tile row
     auto prefetch = [&](int unit, int buf) {
       const int g = unit % p.groups;
       const int t = unit / p.groups;
@@ -224,20 +207,38 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
         for (int kt = 0; kt < 3; ++kt) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sA = a_ring + stage * sf_a_stage_bytes(kTerms);
-          if (kt < 2 || chunk < (kSfK - 128) / 8) {
+          // chunk gc = kt*8 + bw = r*3 + c holds input columns 2q-3 .. 2q+3 (+ one zero-weight pad) of input row
+          // (c, 2d + r): the 8 floats around them are four aligned 8-byte loads, contiguous across the warp's
+          // 32 consecutive stem columns (conflict-free); chunk 21 pads K to a multiple of 16 and must be zero
+          const int gc = kt * 8 + bw;
+          if (gc < kSfK / 8) {
+            const int r = gc / 3, c = gc - 3 * r;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              const int m = it * 32 + rsub;
-              const int base = 2 * d * kSfInStride + 2 * (30 * it + rsub - 1);
+              const int m = it * 32 + lane;
               float v[8];
+              if (gc < 21) {
+                const float2* src =
+                    reinterpret_cast<const float2*>(sin + (c * kSfInRows + 2 * d + r) * kSfInStride + 60 * it + 2 * lane + 2);
+                const float2 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
+                v[0] = a0.y;  // s = 0: staged column 60 it + 2 lane + 3
+                v[1] = a1.x;
+                v[2] = a1.y;
+                v[3] = a2.x;
+                v[4] = a2.y;
+                v[5] = a3.x;
+                v[6] = a3.y;
+                v[7] = 0.f;   // s = 7: zero weight
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = off[kt][e] >= 0 ? sin[off[kt][e] + base] : 0.f;
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+              }
               uint4 uh;
               uh.x = ptx::pack_half2(v[0], v[1]);
               uh.y = ptx::pack_half2(v[2], v[3]);
               uh.z = ptx::pack_half2(v[4], v[5]);
               uh.w = ptx::pack_half2(v[6], v[7]);
-              const uint32_t so = static_cast<uint32_t>(m * 128 + ((chunk ^ (m & 7)) << 4));
+              const uint32_t so = static_cast<uint32_t>(m * 128 + ((bw ^ (m & 7)) << 4));
               *reinterpret_cast<uint4*>(sA + so) = uh;
               if (kTerms == 3) {
                 uint4 ul;
