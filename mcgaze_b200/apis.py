@@ -10,7 +10,7 @@ from . import detector as _detector  # noqa: F401  (registers the model classes)
 
 
 def init_detector(config: Union[str, Config], checkpoint: Optional[str] = None, device: str = 'cuda:0',
-                  cfg_options: Optional[dict] = None, precision: str = 'fp16x3'):
+                  cfg_options: Optional[dict] = None, precision: str = 'fp16c8'):
     if isinstance(config, str):
         config = Config.fromfile(config)
     elif not isinstance(config, Config):

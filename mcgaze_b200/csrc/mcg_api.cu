@@ -173,6 +173,13 @@ class Engine {
       if (slot_[i].pin_out) cudaFreeHost(slot_[i].pin_out);
     }
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (side_stream_) {
+      cudaStreamDestroy(side_stream_);
+      for (int i = 0; i < 4; ++i) {
+        cudaEventDestroy(fork_ev_[i]);
+        cudaEventDestroy(join_ev_[i]);
+      }
+    }
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
     if (pin_meta_) cudaFreeHost(pin_meta_);
@@ -663,6 +670,15 @@ class Engine {
     hf_.lo = arena_.alloc<__half>(Rr * 12544);
   }
 
+  void ensure_side_stream() {
+    if (side_stream_) return;
+    MCG_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+      MCG_CUDA(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming));
+      MCG_CUDA(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming));
+    }
+  }
+
   void drop_graph() {
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
     graphs_.clear();
@@ -1048,9 +1064,21 @@ class Engine {
       float* boxes_out = boxes_[cur ^ 1];
       float* obj_in = obj_[cur];
       float* obj_out = obj_[cur ^ 1];
-      roi_align_kernel<<<(R * 49 + 7) / 8, 256, 0, st>>>(fl, boxes_in, R, roi_);
+      // RoIAlign (needs this stage's boxes) and the attention block (needs the object features) are independent
+      // until DynamicConv: RoIAlign runs on a forked side stream (both are latency-bound, neither fills the GPU).
+      // Per-kernel timing mode keeps everything on one stream.
+      const bool fork = !(time_kernels_ && !graph_mode_);
+      cudaStream_t rs = st;
+      if (fork) {
+        ensure_side_stream();
+        MCG_CUDA(cudaEventRecord(fork_ev_[s], st));
+        MCG_CUDA(cudaStreamWaitEvent(side_stream_, fork_ev_[s], 0));
+        rs = side_stream_;
+      }
+      roi_align_kernel<<<(R * 49 + 7) / 8, 256, 0, rs>>>(fl, boxes_in, R, roi_);
       MCG_CUDA(cudaGetLastError());
       count("roi_align_kernel");
+      if (fork) MCG_CUDA(cudaEventRecord(join_ev_[s], side_stream_));
       // spatial then temporal self-attention with the SAME weights (gaze_stqi_head.py:148-166)
       const float* xin = obj_in;
       float* xout[2] = {xa_, xb_};
@@ -1068,6 +1096,7 @@ class Engine {
       const float* attn = xb_;
       // DynamicConv (transformer.py:1116-1164)
       linear_tc(sk + "dyn", attn, 256, hq_, tc, sw.dyn, R, params_, false, nullptr, st);
+      if (fork) MCG_CUDA(cudaStreamWaitEvent(st, join_ev_[s], 0));
       dynconv_kernel<<<R, 256, kDynSmemBytes, st>>>(roi_, params_, sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
                                                     sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr, tc ? hf_.lo : nullptr);
       MCG_CUDA(cudaGetLastError());
@@ -1233,6 +1262,8 @@ class Engine {
   std::map<GraphKey, cudaGraphExec_t> graphs_;
 
   cudaStream_t own_stream_ = nullptr;
+  cudaStream_t side_stream_ = nullptr;  // forked branch of the head (RoIAlign beside the attention block)
+  cudaEvent_t fork_ev_[4] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t cap_stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   struct HostSlot {

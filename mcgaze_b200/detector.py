@@ -121,7 +121,7 @@ class MultiClueGaze:
     CLASSES = ('face', 'eyes', 'head')
 
     def __init__(self, backbone, rpn_head, roi_head, train_cfg=None, test_cfg=None, neck=None, pretrained=None,
-                 init_cfg=None, precision: str = 'fp16x3'):
+                 init_cfg=None, precision: str = 'fp16c8'):
         self.backbone = build_backbone(backbone)
         self.neck = build_neck(neck) if neck is not None else None
         if self.neck is None:

@@ -78,7 +78,7 @@ class Engine:
     exactly what `mmcv.runner.load_checkpoint` would hand to the reference's `MultiClueGaze`.
     """
 
-    def __init__(self, state_dict: Dict[str, object], device: int = 0, precision: str = 'fp16x3'):
+    def __init__(self, state_dict: Dict[str, object], device: int = 0, precision: str = 'fp16c8'):
         import numpy as np
         import torch
         if not torch.cuda.is_available():
