@@ -26,6 +26,13 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel of the stream (launched with programmatic stream serialization) may start
+// once every CTA of this grid has called it; wait: block until the previous grid has completed and its memory
+// operations are visible.  Together they overlap a kernel's prologue with the previous kernel's tail.
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -74,6 +74,7 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  ptx::grid_dep_launch_dependents();  // the first GEMM's prologue may run under this kernel's tail
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);  // [kSfStages] builders -> MMA
   uint64_t* empty_bar = full_bar + kSfStages;              // MMA -> builders
   uint64_t* tfull_bar = empty_bar + kSfStages;             // [2] MMA -> epilogue

@@ -152,6 +152,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  // programmatic dependent launch: the next GEMM's CTAs may take this SM as soon as this CTA exits and run their
+  // prologue (barrier init, TMEM allocation, descriptor prefetch) under the tail of this grid
+  ptx::grid_dep_launch_dependents();
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -222,6 +225,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   if (kPair) ptx::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything below reads or writes tensors of earlier kernels
+  ptx::grid_dep_wait();
   // persistent tile walk: a CTA pair walks the tile list together
   const int walker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int walkers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -1025,34 +1030,44 @@ inline void umma_set_attrs() {
 
 inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   umma_set_attrs();
+  static const int tune_pdl = tune_env("MCG_TUNE_NO_PDL");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (pl.pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = pl.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (!tune_pdl) {
+    // may start while the previous kernel of the stream drains (the kernel waits with griddepcontrol.wait)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (pl.pair) {
     if (pl.terms == 3)
       MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<3, true>, pl.tm, pl.p));
     else if (pl.terms == 2)
       MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<2, true>, pl.tm, pl.p));
     else
       MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1, true>, pl.tm, pl.p));
-    return;
+  } else {
+    if (pl.terms == 3)
+      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<3, false>, pl.tm, pl.p));
+    else if (pl.terms == 2)
+      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<2, false>, pl.tm, pl.p));
+    else
+      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1, false>, pl.tm, pl.p));
   }
-  if (pl.terms == 3)
-    umma_gemm_kernel<3, false><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
-  else if (pl.terms == 2)
-    umma_gemm_kernel<2, false><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
-  else
-    umma_gemm_kernel<1, false><<<pl.grid, kGemmThreads, pl.smem, stream>>>(pl.tm, pl.p);
-  MCG_CUDA(cudaGetLastError());
 }
 
 }  // namespace mcg

@@ -10,7 +10,8 @@ import os
 from typing import Dict, Optional, Sequence
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libmcgaze_b200.so')
+# MCG_LIB_PATH: A/B experiments against another build of the same C ABI (tools/ only)
+LIB_PATH = os.environ.get('MCG_LIB_PATH') or os.path.join(HERE, 'libmcgaze_b200.so')
 
 PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 
