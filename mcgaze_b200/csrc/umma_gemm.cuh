@@ -59,6 +59,12 @@ constexpr int kMaxDynSmem = 232448;  // 227 KB: the sm_100 opt-in limit per bloc
 constexpr int kEpiChunk = 32;        // columns per epilogue chunk (64 B of fp16 per row)
 constexpr int kEpiPlaneBytes = kBlockM * kEpiChunk * 2;  // [128 rows x 32 cols] fp16 staging tile = 8 KB
 constexpr int kResBufs = 2;          // residual chunks in flight per epilogue group
+// Attribution experiments (env MCG_DEBUG_FLAGS -> UmmaParams::dbg) are compiled in only with -DMCG_KERNEL_DEBUG=1:
+// the issue loops are single-warp, latency-bound code and every runtime flag test costs them cycles.
+#ifndef MCG_KERNEL_DEBUG
+#define MCG_KERNEL_DEBUG 0
+#endif
+constexpr bool kDbg = MCG_KERNEL_DEBUG != 0;
 
 struct UmmaParams {
   int M = 0, N = 0, K = 0;
@@ -266,7 +272,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
         int tr = tap / p.a.S, tsx = tap - tr * p.a.S;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (p.dbg & 128) {
+          if (kDbg && (p.dbg & 128)) {
             const long long w0 = clock64();
             ptx::mbar_wait_a(empty_a + stage * 8, phase ^ 1u);
             dbg_wait += clock64() - w0;
@@ -279,8 +285,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             // pair: both CTAs' loads signal the LEADER's full barrier (it counts the bytes of both)
             const uint32_t fb = kPair ? ptx::mapa(full_a + stage * 8, 0) : full_a + stage * 8;
             uint32_t tx = static_cast<uint32_t>(stage_bytes);
-            if (p.dbg & 4) tx -= static_cast<uint32_t>(a_bytes);
-            if (p.dbg & 8) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
+            if (kDbg && (p.dbg & 4)) tx -= static_cast<uint32_t>(a_bytes);
+            if (kDbg && (p.dbg & 8)) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
             if (kPair) {
               if (leader_cta)
                 ptx::mbar_arrive_expect_tx_a(full_a + stage * 8, 2 * tx);
@@ -309,7 +315,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             const CUtensorMap* ma1 = f8 ? &tm.a_hi8 : &tm.a_lo;
             const uint32_t sA1 = s + (f8 ? off_a_hi8 : kATileBytes);
             const bool two_a = kTerms == 3 || f8;
-            if (p.dbg & 4) {
+            if (kDbg && (p.dbg & 4)) {
             } else if (p.a.kind == 1) {
               tma_im2col(s, ma0, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
                                         static_cast<uint16_t>(tr));
@@ -320,7 +326,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               tma_2d(s, ma0, fb, kb * kBlockK, static_cast<int>(m0));
               if (two_a) tma_2d(sA1, ma1, fb, kb * kBlockK, static_cast<int>(m0));
             }
-            if (!(p.dbg & 8)) {
+            if (!(kDbg && (p.dbg & 8))) {
               if (f8) {
                 tma_2d(sW, &tm.w_hi8, fb, kb * kBlockK, n0);
                 tma_2d(s + off_w_lo8, &tm.w_lo, fb, kb * kBlockK, n0);
@@ -346,7 +352,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         }
       }
     }
-    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0)
+    if ((kDbg && (p.dbg & 128)) && blockIdx.x == 0 && lane == 0)
       printf("prod M=%d N=%d K=%d: %lld cycles, %lld waiting for a free stage\n", p.M, p.N, p.K, clock64() - dbg_p0, dbg_wait);
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
@@ -380,14 +386,14 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     int local = 0;
     long long dbg_c0 = 0, dbg_wfull = 0, dbg_wacc = 0;
     unsigned long long dbg_t0 = 0;
-    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
+    if ((kDbg && (p.dbg & 128)) && blockIdx.x == 0 && lane == 0) {
       dbg_c0 = clock64();
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     }
     for (int tile = walker; tile < num_tiles && leader_cta; tile += walkers, ++local) {
       const int acc = local % p.num_acc;
       const uint32_t acc_phase = static_cast<uint32_t>(local / p.num_acc) & 1u;
-      if (p.dbg & 128) {
+      if (kDbg && (p.dbg & 128)) {
         const long long w0 = clock64();
         ptx::mbar_wait_a(tempty_a + acc * 8, acc_phase ^ 1u);
         dbg_wacc += clock64() - w0;
@@ -402,7 +408,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       for (int pass = 0; pass < passes; ++pass) {
         const bool f8 = kTerms == 2 && pass == 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (p.dbg & 128) {
+          if (kDbg && (p.dbg & 128)) {
             const long long w0 = clock64();
             ptx::mbar_wait_a(full_a + stage * 8, phase);
             dbg_wfull += clock64() - w0;
@@ -410,7 +416,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             ptx::mbar_wait_a(full_a + stage * 8, phase);
           }
           ptx::tc_fence_after();
-          if (!(p.dbg & 16)) {
+          if (!(kDbg && (p.dbg & 16))) {
             const uint32_t s = stage_base_u32 + static_cast<uint32_t>(stage * stage_bytes);
             const uint32_t first = kb > kb_begin ? 1u : 0u;
             // descriptors of the k = 0 slice; slice j advances the 16-byte-granular start address by 2 (32 B)
@@ -459,7 +465,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         }
       }
     }
-    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
+    if ((kDbg && (p.dbg & 128)) && blockIdx.x == 0 && lane == 0) {
       // effective SM clock while this launch ran (attribution experiments only)
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -489,7 +495,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const int t = walker + ri_local * walkers;
       if (t >= num_tiles) return;
       const uint32_t b = r_issued % kResBufs;
-      if (leader && (p.dbg & 32)) {
+      if (leader && (kDbg && (p.dbg & 32))) {
         ptx::mbar_arrive(&rbar[b]);
       } else if (leader) {
         const int mn_i = t % mn_tiles;
@@ -576,7 +582,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (!(p.dbg & 2)) {
+        if (!(kDbg && (p.dbg & 2))) {
           if (ep.bias && p.k_split == 1) {
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
 #pragma unroll
@@ -650,7 +656,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             if (leader) ptx::tma_store_wait_read<0>();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           }
-          if (!(p.dbg & 2)) {
+          if (!(kDbg && (p.dbg & 2))) {
             uint2 l8[4], h8[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -695,7 +701,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (p.res_tma) res_issue();
           if (leader) {
-            if (!(p.dbg & 1)) {
+            if (!(kDbg && (p.dbg & 1))) {
               const int m0 = m_tile_cta * kBlockM;
               ptx::tma_store_2d(&tm.o_hi, ob, n, m0);
               if (kFmt != 0) ptx::tma_store_2d(&tm.o_lo, ob + kEpiPlaneBytes, n, m0);  // fp16 lo / e4m3 lo8
@@ -704,7 +710,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             ptx::tma_store_commit();
           }
           ++ostores;
-        } else if (valid && !(p.dbg & 2)) {
+        } else if (valid && !(kDbg && (p.dbg & 2))) {
           if (ep.out_f32) {
             float4* o = reinterpret_cast<float4*>(ep.out_f32 + ks * p.split_stride + m * ep.ldo + n);
 #pragma unroll
