@@ -147,7 +147,9 @@ __device__ __forceinline__ uint32_t sw64_off(int row, int j) {
 // columns through tcgen05 cta_group::2: every CTA loads its own 128 rows of A and HALF of the W rows, the leader
 // CTA issues one M = 256 MMA over both, each CTA drains its own 128 accumulator rows.  Halves the W bytes every
 // SM pulls from L2 per FLOP (the 3x3 convolutions are L2 -> shared-memory bound with 128 x 256 tiles).
-template <int kTerms, bool kPair>
+// kKbs: 64-wide k-blocks per pipeline stage (compile time, so the per-stage loops unroll): layers with little work
+// per k-block (narrow tiles) amortise the barrier handshake and issue-loop overhead of a stage over 2-3 k-blocks.
+template <int kTerms, bool kPair, int kKbs>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   // storage format of the activation planes this instantiation reads / writes: 0 hi, 1 hi + fp16 lo,
@@ -176,7 +178,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   const bool leader_cta = cta_rank == 0;
   const int w_tile_bytes = w_rows * kBlockK * 2;
   const int a_bytes = a_stage_bytes(kTerms);
-  const int stage_bytes = a_bytes + w_stage_bytes(kTerms, w_rows);
+  const int sub_bytes = a_bytes + w_stage_bytes(kTerms, w_rows);  // one k-block: A tile(s) + W tile(s)
+  const int stage_bytes = kKbs * sub_bytes;
   // kTerms == 2, pass 1 (e4m3 tiles) re-uses the stage: [A_lo8 8K | A_hi8 8K] [W_hi8 | W_lo8]
   const int w8_tile_bytes = w_rows * kBlockK;
   const int off_a_hi8 = kATileBytes / 2;
@@ -271,7 +274,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         const bool f8 = kTerms == 2 && pass == 0;
         int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
         int tr = tap / p.a.S, tsx = tap - tr * p.a.S;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; kb += kKbs) {
           if (kDbg && (p.dbg & 128)) {
             const long long w0 = clock64();
             ptx::mbar_wait_a(empty_a + stage * 8, phase ^ 1u);
@@ -280,13 +283,12 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             ptx::mbar_wait_a(empty_a + stage * 8, phase ^ 1u);
           }
           if (ptx::elect_one()) {
-            const uint32_t s = ring_a + static_cast<uint32_t>(stage * stage_bytes);
-            const uint32_t sW = s + a_bytes;
+            const uint32_t s0 = ring_a + static_cast<uint32_t>(stage * stage_bytes);
             // pair: both CTAs' loads signal the LEADER's full barrier (it counts the bytes of both)
             const uint32_t fb = kPair ? ptx::mapa(full_a + stage * 8, 0) : full_a + stage * 8;
             uint32_t tx = static_cast<uint32_t>(stage_bytes);
-            if (kDbg && (p.dbg & 4)) tx -= static_cast<uint32_t>(a_bytes);
-            if (kDbg && (p.dbg & 8)) tx -= static_cast<uint32_t>(stage_bytes - a_bytes);
+            if (kDbg && (p.dbg & 4)) tx -= static_cast<uint32_t>(kKbs * a_bytes);
+            if (kDbg && (p.dbg & 8)) tx -= static_cast<uint32_t>(kKbs * (sub_bytes - a_bytes));
             if (kPair) {
               if (leader_cta)
                 ptx::mbar_arrive_expect_tx_a(full_a + stage * 8, 2 * tx);
@@ -310,39 +312,56 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               else
                 ptx::tma_load_im2col_4d_a(dst, m, bar, c, w, h, n, ow, oh);
             };
-            // first / second A tile of the stage: (hi, lo) fp16 planes, or the (lo8, hi8) e4m3 planes in pass 1
+            // first / second A tile of a k-block: (hi, lo) fp16 planes, or the (lo8, hi8) e4m3 planes in pass 1
             const CUtensorMap* ma0 = f8 ? &tm.a_lo : &tm.a_hi;
             const CUtensorMap* ma1 = f8 ? &tm.a_hi8 : &tm.a_lo;
-            const uint32_t sA1 = s + (f8 ? off_a_hi8 : kATileBytes);
             const bool two_a = kTerms == 3 || f8;
-            if (kDbg && (p.dbg & 4)) {
-            } else if (p.a.kind == 1) {
-              tma_im2col(s, ma0, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
-                                        static_cast<uint16_t>(tr));
-              if (two_a)
-                tma_im2col(sA1, ma1, fb, cb * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx),
-                                          static_cast<uint16_t>(tr));
-            } else {
-              tma_2d(s, ma0, fb, kb * kBlockK, static_cast<int>(m0));
-              if (two_a) tma_2d(sA1, ma1, fb, kb * kBlockK, static_cast<int>(m0));
-            }
-            if (!(kDbg && (p.dbg & 8))) {
-              if (f8) {
-                tma_2d(sW, &tm.w_hi8, fb, kb * kBlockK, n0);
-                tma_2d(s + off_w_lo8, &tm.w_lo, fb, kb * kBlockK, n0);
+            int cb2 = cb, tsx2 = tsx, tr2 = tr;  // filter tap / channel block of the k-block being loaded
+#pragma unroll
+            for (int sub = 0; sub < kKbs; ++sub) {
+              const uint32_t s = s0 + static_cast<uint32_t>(sub * sub_bytes);
+              const uint32_t sW = s + a_bytes;
+              const uint32_t sA1 = s + (f8 ? off_a_hi8 : kATileBytes);
+              const int kbk = kb + sub;
+              if (kDbg && (p.dbg & 4)) {
+              } else if (p.a.kind == 1) {
+                tma_im2col(s, ma0, fb, cb2 * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx2),
+                           static_cast<uint16_t>(tr2));
+                if (two_a)
+                  tma_im2col(sA1, ma1, fb, cb2 * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx2),
+                             static_cast<uint16_t>(tr2));
+                if (kKbs > 1 && ++cb2 == p.cblocks) {
+                  cb2 = 0;
+                  if (++tsx2 == p.a.S) {
+                    tsx2 = 0;
+                    ++tr2;
+                  }
+                }
               } else {
-                tma_2d(sW, &tm.w_hi, fb, kb * kBlockK, n0);
-                if (kTerms == 3) tma_2d(sW + w_tile_bytes, &tm.w_lo, fb, kb * kBlockK, n0);
+                tma_2d(s, ma0, fb, kbk * kBlockK, static_cast<int>(m0));
+                if (two_a) tma_2d(sA1, ma1, fb, kbk * kBlockK, static_cast<int>(m0));
+              }
+              if (!(kDbg && (p.dbg & 8))) {
+                if (f8) {
+                  tma_2d(sW, &tm.w_hi8, fb, kbk * kBlockK, n0);
+                  tma_2d(s + off_w_lo8, &tm.w_lo, fb, kbk * kBlockK, n0);
+                } else {
+                  tma_2d(sW, &tm.w_hi, fb, kbk * kBlockK, n0);
+                  if (kTerms == 3) tma_2d(sW + w_tile_bytes, &tm.w_lo, fb, kbk * kBlockK, n0);
+                }
               }
             }
           }
           __syncwarp();
           // next filter tap / channel block (im2col view: kb = tap * cblocks + cb, tap = r * S + s)
-          if (++cb == p.cblocks) {
-            cb = 0;
-            if (++tsx == p.a.S) {
-              tsx = 0;
-              ++tr;
+#pragma unroll
+          for (int sub = 0; sub < kKbs; ++sub) {
+            if (++cb == p.cblocks) {
+              cb = 0;
+              if (++tsx == p.a.S) {
+                tsx = 0;
+                ++tr;
+              }
             }
           }
           if (++stage == p.num_stages) {
@@ -407,7 +426,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       const int kb_end = static_cast<int>(static_cast<long long>(ks + 1) * p.num_kb / p.k_split);
       for (int pass = 0; pass < passes; ++pass) {
         const bool f8 = kTerms == 2 && pass == 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; kb += kKbs) {
           if (kDbg && (p.dbg & 128)) {
             const long long w0 = clock64();
             ptx::mbar_wait_a(full_a + stage * 8, phase);
@@ -416,9 +435,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             ptx::mbar_wait_a(full_a + stage * 8, phase);
           }
           ptx::tc_fence_after();
-          if (!(kDbg && (p.dbg & 16))) {
-            const uint32_t s = stage_base_u32 + static_cast<uint32_t>(stage * stage_bytes);
-            const uint32_t first = kb > kb_begin ? 1u : 0u;
+#pragma unroll
+          for (int sub = 0; sub < kKbs; ++sub) {
+            if (kDbg && (p.dbg & 16)) break;
+            const uint32_t s = stage_base_u32 + static_cast<uint32_t>(stage * stage_bytes + sub * sub_bytes);
+            const uint32_t first = (sub > 0 || kb > kb_begin) ? 1u : 0u;
             // descriptors of the k = 0 slice; slice j advances the 16-byte-granular start address by 2 (32 B)
             if (f8) {
               // pass 1, e4m3 corrections x 2^15 (K = 32 per MMA): lo8_a * hi8_w + hi8_a * lo8_w
@@ -457,7 +478,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
             }
           }
           commit(empty_a + stage * 8);  // smem slot reusable once these MMAs retire
-          if (kb == kb_end - 1 && pass == passes - 1) commit(tfull_a + acc * 8);
+          if (kb + kKbs >= kb_end && pass == passes - 1) commit(tfull_a + acc * 8);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
@@ -874,6 +895,7 @@ struct UmmaPlan {
   UmmaMaps tm;
   UmmaParams p;
   int pair = 0;  // 1: clusters of two CTAs, tcgen05 cta_group::2 (tiles of 256 rows)
+  int kbs = 1;   // k-blocks per pipeline stage (kernel template parameter)
   int terms = 3;
   int grid = 0;
   int smem = 0;
@@ -954,7 +976,22 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   MCG_CHECK(bn > 0 && N % bn == 0 && bn % 64 == 0 && bn <= 256, "bad block_n");
   p.block_n = bn;
   const int w_rows = pair ? bn / 2 : bn;  // W rows per CTA
-  const int stage_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, w_rows);
+  const int sub_bytes = a_stage_bytes(terms) + w_stage_bytes(terms, w_rows);
+  // k-blocks per stage (1, 2 or 3): as many as divide the tile's k-blocks, keep a stage within 64 KB and the ring
+  // at >= 3 stages beside double-buffered epilogue staging
+  static const int tune_kbs = tune_env("MCG_TUNE_KBS");
+  int kbs = 1;
+  if (k_split == 1 && tune_kbs != 1) {
+    const int nkb = K / kBlockK;
+    for (int c = 3; c >= 2; --c) {
+      if (nkb % c == 0 && c * sub_bytes <= 64 * 1024 && ring_budget(1) / (c * sub_bytes) >= 3) {
+        kbs = c;
+        break;
+      }
+    }
+  }
+  pl.kbs = kbs;
+  const int stage_bytes = kbs * sub_bytes;
   // double-buffer the staging when that does not cost a needed pipeline stage
   p.out_sets = 1;
   if (p.out_tma && ring_budget(2) / stage_bytes >= min_stages) p.out_sets = 2;
@@ -1022,20 +1059,36 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   return pl;
 }
 
-inline void umma_set_attrs() {
-  static bool done = false;
-  if (done) return;
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  done = true;
+template <int kTerms, bool kPair, int kKbs>
+inline void umma_launch_one(const cudaLaunchConfig_t& cfg, const UmmaPlan& pl) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<kTerms, kPair, kKbs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kMaxDynSmem));
+    attr_set = true;
+  }
+  MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<kTerms, kPair, kKbs>, pl.tm, pl.p));
+}
+template <int kTerms, bool kPair>
+inline void umma_launch_kbs(const cudaLaunchConfig_t& cfg, const UmmaPlan& pl) {
+  if (pl.kbs == 3)
+    umma_launch_one<kTerms, kPair, 3>(cfg, pl);
+  else if (pl.kbs == 2)
+    umma_launch_one<kTerms, kPair, 2>(cfg, pl);
+  else
+    umma_launch_one<kTerms, kPair, 1>(cfg, pl);
+}
+template <int kTerms>
+inline void umma_launch_pair(const cudaLaunchConfig_t& cfg, const UmmaPlan& pl) {
+  if (pl.pair)
+    umma_launch_kbs<kTerms, true>(cfg, pl);
+  else
+    umma_launch_kbs<kTerms, false>(cfg, pl);
 }
 
+inline void umma_set_attrs() {}  // (the dynamic shared-memory attribute is set per instantiation at first launch)
+
 inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
-  umma_set_attrs();
   static const int tune_pdl = tune_env("MCG_TUNE_NO_PDL");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
@@ -1059,21 +1112,12 @@ inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (pl.pair) {
-    if (pl.terms == 3)
-      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<3, true>, pl.tm, pl.p));
-    else if (pl.terms == 2)
-      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<2, true>, pl.tm, pl.p));
-    else
-      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1, true>, pl.tm, pl.p));
-  } else {
-    if (pl.terms == 3)
-      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<3, false>, pl.tm, pl.p));
-    else if (pl.terms == 2)
-      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<2, false>, pl.tm, pl.p));
-    else
-      MCG_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<1, false>, pl.tm, pl.p));
-  }
+  if (pl.terms == 3)
+    umma_launch_pair<3>(cfg, pl);
+  else if (pl.terms == 2)
+    umma_launch_pair<2>(cfg, pl);
+  else
+    umma_launch_pair<1>(cfg, pl);
 }
 
 }  // namespace mcg
