@@ -962,15 +962,27 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   if (bn == 0 && p.res_tma && tune_res_bn > 0 && N % tune_res_bn == 0) bn = tune_res_bn;
   if (bn == 0 && tune_bn > 0 && N % tune_bn == 0) bn = tune_bn;
   if (bn == 0) {
-    // largest tile that divides N and still leaves enough pipeline stages beside one staging set per group
+    // Tile width by a wave model: persistent workers (SMs, or SM pairs) each take ceil(tiles / workers) tiles of
+    // cost ~ block_n (MMA cycles and W bytes per 128 rows); narrow tiles pay more A traffic / issue overhead per
+    // FLOP, N = 64 MMAs run at 2/3 efficiency.  Widest tile wins ties; it must leave min_stages pipeline stages.
+    static const int tune_wave = tune_env("MCG_TUNE_NO_WAVE_MODEL");
+    const long long workers = pair ? num_sms / 2 : num_sms;
+    const long long mt = (M + (pair ? 2 : 1) * kBlockM - 1) / ((pair ? 2 : 1) * kBlockM);
+    double best = 0.0;
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (N % c) continue;
       const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, pair ? c / 2 : c);
-      if (ring_budget(1) / sb >= min_stages || c == 64) {
+      if (!(ring_budget(1) / sb >= min_stages || c == 64)) continue;
+      const long long tiles = mt * (N / c);
+      const long long waves = (tiles + workers - 1) / workers;
+      const double unit = c == 256 ? 256.0 : c == 128 ? 128.0 * 1.25 : 64.0 * 1.9;  // measured: layer3 / layer4 A-B
+      const double cost = static_cast<double>(waves) * unit;
+      if (bn == 0 || cost < best * 0.97) {
         bn = c;
-        break;
+        best = cost;
       }
+      if (tune_wave) break;  // previous rule: the widest tile that fits
     }
   }
   MCG_CHECK(bn > 0 && N % bn == 0 && bn % 64 == 0 && bn <= 256, "bad block_n");
