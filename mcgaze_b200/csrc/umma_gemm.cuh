@@ -58,7 +58,7 @@ constexpr int kSmemBarrierBytes = 1024;
 constexpr int kMaxDynSmem = 232448;  // 227 KB: the sm_100 opt-in limit per block
 constexpr int kEpiChunk = 32;        // columns per epilogue chunk (64 B of fp16 per row)
 constexpr int kEpiPlaneBytes = kBlockM * kEpiChunk * 2;  // [128 rows x 32 cols] fp16 staging tile = 8 KB
-constexpr int kResBufs = 2;          // residual chunks in flight per epilogue group
+constexpr int kMaxResBufs = 4;       // residual chunks in flight per epilogue group (UmmaParams::res_bufs: 2..4)
 // Attribution experiments (env MCG_DEBUG_FLAGS -> UmmaParams::dbg) are compiled in only with -DMCG_KERNEL_DEBUG=1:
 // the issue loops are single-warp, latency-bound code and every runtime flag test costs them cycles.
 #ifndef MCG_KERNEL_DEBUG
@@ -82,6 +82,7 @@ struct UmmaParams {
   int out_tma = 0;  // planes output through smem staging + TMA store
   int out_sets = 1; // staging sets per epilogue group for the TMA-store epilogue (2 = double buffered)
   int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
+  int res_bufs = 2; // ... this many [128 x 32] chunks ahead per epilogue group
   int out_fmt = 0;  // planes written by the epilogue: 0 hi, 1 hi + fp16 lo, 2 hi + e4m3 lo8 (+ e4m3 hi8 if out_hi8)
   int out_hi8 = 0;
   int res_fmt = 0;  // planes of the residual: 0 hi, 1 hi + fp16 lo, 2 hi + e4m3 lo8
@@ -169,7 +170,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + kMaxAcc;
   uint64_t* res_bar = tempty_bar + kMaxAcc;  // [kEpiGroups][kResBufs]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiGroups * kResBufs);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + kEpiGroups * kMaxResBufs);
   uint8_t* stage_base = smem + kSmemBarrierBytes;
 
   // rows of W this CTA keeps in shared memory (a CTA pair splits the block_n rows)
@@ -217,7 +218,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       // one arrive per warp of the owning epilogue group (pair: of both CTAs, on the leader's barrier)
       ptx::mbar_init(&tempty_bar[i], kPair ? 8 : 4);
     }
-    for (int i = 0; i < kEpiGroups * kResBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kEpiGroups * kMaxResBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -507,15 +508,16 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     const int nchunks = p.block_n / kEpiChunk;
     const uint32_t osets = static_cast<uint32_t>(p.out_sets);
     uint8_t* obuf = obuf_base + grp * p.out_sets * kSet;
-    uint8_t* rbuf = rbuf_base + grp * kResBufs * kRSet;
-    uint64_t* rbar = res_bar + grp * kResBufs;
+    const uint32_t res_bufs = static_cast<uint32_t>(p.res_bufs);
+    uint8_t* rbuf = rbuf_base + grp * p.res_bufs * kRSet;
+    uint64_t* rbar = res_bar + grp * kMaxResBufs;
     // residual chunk stream of this group's tiles, prefetched kResBufs chunks ahead across tile boundaries
     int ri_local = grp, ri_c = 0;
     uint32_t r_issued = 0, r_consumed = 0;
     auto res_issue = [&]() {
       const int t = walker + ri_local * walkers;
       if (t >= num_tiles) return;
-      const uint32_t b = r_issued % kResBufs;
+      const uint32_t b = r_issued % res_bufs;
       if (leader && (kDbg && (p.dbg & 32))) {
         ptx::mbar_arrive(&rbar[b]);
       } else if (leader) {
@@ -539,8 +541,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       }
     };
     if (p.res_tma) {
-#pragma unroll
-      for (int i = 0; i < kResBufs; ++i) res_issue();
+      for (int i = 0; i < p.res_bufs; ++i) res_issue();
     }
     uint32_t ostores = 0;  // chunks handed to TMA so far (staging set = ostores % osets)
     for (int local = grp;; local += kEpiGroups) {
@@ -594,8 +595,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         }
         const uint8_t* rcur = nullptr;
         if (p.res_tma) {
-          const uint32_t b = r_consumed % kResBufs;
-          ptx::mbar_wait(&rbar[b], (r_consumed / kResBufs) & 1u);
+          const uint32_t b = r_consumed % res_bufs;
+          ptx::mbar_wait(&rbar[b], (r_consumed / res_bufs) & 1u);
           rcur = rbuf + b * kRSet;
           ++r_consumed;
         }
@@ -953,7 +954,19 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0) ? 1 : 0;
   p.out_hi8 = (p.out_tma && ep.out_hi8 != nullptr) ? 1 : 0;
   const int set_bytes = epi_set_bytes(p.out_fmt);
-  const int res_bytes = p.res_tma ? kEpiGroups * kResBufs * epi_set_bytes(p.res_fmt) : 0;
+  // residual chunks in flight per epilogue group (more chunks cost pipeline stages: measured slower)
+  static const int tune_res_bufs = tune_env("MCG_TUNE_RES_BUFS");
+  p.res_bufs = tune_res_bufs >= 2 && tune_res_bufs <= kMaxResBufs ? tune_res_bufs : 2;  // measured: 2 > 3 > 4 (ring depth matters more)
+  // ... as long as two stages of the widest usable tile (block_n >= 128 where N allows) still fit
+  while (p.res_tma && p.res_bufs > 2) {
+    const int wide = force_block_n ? force_block_n : (N % 128 == 0 ? 128 : 64);
+    const int sb = a_stage_bytes(terms) + w_stage_bytes(terms, pair ? wide / 2 : wide);
+    const int left = kMaxDynSmem - 1024 - kSmemBarrierBytes - kEpiGroups * p.res_bufs * epi_set_bytes(p.res_fmt) -
+                     kEpiGroups * set_bytes;
+    if (left / sb >= 2) break;
+    --p.res_bufs;
+  }
+  const int res_bytes = p.res_tma ? kEpiGroups * p.res_bufs * epi_set_bytes(p.res_fmt) : 0;
   const int fixed = 1024 + kSmemBarrierBytes + res_bytes;
   auto ring_budget = [&](int out_sets) { return kMaxDynSmem - fixed - (p.out_tma ? kEpiGroups * out_sets * set_bytes : 0); };
   // residual (bottleneck conv3) layers are HBM-bound with short K loops: 2 stages are enough there
