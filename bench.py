@@ -147,6 +147,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# measured DRAM traffic (bytes) of the dominant GEMM launch, from the ncu capture committed under profiles/
+NCU_TRAFFIC = {'fp16c8': 722255616 + 505873152}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -264,7 +268,12 @@ def main():
     step_tflops = value / world * GFLOP_PER_CLIP / 1e3
     roofline = {'bound': 'tensor', 'kernel': 'mcg::umma_gemm_kernel (tcgen05 implicit-GEMM conv / linear)',
                 'achieved': achieved, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': (achieved / peaks['tflops_sustained']) if achieved else None, 'traffic': None,
+                'frac': (achieved / peaks['tflops_sustained']) if achieved else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the step (FPN 3x3 on P2, 26 % of
+                # the step's FLOPs) from the committed `ncu --set full` capture; its algorithmic bytes are 1259 MB
+                'traffic': NCU_TRAFFIC.get(args.precision),
+                'traffic_source': 'profiles/r01_ncu_umma_fp16c8_summary.md (fpn0 launch: 722 MB read + 506 MB written)'
+                if args.precision in NCU_TRAFFIC else None,
                 'peak_source': peaks['source'] + ', bf16 dense sustained (kernel timed inside a long step)',
                 'launches_per_step': um_n // 3, 'algorithmic_gflop_per_step': um_fl / 3 / 1e9,
                 'kernel_ms_per_step': um_ms / 3, 'kernel_share_of_step': (um_ms / 3) / ms_per_step,

@@ -36,7 +36,8 @@ enum {
   MCG_PRECISION_FP16 = 1,   /* tcgen05, single fp16 operands, fp32 accumulate: fast mode */
   MCG_PRECISION_SIMT = 2,   /* fp32 CUDA-core kernels only (cross-check / bring-up) */
   MCG_PRECISION_FP16C8 = 3  /* tcgen05, fp16 hi*hi + both rounding corrections as e4m3 MMAs (2 instead of 3 MMA
-                               units per k-step), activations stored fp16 hi + e4m3 lo (3 B/element): parity mode */
+                               units per k-step), activations stored fp16 hi + e4m3 lo8 + e4m3 hi8: parity mode,
+                               the default of the Python surface */
 };
 
 enum {
