@@ -71,6 +71,22 @@ def test_vs_reference_fixtures(engines, golden_dir, name, precision):
 
 
 @pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3'])
+@pytest.mark.parametrize('shape', [(1, 15, 224, 224), (1, 7, 320, 320), (2, 2, 448, 448), (3, 1, 224, 224)],
+                         ids=['T15_224', 'T7_320', 'B2_T2_448_l2cs', 'B3_T1_224'])
+def test_config_sweep_shapes_vs_oracle(engines, synthetic_sd, precision, shape):
+    """BASELINE configs[2] (l2cs setting: 448 x 448, stage-0 RoIs land on FPN level 3) and configs[4] (clip-length /
+    resolution sweep) as parity cases: (yaw,pitch) against the fp32 oracle on the same seeded inputs."""
+    B, T, H, W = shape
+    img = torch.cat([O.make_clip(40 + b, T, H, W) for b in range(B)])
+    ref = O.forward(synthetic_sd, img, clip_length=T)
+    out = engines(precision).forward(img.cuda(), clip_length=T)
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(out['gaze'][:, i].cpu(), ref[k]) < 1e-3, k
+    assert (out['boxes'].cpu() - ref['boxes']).abs().max() < 0.1
+    assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3'])
 def test_batched_clips_and_ragged_meta(engines, synthetic_sd, precision):
     """B=2 clips of T=3 on a non-square padded image with unpadded img_shape and rescale."""
     T, H, W = 3, 160, 224
