@@ -162,7 +162,6 @@ class Engine {
     MCG_CUDA(cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
     MCG_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     MCG_CUDA(cudaFuncSetAttribute(linear256_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    if (precision != MCG_PRECISION_SIMT) umma_set_attrs();
   }
 
   ~Engine() {

@@ -1111,8 +1111,6 @@ inline void umma_launch_pair(const cudaLaunchConfig_t& cfg, const UmmaPlan& pl) 
     umma_launch_kbs<kTerms, false>(cfg, pl);
 }
 
-inline void umma_set_attrs() {}  // (the dynamic shared-memory attribute is set per instantiation at first launch)
-
 inline void launch_umma(const UmmaPlan& pl, cudaStream_t stream) {
   static const int tune_pdl = tune_env("MCG_TUNE_NO_PDL");
   cudaLaunchConfig_t cfg = {};
