@@ -1115,14 +1115,17 @@ class Engine {
       ln(xc_, 256, nullptr, 0, sw.ffn_norm, obj_out, 256, R, false, st);
       // cls / reg towers + per-clue heads (gaze_stqi_head.py:185-201); the cls tower and the first reg layer
       // read the same input and run as one grouped launch, as do the three per-clue heads of each kind
+      // The classification branch only feeds the detection scores, and only the last stage's reach the output
+      // (multiclue_gaze_roi_head.py:351-366): stages 0-2 skip it unless their intermediates are being recorded.
+      const bool need_cls = s == 3 || (keep_stage_interm_ && !graph_mode_);
       {
         const float* xs[2] = {obj_out, obj_out};
-        const GemmW* ws[2] = {&sw.cls_fc, &sw.reg_fc[0]};
-        const LnW* ns[2] = {&sw.cls_ln, &sw.reg_ln[0]};
-        float* ys[2] = {t256a_, t256b_};
-        linear_ln_grouped(2, xs, 256, ws, ns, R, ys, 256, true, nullptr, 0, st);
+        const GemmW* ws[2] = {&sw.reg_fc[0], &sw.cls_fc};
+        const LnW* ns[2] = {&sw.reg_ln[0], &sw.cls_ln};
+        float* ys[2] = {t256b_, t256a_};
+        linear_ln_grouped(need_cls ? 2 : 1, xs, 256, ws, ns, R, ys, 256, true, nullptr, 0, st);
       }
-      {
+      if (need_cls) {
         const float* xs[3] = {t256a_, t256a_ + 256, t256a_ + 512};
         const GemmW* ws[3] = {&sw.fc_cls[0], &sw.fc_cls[1], &sw.fc_cls[2]};
         float* ys[3] = {cls_logit_, cls_logit_ + 1, cls_logit_ + 2};
