@@ -4,6 +4,7 @@
 // NHWC / row-major so that every warp access is contiguous along channels.
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace mcg {
 
@@ -189,8 +190,11 @@ __device__ __forceinline__ void acc8(float (&a)[8], const uint4& u, float w) {
 
 // One warp per (roi, bin); each lane owns 8 consecutive channels, so every bilinear tap is one
 // 16-byte load per lane (512 B per warp) per plane and the output row is written as 2 float4.
+// Output either fp32 X[r, bin, c] or, for the tensor-core DynamicConv, the same tensor as split-fp16 planes.
 __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const float* __restrict__ boxes /*[R,4]*/,
-                                                        int R, float* __restrict__ out /*[R,49,256]*/) {
+                                                        int R, float* __restrict__ out /*[R,49,256]*/,
+                                                        __half* __restrict__ out_hi = nullptr,
+                                                        __half* __restrict__ out_lo = nullptr) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (gw >= R * 49) return;
   const int lane = threadIdx.x & 31;
@@ -262,7 +266,25 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
       }
     }
   }
-  float4* o = reinterpret_cast<float4*>(out + (static_cast<long long>(r) * 49 + bin) * 256 + lane * 8);
+  const long long oi = (static_cast<long long>(r) * 49 + bin) * 256 + lane * 8;
+  if (out_hi) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j] * 0.25f;
+    uint4 uh, ul;
+    uh.x = ptx::pack_half2(v[0], v[1]);
+    uh.y = ptx::pack_half2(v[2], v[3]);
+    uh.z = ptx::pack_half2(v[4], v[5]);
+    uh.w = ptx::pack_half2(v[6], v[7]);
+    ul.x = ptx::residue_half2(v[0], v[1], uh.x);
+    ul.y = ptx::residue_half2(v[2], v[3], uh.y);
+    ul.z = ptx::residue_half2(v[4], v[5], uh.z);
+    ul.w = ptx::residue_half2(v[6], v[7], uh.w);
+    *reinterpret_cast<uint4*>(out_hi + oi) = uh;
+    *reinterpret_cast<uint4*>(out_lo + oi) = ul;
+    return;
+  }
+  float4* o = reinterpret_cast<float4*>(out + oi);
   o[0] = make_float4(acc[0] * 0.25f, acc[1] * 0.25f, acc[2] * 0.25f, acc[3] * 0.25f);
   o[1] = make_float4(acc[4] * 0.25f, acc[5] * 0.25f, acc[6] * 0.25f, acc[7] * 0.25f);
 }
@@ -473,6 +495,226 @@ __global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ 
         else
           out[o + c] = t;
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// DynamicConv on the warp-level tensor cores (mma.sync m16n8k16, fp16 x fp16 -> fp32, 3-term split operands:
+// lo*hi + hi*lo + hi*hi, i.e. fp32-class products).  Measured on B200: 2.0 cycles per m16n8k16 per SM
+// (tools/micro/hmma_rate.cu) = 2048 dense FLOP/clk/SM, 16x the FFMA rate the kernel above is bound by.
+//   X      : RoIAlign output as split-fp16 planes [R, 49, 256]            (A operand of bmm1, via ldmatrix)
+//   params : dynamic_layer output with PERMUTED rows (Engine::load_weights): PinT [64 n][256 k] then PoutT [256 n][64 k],
+//            fp32 - both B operands are then K-contiguous and are split into hi / lo fragments on the fly
+// One CTA (8 warps) per RoI.  bmm1: warp w owns the n8 tile w and all four m16 tiles (M = 49 padded to 64);
+// LN(64) + ReLU one warp per position, written back as fp16 hi / lo (A operand of bmm2); bmm2: warp w owns n8 tiles
+// 4w..4w+3 (64 fp32 accumulators per thread); LN(256) + ReLU one warp per position from an fp32 staging copy.
+// ---------------------------------------------------------------------------------------
+constexpr int kDmXPitch = 264;    // halves per X row (256 + 8: ldmatrix rows 528 B apart, conflict-free)
+constexpr int kDmPinPitch = 264;  // floats per PinT row (bank shift of 8 words per n row)
+constexpr int kDmPoutPitch = 72;  // floats per PoutT row
+constexpr int kDmF1Pitch = 72;    // halves per F1 row (and floats per raw F1 row: the two uses overlay)
+constexpr int kDmF2Pitch = 264;   // floats per F2 staging row (overlays PinT)
+constexpr int kDmOffXl = 64 * kDmXPitch * 2;
+constexpr int kDmOffPin = 2 * kDmOffXl;
+constexpr int kDmOffPout = kDmOffPin + 64 * kDmPinPitch * 4;
+constexpr int kDmOffF1 = kDmOffPout + 256 * kDmPoutPitch * 4;
+constexpr int kDynMmaSmemBytes = kDmOffF1 + 64 * kDmF1Pitch * 4;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fp32 pair -> (hi, lo) fp16x2
+__device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo) {
+  hi = ptx::pack_half2(v.x, v.y);
+  lo = ptx::residue_half2(v.x, v.y, hi);
+}
+
+__global__ void __launch_bounds__(256) dynconv_mma_kernel(const __half* __restrict__ Xh, const __half* __restrict__ Xl,
+                                                          const float* __restrict__ params /*[R, 32768] permuted*/,
+                                                          const float* __restrict__ g_in, const float* __restrict__ b_in,
+                                                          const float* __restrict__ g_out, const float* __restrict__ b_out,
+                                                          float* __restrict__ out /*[R,12544]*/,
+                                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  extern __shared__ __align__(16) uint8_t dms[];
+  __half* sXh = reinterpret_cast<__half*>(dms);
+  __half* sXl = reinterpret_cast<__half*>(dms + kDmOffXl);
+  float* sPin = reinterpret_cast<float*>(dms + kDmOffPin);     // PinT [64][pitch]; later the F2 staging copy
+  float* sPout = reinterpret_cast<float*>(dms + kDmOffPout);   // PoutT [256][pitch]
+  float* sF1raw = reinterpret_cast<float*>(dms + kDmOffF1);    // [64][pitch] fp32, then overlaid by:
+  __half* sF1h = reinterpret_cast<__half*>(dms + kDmOffF1);    // [64][pitch] fp16 hi
+  __half* sF1l = sF1h + 64 * kDmF1Pitch;                       //             fp16 lo
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const __half* gxh = Xh + static_cast<long long>(r) * 12544;
+  const __half* gxl = Xl + static_cast<long long>(r) * 12544;
+  const float* gp = params + static_cast<long long>(r) * 32768;
+  // X planes: 49 rows x 512 B each; PinT: 64 rows x 1 KB; PoutT: 256 rows x 256 B
+  for (int i = tid; i < 49 * 32; i += 256) {
+    const int row = i >> 5, ch = i & 31;
+    cp_async16(sXh + row * kDmXPitch + ch * 8, gxh + row * 256 + ch * 8);
+    cp_async16(sXl + row * kDmXPitch + ch * 8, gxl + row * 256 + ch * 8);
+  }
+  for (int i = tid; i < 64 * 64; i += 256) {
+    const int row = i >> 6, ch = i & 63;
+    cp_async16(sPin + row * kDmPinPitch + ch * 4, gp + row * 256 + ch * 4);
+  }
+  cp_async_commit();
+  for (int i = tid; i < 256 * 16; i += 256) {
+    const int row = i >> 4, ch = i & 15;
+    cp_async16(sPout + row * kDmPoutPitch + ch * 4, gp + 16384 + row * 64 + ch * 4);
+  }
+  cp_async_commit();
+  // rows 49..63 of the A operand (M padding): zeros
+  for (int i = tid; i < 15 * 32; i += 256) {
+    const int row = 49 + (i >> 5), ch = i & 31;
+    *reinterpret_cast<uint4*>(sXh + row * kDmXPitch + ch * 8) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sXl + row * kDmXPitch + ch * 8) = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_wait<1>();
+  __syncthreads();
+  // ---- bmm1: F1[64 x 64] = X[64 x 256] . PinT^T ; warp = n8 tile, 4 m16 tiles
+  {
+    float acc[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+    const float* brow = sPin + (warp * 8 + g) * kDmPinPitch + 2 * t;
+    const int arow = lane & 15, acol = (lane >> 4) * 8;
+#pragma unroll 2
+    for (int kk = 0; kk < 256; kk += 16) {
+      uint32_t bh0, bl0, bh1, bl1;
+      split2(*reinterpret_cast<const float2*>(brow + kk), bh0, bl0);
+      split2(*reinterpret_cast<const float2*>(brow + kk + 8), bh1, bl1);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t ah[4], al[4];
+        ldmatrix_x4(ah, sXh + (mt * 16 + arow) * kDmXPitch + kk + acol);
+        ldmatrix_x4(al, sXl + (mt * 16 + arow) * kDmXPitch + kk + acol);
+        mma16816(acc[mt], al, bh0, bh1);
+        mma16816(acc[mt], ah, bl0, bl1);
+        mma16816(acc[mt], ah, bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      *reinterpret_cast<float2*>(sF1raw + (mt * 16 + g) * kDmF1Pitch + warp * 8 + 2 * t) = make_float2(acc[mt][0], acc[mt][1]);
+      *reinterpret_cast<float2*>(sF1raw + (mt * 16 + g + 8) * kDmF1Pitch + warp * 8 + 2 * t) = make_float2(acc[mt][2], acc[mt][3]);
+    }
+  }
+  __syncthreads();
+  // ---- LN(64) + ReLU per position; the fp16 hi / lo copy overlays the raw fp32 rows, so read all rows first
+  {
+    float va[8], vb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = warp + 8 * i;  // rows 0..63
+      va[i] = sF1raw[p * kDmF1Pitch + lane];
+      vb[i] = sF1raw[p * kDmF1Pitch + 32 + lane];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = warp + 8 * i;
+      float a = va[i], b = vb[i];
+      float s = a + b;
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / 64.f;
+      float q = (a - mean) * (a - mean) + (b - mean) * (b - mean);
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / 64.f + 1e-5f);
+      a = p < 49 ? fmaxf((a - mean) * rstd * g_in[lane] + b_in[lane], 0.f) : 0.f;
+      b = p < 49 ? fmaxf((b - mean) * rstd * g_in[32 + lane] + b_in[32 + lane], 0.f) : 0.f;
+      const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+      sF1h[p * kDmF1Pitch + lane] = ha;
+      sF1h[p * kDmF1Pitch + 32 + lane] = hb;
+      sF1l[p * kDmF1Pitch + lane] = __float2half_rn(a - __half2float(ha));
+      sF1l[p * kDmF1Pitch + 32 + lane] = __float2half_rn(b - __half2float(hb));
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- bmm2: F2[64 x 256] = F1[64 x 64] . PoutT^T ; warp = n8 tiles 4w..4w+3, 4 m16 tiles
+  {
+    float acc[4][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+    const int arow = lane & 15, acol = (lane >> 4) * 8;
+#pragma unroll
+    for (int kk = 0; kk < 64; kk += 16) {
+      uint32_t ah[4][4], al[4][4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        ldmatrix_x4(ah[mt], sF1h + (mt * 16 + arow) * kDmF1Pitch + kk + acol);
+        ldmatrix_x4(al[mt], sF1l + (mt * 16 + arow) * kDmF1Pitch + kk + acol);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* brow = sPout + (warp * 32 + nt * 8 + g) * kDmPoutPitch + kk + 2 * t;
+        uint32_t bh0, bl0, bh1, bl1;
+        split2(*reinterpret_cast<const float2*>(brow), bh0, bl0);
+        split2(*reinterpret_cast<const float2*>(brow + 8), bh1, bl1);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          mma16816(acc[mt][nt], al[mt], bh0, bh1);
+          mma16816(acc[mt][nt], ah[mt], bl0, bl1);
+          mma16816(acc[mt][nt], ah[mt], bh0, bh1);
+        }
+      }
+    }
+    // stage F2 as fp32 over the (dead) PinT region for the row-wise LayerNorm
+    float* sF2 = sPin;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = warp * 32 + nt * 8 + 2 * t;
+        if (mt * 16 + g < 49)
+          *reinterpret_cast<float2*>(sF2 + (mt * 16 + g) * kDmF2Pitch + c) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        if (mt * 16 + g + 8 < 49)
+          *reinterpret_cast<float2*>(sF2 + (mt * 16 + g + 8) * kDmF2Pitch + c) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+  }
+  __syncthreads();
+  // ---- LN(256) + ReLU per position, output in the flatten order (position, channel)
+  for (int p = warp; p < 49; p += 8) {
+    const float* row = sPin + p * kDmF2Pitch;
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = row[lane + 32 * j];
+      s += v[j];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / 256.f;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / 256.f + 1e-5f);
+    const long long o = static_cast<long long>(r) * 12544 + p * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      const float tv = fmaxf((v[j] - mean) * rstd * g_out[c] + b_out[c], 0.f);
+      if (out_hi)
+        split_store(tv, out_hi, out_lo, o + c);
+      else
+        out[o + c] = tv;
     }
   }
 }

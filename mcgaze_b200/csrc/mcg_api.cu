@@ -157,9 +157,13 @@ class Engine {
       for (int d = 0; d < w[i].ndim; ++d) cnt *= static_cast<size_t>(w[i].shape[d]);
       host_[w[i].name] = {w[i].data, cnt};
     }
+    // DynamicConv on the warp-level tensor cores (needs the permuted dynamic_layer rows); the fp32 CUDA-core mode and
+    // MCG_TUNE_DYNCONV_FFMA=1 keep the FFMA kernel and the reference's row order
+    dyn_mma_ = precision != MCG_PRECISION_SIMT && std::getenv("MCG_TUNE_DYNCONV_FFMA") == nullptr;
     load_weights();
     host_.clear();
     MCG_CUDA(cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+    MCG_CUDA(cudaFuncSetAttribute(dynconv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMmaSmemBytes));
     MCG_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     MCG_CUDA(cudaFuncSetAttribute(linear256_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   }
@@ -521,7 +525,25 @@ class Engine {
       st.out_proj = pack_linear(p + ".attention.attn.out_proj.weight", p + ".attention.attn.out_proj.bias", 256, 256);
       st.attn_norm = pack_ln(p + ".attention_norm", 256);
       const std::string q = p + ".instance_interactive_conv";
-      st.dyn = pack_linear(q + ".dynamic_layer.weight", q + ".dynamic_layer.bias", 32768, 256);
+      if (dyn_mma_) {
+        // rows of dynamic_layer permuted so that its output is [PinT (64 n x 256 k) | PoutT (256 n x 64 k)] instead of
+        // the reference's [Pin (256 k x 64 n) | Pout (64 k x 256 n)] (transformer.py:1126-1130): both bmm B operands
+        // become K-contiguous for the tensor-core DynamicConv kernel
+        const float* w = need(q + ".dynamic_layer.weight", static_cast<size_t>(32768) * 256).p;
+        const float* b = need(q + ".dynamic_layer.bias", 32768).p;
+        std::vector<float> wp(static_cast<size_t>(32768) * 256), bp(32768);
+        auto move_row = [&](int dst, int src) {
+          std::memcpy(&wp[static_cast<size_t>(dst) * 256], w + static_cast<size_t>(src) * 256, 256 * sizeof(float));
+          bp[dst] = b[src];
+        };
+        for (int k = 0; k < 256; ++k)
+          for (int n = 0; n < 64; ++n) move_row(n * 256 + k, k * 64 + n);
+        for (int k = 0; k < 64; ++k)
+          for (int n = 0; n < 256; ++n) move_row(16384 + n * 64 + k, 16384 + k * 256 + n);
+        st.dyn = pack_gemm(wp, 32768, 256, bp.data());
+      } else {
+        st.dyn = pack_linear(q + ".dynamic_layer.weight", q + ".dynamic_layer.bias", 32768, 256);
+      }
       st.norm_in = pack_ln(q + ".norm_in", 64);
       st.norm_out = pack_ln(q + ".norm_out", 256);
       st.fc = pack_linear(q + ".fc_layer.weight", q + ".fc_layer.bias", 256, 12544);
@@ -647,6 +669,8 @@ class Engine {
     xc_ = arena_.alloc<float>(Rr * 256);
     params_ = arena_.alloc<float>(Rr * 32768);
     roi_ = arena_.alloc<float>(Rr * 12544);
+    roih_.hi = arena_.alloc<__half>(Rr * 12544);  // RoIAlign output as planes (tensor-core DynamicConv)
+    roih_.lo = arena_.alloc<__half>(Rr * 12544);
     dynf_ = arena_.alloc<float>(Rr * 12544);
     fc_ = arena_.alloc<float>(Rr * 256);
     fcp_ = arena_.alloc<float>(Rr * 256 * kFcSplit);
@@ -1074,7 +1098,8 @@ class Engine {
         MCG_CUDA(cudaStreamWaitEvent(side_stream_, fork_ev_[s], 0));
         rs = side_stream_;
       }
-      roi_align_kernel<<<(R * 49 + 7) / 8, 256, 0, rs>>>(fl, boxes_in, R, roi_);
+      roi_align_kernel<<<(R * 49 + 7) / 8, 256, 0, rs>>>(fl, boxes_in, R, roi_, dyn_mma_ ? roih_.hi : nullptr,
+                                                          dyn_mma_ ? roih_.lo : nullptr);
       MCG_CUDA(cudaGetLastError());
       count("roi_align_kernel");
       if (fork) MCG_CUDA(cudaEventRecord(join_ev_[s], side_stream_));
@@ -1096,10 +1121,16 @@ class Engine {
       // DynamicConv (transformer.py:1116-1164)
       linear_tc(sk + "dyn", attn, 256, hq_, tc, sw.dyn, R, params_, false, nullptr, st);
       if (fork) MCG_CUDA(cudaStreamWaitEvent(st, join_ev_[s], 0));
-      dynconv_kernel<<<R, 256, kDynSmemBytes, st>>>(roi_, params_, sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
-                                                    sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr, tc ? hf_.lo : nullptr);
+      if (dyn_mma_) {
+        dynconv_mma_kernel<<<R, 256, kDynMmaSmemBytes, st>>>(roih_.hi, roih_.lo, params_, sw.norm_in.g, sw.norm_in.b,
+                                                             sw.norm_out.g, sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr,
+                                                             tc ? hf_.lo : nullptr);
+      } else {
+        dynconv_kernel<<<R, 256, kDynSmemBytes, st>>>(roi_, params_, sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
+                                                      sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr, tc ? hf_.lo : nullptr);
+      }
       MCG_CUDA(cudaGetLastError());
-      count("dynconv_kernel");
+      count(dyn_mma_ ? "dynconv_mma_kernel" : "dynconv_kernel");
       {
         // 12544 -> 256 over only 3*frames rows: split K so that >100 tiles exist; the partial sums are
         // reduced (and the bias added) inside the fc_norm LayerNorm kernel
@@ -1145,6 +1176,10 @@ class Engine {
       if (keep_stage_interm_ && !graph_mode_) {
         // head buffers are reused by every stage: snapshot them for per-op parity tests
         const std::string nm = "stage" + std::to_string(s);
+        if (dyn_mma_) {  // the RoI features live as planes: export them as fp32
+          planes_to_f32_kernel<<<1024, 256, 0, st>>>(roih_.hi, roih_.lo, nullptr, static_cast<long long>(R) * 12544, roi_);
+          MCG_CUDA(cudaGetLastError());
+        }
         reg_f32(nm + ".roi_feat", snapshot(roi_, static_cast<size_t>(R) * 12544, st), R, 49, 256);
         reg_f32(nm + ".attn", snapshot(attn, static_cast<size_t>(R) * 256, st), NB, 3, 256);
         reg_f32(nm + ".obj", snapshot(obj_out, static_cast<size_t>(R) * 256, st), NB, 3, 256);
@@ -1244,7 +1279,8 @@ class Engine {
         *roi_ = nullptr, *dynf_ = nullptr, *fc_ = nullptr, *fcp_ = nullptr, *ffn_h_ = nullptr, *t256a_ = nullptr, *t256b_ = nullptr,
         *cls_logit_ = nullptr, *delta_ = nullptr, *gz_a_ = nullptr, *gz_b_ = nullptr, *gvec_ = nullptr,
         *conf_ = nullptr, *d_meta_ = nullptr;
-  Planes hq_, hh_, hf_;
+  Planes hq_, hh_, hf_, roih_;
+  bool dyn_mma_ = false;
   float* pin_meta_ = nullptr;
   bool has_scale_ = false;
 
