@@ -505,7 +505,8 @@ __global__ void __launch_bounds__(256) dynconv_kernel(const float* __restrict__ 
 // (tools/micro/hmma_rate.cu) = 2048 dense FLOP/clk/SM, 16x the FFMA rate the kernel above is bound by.
 //   X      : RoIAlign output as split-fp16 planes [R, 49, 256]            (A operand of bmm1, via ldmatrix)
 //   params : dynamic_layer output with PERMUTED rows (Engine::load_weights): PinT [64 n][256 k] then PoutT [256 n][64 k],
-//            fp32 - both B operands are then K-contiguous and are split into hi / lo fragments on the fly
+//            so that both B operands are K-contiguous; either split-fp16 planes written by the tcgen05 GEMM's TMA-store
+//            epilogue (kPlanes: fragments are plain 32-bit shared-memory loads) or fp32 (split into hi / lo on the fly)
 // One CTA (8 warps) per RoI.  bmm1: warp w owns the n8 tile w and all four m16 tiles (M = 49 padded to 64);
 // LN(64) + ReLU one warp per position, written back as fp16 hi / lo (A operand of bmm2); bmm2: warp w owns n8 tiles
 // 4w..4w+3 (64 fp32 accumulators per thread); LN(256) + ReLU one warp per position from an fp32 staging copy.
@@ -537,8 +538,10 @@ __device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo) {
   lo = ptx::residue_half2(v.x, v.y, hi);
 }
 
+template <bool kPlanes>
 __global__ void __launch_bounds__(256) dynconv_mma_kernel(const __half* __restrict__ Xh, const __half* __restrict__ Xl,
-                                                          const float* __restrict__ params /*[R, 32768] permuted*/,
+                                                          const float* __restrict__ params /*[R, 32768] permuted, fp32*/,
+                                                          const __half* __restrict__ Ph, const __half* __restrict__ Pl,
                                                           const float* __restrict__ g_in, const float* __restrict__ b_in,
                                                           const float* __restrict__ g_out, const float* __restrict__ b_out,
                                                           float* __restrict__ out /*[R,12544]*/,
@@ -557,22 +560,44 @@ __global__ void __launch_bounds__(256) dynconv_mma_kernel(const __half* __restri
   const __half* gxh = Xh + static_cast<long long>(r) * 12544;
   const __half* gxl = Xl + static_cast<long long>(r) * 12544;
   const float* gp = params + static_cast<long long>(r) * 32768;
+  // the same regions as half planes (kPlanes): hi rows first, then lo rows, pitches in halves = 2 x pitch in floats / 2
+  __half* sPinH = reinterpret_cast<__half*>(sPin);
+  __half* sPinL = sPinH + 64 * kDmXPitch;        // [64][264] halves each
+  __half* sPoutH = reinterpret_cast<__half*>(sPout);
+  __half* sPoutL = sPoutH + 256 * kDmF1Pitch;    // [256][72] halves each
   // X planes: 49 rows x 512 B each; PinT: 64 rows x 1 KB; PoutT: 256 rows x 256 B
   for (int i = tid; i < 49 * 32; i += 256) {
     const int row = i >> 5, ch = i & 31;
     cp_async16(sXh + row * kDmXPitch + ch * 8, gxh + row * 256 + ch * 8);
     cp_async16(sXl + row * kDmXPitch + ch * 8, gxl + row * 256 + ch * 8);
   }
-  for (int i = tid; i < 64 * 64; i += 256) {
-    const int row = i >> 6, ch = i & 63;
-    cp_async16(sPin + row * kDmPinPitch + ch * 4, gp + row * 256 + ch * 4);
+  if (kPlanes) {
+    const __half* gh = Ph + static_cast<long long>(r) * 32768;
+    const __half* gl = Pl + static_cast<long long>(r) * 32768;
+    for (int i = tid; i < 64 * 32; i += 256) {
+      const int row = i >> 5, ch = i & 31;
+      cp_async16(sPinH + row * kDmXPitch + ch * 8, gh + row * 256 + ch * 8);
+      cp_async16(sPinL + row * kDmXPitch + ch * 8, gl + row * 256 + ch * 8);
+    }
+    cp_async_commit();
+    for (int i = tid; i < 256 * 8; i += 256) {
+      const int row = i >> 3, ch = i & 7;
+      cp_async16(sPoutH + row * kDmF1Pitch + ch * 8, gh + 16384 + row * 64 + ch * 8);
+      cp_async16(sPoutL + row * kDmF1Pitch + ch * 8, gl + 16384 + row * 64 + ch * 8);
+    }
+    cp_async_commit();
+  } else {
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int row = i >> 6, ch = i & 63;
+      cp_async16(sPin + row * kDmPinPitch + ch * 4, gp + row * 256 + ch * 4);
+    }
+    cp_async_commit();
+    for (int i = tid; i < 256 * 16; i += 256) {
+      const int row = i >> 4, ch = i & 15;
+      cp_async16(sPout + row * kDmPoutPitch + ch * 4, gp + 16384 + row * 64 + ch * 4);
+    }
+    cp_async_commit();
   }
-  cp_async_commit();
-  for (int i = tid; i < 256 * 16; i += 256) {
-    const int row = i >> 4, ch = i & 15;
-    cp_async16(sPout + row * kDmPoutPitch + ch * 4, gp + 16384 + row * 64 + ch * 4);
-  }
-  cp_async_commit();
   // rows 49..63 of the A operand (M padding): zeros
   for (int i = tid; i < 15 * 32; i += 256) {
     const int row = 49 + (i >> 5), ch = i & 31;
@@ -589,12 +614,21 @@ __global__ void __launch_bounds__(256) dynconv_mma_kernel(const __half* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
     const float* brow = sPin + (warp * 8 + g) * kDmPinPitch + 2 * t;
+    const __half* browh = sPinH + (warp * 8 + g) * kDmXPitch + 2 * t;
+    const __half* browl = sPinL + (warp * 8 + g) * kDmXPitch + 2 * t;
     const int arow = lane & 15, acol = (lane >> 4) * 8;
 #pragma unroll 2
     for (int kk = 0; kk < 256; kk += 16) {
       uint32_t bh0, bl0, bh1, bl1;
-      split2(*reinterpret_cast<const float2*>(brow + kk), bh0, bl0);
-      split2(*reinterpret_cast<const float2*>(brow + kk + 8), bh1, bl1);
+      if (kPlanes) {
+        bh0 = *reinterpret_cast<const uint32_t*>(browh + kk);
+        bh1 = *reinterpret_cast<const uint32_t*>(browh + kk + 8);
+        bl0 = *reinterpret_cast<const uint32_t*>(browl + kk);
+        bl1 = *reinterpret_cast<const uint32_t*>(browl + kk + 8);
+      } else {
+        split2(*reinterpret_cast<const float2*>(brow + kk), bh0, bl0);
+        split2(*reinterpret_cast<const float2*>(brow + kk + 8), bh1, bl1);
+      }
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         uint32_t ah[4], al[4];
@@ -663,10 +697,18 @@ __global__ void __launch_bounds__(256) dynconv_mma_kernel(const __half* __restri
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const float* brow = sPout + (warp * 32 + nt * 8 + g) * kDmPoutPitch + kk + 2 * t;
+        const int bn = warp * 32 + nt * 8 + g;
         uint32_t bh0, bl0, bh1, bl1;
-        split2(*reinterpret_cast<const float2*>(brow), bh0, bl0);
-        split2(*reinterpret_cast<const float2*>(brow + 8), bh1, bl1);
+        if (kPlanes) {
+          bh0 = *reinterpret_cast<const uint32_t*>(sPoutH + bn * kDmF1Pitch + kk + 2 * t);
+          bh1 = *reinterpret_cast<const uint32_t*>(sPoutH + bn * kDmF1Pitch + kk + 2 * t + 8);
+          bl0 = *reinterpret_cast<const uint32_t*>(sPoutL + bn * kDmF1Pitch + kk + 2 * t);
+          bl1 = *reinterpret_cast<const uint32_t*>(sPoutL + bn * kDmF1Pitch + kk + 2 * t + 8);
+        } else {
+          const float* brow = sPout + bn * kDmPoutPitch + kk + 2 * t;
+          split2(*reinterpret_cast<const float2*>(brow), bh0, bl0);
+          split2(*reinterpret_cast<const float2*>(brow + 8), bh1, bl1);
+        }
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
           mma16816(acc[mt][nt], al[mt], bh0, bh1);

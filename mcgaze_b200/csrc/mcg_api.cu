@@ -163,7 +163,8 @@ class Engine {
     load_weights();
     host_.clear();
     MCG_CUDA(cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
-    MCG_CUDA(cudaFuncSetAttribute(dynconv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMmaSmemBytes));
+    MCG_CUDA(cudaFuncSetAttribute(dynconv_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMmaSmemBytes));
+    MCG_CUDA(cudaFuncSetAttribute(dynconv_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMmaSmemBytes));
     MCG_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     MCG_CUDA(cudaFuncSetAttribute(linear256_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   }
@@ -1119,12 +1120,24 @@ class Engine {
       }
       const float* attn = xb_;
       // DynamicConv (transformer.py:1116-1164)
-      linear_tc(sk + "dyn", attn, 256, hq_, tc, sw.dyn, R, params_, false, nullptr, st);
+      // with the tensor-core DynamicConv the parameters leave the GEMM as split-fp16 planes (TMA-store epilogue) in
+      // the same buffer: hi plane, then lo plane
+      Planes pp;
+      pp.hi = reinterpret_cast<__half*>(params_);
+      pp.lo = pp.hi + static_cast<size_t>(R) * 32768;
+      const bool par_planes = dyn_mma_ && tc;
+      linear_tc(sk + "dyn", attn, 256, hq_, tc, sw.dyn, R, params_, false, nullptr, st, 1, par_planes ? &pp : nullptr);
       if (fork) MCG_CUDA(cudaStreamWaitEvent(st, join_ev_[s], 0));
       if (dyn_mma_) {
-        dynconv_mma_kernel<<<R, 256, kDynMmaSmemBytes, st>>>(roih_.hi, roih_.lo, params_, sw.norm_in.g, sw.norm_in.b,
-                                                             sw.norm_out.g, sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr,
-                                                             tc ? hf_.lo : nullptr);
+        if (par_planes)
+          dynconv_mma_kernel<true><<<R, 256, kDynMmaSmemBytes, st>>>(roih_.hi, roih_.lo, nullptr, pp.hi, pp.lo, sw.norm_in.g,
+                                                                     sw.norm_in.b, sw.norm_out.g, sw.norm_out.b, dynf_,
+                                                                     hf_.hi, hf_.lo);
+        else
+          dynconv_mma_kernel<false><<<R, 256, kDynMmaSmemBytes, st>>>(roih_.hi, roih_.lo, params_, nullptr, nullptr,
+                                                                      sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
+                                                                      sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr,
+                                                                      tc ? hf_.lo : nullptr);
       } else {
         dynconv_kernel<<<R, 256, kDynSmemBytes, st>>>(roi_, params_, sw.norm_in.g, sw.norm_in.b, sw.norm_out.g,
                                                       sw.norm_out.b, dynf_, tc ? hf_.hi : nullptr, tc ? hf_.lo : nullptr);
