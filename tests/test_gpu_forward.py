@@ -231,6 +231,22 @@ def test_full_batch_properties(engines, precision):
     assert torch.equal(shuffled['gaze'], gz[idx])
 
 
+def test_head_linears_on_cuda_cores_option(engines, synthetic_sd):
+    """Option head_tensor_cores = 0: the head's large Linears run on the fp32 CUDA-core kernel and the tensor-core
+    DynamicConv reads fp32 parameters (its on-the-fly split path) - same parity bar."""
+    img = O.make_clip(5, 7)
+    ref = O.forward(synthetic_sd, img)
+    eng = engines('fp16c8')
+    eng.set_option('head_tensor_cores', 0)
+    try:
+        out = eng.forward(img.cuda())
+        g = out['gaze'].cpu()
+    finally:
+        eng.set_option('head_tensor_cores', 1)
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(g[:, i], ref[k]) < 1e-3, k
+
+
 def test_errors_are_reported(engines):
     from mcgaze_b200 import lib
     eng = engines('fp16x3')
