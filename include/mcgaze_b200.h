@@ -128,6 +128,31 @@ int mcg_debug_conv(int engine, const float* x, int NB, int H, int W, int C, cons
                    int stride, int pad, const float* bias, const float* res, int res_mode, int relu,
                    int force_im2col, int force_block_n, int out_mode, float* out, void* stream);
 
+/* ---- test-time image pipeline -------------------------------------------------
+ * One decoded frame and the geometry the reference's test_pipeline applies to it
+ * (configs/_base_/datasets/gaze360.py:27-36): the CenterCrop window (mmdet/datasets/pipelines/transforms.py:1036-1047;
+ * the whole image when the config has no CenterCrop, as in multiclue_gaze_r50_l2cs.py:31-39) and the size
+ * Resize(keep_ratio=True) gives it (mmcv.imrescale; transforms.py:217-228). */
+typedef struct {
+  const uint8_t* src;  /* DEVICE uint8 [src_h, src_w, 3], channel order as decoded by LoadImageFromFile (BGR) */
+  int64_t src_stride;  /* bytes per source row (>= 3 * src_w) */
+  int32_t src_h, src_w;
+  int32_t crop_y, crop_x, crop_h, crop_w;
+  int32_t dst_h, dst_w;
+} mcg_frame;
+
+/* Replaces Resize -> RandomFlip(0.0) -> Normalize -> Pad(size_divisor) -> DefaultFormatBundle -> collate of the
+ * reference's test_pipeline (transforms.py:213-241, 739-754, 665-681; formatting.py:96; the crop of CenterCrop is the
+ * window in mcg_frame) for n frames: bit-exact cv2.resize(INTER_LINEAR) of the crop window to (dst_h, dst_w),
+ * BGR->RGB when to_rgb, (x - mean) / std in mmcv.imnormalize's arithmetic, zeros outside (dst_h, dst_w).
+ *   frames  HOST   n descriptors (device source pointers inside)
+ *   mean, std  HOST fp32 [3], output-channel order (img_norm_cfg)
+ *   out     DEVICE fp32 [n, 3, Hp, Wp], 16-byte aligned, Wp % 4 == 0, every dst_h <= Hp, dst_w <= Wp;
+ *           this is the `img` argument of mcg_forward
+ * Asynchronous on `stream`; needs no engine handle. */
+int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const float* std, int to_rgb, float* out,
+                   int Hp, int Wp, void* stream);
+
 const char* mcg_last_error(void);
 const char* mcg_version(void);
 

@@ -12,33 +12,47 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmcgaze_b200.so')
-SOURCES = ['mcg_api.cu']
-HEADERS = ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh',
-           os.path.join('..', '..', 'include', 'mcgaze_b200.h')]
+OBJ = os.path.join(HERE, 'build')
+API_H = os.path.join('..', '..', 'include', 'mcgaze_b200.h')
+# source -> headers it depends on (each source is compiled to its own object, then linked)
+SOURCES = {
+    'mcg_api.cu': ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh', API_H],
+    'preprocess.cu': ['common.cuh', API_H],
+}
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _newer(deps, target) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source with `-gencode arch=compute_100a,code=sm_100a -lineinfo`."""
-    if not force and not _stale():
-        return LIB
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-           '-Xcompiler', '-fPIC', '-shared'] + (['-Xptxas', '-v'] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB + '.tmp']
+def _run(cmd, verbose: bool) -> None:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError('nvcc failed building libmcgaze_b200.so')
     if verbose:
         sys.stderr.write(r.stderr)
-    os.replace(LIB + '.tmp', LIB)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source with `-gencode arch=compute_100a,code=sm_100a -lineinfo` and link the library."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    flags = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC'] + \
+            (['-Xptxas', '-v'] if verbose else [])
+    os.makedirs(OBJ, exist_ok=True)
+    objs, relink = [], force or not os.path.exists(LIB)
+    for src, deps in SOURCES.items():
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + '.o')
+        objs.append(obj)
+        if force or _newer([src] + deps, obj):
+            _run([nvcc] + flags + ['-c', os.path.join(CSRC, src), '-o', obj], verbose)
+            relink = True
+    if relink or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        _run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared'] + objs + ['-o', LIB + '.tmp'], verbose)
+        os.replace(LIB + '.tmp', LIB)
     return LIB
 
 

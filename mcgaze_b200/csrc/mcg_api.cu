@@ -1331,6 +1331,12 @@ class Engine {
 
 }  // namespace mcg
 
+namespace mcg {
+// preprocess.cu
+void preprocess_launch(const mcg_frame* frames, int n, const float* mean, const float* std_, int to_rgb, float* out,
+                       int Hp, int Wp, cudaStream_t st, int* launches);
+}  // namespace mcg
+
 // ========================================================================================
 // C ABI
 // ========================================================================================
@@ -1431,6 +1437,19 @@ int mcg_wait_host(mcg_handle h, int ticket, float* out_gaze_host, float* out_box
       return MCG_ERR_INVALID;
     }
     h->impl->wait_host(ticket, out_gaze_host, out_boxes_host, out_scores_host);
+    return MCG_OK;
+  });
+}
+
+int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const float* std, int to_rgb, float* out,
+                   int Hp, int Wp, void* stream) {
+  return guarded([&]() -> int {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      mcg::g_last_error = "mcg_preprocess: no CUDA device visible (this library has no CPU fallback)";
+      return MCG_ERR_CUDA;
+    }
+    mcg::preprocess_launch(frames, n, mean, std, to_rgb, out, Hp, Wp, static_cast<cudaStream_t>(stream), nullptr);
     return MCG_OK;
   });
 }

@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
            'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
-           'mcg_last_error', 'mcg_version')
+           'mcg_preprocess', 'mcg_last_error', 'mcg_version')
 
 
 class McgError(RuntimeError):
@@ -29,6 +29,13 @@ class McgError(RuntimeError):
 class mcg_tensor(ctypes.Structure):
     _fields_ = [('name', ctypes.c_char_p), ('data', ctypes.c_void_p), ('ndim', ctypes.c_int),
                 ('shape', ctypes.c_int64 * 4)]
+
+
+class mcg_frame(ctypes.Structure):
+    _fields_ = [('src', ctypes.c_void_p), ('src_stride', ctypes.c_int64), ('src_h', ctypes.c_int32),
+                ('src_w', ctypes.c_int32), ('crop_y', ctypes.c_int32), ('crop_x', ctypes.c_int32),
+                ('crop_h', ctypes.c_int32), ('crop_w', ctypes.c_int32), ('dst_h', ctypes.c_int32),
+                ('dst_w', ctypes.c_int32)]
 
 
 _lib = None
@@ -57,6 +64,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_last_umma_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ci]
     lib.mcg_last_kernel_profile.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    lib.mcg_preprocess.argtypes = [ctypes.POINTER(mcg_frame), ci, cf, cf, ci, vp, ci, ci, vp]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -70,6 +78,54 @@ def _check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load_library().mcg_last_error()
         raise McgError(f'{what} failed (code {rc}): {msg.decode() if msg else ""}')
+
+
+_FRAME_DTYPE = None
+
+
+def preprocess(frames, geometry, mean, std, to_rgb, out, stream: Optional[int] = None) -> None:
+    """mcg_preprocess: `frames` = CUDA uint8 HWC tensors (decoded BGR frames; a list, or ONE [n, h, w, 3] tensor),
+    `geometry` = per frame (crop_y, crop_x, crop_h, crop_w, dst_h, dst_w), `out` = CUDA fp32 [n, 3, Hp, Wp].
+    Asynchronous on `stream` (default: torch's current stream)."""
+    import numpy as np
+    import torch
+    global _FRAME_DTYPE
+    if not torch.cuda.is_available():
+        raise McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    lib = load_library()
+    if _FRAME_DTYPE is None:
+        _FRAME_DTYPE = np.dtype([('src', np.uint64), ('src_stride', np.int64), ('src_h', np.int32), ('src_w', np.int32),
+                                 ('geo', np.int32, (6,))])
+        assert _FRAME_DTYPE.itemsize == ctypes.sizeof(mcg_frame)
+    n = len(frames)
+    geo = np.asarray(geometry, dtype=np.int32)
+    if n == 0 or geo.shape != (n, 6):
+        raise McgError('preprocess: need one (crop_y, crop_x, crop_h, crop_w, dst_h, dst_w) per frame')
+    if out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or out.dim() != 4 or out.shape[0] != n \
+            or out.shape[1] != 3:
+        raise McgError('preprocess: `out` must be a contiguous CUDA fp32 tensor [n, 3, Hp, Wp]')
+    desc = np.zeros(n, dtype=_FRAME_DTYPE)
+    bad = 'preprocess: frames must be CUDA uint8 [h, w, 3] tensors with packed pixels'
+    if hasattr(frames, 'data_ptr'):               # one batched tensor: descriptors without a python loop
+        f = frames
+        if f.dtype != torch.uint8 or not f.is_cuda or f.dim() != 4 or f.shape[3] != 3 or f.stride(3) != 1 or f.stride(2) != 3:
+            raise McgError(bad)
+        desc['src'] = f.data_ptr() + np.arange(n, dtype=np.uint64) * np.uint64(f.stride(0))
+        desc['src_stride'], desc['src_h'], desc['src_w'] = f.stride(1), f.shape[1], f.shape[2]
+    else:
+        for f in frames:
+            if f.dtype != torch.uint8 or not f.is_cuda or f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                raise McgError(bad)
+        desc['src'] = [f.data_ptr() for f in frames]
+        desc['src_stride'] = [f.stride(0) for f in frames]
+        desc['src_h'] = [f.shape[0] for f in frames]
+        desc['src_w'] = [f.shape[1] for f in frames]
+    desc['geo'] = geo
+    c3 = ctypes.c_float * 3
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    _check(lib.mcg_preprocess(ctypes.cast(desc.ctypes.data, ctypes.POINTER(mcg_frame)), n,
+                              c3(*[float(v) for v in mean]), c3(*[float(v) for v in std]), 1 if to_rgb else 0,
+                              out.data_ptr(), out.shape[2], out.shape[3], st), 'mcg_preprocess')
 
 
 class Engine:
@@ -188,16 +244,19 @@ class Engine:
         del k1, k2
         return {'gaze': gaze, 'boxes': boxes, 'scores': scores}
 
-    def forward_into(self, img, clip_length: int, out):
+    def forward_into(self, img, clip_length: int, out, img_hw=None, scale_factor=None):
         """Like forward() but writes into the preallocated dict `out` (stable pointers: lets the
         CUDA-graph replay path engage)."""
         import torch
         N, _, H, W = img.shape
         T = int(clip_length)
+        k1, p1 = self._meta(img_hw, N, 2)
+        k2, p2 = self._meta(scale_factor, N, 4)
         stream = torch.cuda.current_stream(img.device).cuda_stream
-        _check(self._lib.mcg_forward(self._h, img.data_ptr(), N // T, T, H, W, None, None, out['gaze'].data_ptr(),
+        _check(self._lib.mcg_forward(self._h, img.data_ptr(), N // T, T, H, W, p1, p2, out['gaze'].data_ptr(),
                                      out['boxes'].data_ptr(), out['scores'].data_ptr(), ctypes.c_void_p(stream)),
                'mcg_forward')
+        del k1, k2
         return out
 
     def forward_host(self, img, clip_length: Optional[int] = None, img_hw=None, scale_factor=None):

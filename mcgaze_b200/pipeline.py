@@ -1,0 +1,187 @@
+"""The reference's test-time image pipeline on the GPU.
+
+`GpuTestPipeline(cfg.data.test.pipeline)` takes the SAME list of `dict(type=...)` entries the reference feeds to
+`mmdet.datasets.pipelines.Compose` (tools/test_gaze360_gaze.py:58; configs/_base_/datasets/gaze360.py:27-36,
+configs/multiclue_gaze/multiclue_gaze_r50_l2cs.py:31-39) and produces the same `img` / `img_metas` the reference's
+pipeline + collate produce, but the pixel work (resize, colour swap, normalisation, padding, HWC -> CHW, batching)
+runs in one CUDA kernel behind `mcg_preprocess` on uint8 frames already in HBM: 1 byte per sample crosses PCIe
+instead of the 4 of the reference's fp32 tensors.
+
+Host side (this file) = only the per-frame geometry, in the reference's own python arithmetic:
+  CenterCrop._get_crop_size / _crop_data   mmdet/datasets/pipelines/transforms.py:1101-1130, 1036-1047
+  Resize._resize_img (mmcv.imrescale / imresize, rescale_size)   transforms.py:213-241
+  Pad._pad_img (mmcv.impad_to_multiple / impad)                  transforms.py:665-681
+The crop of the reference's test run is random (one np.random.rand(1) per pipeline call, i.e. per frame in
+tools/test_gaze360_gaze.py:96-100); here the draws come from `np.random` as well (so np.random.seed pins them), from
+an own seeded generator (`seed=`), or from the caller (`rands=`).
+
+There is no CPU fallback: without the CUDA library / a GPU the calls raise.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import lib
+
+_SKIPPED = ('LoadImageFromFile', 'DefaultFormatBundle', 'Collect', 'ImageToTensor')
+
+
+class GpuTestPipeline:
+    def __init__(self, pipeline_cfg: Sequence[Dict[str, Any]], device: int = 0, seed: Optional[int] = None):
+        self.device = int(device)
+        self.crop: Optional[Tuple[str, Tuple[float, float]]] = None
+        self.scale: Optional[Tuple[int, int]] = None
+        self.keep_ratio = True
+        self.mean = self.std = None
+        self.to_rgb = True
+        self.size_divisor: Optional[int] = None
+        self.pad_size: Optional[Tuple[int, int]] = None
+        self._rng = np.random.RandomState(seed) if seed is not None else None
+        for step in pipeline_cfg:
+            step = dict(step)
+            t = step.pop('type')
+            if t in _SKIPPED:
+                continue                      # frames arrive decoded; bundling / collecting is what batch() returns
+            if t == 'CenterCrop':
+                ctype = step.get('crop_type', 'absolute')
+                if ctype not in ('relative_range', 'relative', 'absolute'):
+                    raise NotImplementedError(f'CenterCrop crop_type={ctype!r} is not supported by the GPU pipeline')
+                self.crop = (ctype, tuple(step['crop_size']))
+            elif t == 'Resize':
+                scale = step.get('img_scale')
+                if isinstance(scale, list):
+                    if len(scale) != 1:
+                        raise NotImplementedError('multi-scale Resize is a training-time feature')
+                    scale = scale[0]
+                if scale is None or step.get('ratio_range') is not None:
+                    raise NotImplementedError('Resize needs one fixed img_scale')
+                if step.get('backend', 'cv2') != 'cv2' or step.get('interpolation', 'bilinear') != 'bilinear':
+                    raise NotImplementedError('only cv2 bilinear Resize is implemented on the GPU')
+                self.scale = (int(scale[0]), int(scale[1]))
+                self.keep_ratio = bool(step.get('keep_ratio', True))
+            elif t == 'RandomFlip':
+                if step.get('flip_ratio') not in (None, 0, 0.0):
+                    raise NotImplementedError('test pipelines use RandomFlip(flip_ratio=0.0); flipping is not implemented')
+            elif t == 'Normalize':
+                # Normalize.__init__ stores float32 arrays (transforms.py:735-736)
+                self.mean = np.array(step['mean'], dtype=np.float32)
+                self.std = np.array(step['std'], dtype=np.float32)
+                self.to_rgb = bool(step.get('to_rgb', True))
+            elif t == 'Pad':
+                if step.get('pad_to_square') or step.get('pad_val', 0) not in (0, dict(img=0, masks=0, seg=255)):
+                    raise NotImplementedError('only zero padding to a size / size_divisor is implemented')
+                self.size_divisor = step.get('size_divisor')
+                self.pad_size = tuple(step['size']) if step.get('size') is not None else None
+            else:
+                raise NotImplementedError(f'pipeline step {t!r} is not part of the reference test pipelines')
+        if self.scale is None or self.mean is None:
+            raise ValueError('the GPU pipeline needs a Resize and a Normalize step')
+
+    # ---------------------------------------------------------------------------- geometry (host, python floats)
+    def _draw(self) -> float:
+        return float((self._rng.rand(1) if self._rng is not None else np.random.rand(1))[0])
+
+    def crop_window(self, h: int, w: int, rand: float) -> Tuple[int, int, int, int]:
+        """-> (y, x, crop_h, crop_w) of the CenterCrop slice, clipped to the image like the numpy slice is."""
+        if self.crop is None:
+            return 0, 0, h, w
+        ctype, size = self.crop
+        if ctype == 'absolute':
+            ch, cw = min(size[0], h), min(size[1], w)
+        elif ctype == 'relative':
+            ch, cw = int(h * size[0] + 0.5), int(w * size[1] + 0.5)
+        else:   # relative_range: ONE draw for both sides (transforms.py:1127-1130), float32 ratio + float64 draw
+            cs = np.asarray(size, dtype=np.float32)
+            rh, rw = cs + np.asarray([rand], dtype=np.float64) * (1 - cs)
+            ch, cw = int(h * rh + 0.5), int(w * rw + 0.5)
+        if ch <= 0 or cw <= 0:
+            raise ValueError('CenterCrop produced an empty window')
+        y = int(max(h - ch, 0) / 2 + 0.5)
+        x = int(max(w - cw, 0) / 2 + 0.5)
+        return y, x, min(y + ch, h) - y, min(x + cw, w) - x
+
+    def resized_size(self, h: int, w: int) -> Tuple[int, int]:
+        """-> (new_h, new_w) of Resize (mmcv.rescale_size when keep_ratio, else img_scale = (w, h))."""
+        if not self.keep_ratio:
+            return self.scale[1], self.scale[0]
+        f = min(max(self.scale) / max(h, w), min(self.scale) / min(h, w))
+        return int(h * float(f) + 0.5), int(w * float(f) + 0.5)
+
+    def padded_size(self, h: int, w: int) -> Tuple[int, int]:
+        if self.pad_size is not None:
+            return max(self.pad_size[0], h), max(self.pad_size[1], w)
+        if self.size_divisor:
+            d = self.size_divisor
+            return int(np.ceil(h / d)) * d, int(np.ceil(w / d)) * d
+        return h, w
+
+    def plan(self, shapes: Sequence[Tuple[int, int]], rands: Optional[Sequence[float]] = None):
+        """Per-frame geometry + metas for frames of the given (h, w); -> (geometry, metas, (Hp, Wp))."""
+        if rands is None:
+            rands = [self._draw() if self.crop is not None and self.crop[0] == 'relative_range' else 0.0 for _ in shapes]
+        geometry, metas = [], []
+        Hp = Wp = 0
+        for (h, w), r in zip(shapes, rands):
+            y, x, ch, cw = self.crop_window(h, w, r)
+            nh, nw = self.resized_size(ch, cw)
+            ph, pw = self.padded_size(nh, nw)
+            Hp, Wp = max(Hp, ph), max(Wp, pw)
+            geometry.append((y, x, ch, cw, nh, nw))
+            w_scale, h_scale = nw / cw, nh / ch
+            metas.append(dict(
+                filename=None, ori_filename=None, ori_shape=(h, w, 3), img_shape=(nh, nw, 3), pad_shape=(ph, pw, 3),
+                scale_factor=np.array([w_scale, h_scale, w_scale, h_scale], dtype=np.float32),
+                flip=False, flip_direction=None,
+                img_norm_cfg=dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb)))
+        if Wp % 4:
+            Wp += 4 - Wp % 4                   # the kernel stores float4; configs pad to 32 anyway
+        return geometry, metas, (Hp, Wp)
+
+    # ---------------------------------------------------------------------------- device work
+    def batch(self, frames: Sequence[Any], rands: Optional[Sequence[float]] = None, out=None,
+              filenames: Optional[Sequence[str]] = None) -> Dict[str, Any]:
+        """frames: decoded BGR uint8 [h, w, 3] arrays (numpy -> copied to the device) or CUDA uint8 tensors, or one
+        [n, h, w, 3] array / CUDA tensor when all frames have one size.
+        -> dict(img=[Tensor[n, 3, Hp, Wp]], img_metas=[[meta] * n]) ready for `model(return_loss=False, **data)`:
+        the collate of the reference (tools/test_gaze360_gaze.py:102-105) pads every frame to the largest one."""
+        import torch
+        if not torch.cuda.is_available():
+            raise lib.McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        dev = torch.device('cuda', self.device)
+        if hasattr(frames, 'data_ptr') or (isinstance(frames, np.ndarray) and frames.ndim == 4):
+            # one [n, h, w, 3] block (frames of one size): a single H2D copy, descriptors without a python loop
+            dframes = torch.from_numpy(np.ascontiguousarray(frames)).to(dev, non_blocking=True) \
+                if isinstance(frames, np.ndarray) else frames
+            shapes = [(int(dframes.shape[1]), int(dframes.shape[2]))] * int(dframes.shape[0])
+        else:
+            dframes = []
+            for f in frames:
+                if isinstance(f, np.ndarray):
+                    if f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] != 3:
+                        raise ValueError('frames must be uint8 [h, w, 3] (BGR as decoded by LoadImageFromFile)')
+                    f = torch.from_numpy(np.ascontiguousarray(f)).to(dev, non_blocking=True)
+                dframes.append(f)
+            shapes = [(int(f.shape[0]), int(f.shape[1])) for f in dframes]
+        geometry, metas, (Hp, Wp) = self.plan(shapes, rands)
+        if filenames is not None:
+            for m, name in zip(metas, filenames):
+                m['filename'] = m['ori_filename'] = name
+        n = len(dframes)
+        if out is None:
+            out = torch.empty((n, 3, Hp, Wp), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (n, 3, Hp, Wp):
+            raise ValueError(f'out must have shape {(n, 3, Hp, Wp)}')
+        with torch.cuda.device(dev):
+            lib.preprocess(dframes, geometry, self.mean, self.std, self.to_rgb, out)
+        return dict(img=[out], img_metas=[metas])
+
+    def __call__(self, data: Dict[str, Any]) -> Dict[str, Any]:
+        """Per-frame call of the reference's Compose (tools/test_gaze360_gaze.py:48-49): `data['img']` holds the
+        decoded frame.  -> dict(img=Tensor[3, Hp, Wp] on the device, img_metas=meta)."""
+        if 'img' not in data:
+            raise KeyError("the GPU pipeline takes decoded frames: pass dict(img=uint8 BGR array)")
+        name = (data.get('img_info') or {}).get('filename')
+        res = self.batch([data['img']], filenames=[name] if name is not None else None)
+        return dict(img=res['img'][0][0], img_metas=res['img_metas'][0][0])

@@ -25,6 +25,7 @@ import math
 import sys
 import types
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -292,3 +293,83 @@ def install() -> None:
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     _installed = True
+
+
+# ----------------------------------------------------------------------------------------------------
+# mmcv.image functions the reference's test pipeline calls (mmdet/datasets/pipelines/transforms.py:217-228,
+# 671-679, 751-752), restated from the published mmcv 1.4.8 source (mmcv/image/geometric.py, photometric.py):
+# thin wrappers over OpenCV, which IS available here (cv2 4.13) — so the pixel arithmetic of the goldens is
+# OpenCV's own.  Used by oracle/gen_golden_preprocess.py only.
+# ----------------------------------------------------------------------------------------------------
+def _scale_size(size, scale):
+    if isinstance(scale, (float, int)):
+        scale = (scale, scale)
+    w, h = size
+    return int(w * float(scale[0]) + 0.5), int(h * float(scale[1]) + 0.5)
+
+
+def rescale_size(old_size, scale, return_scale=False):
+    w, h = old_size
+    if isinstance(scale, (float, int)):
+        scale_factor = scale
+    else:
+        max_long_edge, max_short_edge = max(scale), min(scale)
+        scale_factor = min(max_long_edge / max(h, w), max_short_edge / min(h, w))
+    new_size = _scale_size((w, h), scale_factor)
+    return (new_size, scale_factor) if return_scale else new_size
+
+
+def imresize(img, size, return_scale=False, interpolation='bilinear', out=None, backend=None):
+    import cv2
+    assert interpolation == 'bilinear' and backend in (None, 'cv2')
+    h, w = img.shape[:2]
+    resized = cv2.resize(img, size, dst=out, interpolation=cv2.INTER_LINEAR)
+    if not return_scale:
+        return resized
+    return resized, size[0] / w, size[1] / h
+
+
+def imrescale(img, scale, return_scale=False, interpolation='bilinear', backend=None):
+    h, w = img.shape[:2]
+    new_size, scale_factor = rescale_size((w, h), scale, return_scale=True)
+    rescaled = imresize(img, new_size, interpolation=interpolation, backend=backend)
+    return (rescaled, scale_factor) if return_scale else rescaled
+
+
+def imnormalize(img, mean, std, to_rgb=True):
+    import cv2
+    img = img.copy().astype(np.float32)
+    assert img.dtype != np.uint8
+    mean = np.float64(mean.reshape(1, -1))
+    stdinv = 1 / np.float64(std.reshape(1, -1))
+    if to_rgb:
+        cv2.cvtColor(img, cv2.COLOR_BGR2RGB, img)
+    cv2.subtract(img, mean, img)
+    cv2.multiply(img, stdinv, img)
+    return img
+
+
+def impad(img, *, shape=None, padding=None, pad_val=0, padding_mode='constant'):
+    import cv2
+    assert (shape is not None) ^ (padding is not None) and padding_mode == 'constant'
+    if shape is not None:
+        padding = (0, 0, shape[1] - img.shape[1], shape[0] - img.shape[0])
+    return cv2.copyMakeBorder(img, padding[1], padding[3], padding[0], padding[2], cv2.BORDER_CONSTANT, value=pad_val)
+
+
+def impad_to_multiple(img, divisor, pad_val=0):
+    pad_h = int(np.ceil(img.shape[0] / divisor)) * divisor
+    pad_w = int(np.ceil(img.shape[1] / divisor)) * divisor
+    return impad(img, shape=(pad_h, pad_w), pad_val=pad_val)
+
+
+def imflip(img, direction='horizontal'):
+    return np.flip(img, axis=1) if direction == 'horizontal' else np.flip(img, axis=0)
+
+
+def install_image_ops() -> None:
+    """install() + the image functions above on the stand-in `mmcv` module."""
+    install()
+    import mmcv
+    for fn in (rescale_size, imresize, imrescale, imnormalize, impad, impad_to_multiple, imflip):
+        setattr(mmcv, fn.__name__, fn)
