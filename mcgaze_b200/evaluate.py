@@ -1,0 +1,166 @@
+"""Batched, multi-GPU evaluation driver (SURVEY.md section 8, rows f1 + f2).
+
+The reference evaluates with tools/test_gaze360_gaze.py: one clip per forward, T python threads running the CPU
+pipeline per clip, `.cpu().tolist()` per frame (:60-269); its generic `tools/test.py` / `dist_test.sh` path cannot run
+the gaze configs because `Gaze360Dataset.__getitem__` raises NotImplementedError in test mode
+(mmdet/datasets/gaze360.py:310-312).  This module provides what that path needs, on the new backend:
+
+  Gaze360ClipDataset   test-mode dataset: item i = one clip (7-frame window, stride 4, right-aligned last window:
+                       tools/test_gaze360_gaze.py:73-86) of one video of `test.json`
+  single_gpu_test /    mmdet/apis/test.py:17-78 / :81-209 for clips: every rank takes the clips
+  multi_gpu_test       DistributedSampler(shuffle=False) would give it (samplers/distributed_sampler.py:53), MANY
+                       clips go through one forward (`clips_per_batch`), results are all-gathered ONCE and put back
+                       in dataset order (the `zip(*part_list)` re-ordering of :204-206)
+  videos_from_clips    overlap merge + JSON records exactly as tools/test_gaze360_gaze.py:129-260
+  evaluate             tools/calculate_mae_gaze360.py on those records
+
+`model` is anything with the reference's call contract `model(return_loss=False, rescale=True, format=False,
+img=[Tensor], img_metas=[[meta...]], clip_length=T)` (mcgaze_b200.detector.MultiClueGaze); `pipeline` is a
+mcgaze_b200.pipeline.GpuTestPipeline (or any object with `.batch(frames) -> dict(img, img_metas)`).
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import dist as mdist
+from . import metric, slicer
+
+ROW = 3 * 4 + 3 + 4 * 3          # per frame: boxes [3,4], scores [3], gaze [4,3]
+
+
+def _default_loader(path: str) -> np.ndarray:
+    """LoadImageFromFile (mmdet/datasets/pipelines/loading.py:58-69): cv2 decode, BGR uint8.  Decoding stays on the host."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_COLOR)
+    if img is None:
+        raise FileNotFoundError(path)
+    return img
+
+
+class Gaze360ClipDataset:
+    def __init__(self, ann_file, img_prefix: str = '', clip_len: int = slicer.CLIP_LEN, stride: int = slicer.STRIDE,
+                 loader: Optional[Callable[[str], np.ndarray]] = None, test_mode: bool = True):
+        if not test_mode:
+            raise NotImplementedError('training is out of scope for the B200 inference backend')
+        self.anno = json.load(open(ann_file)) if isinstance(ann_file, (str, os.PathLike)) else ann_file
+        self.img_prefix = img_prefix
+        self.clip_len, self.stride = clip_len, stride
+        self.loader = loader or _default_loader
+        self.videos: List[List[str]] = [list(v['file_names']) for v in self.anno['videos']]
+        self.plans = [slicer.plan_clips(len(v), clip_len, stride) for v in self.videos]
+        # flat clip index -> (video index, clip index within the video)
+        self.index: List[Tuple[int, int]] = [(vi, ci) for vi, p in enumerate(self.plans) for ci in range(len(p))]
+
+    def __len__(self) -> int:
+        return len(self.index)
+
+    def clip_info(self, i: int) -> Dict[str, Any]:
+        vi, ci = self.index[i]
+        start, n, overlap = self.plans[vi][ci]
+        return dict(video=vi, clip=ci, start=start, n=n, overlap=overlap, filenames=self.videos[vi][start:start + n])
+
+    def __getitem__(self, i: int) -> Dict[str, Any]:
+        info = self.clip_info(i)
+        info['frames'] = [self.loader(os.path.join(self.img_prefix, f) if self.img_prefix else f) for f in info['filenames']]
+        return info
+
+
+def _batches(dataset: Gaze360ClipDataset, indices: Sequence[int], clips_per_batch: int) -> List[List[int]]:
+    """Clips of one length share a forward (the temporal attention needs one clip_length per call)."""
+    by_len: Dict[int, List[int]] = {}
+    for i in indices:
+        by_len.setdefault(dataset.clip_info(i)['n'], []).append(i)
+    out = []
+    for n in sorted(by_len, reverse=True):
+        idx = by_len[n]
+        out += [idx[k:k + clips_per_batch] for k in range(0, len(idx), clips_per_batch)]
+    return out
+
+
+def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[int], clips_per_batch: int = 32) -> Dict[int, np.ndarray]:
+    """-> {clip index: float32 [n_frames, ROW]} for the given clips; frames of a batch go through ONE pipeline call
+    and ONE forward."""
+    import torch
+    results: Dict[int, np.ndarray] = {}
+    for batch in _batches(dataset, indices, clips_per_batch):
+        items = [dataset[i] for i in batch]
+        T = items[0]['n']
+        frames = [f for it in items for f in it['frames']]
+        names = [f for it in items for f in it['filenames']]
+        try:
+            data = pipeline.batch(frames, filenames=names)
+        except TypeError:
+            data = pipeline.batch(frames)
+        (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
+        det = torch.stack(list(det_bboxes)).float()                                  # [B*T, 3, 5]
+        gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
+        rows = torch.cat([det[..., :4].reshape(len(frames), 12), det[..., 4], gaze.reshape(len(frames), 12).float()], 1)
+        rows = rows.cpu().numpy().astype(np.float32)                                 # ONE device->host read per batch
+        for k, i in enumerate(batch):
+            results[i] = rows[k * T:(k + 1) * T]
+    return results
+
+
+def single_gpu_test(model, dataset: Gaze360ClipDataset, pipeline, clips_per_batch: int = 32) -> List[np.ndarray]:
+    res = run_clips(model, dataset, pipeline, range(len(dataset)), clips_per_batch)
+    return [res[i] for i in range(len(dataset))]
+
+
+def multi_gpu_test(model, dataset: Gaze360ClipDataset, pipeline, clips_per_batch: int = 32, group=None,
+                   device=None) -> List[np.ndarray]:
+    """Every rank returns the results of ALL clips in dataset order (one all-gather; NCCL on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as tdist
+    rank, world = tdist.get_rank(group), tdist.get_world_size(group)
+    n = len(dataset)
+    mine = mdist.padded_shard(n, rank, world)
+    res = run_clips(model, dataset, pipeline, sorted(set(mine)), clips_per_batch)
+    packed = np.zeros((len(mine), dataset.clip_len, ROW), dtype=np.float32)
+    for k, i in enumerate(mine):
+        packed[k, :res[i].shape[0]] = res[i]
+    local = torch.from_numpy(packed)
+    if device is not None:
+        local = local.to(device)
+    full = mdist.gather_results(local, n, group=group).numpy()
+    return [full[i, :dataset.clip_info(i)['n']] for i in range(n)]
+
+
+def videos_from_clips(dataset: Gaze360ClipDataset, clip_rows: Sequence[np.ndarray]) -> Tuple[List[Dict[str, Any]], List[Dict[str, np.ndarray]]]:
+    """Per-clip rows in dataset order -> (JSON records of tools/test_gaze360_gaze.py:210-260, merged per-video arrays)."""
+    records, merged_all = [], []
+    k = 0
+    for vi, plan in enumerate(dataset.plans):
+        rows = clip_rows[k:k + len(plan)]
+        k += len(plan)
+        boxes = [r[:, :12].reshape(-1, 3, 4) for r in rows]
+        scores = [r[:, 12:15] for r in rows]
+        gaze = [r[:, 15:].reshape(-1, 4, 3) for r in rows]
+        merged = slicer.merge_video(plan, boxes, scores, gaze)
+        merged_all.append(merged)
+        vid = dataset.anno['videos'][vi].get('id', vi + 1)
+        records.append(slicer.video_record(vid, merged))
+    return records, merged_all
+
+
+def ground_truth_videos(dataset: Gaze360ClipDataset) -> Optional[List[np.ndarray]]:
+    """Per-video GT gaze vectors from the annotation file, in the frame order of the videos
+    (tools/calculate_mae_gaze360.py:117-135 walks anno['annotations'] in order, one entry per frame)."""
+    ann = dataset.anno.get('annotations')
+    if not ann:
+        return None
+    gt, k = [], 0
+    for v in dataset.videos:
+        gt.append(np.asarray([ann[k + t]['gaze'] for t in range(len(v))], dtype=np.float64).reshape(len(v), 3))
+        k += len(v)
+    return gt
+
+
+def evaluate(dataset: Gaze360ClipDataset, records: Sequence[Dict[str, Any]], key: str = 'fusion_gazes') -> Dict[str, float]:
+    gt = ground_truth_videos(dataset)
+    if gt is None:
+        raise ValueError('the annotation file carries no ground-truth gazes')
+    return metric.gaze_error([np.asarray(r[key], dtype=np.float64) for r in records], gt)

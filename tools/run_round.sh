@@ -11,4 +11,6 @@ timeout 600 python bench.py 2>&1 | tail -3
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python tools/profile_step.py fp16c8 32 1 > gpurun_out/ncu_list_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_list_${TAG}.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:preprocess_kernel -s 3 -c 1 -o gpurun_out/preprocess_${TAG} \
+   python tools/bench_preprocess.py 320 320 2 > gpurun_out/ncu_pp_${TAG}.log 2>&1
 tail -12 gpurun_out/${TAG}.log
