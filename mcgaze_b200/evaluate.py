@@ -147,15 +147,14 @@ def videos_from_clips(dataset: Gaze360ClipDataset, clip_rows: Sequence[np.ndarra
 
 
 def ground_truth_videos(dataset: Gaze360ClipDataset) -> Optional[List[np.ndarray]]:
-    """Per-video GT gaze vectors from the annotation file, in the frame order of the videos
-    (tools/calculate_mae_gaze360.py:117-135 walks anno['annotations'] in order, one entry per frame)."""
+    """Per-video GT gaze vectors: annotation k belongs to video k and carries one vector per frame
+    (tools/calculate_mae_gaze360.py:118-121)."""
     ann = dataset.anno.get('annotations')
     if not ann:
         return None
-    gt, k = [], 0
-    for v in dataset.videos:
-        gt.append(np.asarray([ann[k + t]['gaze'] for t in range(len(v))], dtype=np.float64).reshape(len(v), 3))
-        k += len(v)
+    gt = [np.asarray(a['gaze'], dtype=np.float64).reshape(-1, 3) for a in ann]
+    if len(gt) != len(dataset.videos) or any(len(g) != len(v) for g, v in zip(gt, dataset.videos)):
+        raise ValueError('annotations do not match the videos (one annotation per video, one gaze per frame)')
     return gt
 
 

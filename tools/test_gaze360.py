@@ -1,0 +1,63 @@
+"""Evaluation entry point of the B200 backend: same arguments as the reference's tools/test_gaze360_gaze.py
+(config, checkpoint, --json, --root, --device, --cfg-options), same results JSON (results/results_<config>_<json>),
+but MANY clips per forward, the image pipeline on the GPU, and -- under torchrun -- clips sharded over the ranks with
+one all-gather (what the reference's dist_test.sh path would do if its test-mode dataset existed).
+
+    python tools/test_gaze360.py configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py ckpt.pth
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/test_gaze360.py <config> <ckpt>
+"""
+import json
+import os
+import sys
+from argparse import ArgumentParser
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mcgaze_b200 import evaluate as ev  # noqa: E402
+from mcgaze_b200.apis import init_detector  # noqa: E402
+from mcgaze_b200.compat import DictAction  # noqa: E402
+from mcgaze_b200.pipeline import GpuTestPipeline  # noqa: E402
+
+
+def main():
+    ap = ArgumentParser()
+    ap.add_argument('config')
+    ap.add_argument('checkpoint')
+    ap.add_argument('--json', default='data/gaze360/test.json')
+    ap.add_argument('--root', default='data/gaze360/test_rawframes/')
+    ap.add_argument('--device', default=None)
+    ap.add_argument('--cfg-options', nargs='+', action=DictAction)
+    ap.add_argument('--clips-per-batch', type=int, default=32)
+    ap.add_argument('--seed', type=int, default=None, help='pins the CenterCrop draws (the reference run is unseeded)')
+    args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    device = args.device or f'cuda:{local}'
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device(device))
+    model = init_detector(args.config, args.checkpoint, device=device, cfg_options=args.cfg_options)
+    pipe = GpuTestPipeline(model.cfg.data.test.pipeline, device=int(device.split(':')[1]), seed=args.seed)
+    ds = ev.Gaze360ClipDataset(args.json, img_prefix=args.root)
+    if world > 1:
+        rows = ev.multi_gpu_test(model, ds, pipe, args.clips_per_batch, device=device)
+    else:
+        rows = ev.single_gpu_test(model, ds, pipe, args.clips_per_batch)
+    if int(os.environ.get('RANK', '0')) == 0:
+        records, _ = ev.videos_from_clips(ds, rows)
+        os.makedirs('results', exist_ok=True)
+        out = os.path.join('results', f'results_{os.path.basename(args.config)[:-3]}_{os.path.basename(args.json)}')
+        json.dump(records, open(out, 'w'))
+        print('wrote', out)
+        if ds.anno.get('annotations'):
+            for key in ('fusion_gazes', 'face_gazes', 'eyes_gazes', 'head_gazes'):
+                m = ev.evaluate(ds, records, key)
+                print(f"{key}: MAE 360 {m['mae_360']:.2f}  front-180 {m['mae_front90']:.2f}  front-20 {m['mae_front20']:.2f}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
