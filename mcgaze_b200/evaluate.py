@@ -81,44 +81,70 @@ def _batches(dataset: Gaze360ClipDataset, indices: Sequence[int], clips_per_batc
     return out
 
 
-def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[int], clips_per_batch: int = 32) -> Dict[int, np.ndarray]:
+def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool) -> Tuple[int, Any, List[str]]:
+    """Decode the frames of a batch of clips (in parallel on `pool`); frames of one size are stacked into ONE
+    [n, h, w, 3] block so that they cross PCIe in a single copy."""
+    infos = [dataset.clip_info(i) for i in batch]
+    names = [f for it in infos for f in it['filenames']]
+    paths = [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
+    frames = list(pool.map(dataset.loader, paths)) if pool is not None else [dataset.loader(p) for p in paths]
+    if len({f.shape for f in frames}) == 1:
+        frames = np.stack(frames)
+    return infos[0]['n'], frames, names
+
+
+def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[int], clips_per_batch: int = 32,
+              workers: int = 0) -> Dict[int, np.ndarray]:
     """-> {clip index: float32 [n_frames, ROW]} for the given clips; frames of a batch go through ONE pipeline call
-    and ONE forward."""
+    and ONE forward.  With `workers` > 0 the frames of batch k+1 are decoded on a thread pool while the GPU works on
+    batch k (the role of the DataLoader workers in mmdet/apis/test.py:107-109)."""
     import torch
+    from concurrent.futures import ThreadPoolExecutor
     results: Dict[int, np.ndarray] = {}
-    for batch in _batches(dataset, indices, clips_per_batch):
-        items = [dataset[i] for i in batch]
-        T = items[0]['n']
-        frames = [f for it in items for f in it['frames']]
-        names = [f for it in items for f in it['filenames']]
-        try:
-            data = pipeline.batch(frames, filenames=names)
-        except TypeError:
-            data = pipeline.batch(frames)
-        (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
-        det = torch.stack(list(det_bboxes)).float()                                  # [B*T, 3, 5]
-        gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
-        rows = torch.cat([det[..., :4].reshape(len(frames), 12), det[..., 4], gaze.reshape(len(frames), 12).float()], 1)
-        rows = rows.cpu().numpy().astype(np.float32)                                 # ONE device->host read per batch
-        for k, i in enumerate(batch):
-            results[i] = rows[k * T:(k + 1) * T]
+    batches = _batches(dataset, indices, clips_per_batch)
+    pool = ThreadPoolExecutor(workers) if workers > 0 else None
+    feeder = ThreadPoolExecutor(1) if workers > 0 else None
+    try:
+        nxt = feeder.submit(_load_batch, dataset, batches[0], pool) if feeder and batches else None
+        for bi, batch in enumerate(batches):
+            if feeder:
+                T, frames, names = nxt.result()
+                nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool) if bi + 1 < len(batches) else None
+            else:
+                T, frames, names = _load_batch(dataset, batch, None)
+            try:
+                data = pipeline.batch(frames, filenames=names)
+            except TypeError:
+                data = pipeline.batch(frames)
+            (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
+            n = len(names)
+            det = torch.stack(list(det_bboxes)).float()                              # [B*T, 3, 5]
+            gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
+            rows = torch.cat([det[..., :4].reshape(n, 12), det[..., 4], gaze.reshape(n, 12).float()], 1)
+            rows = rows.cpu().numpy().astype(np.float32)                             # ONE device->host read per batch
+            for k, i in enumerate(batch):
+                results[i] = rows[k * T:(k + 1) * T]
+    finally:
+        for ex in (feeder, pool):
+            if ex is not None:
+                ex.shutdown(wait=True)
     return results
 
 
-def single_gpu_test(model, dataset: Gaze360ClipDataset, pipeline, clips_per_batch: int = 32) -> List[np.ndarray]:
-    res = run_clips(model, dataset, pipeline, range(len(dataset)), clips_per_batch)
+def single_gpu_test(model, dataset: Gaze360ClipDataset, pipeline, clips_per_batch: int = 32, workers: int = 0) -> List[np.ndarray]:
+    res = run_clips(model, dataset, pipeline, range(len(dataset)), clips_per_batch, workers)
     return [res[i] for i in range(len(dataset))]
 
 
 def multi_gpu_test(model, dataset: Gaze360ClipDataset, pipeline, clips_per_batch: int = 32, group=None,
-                   device=None) -> List[np.ndarray]:
+                   device=None, workers: int = 0) -> List[np.ndarray]:
     """Every rank returns the results of ALL clips in dataset order (one all-gather; NCCL on GPUs, gloo on CPU)."""
     import torch
     import torch.distributed as tdist
     rank, world = tdist.get_rank(group), tdist.get_world_size(group)
     n = len(dataset)
     mine = mdist.padded_shard(n, rank, world)
-    res = run_clips(model, dataset, pipeline, sorted(set(mine)), clips_per_batch)
+    res = run_clips(model, dataset, pipeline, sorted(set(mine)), clips_per_batch, workers)
     packed = np.zeros((len(mine), dataset.clip_len, ROW), dtype=np.float32)
     for k, i in enumerate(mine):
         packed[k, :res[i].shape[0]] = res[i]

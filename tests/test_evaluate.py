@@ -39,7 +39,7 @@ class StubPipeline:
     """frames -> [n, 3, 4, 4] float tensor (no resize), metas with identity scale."""
 
     def batch(self, frames, filenames=None):
-        img = torch.from_numpy(np.stack(frames).astype(np.float32)).permute(0, 3, 1, 2).contiguous()
+        img = torch.from_numpy(np.asarray(frames).astype(np.float32)).permute(0, 3, 1, 2).contiguous()
         metas = [dict(img_shape=(4, 4, 3), scale_factor=np.ones(4, np.float32), filename=f) for f in (filenames or [None] * len(frames))]
         return dict(img=[img], img_metas=[metas])
 
@@ -93,6 +93,8 @@ def test_batched_driver_equals_one_clip_per_forward():
     ref_records, ref_merged = reference_loop(StubModel(), ds, StubPipeline())
     model = StubModel()
     rows = ev.single_gpu_test(model, ds, StubPipeline(), clips_per_batch=4)
+    rows_w = ev.single_gpu_test(StubModel(), ds, StubPipeline(), clips_per_batch=4, workers=3)     # prefetching loader
+    assert all(np.array_equal(a, b) for a, b in zip(rows, rows_w))
     records, merged = ev.videos_from_clips(ds, rows)
     assert len(model.calls) < len(ds)                                  # many clips per forward
     assert all(n % T == 0 for n, T in model.calls)

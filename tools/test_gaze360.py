@@ -27,6 +27,7 @@ def main():
     ap.add_argument('--device', default=None)
     ap.add_argument('--cfg-options', nargs='+', action=DictAction)
     ap.add_argument('--clips-per-batch', type=int, default=32)
+    ap.add_argument('--workers', type=int, default=8, help='decode threads (frames of the next batch load while the GPU runs)')
     ap.add_argument('--seed', type=int, default=None, help='pins the CenterCrop draws (the reference run is unseeded)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -42,9 +43,9 @@ def main():
     pipe = GpuTestPipeline(model.cfg.data.test.pipeline, device=int(device.split(':')[1]), seed=args.seed)
     ds = ev.Gaze360ClipDataset(args.json, img_prefix=args.root)
     if world > 1:
-        rows = ev.multi_gpu_test(model, ds, pipe, args.clips_per_batch, device=device)
+        rows = ev.multi_gpu_test(model, ds, pipe, args.clips_per_batch, device=device, workers=args.workers)
     else:
-        rows = ev.single_gpu_test(model, ds, pipe, args.clips_per_batch)
+        rows = ev.single_gpu_test(model, ds, pipe, args.clips_per_batch, workers=args.workers)
     if int(os.environ.get('RANK', '0')) == 0:
         records, _ = ev.videos_from_clips(ds, rows)
         os.makedirs('results', exist_ok=True)
