@@ -209,7 +209,7 @@ class MultiClueGaze:
             scale = np.stack([np.asarray(m['scale_factor'], dtype=np.float32).reshape(4) for m in img_metas])
         out = self.engine.forward(img, clip_length=clip_length or T, img_hw=img_hw, scale_factor=scale)
         gaze, boxes, scores = out['gaze'], out['boxes'], out['scores']
-        det_bboxes = [torch.cat([boxes[i], scores[i][:, None]], dim=1) for i in range(T)]
+        det_bboxes = list(torch.cat([boxes, scores[..., None]], dim=2).unbind(0))     # T x [3, 5], one kernel
         det_labels = [[0, 1, 2] for _ in range(T)]
         if format:
             bbox_results = [[det_bboxes[i][c:c + 1].cpu().numpy() for c in range(3)] for i in range(T)]

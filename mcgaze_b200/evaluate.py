@@ -81,15 +81,25 @@ def _batches(dataset: Gaze360ClipDataset, indices: Sequence[int], clips_per_batc
     return out
 
 
-def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool) -> Tuple[int, Any, List[str]]:
+def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging: Optional[Dict[Any, Any]] = None,
+                slot: int = 0) -> Tuple[int, Any, List[str]]:
     """Decode the frames of a batch of clips (in parallel on `pool`); frames of one size are stacked into ONE
-    [n, h, w, 3] block so that they cross PCIe in a single copy."""
+    [n, h, w, 3] block -- in pinned host memory when `staging` (a cache of pinned buffers, two slots per shape) is
+    given -- so that they cross PCIe in a single asynchronous copy."""
     infos = [dataset.clip_info(i) for i in batch]
     names = [f for it in infos for f in it['filenames']]
     paths = [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
     frames = list(pool.map(dataset.loader, paths)) if pool is not None else [dataset.loader(p) for p in paths]
     if len({f.shape for f in frames}) == 1:
-        frames = np.stack(frames)
+        if staging is not None:
+            import torch
+            key = (slot, len(frames)) + frames[0].shape
+            if key not in staging:
+                staging[key] = torch.empty((len(frames),) + frames[0].shape, dtype=torch.uint8, pin_memory=True)
+            np.stack(frames, out=staging[key].numpy())
+            frames = staging[key]
+        else:
+            frames = np.stack(frames)
     return infos[0]['n'], frames, names
 
 
@@ -104,12 +114,16 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
     batches = _batches(dataset, indices, clips_per_batch)
     pool = ThreadPoolExecutor(workers) if workers > 0 else None
     feeder = ThreadPoolExecutor(1) if workers > 0 else None
+    # pinned staging, two slots: batch k+1 is written while batch k's copy / forward run; slot k % 2 is free again
+    # when batch k+2 is loaded because batch k's results were read back (a stream sync) before that load starts
+    staging: Optional[Dict[Any, Any]] = {} if (workers > 0 and torch.cuda.is_available()) else None
     try:
-        nxt = feeder.submit(_load_batch, dataset, batches[0], pool) if feeder and batches else None
+        nxt = feeder.submit(_load_batch, dataset, batches[0], pool, staging, 0) if feeder and batches else None
         for bi, batch in enumerate(batches):
             if feeder:
                 T, frames, names = nxt.result()
-                nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool) if bi + 1 < len(batches) else None
+                nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool, staging, (bi + 1) % 2) \
+                    if bi + 1 < len(batches) else None
             else:
                 T, frames, names = _load_batch(dataset, batch, None)
             try:

@@ -118,9 +118,60 @@ class GpuTestPipeline:
         return h, w
 
     def plan(self, shapes: Sequence[Tuple[int, int]], rands: Optional[Sequence[float]] = None):
-        """Per-frame geometry + metas for frames of the given (h, w); -> (geometry, metas, (Hp, Wp))."""
+        """Per-frame geometry + metas for frames of the given (h, w); -> (geometry, metas, (Hp, Wp)).
+        Vectorised over the frames in float64 / int64 numpy: the same IEEE operations, in the same order, as the
+        scalar methods above (`plan_scalar` keeps the literal per-frame form; the tests compare the two)."""
+        n = len(shapes)
         if rands is None:
             rands = [self._draw() if self.crop is not None and self.crop[0] == 'relative_range' else 0.0 for _ in shapes]
+        hw = np.asarray(shapes, dtype=np.int64).reshape(n, 2)
+        h, w = hw[:, 0], hw[:, 1]
+        r = np.asarray(rands, dtype=np.float64).reshape(n)
+        if self.crop is None:
+            y = x = np.zeros(n, np.int64)
+            ch, cw = h, w
+        else:
+            ctype, size = self.crop
+            if ctype == 'absolute':
+                ch, cw = np.minimum(int(size[0]), h), np.minimum(int(size[1]), w)
+            elif ctype == 'relative':
+                ch, cw = (h * float(size[0]) + 0.5).astype(np.int64), (w * float(size[1]) + 0.5).astype(np.int64)
+            else:
+                cs = np.asarray(size, dtype=np.float32)
+                rest = (1 - cs).astype(np.float64)                       # the subtraction happens in float32
+                ch = (h * (np.float64(cs[0]) + r * rest[0]) + 0.5).astype(np.int64)
+                cw = (w * (np.float64(cs[1]) + r * rest[1]) + 0.5).astype(np.int64)
+            if np.any(ch <= 0) or np.any(cw <= 0):
+                raise ValueError('CenterCrop produced an empty window')
+            y = (np.maximum(h - ch, 0) / 2 + 0.5).astype(np.int64)
+            x = (np.maximum(w - cw, 0) / 2 + 0.5).astype(np.int64)
+            ch, cw = np.minimum(y + ch, h) - y, np.minimum(x + cw, w) - x
+        if self.keep_ratio:
+            f = np.minimum(max(self.scale) / np.maximum(ch, cw), min(self.scale) / np.minimum(ch, cw))
+            nh, nw = (ch * f + 0.5).astype(np.int64), (cw * f + 0.5).astype(np.int64)
+        else:
+            nh, nw = np.full(n, self.scale[1], np.int64), np.full(n, self.scale[0], np.int64)
+        if self.pad_size is not None:
+            ph, pw = np.maximum(self.pad_size[0], nh), np.maximum(self.pad_size[1], nw)
+        elif self.size_divisor:
+            d = self.size_divisor
+            ph, pw = np.ceil(nh / d).astype(np.int64) * d, np.ceil(nw / d).astype(np.int64) * d
+        else:
+            ph, pw = nh, nw
+        Hp, Wp = int(ph.max()), int(pw.max())
+        geometry = np.stack([y, x, ch, cw, nh, nw], 1)
+        ws, hs = nw / cw, nh / ch
+        scale = np.stack([ws, hs, ws, hs], 1).astype(np.float32)
+        norm_cfg = dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb)
+        metas = [dict(filename=None, ori_filename=None, ori_shape=(int(h[i]), int(w[i]), 3),
+                      img_shape=(int(nh[i]), int(nw[i]), 3), pad_shape=(int(ph[i]), int(pw[i]), 3), scale_factor=scale[i],
+                      flip=False, flip_direction=None, img_norm_cfg=norm_cfg) for i in range(n)]
+        if Wp % 4:
+            Wp += 4 - Wp % 4                   # the kernel stores float4; configs pad to 32 anyway
+        return [tuple(int(v) for v in g) for g in geometry], metas, (Hp, Wp)
+
+    def plan_scalar(self, shapes: Sequence[Tuple[int, int]], rands: Sequence[float]):
+        """The literal per-frame form of plan() (python floats, as the reference's transforms compute)."""
         geometry, metas = [], []
         Hp = Wp = 0
         for (h, w), r in zip(shapes, rands):
@@ -136,7 +187,7 @@ class GpuTestPipeline:
                 flip=False, flip_direction=None,
                 img_norm_cfg=dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb)))
         if Wp % 4:
-            Wp += 4 - Wp % 4                   # the kernel stores float4; configs pad to 32 anyway
+            Wp += 4 - Wp % 4
         return geometry, metas, (Hp, Wp)
 
     # ---------------------------------------------------------------------------- device work
@@ -152,8 +203,9 @@ class GpuTestPipeline:
         dev = torch.device('cuda', self.device)
         if hasattr(frames, 'data_ptr') or (isinstance(frames, np.ndarray) and frames.ndim == 4):
             # one [n, h, w, 3] block (frames of one size): a single H2D copy, descriptors without a python loop
-            dframes = torch.from_numpy(np.ascontiguousarray(frames)).to(dev, non_blocking=True) \
-                if isinstance(frames, np.ndarray) else frames
+            dframes = torch.from_numpy(np.ascontiguousarray(frames)) if isinstance(frames, np.ndarray) else frames
+            if not dframes.is_cuda:
+                dframes = dframes.to(dev, non_blocking=True)       # asynchronous when the block is pinned
             shapes = [(int(dframes.shape[1]), int(dframes.shape[2]))] * int(dframes.shape[0])
         else:
             dframes = []

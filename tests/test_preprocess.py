@@ -97,6 +97,25 @@ def test_pipeline_geometry_matches_goldens(golden):
             assert (y, x, ch, cw) == (y1, x1, y2 - y1, x2 - x1)
 
 
+def test_vectorised_plan_equals_the_literal_per_frame_arithmetic():
+    rng = np.random.default_rng(7)
+    shapes = [(int(a), int(b)) for a, b in rng.integers(8, 2000, (500, 2))]
+    rands = [float(v) for v in rng.random(500)]
+    cfgs = [pipeline_cfg('gaze360'), pipeline_cfg('l2cs'),
+            [dict(type='CenterCrop', crop_size=(0.5, 0.8), crop_type='relative'), dict(type='Resize', img_scale=(320, 200), keep_ratio=False),
+             dict(type='Normalize', mean=MEAN, std=STD), dict(type='Pad', size=(256, 352))],
+            [dict(type='CenterCrop', crop_size=(100, 300), crop_type='absolute'), dict(type='Resize', img_scale=(333, 200), keep_ratio=True),
+             dict(type='Normalize', mean=MEAN, std=STD)]]
+    for cfg in cfgs:
+        p = GpuTestPipeline(cfg)
+        g1, m1, c1 = p.plan(shapes, rands)
+        g2, m2, c2 = p.plan_scalar(shapes, rands)
+        assert g1 == g2 and c1 == c2
+        for a, b in zip(m1, m2):
+            assert a['img_shape'] == b['img_shape'] and a['pad_shape'] == b['pad_shape'] and a['ori_shape'] == b['ori_shape']
+            assert np.array_equal(a['scale_factor'], b['scale_factor'])
+
+
 def test_pipeline_random_draws_follow_numpy_like_the_reference():
     """CenterCrop draws np.random.rand(1) per call (transforms.py:1129): seeding numpy pins the GPU pipeline's crops
     exactly as it pins the reference's."""
