@@ -10,8 +10,14 @@
 // 2i-1, 2i, 2i+1 are three M-tiles (accumulators) of 128 rows x 64 channels.  Tile row m maps to stem
 // column q(m) = 120 g - 1 + 30 (m / 32) + (m % 32): every warp-sized slice of 32 rows overlaps the next
 // by two columns so that each 3-wide pooling window lies inside one warp of the epilogue (window of
-// odd lane l = lanes l-1, l, l+1; 15 pooled columns per warp, no cross-warp exchange).  Odd stem rows
-// are computed by two units (x1.5 MMA work on a layer that is 2 % of the FLOPs).
+// odd lane l = lanes l-1, l, l+1; 15 pooled columns per warp, no cross-warp exchange).
+//
+// Units are ordered (frame, column group, pooled row) and every CTA takes a CONTIGUOUS range of them, so the unit after
+// (n, g, i) is (n, g, i + 1) and its first stem row 2i+1 is the previous unit's last one: that accumulator stays in
+// TMEM ("carry") and only two of the three stem rows are built and multiplied per unit (the first unit of a CTA's
+// range computes all three).  TMEM regions of 64 columns: row 2i -> A[local & 1], row 2i+1 -> C[local % 3], row 2i-1 =
+// C[(local + 2) % 3] (the previous unit's C); the accumulator-empty barrier of unit local - 2 frees A[local & 1] and
+// C[local % 3] (last read, as a carry, by that unit's epilogue).
 //
 // Roles (448 threads, persistent, one CTA per SM):
 //   warp 0     : MMA issuer (tcgen05.mma M=128, N=64, K=16; kTerms = 3 issues lo*hi + hi*lo + hi*hi)
@@ -68,6 +74,12 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, boo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(n) : "memory");
 }
 
+// TMEM column of stem row d (0: 2i-1 carried or computed, 1: 2i, 2: 2i+1) of the CTA's local-th unit
+__device__ __forceinline__ uint32_t sf_tmem_col(int local, int d) {
+  return d == 1 ? static_cast<uint32_t>((local & 1) * 64)
+                : static_cast<uint32_t>(128 + ((d == 2 ? local : local + 2) % 3) * 64);
+}
+
 template <int kTerms>
 __global__ void __launch_bounds__(kSfThreads, 1)
 stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParams p) {
@@ -87,6 +99,10 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // contiguous unit range of this CTA; unit = (n * groups + g) * PP + i
+  const int units_per_cta = (p.units + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int u_begin = static_cast<int>(blockIdx.x) * units_per_cta;
+  const int u_end = min(u_begin + units_per_cta, p.units);
 
   if (warp_idx == 0 && lane == 0) {
     for (int i = 0; i < kSfStages; ++i) {
@@ -126,15 +142,15 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++local) {
+    for (int unit = u_begin; unit < u_end; ++unit, ++local) {
       const int ab = local & 1;
       const uint32_t ab_phase = static_cast<uint32_t>(local >> 1) & 1u;
-      const int i = (unit / p.groups) % p.PP;
+      const int i = unit % p.PP;
       ptx::mbar_wait(&tempty_bar[ab], ab_phase ^ 1u);
       ptx::tc_fence_after();
-      const int d_first = i == 0 ? 1 : 0;
+      const int d_first = (i == 0 || local > 0) ? 1 : 0;   // top padding row / carried from the previous unit
       for (int d = d_first; d < 3; ++d) {
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(ab * 192 + d * 64);
+        const uint32_t tmem_d = tmem_base + sf_tmem_col(local, d);
         for (int kt = 0; kt < 3; ++kt) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -173,10 +189,10 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
     const int bt = threadIdx.x - 64;  // 0..255
     const int bw = bt >> 5;           // builder warp = 16-byte chunk (8 consecutive k) inside a k-tile row
     auto prefetch = [&](int unit, int buf) {
-      const int g = unit % p.groups;
-      const int t = unit / p.groups;
-      const int i = t % p.PP;
-      const int n = t / p.PP;
+      const int i = unit % p.PP;
+      const int t = unit / p.PP;
+      const int g = t % p.groups;
+      const int n = t / p.groups;
       const int w0 = 240 * g - 8;
       float* dst = stage_in + buf * (kSfStageBufBytes / 4);
       for (int v = bt; v < 3 * kSfInRows * (kSfInCols / 4); v += kSfBuilderThreads) {
@@ -194,15 +210,15 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    if (static_cast<int>(blockIdx.x) < p.units) prefetch(blockIdx.x, 0);
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++local) {
+    if (u_begin < u_end) prefetch(u_begin, 0);
+    for (int unit = u_begin; unit < u_end; ++unit, ++local) {
       const int buf = local & 1;
-      const int i = (unit / p.groups) % p.PP;
+      const int i = unit % p.PP;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");  // staging of this unit complete; previous unit fully built
-      if (unit + static_cast<int>(gridDim.x) < p.units) prefetch(unit + gridDim.x, buf ^ 1);
+      if (unit + 1 < u_end) prefetch(unit + 1, buf ^ 1);
       const float* sin = stage_in + buf * (kSfStageBufBytes / 4);
-      const int d_first = i == 0 ? 1 : 0;
+      const int d_first = (i == 0 || local > 0) ? 1 : 0;
       for (int d = d_first; d < 3; ++d) {
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
@@ -266,33 +282,33 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
     const int quarter = warp_idx & 3;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     int local = 0;
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++local) {
+    for (int unit = u_begin; unit < u_end; ++unit, ++local) {
       const int ab = local & 1;
       const uint32_t ab_phase = static_cast<uint32_t>(local >> 1) & 1u;
-      const int g = unit % p.groups;
-      const int t = unit / p.groups;
-      const int i = t % p.PP;
-      const int n = t / p.PP;
+      const int i = unit % p.PP;
+      const int t = unit / p.PP;
+      const int g = t % p.groups;
+      const int n = t / p.groups;
       const int q = 120 * g - 1 + 30 * quarter + lane;  // stem column of this lane's row
       const bool q_ok = q >= 0 && q < p.Q;
       const int j = kSfPoolCols * g + 15 * quarter + (lane >> 1);  // pooled column owned by odd lanes < 31
       const bool owner = (lane & 1) && lane < 31 && j < p.QQ;
       ptx::mbar_wait(&tfull_bar[ab], ab_phase);
       ptx::tc_fence_after();
-      const int d_first = i == 0 ? 1 : 0;
+      const int d_first = i == 0 ? 1 : 0;   // row 2i-1 (computed by this unit or carried) exists unless it is the padding row
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float v[32];
         {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + lane_addr + static_cast<uint32_t>(ab * 192 + 2 * 64 + half * 32), r);
+          ptx::tmem_ld_32x32(tmem_base + lane_addr + sf_tmem_col(local, 2) + static_cast<uint32_t>(half * 32), r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
         }
         for (int d = d_first; d < 2; ++d) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + lane_addr + static_cast<uint32_t>(ab * 192 + d * 64 + half * 32), r);
+          ptx::tmem_ld_32x32(tmem_base + lane_addr + sf_tmem_col(local, d) + static_cast<uint32_t>(half * 32), r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], __uint_as_float(r[c]));
