@@ -188,35 +188,49 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
     // ===================== builders =====================
     const int bt = threadIdx.x - 64;  // 0..255
     const int bw = bt >> 5;           // builder warp = 16-byte chunk (8 consecutive k) inside a k-tile row
-    auto prefetch = [&](int unit, int buf) {
+    // carried: the unit's first stem row comes from TMEM, its two top input rows are not read
+    auto prefetch = [&](int unit, int buf, bool carried) {
       const int i = unit % p.PP;
       const int t = unit / p.PP;
       const int g = t % p.groups;
       const int n = t / p.groups;
       const int w0 = 240 * g - 8;
       float* dst = stage_in + buf * (kSfStageBufBytes / 4);
-      for (int v = bt; v < 3 * kSfInRows * (kSfInCols / 4); v += kSfBuilderThreads) {
-        const int row = v / (kSfInCols / 4);  // c * 11 + rr
-        const int vc = v - row * (kSfInCols / 4);
-        const int c = row / kSfInRows, rr = row - c * kSfInRows;
-        const int h = 4 * i - 5 + rr;
-        const int w = w0 + 4 * vc;
-        const bool ok = h >= 0 && h < p.H && w >= 0 && w < p.W;
-        const float* src = ok ? p.img + ((static_cast<long long>(n) * 3 + c) * p.H + h) * p.W + w : p.img;
-        cp_async16_zfill(dst + row * kSfInStride + 4 * vc, src, ok);
+      // thread = (16-byte column chunk vc, row phase rr0): 9 unrolled copies (3 channels x rows rr0, rr0+4, rr0+8) with
+      // compile-time (c, j) -- the generic v -> (row, chunk) -> (c, rr) index arithmetic was a quarter of the builder
+      // warps' instructions
+      static_assert(kSfInCols / 4 == 64 && kSfBuilderThreads == 256 && kSfInRows <= 12, "prefetch thread mapping");
+      const int vc = bt & 63;
+      const int rr0 = bt >> 6;
+      const int w = w0 + 4 * vc;
+      const bool w_ok = w >= 0 && w < p.W;
+      const int h0 = 4 * i - 5;
+      const float* img_n = p.img + static_cast<long long>(n) * 3 * p.H * p.W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int rr = rr0 + 4 * j;
+          if (rr < kSfInRows && !(carried && rr < 2)) {
+            const int h = h0 + rr;
+            const bool ok = w_ok && h >= 0 && h < p.H;
+            const float* src = ok ? img_n + (static_cast<long long>(c) * p.H + h) * p.W + w : p.img;
+            cp_async16_zfill(dst + (c * kSfInRows + rr) * kSfInStride + 4 * vc, src, ok);
+          }
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    if (u_begin < u_end) prefetch(u_begin, 0);
+    if (u_begin < u_end) prefetch(u_begin, 0, false);
     for (int unit = u_begin; unit < u_end; ++unit, ++local) {
       const int buf = local & 1;
       const int i = unit % p.PP;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");  // staging of this unit complete; previous unit fully built
-      if (unit + 1 < u_end) prefetch(unit + 1, buf ^ 1);
+      if (unit + 1 < u_end) prefetch(unit + 1, buf ^ 1, true);
       const float* sin = stage_in + buf * (kSfStageBufBytes / 4);
       const int d_first = (i == 0 || local > 0) ? 1 : 0;
       for (int d = d_first; d < 3; ++d) {
