@@ -193,7 +193,33 @@ def preprocess_extras(eng, dev, steps: int, graph: bool):
             step(i)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
-    return {'kernel': kernel,
+    # the reference's CPU pipeline on the same frames (its transforms' arithmetic = mmcv wrappers over cv2, restated
+    # in oracle/refshim.py), one host thread, a bounded sample
+    cpu = None
+    try:
+        import cv2  # noqa: F401
+        from oracle import refshim
+        cv2.setNumThreads(1)
+        sample = host[0][:64].numpy()
+        mean64, std32 = pipe.mean, pipe.std
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 2.0:
+            for k in range(sample.shape[0]):
+                y, x, ch, cw, nh, nw = geometry[k]
+                im = refshim.imresize(sample[k][y:y + ch, x:x + cw], (nw, nh))
+                im = refshim.imnormalize(im, mean64, std32, pipe.to_rgb)
+                im = refshim.impad_to_multiple(im, 32)
+                np.ascontiguousarray(im.transpose(2, 0, 1))
+            reps += 1
+        el_cpu = time.perf_counter() - t0
+        cpu = {'value': reps * sample.shape[0] / el_cpu, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
+               'sample': f'{reps * sample.shape[0]} frames in {el_cpu:.1f} s: cv2.resize + mmcv.imnormalize + impad + transpose '
+                         '(published mmcv wrappers over cv2, one thread), same frames and crop windows'}
+    except ImportError:
+        pass
+    kernel['frames_per_s'] = NB / k_ms * 1e3
+    return {'kernel': kernel, 'cpu_baseline': cpu,
             'e2e_u8': {'value': CLIPS_PER_STEP * n_steps / el, 'unit': 'clips/s', 'h2d_bytes_per_step': NB * SH * SW * 3,
                        'd2h_bytes_per_step': sum(v.numel() * 4 for v in pinned[0].values()), 'steps': n_steps,
                        'api': 'pinned uint8 frames -> H2D (copy stream, overlapped) -> mcg_preprocess -> mcg_forward -> D2H'}}

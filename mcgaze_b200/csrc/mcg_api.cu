@@ -187,6 +187,8 @@ class Engine {
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
     if (pin_meta_) cudaFreeHost(pin_meta_);
+    for (cudaEvent_t e : meta_ev_)
+      if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (cap_stream_) cudaStreamDestroy(cap_stream_);
   }
@@ -234,10 +236,17 @@ class Engine {
       for (int j = 0; j < 4; ++j) meta[NB * 2 + i * 4 + j] = scale_factor ? scale_factor[i * 4 + j] : 1.f;
     }
     if (meta != meta_host_) {
-      // rare (metadata changed): make sure no earlier async copy still reads the pinned buffer
-      MCG_CUDA(cudaStreamSynchronize(stream));
-      std::memcpy(pin_meta_, meta.data(), meta.size() * sizeof(float));
-      MCG_CUDA(cudaMemcpyAsync(d_meta_, pin_meta_, meta.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      // metadata changed (every batch of an evaluation run: per-frame crops give per-frame scale factors): stage it in
+      // the next slot of a small pinned ring; only the copy issued kMetaSlots changes ago must have completed, so the
+      // host does not wait for the forward that is still running
+      const int slot = meta_slot_;
+      meta_slot_ = (meta_slot_ + 1) % kMetaSlots;
+      if (!meta_ev_[slot]) MCG_CUDA(cudaEventCreateWithFlags(&meta_ev_[slot], cudaEventDisableTiming));
+      else MCG_CUDA(cudaEventSynchronize(meta_ev_[slot]));
+      float* pin = pin_meta_ + static_cast<size_t>(slot) * meta.size();
+      std::memcpy(pin, meta.data(), meta.size() * sizeof(float));
+      MCG_CUDA(cudaMemcpyAsync(d_meta_, pin, meta.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      MCG_CUDA(cudaEventRecord(meta_ev_[slot], stream));
       meta_host_ = meta;
     }
     has_scale_ = scale_factor != nullptr;
@@ -629,7 +638,7 @@ class Engine {
     ws_H_ = H;
     ws_W_ = W;
     if (pin_meta_) cudaFreeHost(pin_meta_);
-    MCG_CUDA(cudaMallocHost(&pin_meta_, static_cast<size_t>(NB) * 6 * sizeof(float)));
+    MCG_CUDA(cudaMallocHost(&pin_meta_, static_cast<size_t>(kMetaSlots) * NB * 6 * sizeof(float)));
     meta_host_.clear();
   }
 
@@ -1294,7 +1303,10 @@ class Engine {
         *conf_ = nullptr, *d_meta_ = nullptr;
   Planes hq_, hh_, hf_, roih_;
   bool dyn_mma_ = false;
-  float* pin_meta_ = nullptr;
+  static constexpr int kMetaSlots = 4;
+  float* pin_meta_ = nullptr;                 // kMetaSlots x [NB * 6] pinned staging of the per-call metadata
+  cudaEvent_t meta_ev_[kMetaSlots] = {};
+  int meta_slot_ = 0;
   bool has_scale_ = false;
 
   std::map<std::string, UmmaPlan> plans_;

@@ -16,7 +16,7 @@ the gaze configs because `Gaze360Dataset.__getitem__` raises NotImplementedError
 
 `model` is anything with the reference's call contract `model(return_loss=False, rescale=True, format=False,
 img=[Tensor], img_metas=[[meta...]], clip_length=T)` (mcgaze_b200.detector.MultiClueGaze); `pipeline` is a
-mcgaze_b200.pipeline.GpuTestPipeline (or any object with `.batch(frames) -> dict(img, img_metas)`).
+mcgaze_b200.pipeline.GpuTestPipeline (or any object with `.batch(frames, filenames=...) -> dict(img, img_metas)`).
 """
 from __future__ import annotations
 
@@ -114,30 +114,38 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
     batches = _batches(dataset, indices, clips_per_batch)
     pool = ThreadPoolExecutor(workers) if workers > 0 else None
     feeder = ThreadPoolExecutor(1) if workers > 0 else None
-    # pinned staging, two slots: batch k+1 is written while batch k's copy / forward run; slot k % 2 is free again
-    # when batch k+2 is loaded because batch k's results were read back (a stream sync) before that load starts
+    # pinned staging, three slots: batch k+2 is decoded into slot (k+2) % 3 while batch k+1 is being launched and batch
+    # k still runs; the last user of that slot, batch k-1, has been read back (a stream sync) by then
     staging: Optional[Dict[Any, Any]] = {} if (workers > 0 and torch.cuda.is_available()) else None
+    pending = None                                # results of the previous batch, still on the device
+
+    def collect(p):
+        batch, T, rows = p
+        rows = rows.cpu().numpy().astype(np.float32)                                 # ONE device->host read per batch
+        for k, i in enumerate(batch):
+            results[i] = rows[k * T:(k + 1) * T]
+
     try:
         nxt = feeder.submit(_load_batch, dataset, batches[0], pool, staging, 0) if feeder and batches else None
         for bi, batch in enumerate(batches):
             if feeder:
                 T, frames, names = nxt.result()
-                nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool, staging, (bi + 1) % 2) \
+                nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool, staging, (bi + 1) % 3) \
                     if bi + 1 < len(batches) else None
             else:
                 T, frames, names = _load_batch(dataset, batch, None)
-            try:
-                data = pipeline.batch(frames, filenames=names)
-            except TypeError:
-                data = pipeline.batch(frames)
+            data = pipeline.batch(frames, filenames=names)
             (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
             n = len(names)
             det = torch.stack(list(det_bboxes)).float()                              # [B*T, 3, 5]
             gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
             rows = torch.cat([det[..., :4].reshape(n, 12), det[..., 4], gaze.reshape(n, 12).float()], 1)
-            rows = rows.cpu().numpy().astype(np.float32)                             # ONE device->host read per batch
-            for k, i in enumerate(batch):
-                results[i] = rows[k * T:(k + 1) * T]
+            # read the PREVIOUS batch back only now, with this batch already queued: the GPU never waits for the host
+            if pending is not None:
+                collect(pending)
+            pending = (batch, T, rows)
+        if pending is not None:
+            collect(pending)
     finally:
         for ex in (feeder, pool):
             if ex is not None:
