@@ -216,8 +216,8 @@ def preprocess_extras(eng, dev, steps: int, graph: bool):
         cpu = {'value': reps * sample.shape[0] / el_cpu, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
                'sample': f'{reps * sample.shape[0]} frames in {el_cpu:.1f} s: cv2.resize + mmcv.imnormalize + impad + transpose '
                          '(published mmcv wrappers over cv2, one thread), same frames and crop windows'}
-    except ImportError:
-        pass
+    except Exception as e:      # the side measurement must never take the headline line down
+        cpu = {'unavailable': f'{type(e).__name__}: {e}'}
     kernel['frames_per_s'] = NB / k_ms * 1e3
     return {'kernel': kernel, 'cpu_baseline': cpu,
             'e2e_u8': {'value': CLIPS_PER_STEP * n_steps / el, 'unit': 'clips/s', 'h2d_bytes_per_step': NB * SH * SW * 3,
@@ -409,7 +409,10 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_extras:
         eng.set_option('time_kernels', 0)
-        extras['preprocess'] = preprocess_extras(eng, dev, args.steps, not args.no_graph)
+        try:
+            extras['preprocess'] = preprocess_extras(eng, dev, args.steps, not args.no_graph)
+        except Exception as e:      # side measurement: never take the headline line down
+            extras['preprocess'] = {'unavailable': f'{type(e).__name__}: {e}'}
         # the other precision modes on the same workload, for context: fp16 (fast) does NOT meet the 1e-3
         # (yaw,pitch) bar (~3e-3); fp16x3 and fp16c8 are the parity modes
         del eng

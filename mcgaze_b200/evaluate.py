@@ -83,24 +83,35 @@ def _batches(dataset: Gaze360ClipDataset, indices: Sequence[int], clips_per_batc
 
 def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging: Optional[Dict[Any, Any]] = None,
                 slot: int = 0) -> Tuple[int, Any, List[str]]:
-    """Decode the frames of a batch of clips (in parallel on `pool`); frames of one size are stacked into ONE
-    [n, h, w, 3] block -- in pinned host memory when `staging` (a cache of pinned buffers, two slots per shape) is
-    given -- so that they cross PCIe in a single asynchronous copy."""
+    """Decode the frames of a batch of clips.  With a thread pool and a `staging` cache every worker decodes its frame
+    and writes it straight into ONE [n, h, w, 3] block in pinned host memory (three slots per shape), so the batch
+    crosses PCIe in a single asynchronous copy; frames of different sizes fall back to a list."""
     infos = [dataset.clip_info(i) for i in batch]
     names = [f for it in infos for f in it['filenames']]
     paths = [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
-    frames = list(pool.map(dataset.loader, paths)) if pool is not None else [dataset.loader(p) for p in paths]
-    if len({f.shape for f in frames}) == 1:
-        if staging is not None:
-            import torch
-            key = (slot, len(frames)) + frames[0].shape
-            if key not in staging:
-                staging[key] = torch.empty((len(frames),) + frames[0].shape, dtype=torch.uint8, pin_memory=True)
-            np.stack(frames, out=staging[key].numpy())
-            frames = staging[key]
-        else:
-            frames = np.stack(frames)
-    return infos[0]['n'], frames, names
+    n = len(paths)
+    if pool is None or staging is None:
+        frames = [dataset.loader(p) for p in paths]
+        return infos[0]['n'], (np.stack(frames) if len({f.shape for f in frames}) == 1 else frames), names
+    import torch
+    first = dataset.loader(paths[0])
+    key = (slot, n) + first.shape
+    if key not in staging:
+        staging[key] = torch.empty((n,) + first.shape, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    block = staging[key].numpy()
+    block[0] = first
+
+    def work(k: int):
+        f = dataset.loader(paths[k])
+        if f.shape != first.shape or f.dtype != np.uint8:
+            return f
+        block[k] = f
+        return None
+
+    odd = [None] + list(pool.map(work, range(1, n)))
+    if all(o is None for o in odd):
+        return infos[0]['n'], staging[key], names
+    return infos[0]['n'], [block[k].copy() if o is None else o for k, o in enumerate(odd)], names
 
 
 def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[int], clips_per_batch: int = 32,
@@ -116,7 +127,7 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
     feeder = ThreadPoolExecutor(1) if workers > 0 else None
     # pinned staging, three slots: batch k+2 is decoded into slot (k+2) % 3 while batch k+1 is being launched and batch
     # k still runs; the last user of that slot, batch k-1, has been read back (a stream sync) by then
-    staging: Optional[Dict[Any, Any]] = {} if (workers > 0 and torch.cuda.is_available()) else None
+    staging: Optional[Dict[Any, Any]] = {} if workers > 0 else None
     pending = None                                # results of the previous batch, still on the device
 
     def collect(p):

@@ -77,6 +77,29 @@ def reference_loop(model, dataset, pipeline):
     return ev.videos_from_clips(dataset, rows)
 
 
+def test_prefetching_loader_handles_ragged_frames():
+    """frames of one size travel as one staged block, mixed sizes as a list; both give the per-frame results"""
+    seen = []
+
+    class ShapePipeline:
+        def batch(self, frames, filenames=None):
+            seen.append('block' if hasattr(frames, 'shape') else 'list')
+            imgs = [torch.from_numpy(np.asarray(f)[:4, :4].astype(np.float32)).permute(2, 0, 1) for f in frames]
+            metas = [dict(img_shape=(4, 4, 3), scale_factor=np.ones(4, np.float32), filename=n) for n in filenames]
+            return dict(img=[torch.stack(imgs)], img_metas=[metas])
+
+    def ragged_loader(path):
+        img = fake_loader(path)
+        return np.pad(img, ((0, 2), (0, 0), (0, 0))) if path.startswith('v003') else img
+
+    ds_a = ev.Gaze360ClipDataset(make_anno(), loader=ragged_loader)
+    ds_b = ev.Gaze360ClipDataset(make_anno(), loader=fake_loader)
+    a = ev.single_gpu_test(StubModel(), ds_a, ShapePipeline(), clips_per_batch=4, workers=2)
+    assert 'block' in seen and 'list' in seen
+    b = ev.single_gpu_test(StubModel(), ds_b, StubPipeline(), clips_per_batch=4)
+    assert all(np.allclose(x, y, rtol=1e-6, atol=1e-6) for x, y in zip(a, b))
+
+
 def test_dataset_plans_clips_like_the_reference():
     ds = ev.Gaze360ClipDataset(make_anno(), loader=fake_loader)
     assert len(ds) == sum(len(slicer.plan_clips(L)) for L in LENGTHS)
