@@ -101,14 +101,20 @@ def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging
     block = staging[key].numpy()
     block[0] = first
 
-    def work(k: int):
-        f = dataset.loader(paths[k])
-        if f.shape != first.shape or f.dtype != np.uint8:
-            return f
-        block[k] = f
-        return None
+    def work(lo_hi: Tuple[int, int]):
+        odd = []
+        for k in range(*lo_hi):                 # a contiguous run of frames per task: 224 one-frame tasks cost more
+            f = dataset.loader(paths[k])        # in executor overhead than the copies themselves
+            if f.shape != first.shape or f.dtype != np.uint8:
+                odd.append(f)
+            else:
+                block[k] = f
+                odd.append(None)
+        return odd
 
-    odd = [None] + list(pool.map(work, range(1, n)))
+    tasks = max(1, min(n - 1, 2 * getattr(pool, '_max_workers', 4)))
+    cuts = np.linspace(1, n, tasks + 1).astype(int)
+    odd = [None] + [o for part in pool.map(work, zip(cuts[:-1], cuts[1:])) for o in part]
     if all(o is None for o in odd):
         return infos[0]['n'], staging[key], names
     return infos[0]['n'], [block[k].copy() if o is None else o for k, o in enumerate(odd)], names

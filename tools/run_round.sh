@@ -14,3 +14,5 @@ tail -2 gpurun_out/ncu_list_${TAG}.log
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:preprocess_kernel -s 3 -c 1 -o gpurun_out/preprocess_${TAG} \
    python tools/bench_preprocess.py 320 320 2 > gpurun_out/ncu_pp_${TAG}.log 2>&1
 tail -12 gpurun_out/${TAG}.log
+timeout 300 python tools/bench_testsplit.py 32 8 2>&1 | tail -1 > gpurun_out/testsplit_${TAG}.json
+cat gpurun_out/testsplit_${TAG}.json | cut -c1-400
