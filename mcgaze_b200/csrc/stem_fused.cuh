@@ -236,47 +236,56 @@ stem_fused_kernel(const __grid_constant__ StemFusedMaps tm, const StemFusedParam
       for (int d = d_first; d < 3; ++d) {
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sA = a_ring + stage * sf_a_stage_bytes(kTerms);
           // chunk gc = kt*8 + bw = r*3 + c holds input columns 2q-3 .. 2q+3 (+ one zero-weight pad) of input row
           // (c, 2d + r): the 8 floats around them are four aligned 8-byte loads, contiguous across the warp's
           // 32 consecutive stem columns (conflict-free); chunk 21 pads K to a multiple of 16 and must be zero
           const int gc = kt * 8 + bw;
-          if (gc < kSfK / 8) {
-            const int r = gc / 3, c = gc - 3 * r;
+          const int r = gc / 3, c = gc - 3 * r;
+          float v[4][8];
+          {
+            // all 16 loads of the four 32-row slices first, then the conversions and stores: the compiler cannot move a
+            // shared-memory load above the previous slice's shared-memory stores (possible aliasing), which left every
+            // F2FP waiting on its own LDS (ncu: short_scoreboard was the builders' top stall).  The loads read the
+            // staging area only, so they are issued before waiting for the ring stage to drain.
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              const int m = it * 32 + lane;
-              float v[8];
               if (gc < 21) {
                 const float2* src =
                     reinterpret_cast<const float2*>(sin + (c * kSfInRows + 2 * d + r) * kSfInStride + 60 * it + 2 * lane + 2);
                 const float2 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
-                v[0] = a0.y;  // s = 0: staged column 60 it + 2 lane + 3
-                v[1] = a1.x;
-                v[2] = a1.y;
-                v[3] = a2.x;
-                v[4] = a2.y;
-                v[5] = a3.x;
-                v[6] = a3.y;
-                v[7] = 0.f;   // s = 7: zero weight
+                v[it][0] = a0.y;  // s = 0: staged column 60 it + 2 lane + 3
+                v[it][1] = a1.x;
+                v[it][2] = a1.y;
+                v[it][3] = a2.x;
+                v[it][4] = a2.y;
+                v[it][5] = a3.x;
+                v[it][6] = a3.y;
+                v[it][7] = 0.f;   // s = 7: zero weight
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                for (int e = 0; e < 8; ++e) v[it][e] = 0.f;
               }
+            }
+          }
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (gc < kSfK / 8) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int m = it * 32 + lane;
               uint4 uh;
-              uh.x = ptx::pack_half2(v[0], v[1]);
-              uh.y = ptx::pack_half2(v[2], v[3]);
-              uh.z = ptx::pack_half2(v[4], v[5]);
-              uh.w = ptx::pack_half2(v[6], v[7]);
+              uh.x = ptx::pack_half2(v[it][0], v[it][1]);
+              uh.y = ptx::pack_half2(v[it][2], v[it][3]);
+              uh.z = ptx::pack_half2(v[it][4], v[it][5]);
+              uh.w = ptx::pack_half2(v[it][6], v[it][7]);
               const uint32_t so = static_cast<uint32_t>(m * 128 + ((bw ^ (m & 7)) << 4));
               *reinterpret_cast<uint4*>(sA + so) = uh;
               if (kTerms == 3) {
                 uint4 ul;
-                ul.x = ptx::residue_half2(v[0], v[1], uh.x);
-                ul.y = ptx::residue_half2(v[2], v[3], uh.y);
-                ul.z = ptx::residue_half2(v[4], v[5], uh.z);
-                ul.w = ptx::residue_half2(v[6], v[7], uh.w);
+                ul.x = ptx::residue_half2(v[it][0], v[it][1], uh.x);
+                ul.y = ptx::residue_half2(v[it][2], v[it][3], uh.y);
+                ul.z = ptx::residue_half2(v[it][4], v[it][5], uh.z);
+                ul.w = ptx::residue_half2(v[it][6], v[it][7], uh.w);
                 *reinterpret_cast<uint4*>(sA + kATileBytes + so) = ul;
               }
             }
