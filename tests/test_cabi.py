@@ -40,6 +40,17 @@ def test_no_cpu_fallback(lib):
         lib.Engine({'x': torch.zeros(1)})
 
 
+def test_preprocess_has_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    so = lib.load_library()
+    f = (lib.mcg_frame * 1)()
+    c3 = (ctypes.c_float * 3)(1, 1, 1)
+    assert so.mcg_preprocess(f, 1, c3, c3, 1, None, 32, 32, None) == -2
+    assert b'no CPU fallback' in so.mcg_last_error()
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, 'mcgaze_b200')
     for dp, _, files in os.walk(pkg):

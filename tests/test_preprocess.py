@@ -212,6 +212,28 @@ def test_gpu_random_geometry_vs_oracle():
 
 
 @pytest.mark.gpu
+def test_gpu_invalid_arguments_are_rejected_with_error_codes():
+    """C-ABI error behaviour: negative code + message, nothing launched, nothing thrown across the ABI."""
+    import torch
+    from mcgaze_b200 import lib
+    src = torch.zeros((40, 50, 3), dtype=torch.uint8, device='cuda')
+    out = torch.zeros((1, 3, 32, 64), device='cuda')
+    good = (0, 0, 40, 50, 26, 32)
+    lib.preprocess([src], [good], MEAN, STD, True, out)
+    for bad in [(0, 0, 41, 50, 26, 32),        # crop window leaves the source
+                (-1, 0, 40, 50, 26, 32),
+                (0, 0, 40, 50, 33, 32),        # resized frame does not fit the canvas
+                (0, 0, 40, 50, 26, 0)]:
+        with pytest.raises(lib.McgError, match='code -1'):
+            lib.preprocess([src], [bad], MEAN, STD, True, out)
+    with pytest.raises(lib.McgError):
+        lib.preprocess([src], [good], MEAN, STD, True, torch.zeros((1, 3, 32, 62), device='cuda'))   # Wp % 4
+    with pytest.raises(lib.McgError):
+        lib.preprocess([src.float()], [good], MEAN, STD, True, out)                                  # not uint8
+    torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
 def test_gpu_full_batch_properties():
     """BASELINE configs[1] size (224 frames -> 224^2): batch independence (a frame's result does not depend on its
     neighbours or on the launch chunking, bit-exact), constant images map to the normalisation table, identity
