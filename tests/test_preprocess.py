@@ -97,6 +97,18 @@ def test_pipeline_geometry_matches_goldens(golden):
             assert (y, x, ch, cw) == (y1, x1, y2 - y1, x2 - x1)
 
 
+@pytest.mark.skipif(not os.path.exists('/root/reference/configs/multiclue_gaze'), reason='reference tree not mounted')
+def test_reference_pipeline_configs_build_unchanged():
+    """the reference's own config files (Gaze360- and l2cs-setting) give the same pipeline as this repo's copies"""
+    for name in ('gaze360', 'l2cs'):
+        ref = Config.fromfile(os.path.join('/root/reference', CFG[name])).data.test.pipeline
+        ours = pipeline_cfg(name)
+        assert [dict(d) for d in ref] == [dict(d) for d in ours]
+        p = GpuTestPipeline(ref)
+        assert p.scale == ((448, 448) if name == 'l2cs' else (224, 224)) and p.size_divisor == 32 and p.to_rgb
+        assert (p.crop is None) == (name == 'l2cs')
+
+
 def test_vectorised_plan_equals_the_literal_per_frame_arithmetic():
     rng = np.random.default_rng(7)
     shapes = [(int(a), int(b)) for a, b in rng.integers(8, 2000, (500, 2))]
