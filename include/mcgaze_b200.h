@@ -153,6 +153,17 @@ typedef struct {
 int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const float* std, int to_rgb, float* out,
                    int Hp, int Wp, void* stream);
 
+/* ---- scorer ---------------------------------------------------------------------
+ * Replaces gaze_error of tools/calculate_mae_gaze360.py (:110-188: smooth_filter :16-29 with alpha 0.6,
+ * compute_angular_error :77-94, compute_yaw_angular :69-74) for per-frame gaze vectors that are on the device.
+ *   pred, gt     DEVICE fp32 [F, 3]   predicted / ground-truth vectors, the frames of all videos concatenated
+ *   video_start  DEVICE int32 [n_videos + 1]   first frame of each video, video_start[n_videos] = F
+ *   out          DEVICE double [6]    {sum, frames} for 360, front-180 (|yaw(gt)| <= 90 deg), front-20;
+ *                                     sum = per-video mean angle in degrees x frames of that video; MAE = sum / frames
+ * Asynchronous on `stream`; needs no engine handle. */
+int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_start, int n_videos, double* out,
+                   void* stream);
+
 const char* mcg_last_error(void);
 const char* mcg_version(void);
 

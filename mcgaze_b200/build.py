@@ -18,6 +18,7 @@ API_H = os.path.join('..', '..', 'include', 'mcgaze_b200.h')
 SOURCES = {
     'mcg_api.cu': ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh', API_H],
     'preprocess.cu': ['common.cuh', API_H],
+    'metric.cu': ['common.cuh', API_H],
 }
 
 

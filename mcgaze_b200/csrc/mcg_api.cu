@@ -1347,6 +1347,9 @@ namespace mcg {
 // preprocess.cu
 void preprocess_launch(const mcg_frame* frames, int n, const float* mean, const float* std_, int to_rgb, float* out,
                        int Hp, int Wp, cudaStream_t st, int* launches);
+// metric.cu
+void gaze_error_launch(const float* pred, const float* gt, const int32_t* video_start, int n_videos, double* out,
+                       cudaStream_t st);
 }  // namespace mcg
 
 // ========================================================================================
@@ -1462,6 +1465,19 @@ int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const floa
       return MCG_ERR_CUDA;
     }
     mcg::preprocess_launch(frames, n, mean, std, to_rgb, out, Hp, Wp, static_cast<cudaStream_t>(stream), nullptr);
+    return MCG_OK;
+  });
+}
+
+int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_start, int n_videos, double* out,
+                   void* stream) {
+  return guarded([&]() -> int {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      mcg::g_last_error = "mcg_gaze_error: no CUDA device visible (this library has no CPU fallback)";
+      return MCG_ERR_CUDA;
+    }
+    mcg::gaze_error_launch(pred, gt, video_start, n_videos, out, static_cast<cudaStream_t>(stream));
     return MCG_OK;
   });
 }

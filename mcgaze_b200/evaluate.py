@@ -228,3 +228,17 @@ def evaluate(dataset: Gaze360ClipDataset, records: Sequence[Dict[str, Any]], key
     if gt is None:
         raise ValueError('the annotation file carries no ground-truth gazes')
     return metric.gaze_error([np.asarray(r[key], dtype=np.float64) for r in records], gt)
+
+
+def evaluate_on_device(dataset: Gaze360ClipDataset, merged: Sequence[Dict[str, np.ndarray]], clue: int = 0,
+                       device: str = 'cuda:0') -> Dict[str, float]:
+    """The same numbers from mcg_gaze_error: the merged per-video gaze arrays of `videos_from_clips`
+    (clue 0 = fused, 1 / 2 / 3 = face / eyes / head) are scored by one kernel launch on the device."""
+    import torch
+    from . import lib
+    gt = ground_truth_videos(dataset)
+    if gt is None:
+        raise ValueError('the annotation file carries no ground-truth gazes')
+    pred = np.concatenate([m['gaze'][:, clue] for m in merged]).astype(np.float32)
+    gt_all = np.concatenate(gt).astype(np.float32)
+    return lib.gaze_error(torch.from_numpy(pred).to(device), torch.from_numpy(gt_all).to(device), [len(g) for g in gt])

@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
            'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
-           'mcg_preprocess', 'mcg_last_error', 'mcg_version')
+           'mcg_preprocess', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
 
 
 class McgError(RuntimeError):
@@ -65,6 +65,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_last_kernel_profile.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_preprocess.argtypes = [ctypes.POINTER(mcg_frame), ci, cf, cf, ci, vp, ci, ci, vp]
+    lib.mcg_gaze_error.argtypes = [vp, vp, vp, ci, vp, vp]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -126,6 +127,34 @@ def preprocess(frames, geometry, mean, std, to_rgb, out, stream: Optional[int] =
     _check(lib.mcg_preprocess(ctypes.cast(desc.ctypes.data, ctypes.POINTER(mcg_frame)), n,
                               c3(*[float(v) for v in mean]), c3(*[float(v) for v in std]), 1 if to_rgb else 0,
                               out.data_ptr(), out.shape[2], out.shape[3], st), 'mcg_preprocess')
+
+
+def gaze_error(pred, gt, lengths, stream: Optional[int] = None) -> Dict[str, float]:
+    """mcg_gaze_error: `pred`, `gt` = CUDA fp32 [F, 3] (frames of all videos concatenated), `lengths` = frames per
+    video.  Returns the keys of mcgaze_b200.metric.gaze_error (mae_360 / mae_front90 / mae_front20 + frame counts)."""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    lib = load_library()
+    lengths = np.asarray(lengths, dtype=np.int64)
+    for t in (pred, gt):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != 3 \
+                or t.shape[0] != int(lengths.sum()):
+            raise McgError('gaze_error: pred / gt must be contiguous CUDA fp32 [sum(lengths), 3] tensors')
+    if len(lengths) == 0 or np.any(lengths <= 0):
+        raise McgError('gaze_error: every video needs at least one frame')
+    start = torch.from_numpy(np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)).to(pred.device)
+    out = torch.empty(6, dtype=torch.float64, device=pred.device)
+    st = torch.cuda.current_stream(pred.device).cuda_stream if stream is None else stream
+    _check(lib.mcg_gaze_error(pred.data_ptr(), gt.data_ptr(), start.data_ptr(), len(lengths), out.data_ptr(), st),
+           'mcg_gaze_error')
+    o = out.cpu().numpy()
+    res = {}
+    for k, name in enumerate(('360', 'front90', 'front20')):
+        res[f'mae_{name}'] = float(o[2 * k] / max(o[2 * k + 1], 1.0))
+        res[f'frames_{name}'] = int(o[2 * k + 1])
+    return res
 
 
 class Engine:

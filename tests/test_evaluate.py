@@ -240,3 +240,16 @@ def test_gpu_cli_writes_reference_schema_json(synthetic_sd, tmp_path):
         assert set(v) == {'video_id', 'category_id', 'fusion_gazes', 'face_bboxes', 'face_gazes', 'face_score',
                           'eyes_bboxes', 'eyes_gazes', 'eyes_score', 'head_bboxes', 'head_gazes', 'head_score'}
         assert all(b is None or len(b) == 4 for b in v['head_bboxes'])
+
+
+@pytest.mark.gpu
+def test_gpu_device_scorer_matches_host_scorer_on_driver_output():
+    """evaluate_on_device (mcg_gaze_error) == evaluate (host restatement of calculate_mae_gaze360.py) on the merged
+    output of the driver (stub forward: the scorer only sees the merged gaze arrays)."""
+    ds = ev.Gaze360ClipDataset(make_anno(), loader=fake_loader)
+    rows = ev.single_gpu_test(StubModel(), ds, StubPipeline(), clips_per_batch=4)
+    records, merged = ev.videos_from_clips(ds, rows)
+    host = ev.evaluate(ds, records)
+    dev = ev.evaluate_on_device(ds, merged)
+    for k in host:
+        assert abs(host[k] - dev[k]) < 2e-3, (k, host[k], dev[k])
