@@ -123,7 +123,11 @@ class GpuTestPipeline:
         scalar methods above (`plan_scalar` keeps the literal per-frame form; the tests compare the two)."""
         n = len(shapes)
         if rands is None:
-            rands = [self._draw() if self.crop is not None and self.crop[0] == 'relative_range' else 0.0 for _ in shapes]
+            if self.crop is not None and self.crop[0] == 'relative_range':
+                # n draws of rand(1) and one draw of rand(n) consume the generator identically
+                rands = (self._rng if self._rng is not None else np.random).rand(n)
+            else:
+                rands = np.zeros(n)
         hw = np.asarray(shapes, dtype=np.int64).reshape(n, 2)
         h, w = hw[:, 0], hw[:, 1]
         r = np.asarray(rands, dtype=np.float64).reshape(n)
@@ -163,12 +167,13 @@ class GpuTestPipeline:
         ws, hs = nw / cw, nh / ch
         scale = np.stack([ws, hs, ws, hs], 1).astype(np.float32)
         norm_cfg = dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb)
-        metas = [dict(filename=None, ori_filename=None, ori_shape=(int(h[i]), int(w[i]), 3),
-                      img_shape=(int(nh[i]), int(nw[i]), 3), pad_shape=(int(ph[i]), int(pw[i]), 3), scale_factor=scale[i],
-                      flip=False, flip_direction=None, img_norm_cfg=norm_cfg) for i in range(n)]
+        hl, wl, nhl, nwl, phl, pwl = (a.tolist() for a in (h, w, nh, nw, ph, pw))
+        metas = [dict(filename=None, ori_filename=None, ori_shape=(hl[i], wl[i], 3), img_shape=(nhl[i], nwl[i], 3),
+                      pad_shape=(phl[i], pwl[i], 3), scale_factor=scale[i], flip=False, flip_direction=None,
+                      img_norm_cfg=norm_cfg) for i in range(n)]
         if Wp % 4:
             Wp += 4 - Wp % 4                   # the kernel stores float4; configs pad to 32 anyway
-        return [tuple(int(v) for v in g) for g in geometry], metas, (Hp, Wp)
+        return list(map(tuple, geometry.tolist())), metas, (Hp, Wp)
 
     def plan_scalar(self, shapes: Sequence[Tuple[int, int]], rands: Sequence[float]):
         """The literal per-frame form of plan() (python floats, as the reference's transforms compute)."""
