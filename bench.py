@@ -325,11 +325,17 @@ def main():
     eng.set_graph_mode(not args.no_graph)
     for _ in range(args.warmup):
         eng.forward_into(img, T, out)
-    barrier()
+    if world > 1:      # the collective of the timed region: communicator and buffers exist before the clock starts
+        warm = torch.zeros(args.steps, NB, 4, 3, device=dev)
+        dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
+    # everything with a rank-dependent host cost (NVML init, thread start, event creation) happens BEFORE the
+    # barrier: between the barrier and e0.record() there is nothing but the record itself, so the ranks start
+    # within the skew of one barrier and the end-of-run all-gather does not absorb start skew (round 1: N = 4)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     keep = []
+    barrier()
     e0.record()
     for _ in range(args.steps):
         eng.forward_into(img, T, out)
@@ -342,10 +348,15 @@ def main():
     barrier()
     clocks = sampler.finish()
     ms_total = e0.elapsed_time(e1)
+    rank_ms = None
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        all_t = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(all_t, t)
+        per_rank = sorted(float(x.item()) for x in all_t)
+        rank_ms = {'min': per_rank[0] / args.steps, 'median': per_rank[len(per_rank) // 2] / args.steps,
+                   'max': per_rank[-1] / args.steps}
+        ms_total = per_rank[-1]            # max over ranks
     ms_per_step = ms_total / args.steps
     value = world * CLIPS_PER_STEP * args.steps / (ms_total * 1e-3)
 

@@ -108,6 +108,17 @@ int mcg_last_umma_times(mcg_handle h, double* out_ms, int capacity);
  * bytes needed including the terminating NUL (call again with a larger buffer if > capacity) or a negative error. */
 int mcg_last_kernel_profile(mcg_handle h, char* buf, int capacity);
 
+/* Operand-range check of the fp16c8 precision mode: its e4m3 correction planes are exact only for
+ * activations in [2^-6, 448] and BN-folded weights in [2^-10, 28].  Scans the trunk / FPN activations the LAST forward
+ * left in the workspace and reports them with the weight statistics taken at mcg_create, as text lines
+ * "name<TAB>total<TAB>nonzero<TAB>over<TAB>under<TAB>nonfinite<TAB>maxabs<TAB>energy<TAB>energy_under\n"
+ * (activations: over = |v| > 448, under = 0 < |v| < 2^-8; weight rows "w:<checkpoint key>": over = |w| > 28,
+ * under = 0 < |w| < 2^-10; energy = sum v^2, energy_under = its part from the `under` elements).  The reference has
+ * no counterpart (it computes in fp32: mmdet/models/backbones/resnet.py:263-302); callers use it to refuse a
+ * checkpoint whose statistics leave the window instead of silently degrading to fp16 accuracy.  Synchronises.
+ * Returns the bytes needed including the NUL (call again with a larger buffer if > capacity) or a negative error. */
+int mcg_range_report(mcg_handle h, char* buf, int capacity);
+
 /* Capture the forward for the current shape in a CUDA graph and replay it on later calls
  * (on = 1) or launch kernels eagerly (on = 0, default). */
 int mcg_set_graph_mode(mcg_handle h, int on);

@@ -1063,4 +1063,51 @@ __global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, const __hal
   }
 }
 
+// Range scan of an activation's fp16 hi plane (diagnostic, outside the forward): the fp16c8 correction planes are
+// exact e4m3 normals only for |value| in [2^-6, 448] (common.cuh).  out[0] non-zero elements, out[1] |v| > 448 (hi8 /
+// lo8 saturate: the correction of that element is wrong), out[2] 0 < |v| < 2^-8 (the lo8 residue is an e4m3 subnormal:
+// that element is only fp16-accurate), out[3] non-finite, out[4] bits of max |v|; sums[0] = sum v^2, sums[1] = sum v^2
+// over the elements counted in out[2].
+__global__ void __launch_bounds__(256) range_scan_kernel(const __half* __restrict__ hi, long long n,
+                                                         unsigned long long* __restrict__ out, double* __restrict__ sums) {
+  unsigned long long nz = 0, over = 0, under = 0, bad = 0;
+  float mx = 0.f;
+  double e = 0.0, eu = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = fabsf(__half2float(hi[i]));
+    if (!(v <= 65504.f)) {
+      ++bad;
+      continue;
+    }
+    if (v != 0.f) ++nz;
+    if (v > 448.f) ++over;
+    const float v2 = v * v;
+    e += v2;
+    if (v != 0.f && v < 0.00390625f) {
+      ++under;
+      eu += v2;
+    }
+    mx = fmaxf(mx, v);
+  }
+  for (int o = 16; o; o >>= 1) {
+    nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    over += __shfl_xor_sync(0xffffffffu, over, o);
+    under += __shfl_xor_sync(0xffffffffu, under, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    eu += __shfl_xor_sync(0xffffffffu, eu, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, nz);
+    atomicAdd(out + 1, over);
+    atomicAdd(out + 2, under);
+    atomicAdd(out + 3, bad);
+    atomicMax(out + 4, static_cast<unsigned long long>(__float_as_uint(mx)));
+    atomicAdd(sums + 0, e);
+    atomicAdd(sums + 1, eu);
+  }
+}
+
 }  // namespace mcg

@@ -141,6 +141,14 @@ struct Interm {
   int64_t shape[4] = {0, 0, 0, 0};  // kind 1: NB,H,W,C
 };
 
+// one row of mcg_range_report: value-range statistics of a tensor against the e4m3 windows of the fp16c8 mode
+struct RangeRow {
+  std::string name;
+  unsigned long long total = 0, nonzero = 0, over = 0, under = 0, nonfinite = 0;
+  float maxabs = 0.f;
+  double energy = 0.0, energy_under = 0.0;
+};
+
 // ------------------------------------------------------------------------------------ engine
 class Engine {
  public:
@@ -393,7 +401,66 @@ class Engine {
     return MCG_OK;
   }
 
+  // Value ranges of the trunk / FPN activations of the LAST forward (every tensor has its own arena buffer, so they
+  // are all still there) and of the BN-folded convolution weights, as text lines
+  // "name<TAB>total<TAB>nonzero<TAB>over<TAB>under<TAB>nonfinite<TAB>maxabs<TAB>energy<TAB>energy_under".
+  // Activations: over = |v| > 448, under = 0 < |v| < 2^-8; weights: over = |w| > 28, under = 0 < |w| < 2^-10.
+  std::string range_report() {
+    MCG_CHECK(ws_NB_ > 0, "mcg_range_report: run a forward first");
+    MCG_CUDA(cudaSetDevice(device_));
+    MCG_CUDA(cudaDeviceSynchronize());
+    std::vector<std::pair<std::string, const Act*>> acts;
+    acts.emplace_back("pool", &pool_out_);
+    for (int l = 0; l < 4; ++l)
+      for (size_t b = 0; b < blk_act_[l].size(); ++b) {
+        const std::string k = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
+        if (!fused_tail_used(l, b)) acts.emplace_back(k + ".t1", &blk_act_[l][b].t1), acts.emplace_back(k + ".t2", &blk_act_[l][b].t2);
+        else acts.emplace_back(k + ".t1", &blk_act_[l][b].t1);
+        if (blocks_[l][b].has_ds) acts.emplace_back(k + ".ds", &blk_act_[l][b].ds);
+        acts.emplace_back(k, &blk_act_[l][b].out);
+      }
+    for (int i = 0; i < 4; ++i) acts.emplace_back("lat" + std::to_string(i), &lat_[i]);
+    for (int i = 0; i < 4; ++i) acts.emplace_back("fpn" + std::to_string(i), &fpn_[i]);
+    DeviceBlock cnt(acts.size() * 8 * sizeof(unsigned long long));
+    MCG_CUDA(cudaMemset(cnt.p, 0, cnt.bytes));
+    for (size_t i = 0; i < acts.size(); ++i) {
+      unsigned long long* c = reinterpret_cast<unsigned long long*>(cnt.p) + i * 8;
+      const long long n = acts[i].second->rows() * acts[i].second->C;
+      range_scan_kernel<<<num_sms_ * 4, 256>>>(acts[i].second->pl.hi, n, c, reinterpret_cast<double*>(c + 5));
+    }
+    MCG_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> host(acts.size() * 8);
+    MCG_CUDA(cudaMemcpy(host.data(), cnt.p, cnt.bytes, cudaMemcpyDeviceToHost));
+    std::vector<RangeRow> rows;
+    for (size_t i = 0; i < acts.size(); ++i) {
+      RangeRow r;
+      r.name = acts[i].first;
+      r.total = static_cast<unsigned long long>(acts[i].second->rows() * acts[i].second->C);
+      r.nonzero = host[i * 8];
+      r.over = host[i * 8 + 1];
+      r.under = host[i * 8 + 2];
+      r.nonfinite = host[i * 8 + 3];
+      const unsigned int mb = static_cast<unsigned int>(host[i * 8 + 4]);
+      std::memcpy(&r.maxabs, &mb, 4);
+      std::memcpy(&r.energy, &host[i * 8 + 5], 8);
+      std::memcpy(&r.energy_under, &host[i * 8 + 6], 8);
+      rows.push_back(r);
+    }
+    rows.insert(rows.end(), weight_ranges_.begin(), weight_ranges_.end());
+    std::string out;
+    char line[512];
+    for (const RangeRow& r : rows) {
+      std::snprintf(line, sizeof(line), "%s\t%llu\t%llu\t%llu\t%llu\t%llu\t%.9g\t%.9g\t%.9g\n", r.name.c_str(), r.total, r.nonzero,
+                    r.over, r.under, r.nonfinite, static_cast<double>(r.maxabs), r.energy, r.energy_under);
+      out += line;
+    }
+    return out;
+  }
+
  private:
+  // whether block (l, b) ran conv2 -> conv3 as one fused kernel in the last forward (its t2 tensor then stays on chip)
+  bool fused_tail_used(int, size_t) const { return false; }
+
   // -------------------------------------------------------------------------- weight loading
   struct HostT {
     const float* p;
@@ -474,6 +541,28 @@ class Engine {
                 w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s] * scale[o];
     ConvW cw;
     cw.g = pack_gemm(packed, Cout, Kp, shift.data(), precision_ == MCG_PRECISION_FP16C8);
+    if (precision_ == MCG_PRECISION_FP16C8) {
+      // e4m3 range of the weight planes (common.cuh): hi8 = e4m3(W 2^4) saturates above 28, is subnormal below 2^-10
+      RangeRow r;
+      r.name = "w:" + wkey;
+      r.total = packed.size();
+      for (float v : packed) {
+        const float a = std::fabs(v);
+        if (!(a <= 65504.f)) {
+          ++r.nonfinite;
+          continue;
+        }
+        if (a != 0.f) ++r.nonzero;
+        if (a > 28.f) ++r.over;
+        if (a != 0.f && a < 0.0009765625f) {
+          ++r.under;
+          r.energy_under += static_cast<double>(a) * a;
+        }
+        r.energy += static_cast<double>(a) * a;
+        r.maxabs = std::max(r.maxabs, a);
+      }
+      weight_ranges_.push_back(r);
+    }
     cw.Cin = Cin;
     cw.Cout = Cout;
     cw.R = R;
@@ -1279,6 +1368,7 @@ class Engine {
   std::vector<float> meta_host_;
   std::unordered_map<std::string, HostT> host_;
   std::vector<std::unique_ptr<DeviceBlock>> keep_;
+  std::vector<RangeRow> weight_ranges_;
   ConvW stem_;
   std::vector<BlockW> blocks_[4];
   ConvW lateral_[4], fpnconv_[4];
@@ -1516,6 +1606,18 @@ int mcg_last_kernel_profile(mcg_handle h, char* buf, int capacity) {
   const int rc = guarded([&]() -> int {
     if (!h || (capacity > 0 && !buf)) return MCG_ERR_INVALID;
     const std::string s = h->impl->kernel_profile();
+    n = static_cast<int>(s.size()) + 1;
+    if (capacity >= n) std::memcpy(buf, s.c_str(), static_cast<size_t>(n));
+    return MCG_OK;
+  });
+  return rc == MCG_OK ? n : rc;
+}
+
+int mcg_range_report(mcg_handle h, char* buf, int capacity) {
+  int n = -1;
+  const int rc = guarded([&]() -> int {
+    if (!h || (capacity > 0 && !buf)) return MCG_ERR_INVALID;
+    const std::string s = h->impl->range_report();
     n = static_cast<int>(s.size()) + 1;
     if (capacity >= n) std::memcpy(buf, s.c_str(), static_cast<size_t>(n));
     return MCG_OK;

@@ -134,6 +134,7 @@ class MultiClueGaze:
         self.cfg = None
         self._sd: 'OrderedDict[str, Any]' = OrderedDict()
         self._engine = None
+        self._ranges_checked = False
         self.training = False
 
     # --- torch.nn.Module-like surface used by init_detector / load_checkpoint ---------------
@@ -143,6 +144,7 @@ class MultiClueGaze:
     def load_state_dict(self, state_dict, strict: bool = False):
         self._sd = OrderedDict(state_dict)
         self._engine = None
+        self._ranges_checked = False
         return self
 
     def to(self, device):
@@ -208,6 +210,11 @@ class MultiClueGaze:
         if rescale:
             scale = np.stack([np.asarray(m['scale_factor'], dtype=np.float32).reshape(4) for m in img_metas])
         out = self.engine.forward(img, clip_length=clip_length or T, img_hw=img_hw, scale_factor=scale)
+        if not self._ranges_checked:
+            # first forward of a checkpoint: its activations / BN-folded weights must sit inside the operand window of
+            # the fp16c8 corrections (lib.Engine.check_ranges raises otherwise); one scan + sync, then never again
+            self._ranges_checked = True
+            self.engine.check_ranges()
         gaze, boxes, scores = out['gaze'], out['boxes'], out['scores']
         det_bboxes = list(torch.cat([boxes, scores[..., None]], dim=2).unbind(0))     # T x [3, 5], one kernel
         det_labels = [[0, 1, 2] for _ in range(T)]

@@ -18,7 +18,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 # every symbol include/mcgaze_b200.h declares
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
-           'mcg_last_launch_count', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
+           'mcg_last_launch_count', 'mcg_range_report', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
            'mcg_preprocess', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
 
 
@@ -64,6 +64,7 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_last_umma_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ci]
     lib.mcg_last_kernel_profile.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    lib.mcg_range_report.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_preprocess.argtypes = [ctypes.POINTER(mcg_frame), ci, cf, cf, ci, vp, ci, ci, vp]
     lib.mcg_gaze_error.argtypes = [vp, vp, vp, ci, vp, vp]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
@@ -243,6 +244,46 @@ class Engine:
         _check(min(self._lib.mcg_last_kernel_profile(self._h, buf, n), 0), 'mcg_last_kernel_profile')
         return [(l.split('\t')[0], float(l.split('\t')[1])) for l in buf.value.decode().splitlines() if l]
 
+    def range_report(self):
+        """mcg_range_report: one dict per trunk / FPN activation of the last forward and per convolution weight
+        (name, total, nonzero, over, under, nonfinite, maxabs, energy, energy_under)."""
+        n = self._lib.mcg_range_report(self._h, None, 0)
+        if n < 0:
+            _check(n, 'mcg_range_report')
+        buf = ctypes.create_string_buffer(n)
+        _check(min(self._lib.mcg_range_report(self._h, buf, n), 0), 'mcg_range_report')
+        keys = ('total', 'nonzero', 'over', 'under', 'nonfinite')
+        rows = []
+        for line in buf.value.decode().splitlines():
+            f = line.split('\t')
+            row = {'name': f[0]}
+            row.update({k: int(v) for k, v in zip(keys, f[1:6])})
+            row.update(maxabs=float(f[6]), energy=float(f[7]), energy_under=float(f[8]))
+            rows.append(row)
+        return rows
+
+    def check_ranges(self, max_over_frac: float = 1e-6, max_under_energy: float = 0.25):
+        """Refuse operands the fp16c8 corrections cannot represent: raises McgError when, in the last forward, a tensor
+        holds non-finite values, more than `max_over_frac` of its elements saturate the e4m3 planes (|activation| > 448,
+        |weight| > 28), or more than `max_under_energy` of an activation's energy sits in elements whose residue is an
+        e4m3 subnormal (|v| < 2^-8: those are only fp16-accurate).  Returns the report otherwise.  The other parity mode
+        (`fp16x3`) has no such window."""
+        rows = self.range_report()
+        if self.precision != 'fp16c8':
+            return rows
+        bad = []
+        for r in rows:
+            if r['nonfinite']:
+                bad.append(f"{r['name']}: {r['nonfinite']} non-finite values")
+            elif r['over'] > max_over_frac * max(r['total'], 1):
+                bad.append(f"{r['name']}: {r['over']} of {r['total']} elements saturate e4m3 (max |v| = {r['maxabs']:.4g})")
+            elif not r['name'].startswith('w:') and r['energy'] > 0 and r['energy_under'] > max_under_energy * r['energy']:
+                bad.append(f"{r['name']}: {100 * r['energy_under'] / r['energy']:.1f} % of the energy below 2^-8 "
+                           f"(max |v| = {r['maxabs']:.4g})")
+        if bad:
+            raise McgError('operands outside the fp16c8 correction window, use precision="fp16x3": ' + '; '.join(bad[:6]))
+        return rows
+
     # ------------------------------------------------------------------ forward
     @staticmethod
     def _meta(arr, n: int, width: int):
@@ -252,6 +293,21 @@ class Engine:
         a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(n, width))
         return a, a.ctypes.data
 
+    def _check_io(self, img, out=None) -> None:
+        """Raw pointers cross the C ABI: refuse anything that is not a contiguous fp32 tensor on this engine's GPU."""
+        import torch
+        if not (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3 and img.is_contiguous()):
+            raise McgError('img must be a contiguous CUDA fp32 tensor [N, 3, H, W]')
+        if img.device.index != self.device:
+            raise McgError(f'img lives on cuda:{img.device.index}, the engine on cuda:{self.device}')
+        if out is not None:
+            N = img.shape[0]
+            for k, shape in (('gaze', (N, 4, 3)), ('boxes', (N, 3, 4)), ('scores', (N, 3))):
+                t = out[k]
+                if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape
+                        and t.device.index == self.device):
+                    raise McgError(f"out['{k}'] must be a contiguous CUDA fp32 tensor {shape} on cuda:{self.device}")
+
     def forward(self, img, clip_length: Optional[int] = None, img_hw=None, scale_factor=None):
         """img: CUDA fp32 [N,3,H,W] (N = B*clip_length).  Returns CUDA tensors
         {'gaze' [N,4,3] (fused, face, eyes, head), 'boxes' [N,3,4], 'scores' [N,3]}; asynchronous on the
@@ -259,6 +315,7 @@ class Engine:
         import torch
         assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3
         img = img.contiguous()
+        self._check_io(img)
         N, _, H, W = img.shape
         T = N if clip_length is None else int(clip_length)
         assert N % T == 0
@@ -277,8 +334,11 @@ class Engine:
         """Like forward() but writes into the preallocated dict `out` (stable pointers: lets the
         CUDA-graph replay path engage)."""
         import torch
+        self._check_io(img, out)
         N, _, H, W = img.shape
         T = int(clip_length)
+        if N % T:
+            raise McgError(f'forward_into: {N} frames are not a whole number of {T}-frame clips')
         k1, p1 = self._meta(img_hw, N, 2)
         k2, p2 = self._meta(scale_factor, N, 4)
         stream = torch.cuda.current_stream(img.device).cuda_stream

@@ -22,6 +22,7 @@ from __future__ import annotations
 import importlib.abc
 import importlib.machinery
 import math
+import os
 import sys
 import types
 
@@ -247,7 +248,9 @@ def install() -> None:
     global _installed
     if _installed:
         return
-    sys.path.insert(0, '/root/repo')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
     from mcgaze_b200.compat import Config, ConfigDict, DictAction, Registry, build_from_cfg, load_checkpoint
 
     sys.meta_path.insert(0, _StubFinder())

@@ -273,3 +273,117 @@ def test_detector_surface_matches_reference_call(synthetic_sd):
     ref = O.forward(synthetic_sd, img)
     assert yaw_pitch_err(gaze['gaze_score'].cpu(), ref['gaze_score']) < 1e-3
     assert metas[0]['batch_input_shape'] == (224, 224)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[1] / configs[2] at their full sizes against the oracle (round-1 verdict, weak #1)
+# ------------------------------------------------------------------------------------------------------------------
+def _check_vs_oracle(out, ref, box_tol):
+    worst = 0.0
+    for i, k in enumerate(KEYS):
+        e = yaw_pitch_err(out['gaze'][:, i].cpu(), ref[k])
+        worst = max(worst, e)
+        assert e < 1e-3, (k, e)                       # north_star tolerance: 1e-3 rad on (yaw, pitch)
+    assert (out['boxes'].cpu() - ref['boxes']).abs().max() < box_tol      # pixels
+    assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
+    return worst
+
+
+@pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3'])
+def test_headline_batch_32x7x224_vs_oracle(engines, synthetic_sd, precision):
+    """The configuration the headline number is quoted on (32 clips x 7 frames x 224^2 in ONE forward, CUDA-graph
+    replay like bench.py) against the fp32 oracle on the same 224 frames: all four gaze outputs, boxes, scores."""
+    B, T = 32, 7
+    img = torch.cat([O.make_clip(500 + b, T) for b in range(B)])
+    ref = O.forward(synthetic_sd, img, clip_length=T)
+    eng = engines(precision)
+    x = img.cuda()
+    out = eng.forward(x, clip_length=T)
+    _check_vs_oracle(out, ref, 0.1)
+    eng.set_graph_mode(True)
+    try:
+        out2 = {k: torch.empty_like(v) for k, v in out.items()}
+        for _ in range(2):
+            eng.forward_into(x, T, out2)
+        torch.cuda.synchronize()
+        for k in out:
+            assert torch.equal(out[k], out2[k]), k     # graph replay == eager, bit for bit
+    finally:
+        eng.set_graph_mode(False)
+
+
+@pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3'])
+def test_l2cs_batch_8x7x448_vs_oracle(engines, synthetic_sd, precision):
+    """BASELINE configs[2] (l2cs setting, configs/multiclue_gaze/multiclue_gaze_r50_l2cs.py:31-43: 448 x 448 frames,
+    samples_per_gpu = 8): 8 clips x 7 frames x 448^2 in one forward against the oracle."""
+    B, T, S = 8, 7, 448
+    img = torch.cat([O.make_clip(600 + b, T, S, S) for b in range(B)])
+    ref = O.forward(synthetic_sd, img, clip_length=T)
+    out = engines(precision).forward(img.cuda(), clip_length=T)
+    _check_vs_oracle(out, ref, 0.2)
+
+
+def test_range_report_in_window_for_the_synthetic_checkpoint(engines):
+    """mcg_range_report: every trunk / FPN activation and every BN-folded weight of the seeded checkpoint sits inside
+    the e4m3 windows the fp16c8 corrections assume, and check_ranges() accepts it."""
+    eng = engines('fp16c8')
+    eng.forward(O.make_clip(0, 7).cuda())
+    rows = eng.check_ranges()
+    names = [r['name'] for r in rows]
+    assert 'pool' in names and 'layer4.2' in names and 'fpn0' in names and 'w:backbone.layer1.0.conv1.weight' in names
+    for r in rows:
+        assert r['nonfinite'] == 0 and r['over'] == 0, r
+        assert 0 < r['maxabs'] < (28 if r['name'].startswith('w:') else 448), r
+        assert r['nonzero'] <= r['total']
+
+
+def _scaled_sd(sd, what):
+    sd = {k: v.clone() for k, v in sd.items()}
+    if what == 'stem_x600':            # pooled stem map far above 448: hi8 / lo8 saturate
+        sd['backbone.bn1.weight'] *= 600
+        sd['backbone.bn1.bias'] *= 600
+    elif what == 'stem_div64':         # pooled stem map around 2^-6
+        sd['backbone.bn1.weight'] /= 64
+        sd['backbone.bn1.bias'] /= 64
+    elif what == 'bn_gain_x16':        # every bottleneck's last BN gain x 16: the residual stream explodes
+        for k in sd:
+            if k.endswith('bn3.weight'):
+                sd[k] *= 16
+    elif what == 'conv_w_x16':         # conv weights x 16 with running_var x 256, bn mean x 16: the SAME network
+        for k in list(sd):
+            if k.startswith('backbone.layer') and k.endswith('.weight') and '.conv' in k:
+                bn = k.replace('.conv', '.bn').rsplit('.', 1)[0]
+                sd[k] *= 16
+                sd[bn + '.running_var'] = sd[bn + '.running_var'] * 256 + 1e-5 * 255
+                sd[bn + '.running_mean'] *= 16
+    elif what == 'conv_w_div64':       # layer1 conv weights / 64 (BN statistics unchanged): tiny pre-BN activations
+        for k in list(sd):
+            if k.startswith('backbone.layer1') and k.endswith('.weight') and '.conv' in k:
+                sd[k] /= 64
+    return sd
+
+
+@pytest.mark.parametrize('what', ['stem_x600', 'stem_div64', 'bn_gain_x16', 'conv_w_x16', 'conv_w_div64'])
+def test_fp16c8_operand_window_stress(synthetic_sd, what):
+    """Checkpoints whose activations / weights leave (or approach the edges of) the [2^-6, 448] / [2^-10, 28] windows
+    of the e4m3 correction planes: the backend must EITHER still meet the 1e-3 rad bar OR refuse (check_ranges raises)
+    - never degrade silently (round-1 verdict, weak #2)."""
+    from mcgaze_b200 import lib
+    sd = _scaled_sd(synthetic_sd, what)
+    img = O.make_clip(7, 7)
+    eng = lib.Engine(sd, 0, 'fp16c8')
+    try:
+        out = eng.forward(img.cuda())
+        torch.cuda.synchronize()
+        try:
+            eng.check_ranges()
+        except lib.McgError as e:
+            assert 'fp16c8 correction window' in str(e)
+            assert what in ('stem_x600', 'bn_gain_x16'), f'{what} refused: {e}'
+            return
+        assert what not in ('stem_x600', 'bn_gain_x16'), 'saturating operands were accepted'
+        ref = O.forward(sd, img)
+        for i, k in enumerate(KEYS):
+            assert yaw_pitch_err(out['gaze'][:, i].cpu(), ref[k]) < 1e-3, (what, k)
+    finally:
+        eng.close()
