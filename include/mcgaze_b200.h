@@ -125,7 +125,11 @@ int mcg_set_graph_mode(mcg_handle h, int on);
 
 /* Options: "keep_intermediates" (1: snapshot per-stage head buffers for mcg_get_intermediate),
  * "time_kernels" (1: CUDA events around every tcgen05 GEMM launch),
- * "head_tensor_cores" (0: run the head's large Linear layers on the fp32 CUDA-core kernel). */
+ * "head_tensor_cores" (0: run the head's large Linear layers on the fp32 CUDA-core kernel),
+ * "fused_stem" (0: im2col -> GEMM -> max-pool chain instead of the fused stem kernel; exposes "stem"),
+ * "fuse_downsample" (0: a layer's first bottleneck runs its downsample branch as its own convolution and conv3 adds
+ * it as a residual, like mmdet/models/backbones/resnet.py:286-295 literally; default 1: conv3 and the downsample
+ * branch are one GEMM over the concatenated K). */
 int mcg_set_option(mcg_handle h, const char* key, int value);
 
 /* Stand-alone convolution / GEMM with the fused epilogue, for kernel-level parity tests.

@@ -142,10 +142,14 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in_hi, const __ha
 __global__ void init_proposals_kernel(const float* __restrict__ init_boxes /*[3,4] cxcywh*/,
                                       const float* __restrict__ init_feats /*[3,256]*/,
                                       const float* __restrict__ img_hw /*[N,2]*/, int N,
-                                      float* __restrict__ boxes /*[N,3,4]*/, float* __restrict__ obj /*[N,3,256]*/) {
+                                      float* __restrict__ boxes /*[N,3,4]*/, float* __restrict__ obj /*[N,3,256]*/,
+                                      __half* __restrict__ obj_hi = nullptr, __half* __restrict__ obj_lo = nullptr) {
   const int n = blockIdx.x;
   const float h = img_hw[n * 2], w = img_hw[n * 2 + 1];
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) obj[static_cast<long long>(n) * 768 + i] = init_feats[i];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    obj[static_cast<long long>(n) * 768 + i] = init_feats[i];
+    if (obj_hi) split_store(init_feats[i], obj_hi, obj_lo, static_cast<long long>(n) * 768 + i);  // in_proj operand
+  }
   if (threadIdx.x < 3) {
     const float* b = init_boxes + threadIdx.x * 4;
     float* o = boxes + (n * 3 + threadIdx.x) * 4;
@@ -295,41 +299,84 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FpnLevels f, const
 // y[row] = act( LN(x[row] (+ res[row])) * gamma + beta )
 // ---------------------------------------------------------------------------------------
 // x may be `nsplit` split-K partial sums `split_stride` elements apart (+ `xbias`), reduced here.
+// Optional second stage (gamma2 != null):  y = LN2( res2[row] + act(LN(...)) ) - the DynamicConv tail
+// `fc_norm -> ReLU -> + attn_feats -> instance_interactive_conv_norm` (transformer.py:1160-1162,
+// gaze_stqi_head.py:175-176) in one pass over the row.
+template <int kPer>  // C / 32: 2 or 8
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res,
                                  long long ldres, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float* __restrict__ y, long long ldy, long long rows, int C, int relu,
+                                 float* __restrict__ y, long long ldy, long long rows, int relu,
                                  int nsplit = 1, long long split_stride = 0, const float* __restrict__ xbias = nullptr,
-                                 __half* __restrict__ yh = nullptr, __half* __restrict__ yl = nullptr) {
+                                 __half* __restrict__ yh = nullptr, __half* __restrict__ yl = nullptr,
+                                 const float* __restrict__ res2 = nullptr, long long ldres2 = 0,
+                                 const float* __restrict__ gamma2 = nullptr, const float* __restrict__ beta2 = nullptr) {
+  constexpr int C = kPer * 32;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int per = C / 32;  // 2 or 8
-  float v[8];
+  float v[kPer];
+  // split-K partial sums: all loads of a slice are independent, slices are added in order (deterministic)
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) v[j] = x[row * ldx + j * 32 + lane];
+#pragma unroll 2
+  for (int sp = 1; sp < nsplit; ++sp) {
+    const float* xs = x + sp * split_stride + row * ldx;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) v[j] += xs[j * 32 + lane];
+  }
   float s = 0.f;
-  for (int j = 0; j < per; ++j) {
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
     const int c = j * 32 + lane;
-    float t = x[row * ldx + c];
-    for (int sp = 1; sp < nsplit; ++sp) t += x[sp * split_stride + row * ldx + c];
-    if (xbias) t += xbias[c];
-    if (res) t += res[row * ldres + c];
-    v[j] = t;
-    s += t;
+    if (xbias) v[j] += xbias[c];
+    if (res) v[j] += res[row * ldres + c];
+    s += v[j];
   }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
+  float mean = s / C;
   float q = 0.f;
-  for (int j = 0; j < per; ++j) {
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
     const float d = v[j] - mean;
     q += d * d;
   }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + 1e-5f);
-  for (int j = 0; j < per; ++j) {
+  float rstd = rsqrtf(q / C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
     const int c = j * 32 + lane;
     float t = (v[j] - mean) * rstd * gamma[c] + beta[c];
     if (relu) t = fmaxf(t, 0.f);
-    y[row * ldy + c] = t;
-    if (yh) split_store(t, yh, yl, row * C + c);  // dense [rows, C] planes for a following tensor-core Linear
+    v[j] = t;
+  }
+  if (gamma2) {
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      v[j] += res2[row * ldres2 + j * 32 + lane];
+      s += v[j];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / C;
+    q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const float d = v[j] - mean;
+      q += d * d;
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q / C + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int c = j * 32 + lane;
+      v[j] = (v[j] - mean) * rstd * gamma2[c] + beta2[c];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int c = j * 32 + lane;
+    y[row * ldy + c] = v[j];
+    if (yh) split_store(v[j], yh, yl, row * C + c);  // dense [rows, C] planes for a following tensor-core Linear
   }
 }
 
@@ -1010,6 +1057,162 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const LinGroups grp,
         if (relu) t = fmaxf(t, 0.f);
         y[m * ldy + c] = t;
         if (yh) split_store(t, yh, yl, m * 256 + c);  // dense planes for a following tensor-core Linear
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tower chains of the head in ONE launch: up to three Linear(256 -> 256, no bias) + LayerNorm + ReLU layers followed
+// by a small Linear(256 -> nout <= 4) whose weights are selected per row (row % n_classes: the per-clue fc_reg /
+// fc_cls heads), optionally followed by delta2bbox.  Covers the reg tower + fc_reg + refine_bboxes and the cls tower +
+// fc_cls of a stage (gaze_stqi_head.py:185-201, bbox_head.py:380-497) and the six tower chains of the gaze head
+// (gaze_head.py:150-184), which were 4-6 dependent launches each.  A CTA owns 8 rows for the whole chain (rows are
+// independent): the activations never leave shared memory, the weights stream from L2.  blockIdx.y = chain.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxChains = 6;
+constexpr int kChainSmemBytes = (8 * 256 + 4 * 8 * 256) * 4;  // xs + k-slice partial sums = 40 KB
+struct ChainArgs {
+  const float* x;            // [M, 256] rows with stride ldx
+  long long ldx;
+  int n_layers;              // hidden layers (1..3)
+  const float* wt[3];        // [256 (k), 256 (n)] transposed weights
+  const float* gamma[3];
+  const float* beta[3];
+  int n_classes;             // the final Linear of row m is fw[m % n_classes]
+  const float* fw[3];        // [nout, 256]
+  const float* fb[3];        // [nout]
+  int nout;
+  float* y;                  // y[m * ldy + j]
+  long long ldy;
+  const float* boxes_in;     // optional (nout == 4): boxes_out[m] = delta2bbox(boxes_in[m], y[m])
+  float* boxes_out;
+};
+struct ChainGroups {
+  ChainArgs g[kMaxChains];
+};
+
+__global__ void __launch_bounds__(1024) mlp_chain_kernel(const ChainGroups grp, long long M) {
+  const ChainArgs& a = grp.g[blockIdx.y];
+  extern __shared__ __align__(16) float ch_smem[];
+  float* xs = ch_smem;                    // [8][256] input of the current layer
+  float* red = ch_smem + kSlRows * 256;   // [4][8][256] k-slice partial sums
+  const int tid = threadIdx.x;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kSlRows;
+  const int n = tid & 255, kq = tid >> 8;
+  const int k0 = kq * 64;
+  const int warp = tid >> 5, lane = tid & 31;
+  float w[8];
+  {
+    const float* __restrict__ wt = a.wt[0];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = __ldg(wt + static_cast<long long>(k0 + j) * 256 + n);
+  }
+  for (int i = tid; i < kSlRows * 256; i += 1024) {
+    const int rr = i >> 8, k = i & 255;
+    xs[i] = (m0 + rr < M) ? a.x[(m0 + rr) * a.ldx + k] : 0.f;
+  }
+  __syncthreads();
+  for (int layer = 0; layer < a.n_layers; ++layer) {
+    const float* __restrict__ wt = a.wt[layer];
+    float acc[kSlRows];
+#pragma unroll
+    for (int i = 0; i < kSlRows; ++i) acc[i] = 0.f;
+#pragma unroll 1
+    for (int k = k0; k < k0 + 64; k += 8) {
+      float wn[8];
+      if (k + 8 < k0 + 64) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wt + static_cast<long long>(k + 8 + j) * 256 + n);
+      } else if (layer + 1 < a.n_layers) {  // first batch of the next layer's weights
+        const float* __restrict__ wt2 = a.wt[layer + 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wt2 + static_cast<long long>(k0 + j) * 256 + n);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wn[j] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kSlRows; ++i) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xs + i * 256 + k);
+        const float4 x1 = *reinterpret_cast<const float4*>(xs + i * 256 + k + 4);
+        float c = acc[i];
+        c = fmaf(x0.x, w[0], c);
+        c = fmaf(x0.y, w[1], c);
+        c = fmaf(x0.z, w[2], c);
+        c = fmaf(x0.w, w[3], c);
+        c = fmaf(x1.x, w[4], c);
+        c = fmaf(x1.y, w[5], c);
+        c = fmaf(x1.z, w[6], c);
+        c = fmaf(x1.w, w[7], c);
+        acc[i] = c;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = wn[j];
+    }
+#pragma unroll
+    for (int i = 0; i < kSlRows; ++i) red[(kq * kSlRows + i) * 256 + n] = acc[i];
+    __syncthreads();  // partial sums complete; every thread is done reading xs
+    if (warp < kSlRows) {
+      // warp r finishes row r: LayerNorm over its 256 columns + ReLU, back into xs as the next layer's input
+      const float* __restrict__ gamma = a.gamma[layer];
+      const float* __restrict__ beta = a.beta[layer];
+      float v[8];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = j * 32 + lane;
+        v[j] = red[(0 * kSlRows + warp) * 256 + c] + red[(1 * kSlRows + warp) * 256 + c] +
+               red[(2 * kSlRows + warp) * 256 + c] + red[(3 * kSlRows + warp) * 256 + c];
+        s += v[j];
+      }
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / 256.f;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / 256.f + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = j * 32 + lane;
+        xs[warp * 256 + c] = fmaxf((v[j] - mean) * rstd * gamma[c] + beta[c], 0.f);
+      }
+    }
+    __syncthreads();
+  }
+  // final small Linear: warp r -> row r, one warp-wide dot product per output
+  if (warp < kSlRows) {
+    const long long m = m0 + warp;
+    if (m < M) {
+      const int cls = static_cast<int>(m % a.n_classes);
+      const float* __restrict__ fw = a.fw[cls];
+      const float* __restrict__ fb = a.fb[cls];
+      float o4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < a.nout; ++j) {
+        float p = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p = fmaf(xs[warp * 256 + i * 32 + lane], __ldg(fw + j * 256 + i * 32 + lane), p);
+        for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        o4[j] = p + (fb ? fb[j] : 0.f);
+      }
+      if (lane == 0) {
+        for (int j = 0; j < a.nout; ++j) a.y[m * a.ldy + j] = o4[j];
+        if (a.boxes_out) {
+          // delta2bbox with stds (0.5,0.5,1,1), |dwh| <= |ln(16/1000)|, no border clip (delta_xywh_bbox_coder.py:224-260)
+          const float x1 = a.boxes_in[m * 4], y1 = a.boxes_in[m * 4 + 1], x2 = a.boxes_in[m * 4 + 2], y2 = a.boxes_in[m * 4 + 3];
+          const float dx = o4[0] * 0.5f, dy = o4[1] * 0.5f;
+          const float max_ratio = 4.135166556742356f;
+          const float dw = fminf(fmaxf(o4[2], -max_ratio), max_ratio);
+          const float dh = fminf(fmaxf(o4[3], -max_ratio), max_ratio);
+          const float pw = x2 - x1, ph = y2 - y1;
+          const float gx = (x1 + x2) * 0.5f + pw * dx, gy = (y1 + y2) * 0.5f + ph * dy;
+          const float gw = pw * expf(dw), gh = ph * expf(dh);
+          a.boxes_out[m * 4 + 0] = gx - gw * 0.5f;
+          a.boxes_out[m * 4 + 1] = gy - gh * 0.5f;
+          a.boxes_out[m * 4 + 2] = gx + gw * 0.5f;
+          a.boxes_out[m * 4 + 3] = gy + gh * 0.5f;
+        }
       }
     }
   }

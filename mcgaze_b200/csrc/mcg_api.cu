@@ -119,6 +119,7 @@ struct ConvW {
 };
 struct BlockW {
   ConvW c1, c2, c3, ds;
+  ConvW c3ds;  // conv3 and the downsample branch K-concatenated: [Cout, planes + Cin], bias = b3 + b_ds
   bool has_ds = false;
 };
 struct StageW {
@@ -133,6 +134,7 @@ struct GazeW {
 };
 
 constexpr int kFcSplit = 14;  // 196 k-blocks -> 14 per slice
+constexpr int kFfnSplit = 4;  // second FFN Linear (K = 2048): 32 k-blocks -> 8 per slice, 24 -> 96 tiles
 
 struct Interm {
   int kind = 0;  // 0 = fp32 dense, 1 = NHWC planes
@@ -175,6 +177,7 @@ class Engine {
     MCG_CUDA(cudaFuncSetAttribute(dynconv_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynMmaSmemBytes));
     MCG_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     MCG_CUDA(cudaFuncSetAttribute(linear256_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MCG_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
   }
 
   ~Engine() {
@@ -205,6 +208,7 @@ class Engine {
     else if (k == "time_kernels") time_kernels_ = v != 0;
     else if (k == "head_tensor_cores") { head_tc_ = v != 0; plans_.clear(); stem_plan_valid_ = false; drop_graph(); }
     else if (k == "fused_stem") { fused_stem_ = v != 0; drop_graph(); }
+    else if (k == "fuse_downsample") { fuse_ds_ = v != 0; drop_graph(); }
     else throw CudaError("check failed: unknown option " + k);
   }
 
@@ -416,7 +420,7 @@ class Engine {
         const std::string k = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
         if (!fused_tail_used(l, b)) acts.emplace_back(k + ".t1", &blk_act_[l][b].t1), acts.emplace_back(k + ".t2", &blk_act_[l][b].t2);
         else acts.emplace_back(k + ".t1", &blk_act_[l][b].t1);
-        if (blocks_[l][b].has_ds) acts.emplace_back(k + ".ds", &blk_act_[l][b].ds);
+        if (blocks_[l][b].has_ds && !(fuse_ds_ && trunk_terms() != 0)) acts.emplace_back(k + ".ds", &blk_act_[l][b].ds);
         acts.emplace_back(k, &blk_act_[l][b].out);
       }
     for (int i = 0; i < 4; ++i) acts.emplace_back("lat" + std::to_string(i), &lat_[i]);
@@ -572,6 +576,27 @@ class Engine {
     return cw;
   }
 
+  // [N, K1] and [N, K2] packed weights -> [N, K1 + K2] (the fp32 copies are on the device: read them back once)
+  ConvW concat_k(const ConvW& a, const ConvW& b) {
+    MCG_CHECK(a.g.N == b.g.N, "K-concatenation needs equal output channels");
+    const int N = a.g.N, K1 = a.g.K, K2 = b.g.K;
+    std::vector<float> wa(static_cast<size_t>(N) * K1), wb(static_cast<size_t>(N) * K2), ba(N), bb(N);
+    MCG_CUDA(cudaMemcpy(wa.data(), a.g.w_f32, wa.size() * 4, cudaMemcpyDeviceToHost));
+    MCG_CUDA(cudaMemcpy(wb.data(), b.g.w_f32, wb.size() * 4, cudaMemcpyDeviceToHost));
+    MCG_CUDA(cudaMemcpy(ba.data(), a.g.bias, N * 4, cudaMemcpyDeviceToHost));
+    MCG_CUDA(cudaMemcpy(bb.data(), b.g.bias, N * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> w(static_cast<size_t>(N) * (K1 + K2));
+    for (int n = 0; n < N; ++n) {
+      std::memcpy(&w[static_cast<size_t>(n) * (K1 + K2)], &wa[static_cast<size_t>(n) * K1], K1 * sizeof(float));
+      std::memcpy(&w[static_cast<size_t>(n) * (K1 + K2) + K1], &wb[static_cast<size_t>(n) * K2], K2 * sizeof(float));
+      ba[n] += bb[n];
+    }
+    ConvW c = a;
+    c.g = pack_gemm(w, N, K1 + K2, ba.data(), precision_ == MCG_PRECISION_FP16C8);
+    c.Cin = K1 + K2;
+    return c;
+  }
+
   GemmW pack_linear(const std::string& wkey, const std::string& bkey, int N, int K) {
     const float* w = need(wkey, static_cast<size_t>(N) * K).p;
     const float* b = bkey.empty() ? nullptr : need(bkey, N).p;
@@ -601,6 +626,7 @@ class Engine {
         bw.has_ds = has(p + ".downsample.0.weight");
         if (bw.has_ds)
           bw.ds = pack_conv(p + ".downsample.0.weight", p + ".downsample.1", "", planes[l] * 4, cin, 1, 1, stride, 0);
+        if (bw.has_ds) bw.c3ds = concat_k(bw.c3, bw.ds);
         blocks_[l].push_back(bw);
         cin = planes[l] * 4;
       }
@@ -786,6 +812,11 @@ class Engine {
     // split-fp16 staging for the head's tensor-core GEMM operands
     hq_.hi = arena_.alloc<__half>(Rr * 256);
     hq_.lo = arena_.alloc<__half>(Rr * 256);
+    hobj_.hi = arena_.alloc<__half>(Rr * 256);  // object features entering a stage (operand of the spatial in_proj)
+    hobj_.lo = arena_.alloc<__half>(Rr * 256);
+    hx1_.hi = arena_.alloc<__half>(Rr * 256);   // output of the spatial attention (operand of the temporal in_proj)
+    hx1_.lo = arena_.alloc<__half>(Rr * 256);
+    ffn_p_ = arena_.alloc<float>(Rr * 256 * kFfnSplit);
     hh_.hi = arena_.alloc<__half>(Rr * 2048);
     hh_.lo = arena_.alloc<__half>(Rr * 2048);
     hf_.hi = arena_.alloc<__half>(Rr * 12544);
@@ -832,7 +863,9 @@ class Engine {
     }
   }
   void gemm(const std::string& key, const Planes* A, const float* A_f32, const AGeom& geom, const GemmW& w,
-            long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0) {
+            long long M, const Epilogue& ep, cudaStream_t st, int terms, int k_split = 1, long long split_stride = 0,
+            const Planes* A2 = nullptr, const AGeom* geom2 = nullptr) {
+    MCG_CHECK(A2 == nullptr || terms != 0, "the K-concatenated form exists on the tcgen05 path only");
     const bool tensor = terms != 0 && A != nullptr && umma_supported(M, w.N, w.K, geom) &&
                         (terms == 1 || (terms == 3 && A->lo != nullptr) || (terms == 2 && A->lo8 != nullptr && A->hi8 != nullptr && w.w.hi8 != nullptr));
     if (tensor) {
@@ -845,7 +878,7 @@ class Engine {
         const int pair_mode = tune_pair >= 0 ? tune_pair : (terms == 2 ? 2 : 1);
         const bool big = M >= 2 * kBlockM * (num_sms_ / 2) && k_split == 1 && ep.out_f32 == nullptr;
         const int pair = (big && ((pair_mode == 1 && geom.kind == 1) || pair_mode == 2)) ? 1 : 0;
-        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, pair);
+        UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, pair, A2, geom2);
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -866,6 +899,7 @@ class Engine {
       // algorithmic work: the stem's K is zero-padded from 147 to 192
       umma_flops_ += 2.0 * static_cast<double>(M) * w.N * (key == "stem" ? 147 : w.K);
     } else {
+      MCG_CHECK(A2 == nullptr, "K-concatenated GEMM shape not supported by the tcgen05 kernel");
       SimtParams p;
       p.M = M;
       p.N = w.N;
@@ -886,8 +920,10 @@ class Engine {
   }
 
   // convolution over NHWC planes -> NHWC planes
+  // x2 / stride2: second input of a K-concatenated 1x1 convolution pair (conv3 + downsample branch), read with
+  // `stride2` on the same output grid
   void conv(const std::string& key, const Act& x, const ConvW& cw, const Act& y, bool relu, const Act* res,
-            int res_mode, cudaStream_t st) {
+            int res_mode, cudaStream_t st, const Act* x2 = nullptr, int stride2 = 1) {
     AGeom g;
     const bool plain = cw.R == 1 && cw.S == 1 && cw.stride == 1 && cw.pad == 0;
     g.kind = plain ? 0 : 1;
@@ -918,6 +954,21 @@ class Engine {
       ep.ldr = res->C;
       ep.P = y.H;
       ep.Q = y.W;
+    }
+    if (x2) {
+      AGeom g2;
+      g2.kind = stride2 == 1 ? 0 : 1;
+      g2.lda = x2->C;
+      g2.NB = x2->NB;
+      g2.H = x2->H;
+      g2.W = x2->W;
+      g2.C = x2->C;
+      g2.stride = stride2;
+      g2.P = y.H;
+      g2.Q = y.W;
+      g.C = x.C;
+      gemm(key, &x.pl, nullptr, g, cw.g, y.rows(), ep, st, trunk_terms(), 1, 0, &x2->pl, &g2);
+      return;
     }
     gemm(key, &x.pl, nullptr, g, cw.g, y.rows(), ep, st, trunk_terms());
   }
@@ -1041,13 +1092,23 @@ class Engine {
   }
   bool head_on_tc() const { return precision_ != MCG_PRECISION_SIMT && head_tc_; }
 
+  // second stage (w2 != null): y = LN_w2(res2 + act(LN_w(...)))
   void ln(const float* x, long long ldx, const float* res, long long ldres, const LnW& w, float* y, long long ldy,
           long long rows, bool relu, cudaStream_t st, int nsplit = 1, long long split_stride = 0,
-          const float* xbias = nullptr, const Planes* planes = nullptr) {
-    const int wpb = 8;
-    layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-        x, ldx, res, ldres, w.g, w.b, y, ldy, rows, w.C, relu ? 1 : 0, nsplit, split_stride, xbias,
-        planes ? planes->hi : nullptr, planes ? planes->lo : nullptr);
+          const float* xbias = nullptr, const Planes* planes = nullptr, const float* res2 = nullptr, long long ldres2 = 0,
+          const LnW* w2 = nullptr) {
+    const int wpb = 4;  // warps (rows) per block: 168 blocks for 672 rows
+    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+    MCG_CHECK((w.C == 256 || w.C == 64) && (w2 == nullptr || w2->C == w.C), "LayerNorm width must be 64 or 256");
+    auto launch = [&](auto kernel) {
+      kernel<<<grid, wpb * 32, 0, st>>>(x, ldx, res, ldres, w.g, w.b, y, ldy, rows, relu ? 1 : 0, nsplit, split_stride, xbias,
+                                       planes ? planes->hi : nullptr, planes ? planes->lo : nullptr, res2, ldres2,
+                                       w2 ? w2->g : nullptr, w2 ? w2->b : nullptr);
+    };
+    if (w.C == 256)
+      launch(layernorm_kernel<8>);
+    else
+      launch(layernorm_kernel<2>);
     MCG_CUDA(cudaGetLastError());
     count("layernorm_kernel");
   }
@@ -1143,11 +1204,17 @@ class Engine {
         conv(k + "c1", *x, bw.c1, ba.t1, true, nullptr, RES_NONE, st);
         conv(k + "c2", ba.t1, bw.c2, ba.t2, true, nullptr, RES_NONE, st);
         const Act* idn = x;
-        if (bw.has_ds) {
-          conv(k + "ds", *x, bw.ds, ba.ds, false, nullptr, RES_NONE, st);
-          idn = &ba.ds;
+        if (bw.has_ds && fuse_ds_ && trunk_terms() != 0) {
+          // conv3 and the downsample branch as ONE GEMM over the concatenated K (t2 channels, then x channels read with
+          // the block's stride): out = relu(W3 t2 + Wds x + b3 + bds) (resnet.py:286-295)
+          conv(k + "c3ds", ba.t2, bw.c3ds, ba.out, true, nullptr, RES_NONE, st, x, bw.ds.stride);
+        } else {
+          if (bw.has_ds) {
+            conv(k + "ds", *x, bw.ds, ba.ds, false, nullptr, RES_NONE, st);
+            idn = &ba.ds;
+          }
+          conv(k + "c3", ba.t2, bw.c3, ba.out, true, idn, RES_SAME, st);
         }
-        conv(k + "c3", ba.t2, bw.c3, ba.out, true, idn, RES_SAME, st);
         x = &ba.out;
         reg_act("layer" + std::to_string(l + 1) + "." + std::to_string(b), ba.out);
       }
@@ -1166,7 +1233,9 @@ class Engine {
     const int R = NB * 3;
     float* img_hw = d_meta_;
     float* scale = d_meta_ + NB * 2;
-    init_proposals_kernel<<<NB, 256, 0, st>>>(init_boxes_, init_feats_, img_hw, NB, boxes_[0], obj_[0]);
+    const bool tc = head_on_tc();
+    init_proposals_kernel<<<NB, 256, 0, st>>>(init_boxes_, init_feats_, img_hw, NB, boxes_[0], obj_[0], tc ? hobj_.hi : nullptr,
+                                              tc ? hobj_.lo : nullptr);
     MCG_CUDA(cudaGetLastError());
     count("init_proposals_kernel");
     FpnLevels fl;
@@ -1178,7 +1247,6 @@ class Engine {
       fl.W[i] = fpn_[i].W;
     }
     int cur = 0;
-    const bool tc = head_on_tc();
     for (int s = 0; s < 4; ++s) {
       const StageW& sw = stage_[s];
       const std::string sk = "s" + std::to_string(s);
@@ -1206,14 +1274,17 @@ class Engine {
       const float* xin = obj_in;
       float* xout[2] = {xa_, xb_};
       for (int mode = 0; mode < 2; ++mode) {
-        linear(xin, 256, sw.in_proj, R, qkv_, 768, false, nullptr, 0, st);
+        // in_proj (M = 3 frames rows, N = 768, K = 256) on the tcgen05 GEMM: its operand planes come from the kernel
+        // that produced xin (init proposals / the previous stage's ffn_norm / the spatial pass's out_proj + LN)
+        linear_tc(sk + (mode == 0 ? "inproj_s" : "inproj_t"), xin, 256, mode == 0 ? hobj_ : hx1_, tc, sw.in_proj, R, qkv_,
+                  false, nullptr, st);
         attention_kernel<<<(R * 8 * 32 + 255) / 256, 256, 0, st>>>(qkv_, att_, R, T, mode);
         MCG_CUDA(cudaGetLastError());
         count("attention_kernel");
         // out_proj + identity (mmcv MHA) + attention_norm in one kernel; the temporal pass also emits the
         // split-fp16 planes the dynamic_layer GEMM reads
         linear_ln(att_, 256, sw.out_proj, sw.attn_norm, R, xout[mode], 256, false, xin, 256, st,
-                  (mode == 1 && tc) ? &hq_ : nullptr);
+                  tc ? (mode == 1 ? &hq_ : &hx1_) : nullptr);
         xin = xout[mode];
       }
       const float* attn = xb_;
@@ -1247,43 +1318,71 @@ class Engine {
         // reduced (and the bias added) inside the fc_norm LayerNorm kernel
         const int ks = tc ? kFcSplit : 1;
         linear_tc(sk + "fc", dynf_, 12544, hf_, tc, sw.fc, R, fcp_, false, nullptr, st, ks);
-        ln(fcp_, 256, nullptr, 0, sw.fc_norm, fc_, 256, R, true, st, ks, static_cast<long long>(R) * 256,
-           ks > 1 ? sw.fc.bias : nullptr);
+        // fc_norm + ReLU (transformer.py:1160-1162), then obj = LN(attn + iic) (gaze_stqi_head.py:175-176): one kernel
+        ln(fcp_, 256, nullptr, 0, sw.fc_norm, xa_, 256, R, true, st, ks, static_cast<long long>(R) * 256,
+           ks > 1 ? sw.fc.bias : nullptr, tc ? &hq_ : nullptr, attn, 256, &sw.iic_norm);
       }
-      ln(attn, 256, fc_, 256, sw.iic_norm, xa_, 256, R, false, st, 1, 0, nullptr, tc ? &hq_ : nullptr);  // obj = LN(attn + iic)
       // FFN with identity (gaze_stqi_head.py:179): the hidden activations stay split-fp16 planes
       linear_tc(sk + "ffn1", xa_, 256, hq_, tc, sw.ffn1, R, ffn_h_, true, nullptr, st, 1, tc ? &hh_ : nullptr);
-      linear_tc(sk + "ffn2", ffn_h_, 2048, hh_, tc, sw.ffn2, R, xc_, false, xa_, st);
-      ln(xc_, 256, nullptr, 0, sw.ffn_norm, obj_out, 256, R, false, st);
+      {
+        // 256 x 2048 over 3 frames rows is 24 tiles with 32 k-blocks each: split K, the ffn_norm LayerNorm reduces the
+        // partial sums and adds bias + identity (gaze_stqi_head.py:179); it also emits the next stage's in_proj operand
+        const int ks = tc ? kFfnSplit : 1;
+        linear_tc(sk + "ffn2", ffn_h_, 2048, hh_, tc, sw.ffn2, R, ks > 1 ? ffn_p_ : xc_, false, ks > 1 ? nullptr : xa_, st, ks);
+        if (ks > 1)
+          ln(ffn_p_, 256, xa_, 256, sw.ffn_norm, obj_out, 256, R, false, st, ks, static_cast<long long>(R) * 256, sw.ffn2.bias,
+             &hobj_);
+        else
+          ln(xc_, 256, nullptr, 0, sw.ffn_norm, obj_out, 256, R, false, st);
+      }
       // cls / reg towers + per-clue heads (gaze_stqi_head.py:185-201); the cls tower and the first reg layer
       // read the same input and run as one grouped launch, as do the three per-clue heads of each kind
       // The classification branch only feeds the detection scores, and only the last stage's reach the output
       // (multiclue_gaze_roi_head.py:351-366): stages 0-2 skip it unless their intermediates are being recorded.
       const bool need_cls = s == 3 || (keep_stage_interm_ && !graph_mode_);
       {
-        const float* xs[2] = {obj_out, obj_out};
-        const GemmW* ws[2] = {&sw.reg_fc[0], &sw.cls_fc};
-        const LnW* ns[2] = {&sw.reg_ln[0], &sw.cls_ln};
-        float* ys[2] = {t256b_, t256a_};
-        linear_ln_grouped(need_cls ? 2 : 1, xs, 256, ws, ns, R, ys, 256, true, nullptr, 0, st);
+        // one launch: chain 0 = reg tower (3 x Linear + LN + ReLU) -> per-clue fc_reg -> delta2bbox, chain 1 = cls
+        // tower (1 layer) -> per-clue fc_cls
+        ChainGroups cg = {};
+        ChainArgs& r = cg.g[0];
+        r.x = obj_out;
+        r.ldx = 256;
+        r.n_layers = 3;
+        for (int j = 0; j < 3; ++j) {
+          MCG_CHECK(sw.reg_fc[j].w_t != nullptr && sw.reg_fc[j].bias == nullptr, "reg tower layout");
+          r.wt[j] = sw.reg_fc[j].w_t;
+          r.gamma[j] = sw.reg_ln[j].g;
+          r.beta[j] = sw.reg_ln[j].b;
+          r.fw[j] = sw.fc_reg[j].w_f32;
+          r.fb[j] = sw.fc_reg[j].bias;
+        }
+        r.n_classes = 3;
+        r.nout = 4;
+        r.y = delta_;
+        r.ldy = 4;
+        r.boxes_in = boxes_in;
+        r.boxes_out = boxes_out;
+        ChainArgs& c = cg.g[1];
+        c.x = obj_out;
+        c.ldx = 256;
+        c.n_layers = 1;
+        MCG_CHECK(sw.cls_fc.w_t != nullptr && sw.cls_fc.bias == nullptr, "cls tower layout");
+        c.wt[0] = sw.cls_fc.w_t;
+        c.gamma[0] = sw.cls_ln.g;
+        c.beta[0] = sw.cls_ln.b;
+        for (int j = 0; j < 3; ++j) {
+          c.fw[j] = sw.fc_cls[j].w_f32;
+          c.fb[j] = sw.fc_cls[j].bias;
+        }
+        c.n_classes = 3;
+        c.nout = 1;
+        c.y = cls_logit_;
+        c.ldy = 1;
+        dim3 grid(static_cast<unsigned>((R + kSlRows - 1) / kSlRows), need_cls ? 2 : 1);
+        mlp_chain_kernel<<<grid, 1024, kChainSmemBytes, st>>>(cg, R);
+        MCG_CUDA(cudaGetLastError());
+        count("mlp_chain_kernel");
       }
-      if (need_cls) {
-        const float* xs[3] = {t256a_, t256a_ + 256, t256a_ + 512};
-        const GemmW* ws[3] = {&sw.fc_cls[0], &sw.fc_cls[1], &sw.fc_cls[2]};
-        float* ys[3] = {cls_logit_, cls_logit_ + 1, cls_logit_ + 2};
-        linear_grouped(3, xs, 768, ws, NB, ys, 3, false, nullptr, 0, st);
-      }
-      linear_ln(t256b_, 256, sw.reg_fc[1], sw.reg_ln[1], R, xc_, 256, true, nullptr, 0, st);
-      linear_ln(xc_, 256, sw.reg_fc[2], sw.reg_ln[2], R, t256b_, 256, true, nullptr, 0, st);
-      {
-        const float* xs[3] = {t256b_, t256b_ + 256, t256b_ + 512};
-        const GemmW* ws[3] = {&sw.fc_reg[0], &sw.fc_reg[1], &sw.fc_reg[2]};
-        float* ys[3] = {delta_, delta_ + 4, delta_ + 8};
-        linear_grouped(3, xs, 768, ws, NB, ys, 12, false, nullptr, 0, st);
-      }
-      box_decode_kernel<<<(R + 127) / 128, 128, 0, st>>>(boxes_in, delta_, R, boxes_out);
-      MCG_CUDA(cudaGetLastError());
-      count("box_decode_kernel");
       if (keep_stage_interm_ && !graph_mode_) {
         // head buffers are reused by every stage: snapshot them for per-op parity tests
         const std::string nm = "stage" + std::to_string(s);
@@ -1304,41 +1403,37 @@ class Engine {
     reg_f32("boxes", boxes_[cur], NB, 3, 4);
     reg_f32("cls", cls_logit_, NB, 3);
     // ---- gaze head on the last stage's object features (gaze_head.py:138-202)
-    // the 3 clues x {gaze, confidence} branches are six independent tower chains: three grouped launches
+    // the 3 clues x {gaze, confidence} branches are six independent tower chains (2 x Linear + LN + ReLU -> fc): one launch
     const float* obj = obj_[cur];
     {
-      const float* x0[6];
-      const float* x1[6];
-      const float* x2[6];
-      float* y0[6];
-      float* y1[6];
-      float* y2[6];
-      const GemmW* w0[6];
-      const GemmW* w1[6];
-      const GemmW* w2[6];
-      const LnW* n0[6];
-      const LnW* n1[6];
+      ChainGroups cg = {};
       for (int c = 0; c < 3; ++c) {
         for (int branch = 0; branch < 2; ++branch) {
-          const int g = c * 2 + branch;
+          ChainArgs& a = cg.g[c * 2 + branch];
           const GemmW* tw = branch == 0 ? gaze_.tower[c] : gaze_.ctower[c];
           const LnW* tl = branch == 0 ? gaze_.tower_ln[c] : gaze_.ctower_ln[c];
-          x0[g] = obj + c * 256;
-          y0[g] = gz_a_ + static_cast<size_t>(g) * NB * 256;
-          x1[g] = y0[g];
-          y1[g] = gz_b_ + static_cast<size_t>(g) * NB * 256;
-          x2[g] = y1[g];
-          y2[g] = (branch == 0 ? gvec_ : conf_) + static_cast<size_t>(c) * NB * 3;
-          w0[g] = &tw[0];
-          w1[g] = &tw[1];
-          n0[g] = &tl[0];
-          n1[g] = &tl[1];
-          w2[g] = branch == 0 ? &gaze_.fc[c] : &gaze_.fc_conf[c];
+          const GemmW& fc = branch == 0 ? gaze_.fc[c] : gaze_.fc_conf[c];
+          a.x = obj + c * 256;   // rows of clue c: [NB] rows with stride 768
+          a.ldx = 768;
+          a.n_layers = 2;
+          for (int j = 0; j < 2; ++j) {
+            MCG_CHECK(tw[j].w_t != nullptr && tw[j].bias == nullptr, "gaze tower layout");
+            a.wt[j] = tw[j].w_t;
+            a.gamma[j] = tl[j].g;
+            a.beta[j] = tl[j].b;
+          }
+          a.n_classes = 1;
+          a.fw[0] = fc.w_f32;
+          a.fb[0] = fc.bias;
+          a.nout = 3;
+          a.y = (branch == 0 ? gvec_ : conf_) + static_cast<size_t>(c) * NB * 3;
+          a.ldy = 3;
         }
       }
-      linear_ln_grouped(6, x0, 768, w0, n0, NB, y0, 256, true, nullptr, 0, st);
-      linear_ln_grouped(6, x1, 256, w1, n1, NB, y1, 256, true, nullptr, 0, st);
-      linear_grouped(6, x2, 256, w2, NB, y2, 3, false, nullptr, 0, st);
+      dim3 grid(static_cast<unsigned>((NB + kSlRows - 1) / kSlRows), 6);
+      mlp_chain_kernel<<<grid, 1024, kChainSmemBytes, st>>>(cg, NB);
+      MCG_CUDA(cudaGetLastError());
+      count("mlp_chain_kernel");
     }
     finalize_kernel<<<(NB + 127) / 128, 128, 0, st>>>(gvec_, conf_, gaze_.wg, gaze_.bg, cls_logit_, boxes_[cur],
                                                       has_scale_ ? scale : nullptr, NB, out_gaze, out_boxes, out_scores);
@@ -1352,6 +1447,7 @@ class Engine {
   int num_sms_ = 148;
   bool head_tc_ = true;
   bool fused_stem_ = true;
+  bool fuse_ds_ = true;  // conv3 + downsample branch of a layer's first bottleneck as one K-concatenated GEMM
   StemFusedPlan stem_plan_;
   bool stem_plan_valid_ = false;
   bool keep_stage_interm_ = false;
@@ -1391,7 +1487,8 @@ class Engine {
         *roi_ = nullptr, *dynf_ = nullptr, *fc_ = nullptr, *fcp_ = nullptr, *ffn_h_ = nullptr, *t256a_ = nullptr, *t256b_ = nullptr,
         *cls_logit_ = nullptr, *delta_ = nullptr, *gz_a_ = nullptr, *gz_b_ = nullptr, *gvec_ = nullptr,
         *conf_ = nullptr, *d_meta_ = nullptr;
-  Planes hq_, hh_, hf_, roih_;
+  Planes hq_, hh_, hf_, roih_, hobj_, hx1_;
+  float* ffn_p_ = nullptr;  // split-K partial sums of the second FFN Linear
   bool dyn_mma_ = false;
   static constexpr int kMetaSlots = 4;
   float* pin_meta_ = nullptr;                 // kMetaSlots x [NB * 6] pinned staging of the per-call metadata

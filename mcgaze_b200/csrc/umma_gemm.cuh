@@ -88,7 +88,12 @@ struct UmmaParams {
   int res_fmt = 0;  // planes of the residual: 0 hi, 1 hi + fp16 lo, 2 hi + e4m3 lo8
   int dbg = 0;      // attribution experiments only (env MCG_DEBUG_FLAGS): 1 no stores, 2 no epilogue math,
                     // 4 no A loads, 8 no W loads, 16 no MMA issue, 32 no residual loads.  Results are garbage.
+  // K-concatenated second A operand: k-blocks [kb2_begin, num_kb) read the tensor described by `a2` (maps a2_*)
+  // instead of `a`; W is the [N, K1 + K2] concatenation.  D = A1 W1^T + A2 W2^T in one accumulator: a bottleneck's
+  // conv3 and its downsample branch (resnet.py:286-295) as ONE GEMM, the identity never round-trips through HBM.
+  int kb2_begin = 0;  // 0 = single A operand
   AGeom a;
+  AGeom a2;
   Epilogue ep;
 };
 
@@ -96,6 +101,7 @@ struct UmmaParams {
 struct UmmaMaps {
   CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, r_hi, r_lo;
   CUtensorMap a_hi8, w_hi8, o_hi8;
+  CUtensorMap a2_hi, a2_lo, a2_hi8;  // second A operand (UmmaParams::kb2_begin); a2_lo = fp16 lo or e4m3 lo8 like a_lo
 };
 
 // shared-memory bytes of one pipeline stage / one epilogue staging set for a precision mode
@@ -207,6 +213,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     }
     if (p.out_tma) ptx::prefetch_tmap(&tm.o_hi);
     if (p.res_tma) ptx::prefetch_tmap(&tm.r_hi);
+    if (p.kb2_begin) {
+      ptx::prefetch_tmap(&tm.a2_hi);
+      if (kTerms != 1) ptx::prefetch_tmap(&tm.a2_lo);
+      if (kTerms == 2) ptx::prefetch_tmap(&tm.a2_hi8);
+    }
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
@@ -271,6 +282,17 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         base_h = p0 * p.a.stride - p.a.pad;
         base_w = q0 * p.a.stride - p.a.pad;
       }
+      // second A operand (1x1 convolution, plain or strided im2col view on the same output grid)
+      int img_n2 = 0, base_h2 = 0, base_w2 = 0;
+      if (p.kb2_begin && p.a2.kind == 1) {
+        const long long pq = static_cast<long long>(p.a2.P) * p.a2.Q;
+        img_n2 = static_cast<int>(m0 / pq);
+        const int rem = static_cast<int>(m0 - img_n2 * pq);
+        const int p0 = rem / p.a2.Q;
+        const int q0 = rem - p0 * p.a2.Q;
+        base_h2 = p0 * p.a2.stride - p.a2.pad;
+        base_w2 = q0 * p.a2.stride - p.a2.pad;
+      }
       for (int pass = 0; pass < passes; ++pass) {
         const bool f8 = kTerms == 2 && pass == 0;
         int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
@@ -325,6 +347,18 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
               const uint32_t sA1 = s + (f8 ? off_a_hi8 : kATileBytes);
               const int kbk = kb + sub;
               if (kDbg && (p.dbg & 4)) {
+              } else if (p.kb2_begin && kbk >= p.kb2_begin) {
+                // k-blocks of the second A operand (a 1x1 convolution: one filter tap, channel block kbk - kb2_begin)
+                const CUtensorMap* mb0 = f8 ? &tm.a2_lo : &tm.a2_hi;
+                const CUtensorMap* mb1 = f8 ? &tm.a2_hi8 : &tm.a2_lo;
+                const int c0 = (kbk - p.kb2_begin) * kBlockK;
+                if (p.a2.kind == 1) {
+                  tma_im2col(s, mb0, fb, c0, base_w2, base_h2, img_n2, 0, 0);
+                  if (two_a) tma_im2col(sA1, mb1, fb, c0, base_w2, base_h2, img_n2, 0, 0);
+                } else {
+                  tma_2d(s, mb0, fb, c0, static_cast<int>(m0));
+                  if (two_a) tma_2d(sA1, mb1, fb, c0, static_cast<int>(m0));
+                }
               } else if (p.a.kind == 1) {
                 tma_im2col(s, ma0, fb, cb2 * kBlockK, base_w, base_h, img_n, static_cast<uint16_t>(tsx2),
                            static_cast<uint16_t>(tr2));
@@ -919,10 +953,19 @@ inline int tune_env(const char* name) {
 // A planes: for kind 0 the [M,K] matrix, for kind 1 the NHWC activation.  W planes: [N,K].
 // terms == 2 (fp16c8): A = hi + lo8 + hi8, W = hi + hi8 + lo8 (scales: common.cuh).
 // The planes the epilogue writes / the residual carries follow from the pointers set in `ep`.
+// Optional second A operand (A2, a2): K = K1 + K2 with K1 = K - a2 channels; see UmmaParams::kb2_begin.
 inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, long long M, int N, int K,
                                const Epilogue& ep, int num_sms, int force_block_n = 0, int k_split = 1,
-                               long long split_stride = 0, int pair = 0) {
+                               long long split_stride = 0, int pair = 0, const Planes* A2 = nullptr,
+                               const AGeom* a2 = nullptr) {
   MCG_CHECK(umma_supported(M, N, K, a), "shape not supported by the tcgen05 GEMM");
+  if (A2) {
+    MCG_CHECK(a2 != nullptr && a2->R == 1 && a2->S == 1 && a2->pad == 0 && a2->C % kBlockK == 0 && a2->C < K && k_split == 1 &&
+                  a.kind == 0,
+              "the K-concatenated second operand must be a 1x1 convolution beside a plain first operand");
+    MCG_CHECK(terms != 3 || A2->lo, "3-term GEMM needs lo planes");
+    MCG_CHECK(terms != 2 || (A2->lo8 && A2->hi8), "fp16c8 GEMM needs the e4m3 planes of the second operand");
+  }
   MCG_CHECK(!pair || k_split == 1, "CTA-pair tiles do not combine with split-K");
   MCG_CHECK(terms >= 1 && terms <= 3, "the tcgen05 GEMM runs 1, 2 (fp16 + e4m3 corrections) or 3 MMA terms per k-step");
   MCG_CHECK(terms != 3 || (A.lo && W.lo), "3-term GEMM needs lo planes");
@@ -1035,6 +1078,11 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   p.a = a;
   p.cblocks = a.kind == 1 ? a.C / kBlockK : 1;
   if (a.kind == 1) MCG_CHECK(K == a.R * a.S * a.C, "im2col K mismatch");
+  if (A2) {
+    p.a2 = *a2;
+    p.kb2_begin = (K - a2->C) / kBlockK;
+    MCG_CHECK(p.kb2_begin >= 1, "first operand needs at least one k-block");
+  }
   p.ep = ep;
   if (k_split > 1) {
     MCG_CHECK(ep.out_f32 != nullptr && ep.res_mode == RES_NONE && !ep.relu && k_split <= p.num_kb && terms != 2,
@@ -1052,12 +1100,13 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     pl.grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   }
   UmmaMaps& tm = pl.tm;
+  const int K1 = A2 ? K - a2->C : K;  // columns of the first A operand
   if (a.kind == 1) {
     tm.a_hi = make_tmap_im2col(A.hi, a);
     tm.a_lo = terms == 3 ? make_tmap_im2col(A.lo, a) : tm.a_hi;
   } else {
-    tm.a_hi = make_tmap_2d(A.hi, M, K, a.lda, kBlockM);
-    tm.a_lo = terms == 3 ? make_tmap_2d(A.lo, M, K, a.lda, kBlockM) : tm.a_hi;
+    tm.a_hi = make_tmap_2d(A.hi, M, K1, a.lda, kBlockM);
+    tm.a_lo = terms == 3 ? make_tmap_2d(A.lo, M, K1, a.lda, kBlockM) : tm.a_hi;
   }
   tm.w_hi = make_tmap_2d(W.hi, N, K, K, w_rows);
   tm.w_lo = terms == 3 ? make_tmap_2d(W.lo, N, K, K, w_rows) : tm.w_hi;
@@ -1065,10 +1114,29 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   tm.a_hi8 = tm.w_hi8 = tm.o_hi8 = tm.w_hi;
   const CUtensorMapSwizzle sw64 = CU_TENSOR_MAP_SWIZZLE_64B;
   if (terms == 2) {
-    tm.a_lo = a.kind == 1 ? make_tmap_im2col_u8(A.lo8, a) : make_tmap_2d_u8(A.lo8, M, K, a.lda, kBlockM, kBlockK, sw64);
-    tm.a_hi8 = a.kind == 1 ? make_tmap_im2col_u8(A.hi8, a) : make_tmap_2d_u8(A.hi8, M, K, a.lda, kBlockM, kBlockK, sw64);
+    tm.a_lo = a.kind == 1 ? make_tmap_im2col_u8(A.lo8, a) : make_tmap_2d_u8(A.lo8, M, K1, a.lda, kBlockM, kBlockK, sw64);
+    tm.a_hi8 = a.kind == 1 ? make_tmap_im2col_u8(A.hi8, a) : make_tmap_2d_u8(A.hi8, M, K1, a.lda, kBlockM, kBlockK, sw64);
     tm.w_hi8 = make_tmap_2d_u8(W.hi8, N, K, K, w_rows, kBlockK, sw64);
     tm.w_lo = make_tmap_2d_u8(W.lo8, N, K, K, w_rows, kBlockK, sw64);
+  }
+  tm.a2_hi = tm.a2_lo = tm.a2_hi8 = tm.a_hi;
+  if (A2) {
+    const int C2 = a2->C;
+    if (a2->kind == 1) {
+      tm.a2_hi = make_tmap_im2col(A2->hi, *a2);
+      if (terms == 3) tm.a2_lo = make_tmap_im2col(A2->lo, *a2);
+      if (terms == 2) {
+        tm.a2_lo = make_tmap_im2col_u8(A2->lo8, *a2);
+        tm.a2_hi8 = make_tmap_im2col_u8(A2->hi8, *a2);
+      }
+    } else {
+      tm.a2_hi = make_tmap_2d(A2->hi, M, C2, a2->lda, kBlockM);
+      if (terms == 3) tm.a2_lo = make_tmap_2d(A2->lo, M, C2, a2->lda, kBlockM);
+      if (terms == 2) {
+        tm.a2_lo = make_tmap_2d_u8(A2->lo8, M, C2, a2->lda, kBlockM, kBlockK, sw64);
+        tm.a2_hi8 = make_tmap_2d_u8(A2->hi8, M, C2, a2->lda, kBlockM, kBlockK, sw64);
+      }
+    }
   }
   if (p.out_tma) {
     tm.o_hi = make_tmap_2d(ep.out_hi, M, N, ep.ldo, kBlockM, kEpiChunk, sw64);

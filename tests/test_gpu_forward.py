@@ -387,3 +387,31 @@ def test_fp16c8_operand_window_stress(synthetic_sd, what):
             assert yaw_pitch_err(out['gaze'][:, i].cpu(), ref[k]) < 1e-3, (what, k)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3', 'fp16'])
+def test_k_concatenated_downsample_matches_separate_branch(engines, synthetic_sd, precision):
+    """Default schedule: conv3 + downsample branch of layer{1-4}.0 as ONE GEMM over the concatenated K
+    (out = relu(W3 t2 + Wds x + b3 + bds), resnet.py:286-295).  Against the literal form (option fuse_downsample = 0:
+    separate downsample convolution, conv3 adds it as residual) and against the oracle's block outputs."""
+    T = 4
+    img = O.make_clip(77, T)
+    taps = {}
+    O.forward(synthetic_sd, img, clip_length=T, hk=O.Hooks(tap=lambda n, t: taps.__setitem__(n, t.clone())))
+    eng = engines(precision)
+    names = ['layer1.0', 'layer2.0', 'layer3.0', 'layer4.0', 'layer4.2']
+    tol = {'fp16x3': 1e-4, 'fp16c8': 4e-4, 'fp16': 5e-3}[precision]
+    try:
+        fused = eng.forward(img.cuda(), clip_length=T)
+        f = {n: eng.intermediate(n).cpu() for n in names}
+        eng.set_option('fuse_downsample', 0)
+        plain = eng.forward(img.cuda(), clip_length=T)
+        p = {n: eng.intermediate(n).cpu() for n in names}
+    finally:
+        eng.set_option('fuse_downsample', 1)
+    for n in names:
+        if n in taps:
+            assert (f[n] - taps[n]).abs().max() < tol * taps[n].abs().max(), n
+        assert (f[n] - p[n]).abs().max() < tol * p[n].abs().max(), n
+    if precision != 'fp16':
+        assert yaw_pitch_err(fused['gaze'][:, 0].cpu(), plain['gaze'][:, 0].cpu()) < 2e-4
