@@ -876,7 +876,11 @@ class Engine {
         // (measured, profiles/: fp16c8 gains on both, fp16x3 / fp16 only on the 3x3 layers)
         static const int tune_pair = std::getenv("MCG_TUNE_PAIR") ? std::atoi(std::getenv("MCG_TUNE_PAIR")) : -1;
         const int pair_mode = tune_pair >= 0 ? tune_pair : (terms == 2 ? 2 : 1);
-        const bool big = M >= 2 * kBlockM * (num_sms_ / 2) && k_split == 1 && ep.out_f32 == nullptr;
+        // ... for layers with at least `pair_min` 256-row tiles (env MCG_TUNE_PAIR_MIN_MTILES).  Measured (round 2, same
+        // box A/B): 74 (one per SM pair) 9.90 ms per step, 40 (layer4 at 32 clips: 43 tiles) 9.82, 20 9.89
+        static const int tune_pair_min = std::getenv("MCG_TUNE_PAIR_MIN_MTILES") ? std::atoi(std::getenv("MCG_TUNE_PAIR_MIN_MTILES")) : 0;
+        const long long pair_min = tune_pair_min > 0 ? tune_pair_min : (num_sms_ * 40) / 148;
+        const bool big = M >= 2 * kBlockM * pair_min && k_split == 1 && ep.out_f32 == nullptr;
         const int pair = (big && ((pair_mode == 1 && geom.kind == 1) || pair_mode == 2)) ? 1 : 0;
         UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, pair, A2, geom2);
         it = plans_.emplace(key, pl).first;
