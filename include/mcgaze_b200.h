@@ -168,15 +168,35 @@ typedef struct {
 int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const float* std, int to_rgb, float* out,
                    int Hp, int Wp, void* stream);
 
+/* ---- overlap merge ------------------------------------------------------------------
+ * Replaces the clip-to-video merge of tools/test_gaze360_gaze.py:129-201 for per-clip results that are on the device:
+ * windows of clip_len frames every `stride` frames, the last one right-aligned (:73-86); frames a clip adds are copied
+ * with their boxes zeroed where that clip's score < 0.5 (:135-141), frames it shares with earlier clips are averaged
+ * with the running values - coordinates zeroed when either score < 0.5 (:170-174), scores and gaze vectors averaged
+ * without re-normalisation (:182-183).
+ *   rows         DEVICE fp32 [n_clips, clip_len, 27]  per clip and frame: boxes [3,4] xyxy, scores [3], gaze [4,3]
+ *                (fused, face, eyes, head); clips of a video are consecutive, short clips are padded
+ *   clip_start   DEVICE int32 [n_videos + 1]   first clip of each video
+ *   frame_start  DEVICE int32 [n_videos + 1]   first frame of each video in the outputs
+ *   det          DEVICE fp32 [F, 3, 5]  (x1, y1, x2, y2, score)      gaze  DEVICE fp32 [F, 4, 3]
+ * Asynchronous on `stream`; needs no engine handle. */
+int mcg_merge_clips(const float* rows, const int32_t* clip_start, const int32_t* frame_start, int n_videos, int clip_len,
+                    int stride, float* det, float* gaze, void* stream);
+
 /* ---- scorer ---------------------------------------------------------------------
  * Replaces gaze_error of tools/calculate_mae_gaze360.py (:110-188: smooth_filter :16-29 with alpha 0.6,
- * compute_angular_error :77-94, compute_yaw_angular :69-74) for per-frame gaze vectors that are on the device.
+ * compute_angular_error :77-94, compute_yaw_angular :69-74) and of tools/calculate_mae_l2cs.py (:96-182) for
+ * per-frame gaze vectors that are on the device.
  *   pred, gt     DEVICE fp32 [F, 3]   predicted / ground-truth vectors, the frames of all videos concatenated
  *   video_start  DEVICE int32 [n_videos + 1]   first frame of each video, video_start[n_videos] = F
+ *   variant      MCG_SCORER_GAZE360: front-20 = |yaw(gt)| <= 20 deg; MCG_SCORER_L2CS: and |pitch(gt)| <= 20 deg
+ *                (calculate_mae_l2cs.py:139; its ground truth sits at annotations[3 * video], :110 - the caller's job)
  *   out          DEVICE double [6]    {sum, frames} for 360, front-180 (|yaw(gt)| <= 90 deg), front-20;
  *                                     sum = per-video mean angle in degrees x frames of that video; MAE = sum / frames
+ *                                     (sums of several calls / ranks add up: one all-reduce gives the sharded MAE)
  * Asynchronous on `stream`; needs no engine handle. */
-int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_start, int n_videos, double* out,
+enum { MCG_SCORER_GAZE360 = 0, MCG_SCORER_L2CS = 1 };
+int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_start, int n_videos, int variant, double* out,
                    void* stream);
 
 const char* mcg_last_error(void);

@@ -23,8 +23,11 @@ def load_state_dict(module, state_dict: Dict[str, Any], strict: bool = False, lo
     report = {'missing': sorted(k for k in own - given if 'num_batches_tracked' not in k),
               'unexpected': sorted(given - own)}
     module.load_state_dict(state_dict, strict=False)
+    own_report = getattr(module, 'load_report', None)
+    if isinstance(own_report, dict):      # the backend detector knows which reference keys its engine ignores
+        report = {'missing': sorted(own_report['missing']), 'unexpected': sorted(own_report['unexpected'])}
     if strict and (report['missing'] or report['unexpected']):
-        raise RuntimeError(f'state_dict mismatch: {report}')
+        raise RuntimeError(f"state_dict mismatch: missing {report['missing'][:8]}, unexpected {report['unexpected'][:8]}")
     if logger is not None and (report['missing'] or report['unexpected']):
         logger.warning('checkpoint/model key mismatch: %s', report)
     return report

@@ -52,6 +52,7 @@ class Arena {
     off_ = 0;
     return n;
   }
+  // grow-only; reserve(0) just rewinds
   void reserve(size_t bytes) {
     if (bytes > cap_) {
       block_.reset();
@@ -60,6 +61,7 @@ class Arena {
     }
     off_ = 0;
   }
+  size_t capacity() const { return cap_; }
   template <typename T>
   T* alloc(size_t count) {
     const size_t bytes = (count * sizeof(T) + 1023) & ~static_cast<size_t>(1023);
@@ -206,7 +208,7 @@ class Engine {
   void set_option(const std::string& k, int v) {
     if (k == "keep_intermediates") keep_stage_interm_ = v != 0;
     else if (k == "time_kernels") time_kernels_ = v != 0;
-    else if (k == "head_tensor_cores") { head_tc_ = v != 0; plans_.clear(); stem_plan_valid_ = false; drop_graph(); }
+    else if (k == "head_tensor_cores") { head_tc_ = v != 0; drop_graph(true); }
     else if (k == "fused_stem") { fused_stem_ = v != 0; drop_graph(); }
     else if (k == "fuse_downsample") { fuse_ds_ = v != 0; drop_graph(); }
     else throw CudaError("check failed: unknown option " + k);
@@ -735,25 +737,58 @@ class Engine {
     return pl;
   }
 
+  // Shape change (tail batch of an evaluation run, another canvas): the arena only ever grows, so going back and
+  // forth between shapes re-uses the memory AND the launch plans / captured graphs of a shape seen before (same
+  // layout order -> same addresses).  The device is synchronised only when the arena has to be re-allocated; otherwise
+  // everything already queued keeps its pointers into the same allocation and the stream order keeps it safe.
   void ensure_workspace(int NB, int T, int H, int W) {
     if (NB == ws_NB_ && T == ws_T_ && H == ws_H_ && W == ws_W_) return;
-    MCG_CUDA(cudaDeviceSynchronize());
-    drop_graph();
+    if (ws_NB_ > 0) {
+      ShapeCtx& old = ctx_[std::make_tuple(ws_NB_, ws_T_, ws_H_, ws_W_)];
+      old.plans.swap(plans_);
+      old.graphs.swap(graphs_);
+      old.stem_plan = stem_plan_;
+      old.stem_valid = stem_plan_valid_;
+    }
     plans_.clear();
+    graphs_.clear();
     stem_plan_valid_ = false;
     interm_.clear();
-    dbg_.clear();
     arena_.begin_measure();
     layout_workspace(NB, H, W);
-    const size_t bytes = arena_.end_measure();
-    arena_.reserve(bytes + 4096);
+    const size_t bytes = arena_.end_measure() + 4096;
+    if (bytes > arena_.capacity()) {
+      MCG_CUDA(cudaDeviceSynchronize());
+      for (auto& kv : ctx_)
+        for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
+      ctx_.clear();                      // their plans and graphs point into the allocation that goes away
+      dbg_.clear();
+      arena_.reserve(bytes);
+    } else {
+      arena_.reserve(0);                 // rewind
+      auto it = ctx_.find(std::make_tuple(NB, T, H, W));
+      if (it != ctx_.end()) {
+        plans_.swap(it->second.plans);
+        graphs_.swap(it->second.graphs);
+        stem_plan_ = it->second.stem_plan;
+        stem_plan_valid_ = it->second.stem_valid;
+        ctx_.erase(it);
+      }
+    }
     layout_workspace(NB, H, W);
     ws_NB_ = NB;
     ws_T_ = T;
     ws_H_ = H;
     ws_W_ = W;
-    if (pin_meta_) cudaFreeHost(pin_meta_);
-    MCG_CUDA(cudaMallocHost(&pin_meta_, static_cast<size_t>(kMetaSlots) * NB * 6 * sizeof(float)));
+    const size_t meta_bytes = static_cast<size_t>(kMetaSlots) * NB * 6 * sizeof(float);
+    if (meta_bytes > pin_meta_bytes_) {
+      if (pin_meta_) {
+        MCG_CUDA(cudaDeviceSynchronize());
+        cudaFreeHost(pin_meta_);
+      }
+      MCG_CUDA(cudaMallocHost(&pin_meta_, meta_bytes));
+      pin_meta_bytes_ = meta_bytes;
+    }
     meta_host_.clear();
   }
 
@@ -832,7 +867,20 @@ class Engine {
     }
   }
 
-  void drop_graph() {
+  // forget every captured graph and (plans = true) every launch plan, of the current shape and of the stashed ones
+  void drop_graph(bool plans = false) {
+    for (auto& kv : ctx_) {
+      for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
+      kv.second.graphs.clear();
+      if (plans) {
+        kv.second.plans.clear();
+        kv.second.stem_valid = false;
+      }
+    }
+    if (plans) {
+      plans_.clear();
+      stem_plan_valid_ = false;
+    }
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
     graphs_.clear();
   }
@@ -1496,6 +1544,7 @@ class Engine {
   bool dyn_mma_ = false;
   static constexpr int kMetaSlots = 4;
   float* pin_meta_ = nullptr;                 // kMetaSlots x [NB * 6] pinned staging of the per-call metadata
+  size_t pin_meta_bytes_ = 0;
   cudaEvent_t meta_ev_[kMetaSlots] = {};
   int meta_slot_ = 0;
   bool has_scale_ = false;
@@ -1514,6 +1563,13 @@ class Engine {
     }
   };
   std::map<GraphKey, cudaGraphExec_t> graphs_;
+  struct ShapeCtx {  // launch plans / graphs of a (NB, T, H, W) seen before (valid while the arena is not re-allocated)
+    std::map<std::string, UmmaPlan> plans;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    StemFusedPlan stem_plan;
+    bool stem_valid = false;
+  };
+  std::map<std::tuple<int, int, int, int>, ShapeCtx> ctx_;
 
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t side_stream_ = nullptr;  // forked branch of the head (RoIAlign beside the attention block)
@@ -1539,8 +1595,10 @@ namespace mcg {
 void preprocess_launch(const mcg_frame* frames, int n, const float* mean, const float* std_, int to_rgb, float* out,
                        int Hp, int Wp, cudaStream_t st, int* launches);
 // metric.cu
-void gaze_error_launch(const float* pred, const float* gt, const int32_t* video_start, int n_videos, double* out,
-                       cudaStream_t st);
+void gaze_error_launch(const float* pred, const float* gt, const int32_t* video_start, int n_videos, int variant,
+                       double* out, cudaStream_t st);
+void merge_clips_launch(const float* rows, const int32_t* clip_start, const int32_t* frame_start, int n_videos, int clip_len,
+                        int stride, float* det, float* gaze, cudaStream_t st);
 }  // namespace mcg
 
 // ========================================================================================
@@ -1660,7 +1718,21 @@ int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const floa
   });
 }
 
-int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_start, int n_videos, double* out,
+int mcg_merge_clips(const float* rows, const int32_t* clip_start, const int32_t* frame_start, int n_videos, int clip_len,
+                    int stride, float* det, float* gaze, void* stream) {
+  return guarded([&]() -> int {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      mcg::g_last_error = "mcg_merge_clips: no CUDA device visible (this library has no CPU fallback)";
+      return MCG_ERR_CUDA;
+    }
+    mcg::merge_clips_launch(rows, clip_start, frame_start, n_videos, clip_len, stride, det, gaze,
+                            static_cast<cudaStream_t>(stream));
+    return MCG_OK;
+  });
+}
+
+int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_start, int n_videos, int variant, double* out,
                    void* stream) {
   return guarded([&]() -> int {
     int ndev = 0;
@@ -1668,7 +1740,7 @@ int mcg_gaze_error(const float* pred, const float* gt, const int32_t* video_star
       mcg::g_last_error = "mcg_gaze_error: no CUDA device visible (this library has no CPU fallback)";
       return MCG_ERR_CUDA;
     }
-    mcg::gaze_error_launch(pred, gt, video_start, n_videos, out, static_cast<cudaStream_t>(stream));
+    mcg::gaze_error_launch(pred, gt, video_start, n_videos, variant, out, static_cast<cudaStream_t>(stream));
     return MCG_OK;
   });
 }

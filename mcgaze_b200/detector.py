@@ -22,13 +22,20 @@ from .registry import (BACKBONES, DETECTORS, HEADS, LOSSES, NECKS, ROI_EXTRACTOR
 
 
 class _Spec:
-    """Config-carrying node; `expect` pins the hyper-parameters the kernels hard-wire."""
+    """Config-carrying node; `expect` pins the hyper-parameters the kernels hard-wire, `only` lists for options that
+    change the architecture the one value (or values) the compiled kernels implement - anything else raises instead of
+    loading a checkpoint into the wrong network."""
     expect: Dict[str, Any] = {}
+    only: Dict[str, Any] = {}
 
     def __init__(self, **cfg):
         cfg.pop('init_cfg', None)
         cfg.pop('train_cfg', None)
         cfg.pop('test_cfg', None)
+        for k, allowed in self.only.items():
+            if k in cfg and cfg[k] not in allowed:
+                raise NotImplementedError(f'{type(self).__name__}: {k}={cfg[k]!r} is not supported by the sm_100a kernels '
+                                          f'(supported: {list(allowed)!r})')
         for k, want in self.expect.items():
             if k in cfg:
                 got = cfg[k]
@@ -44,11 +51,26 @@ class _Spec:
 @BACKBONES.register_module()
 class ResNet(_Spec):
     expect = dict(depth=50, num_stages=4, out_indices=(0, 1, 2, 3), style='pytorch')
+    # resnet.py:370-410: options that would change the computation (deformable convs, deep stem, avg-pool downsample,
+    # plugins, other norms) must not pass silently; frozen_stages / norm_eval / with_cp only matter for training
+    only = dict(dcn=(None,), stage_with_dcn=((False, False, False, False), [False, False, False, False]), deep_stem=(False,),
+                avg_down=(False,), plugins=(None,), conv_cfg=(None,), in_channels=(3,), base_channels=(64,),
+                strides=((1, 2, 2, 2), [1, 2, 2, 2]), dilations=((1, 1, 1, 1), [1, 1, 1, 1]), stem_channels=(None, 64))
+
+    def __init__(self, **cfg):
+        super().__init__(**cfg)
+        norm = cfg.get('norm_cfg') or dict(type='BN')
+        if norm.get('type') not in ('BN', 'SyncBN'):
+            raise NotImplementedError(f'ResNet: norm_cfg={norm!r} is not supported (eval-mode BatchNorm is folded into the convs)')
 
 
 @NECKS.register_module()
 class FPN(_Spec):
     expect = dict(in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=0, num_outs=4)
+    # fpn.py:62-129: no extra levels, no norm / activation inside the ConvModules, nearest 2x top-down
+    only = dict(add_extra_convs=(False, 'on_input'), relu_before_extra_convs=(False,), no_norm_on_lateral=(False,),
+                conv_cfg=(None,), norm_cfg=(None,), act_cfg=(None,), end_level=(-1,),
+                upsample_cfg=(dict(mode='nearest'),))
 
 
 @HEADS.register_module()
@@ -114,6 +136,97 @@ class MultiClueGazeROIHead(_Spec):
         self.gaze_head = [build_head(h) for h in gaze_head]
 
 
+def consumed_keys() -> 'OrderedDict[str, tuple]':
+    """Checkpoint keys (reference layout) and shapes the engine reads: the `need()` calls of
+    Engine::load_weights (mcgaze_b200/csrc/mcg_api.cu)."""
+    k: 'OrderedDict[str, tuple]' = OrderedDict()
+
+    def bn(prefix, c):
+        for n in ('weight', 'bias', 'running_mean', 'running_var'):
+            k[f'{prefix}.{n}'] = (c,)
+
+    def ln(prefix, c):
+        k[f'{prefix}.weight'] = (c,)
+        k[f'{prefix}.bias'] = (c,)
+
+    k['backbone.conv1.weight'] = (64, 3, 7, 7)
+    bn('backbone.bn1', 64)
+    cin = 64
+    for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), (3, 4, 6, 3))):
+        for b in range(blocks):
+            p = f'backbone.layer{li + 1}.{b}'
+            k[f'{p}.conv1.weight'] = (planes, cin, 1, 1)
+            bn(f'{p}.bn1', planes)
+            k[f'{p}.conv2.weight'] = (planes, planes, 3, 3)
+            bn(f'{p}.bn2', planes)
+            k[f'{p}.conv3.weight'] = (planes * 4, planes, 1, 1)
+            bn(f'{p}.bn3', planes * 4)
+            if b == 0:
+                k[f'{p}.downsample.0.weight'] = (planes * 4, cin, 1, 1)
+                bn(f'{p}.downsample.1', planes * 4)
+            cin = planes * 4
+    for i, c in enumerate((256, 512, 1024, 2048)):
+        k[f'neck.lateral_convs.{i}.conv.weight'] = (256, c, 1, 1)
+        k[f'neck.lateral_convs.{i}.conv.bias'] = (256,)
+        k[f'neck.fpn_convs.{i}.conv.weight'] = (256, 256, 3, 3)
+        k[f'neck.fpn_convs.{i}.conv.bias'] = (256,)
+    k['rpn_head.init_proposal_bboxes.weight'] = (3, 4)
+    k['rpn_head.init_proposal_features.weight'] = (3, 256)
+    for s in range(4):
+        p = f'roi_head.bbox_head.{s}'
+        k[f'{p}.attention.attn.in_proj_weight'] = (768, 256)
+        k[f'{p}.attention.attn.in_proj_bias'] = (768,)
+        k[f'{p}.attention.attn.out_proj.weight'] = (256, 256)
+        k[f'{p}.attention.attn.out_proj.bias'] = (256,)
+        ln(f'{p}.attention_norm', 256)
+        q = f'{p}.instance_interactive_conv'
+        k[f'{q}.dynamic_layer.weight'] = (32768, 256)
+        k[f'{q}.dynamic_layer.bias'] = (32768,)
+        ln(f'{q}.norm_in', 64)
+        ln(f'{q}.norm_out', 256)
+        k[f'{q}.fc_layer.weight'] = (256, 12544)
+        k[f'{q}.fc_layer.bias'] = (256,)
+        ln(f'{q}.fc_norm', 256)
+        ln(f'{p}.instance_interactive_conv_norm', 256)
+        k[f'{p}.ffn.layers.0.0.weight'] = (2048, 256)
+        k[f'{p}.ffn.layers.0.0.bias'] = (2048,)
+        k[f'{p}.ffn.layers.1.weight'] = (256, 2048)
+        k[f'{p}.ffn.layers.1.bias'] = (256,)
+        ln(f'{p}.ffn_norm', 256)
+        k[f'{p}.cls_fcs.0.weight'] = (256, 256)
+        ln(f'{p}.cls_fcs.1', 256)
+        for j in range(3):
+            k[f'{p}.reg_fcs.{3 * j}.weight'] = (256, 256)
+            ln(f'{p}.reg_fcs.{3 * j + 1}', 256)
+        for clue in ('face', 'eyes', 'head'):
+            k[f'{p}.{clue}_fc_cls.weight'] = (1, 256)
+            k[f'{p}.{clue}_fc_cls.bias'] = (1,)
+            k[f'{p}.{clue}_fc_reg.weight'] = (4, 256)
+            k[f'{p}.{clue}_fc_reg.bias'] = (4,)
+    h = 'roi_head.gaze_head.3'          # only the last stage's gaze head runs at test time
+    for clue in ('face', 'eyes', 'head'):
+        for tower in (f'{h}.gaze_{clue}_fcs', f'{h}.gaze_{clue}_confidence'):
+            for j in range(2):
+                k[f'{tower}.{3 * j}.weight'] = (256, 256)
+                ln(f'{tower}.{3 * j + 1}', 256)
+        for fc in (f'{h}.fc_{clue}', f'{h}.fc_{clue}_confidence'):
+            k[f'{fc}.weight'] = (3, 256)
+            k[f'{fc}.bias'] = (3,)
+    k[f'{h}.fc_gaze.weight'] = (3, 9)
+    k[f'{h}.fc_gaze.bias'] = (3,)
+    return k
+
+
+def tolerated_key(key: str) -> bool:
+    """Checkpoint keys of the reference model that the inference engine does not read: BN batch counters, the unused
+    fc_cls / fc_reg every BBoxHead creates (bbox_head.py:66-81), the gaze heads of stages 0-2
+    (multiclue_gaze_roi_head.py:367-378 uses the last one only)."""
+    import re
+    return bool(key.endswith('num_batches_tracked')
+                or re.match(r'roi_head\.bbox_head\.\d\.fc_(cls|reg)\.(weight|bias)$', key)
+                or re.match(r'roi_head\.gaze_head\.[0-2]\.', key))
+
+
 @DETECTORS.register_module()
 class MultiClueGaze:
     """reference: mmdet/models/detectors/multiclue_gaze.py:8-131 (+ base.py:112-174 dispatch)."""
@@ -139,9 +252,25 @@ class MultiClueGaze:
 
     # --- torch.nn.Module-like surface used by init_detector / load_checkpoint ---------------
     def state_dict(self):
-        return self._sd
+        """The loaded checkpoint tensors; before a load, the keys the engine consumes (values None) so that
+        `load_checkpoint` can report missing / unexpected keys like it does for a torch module."""
+        return self._sd if self._sd else OrderedDict((k, None) for k in consumed_keys())
 
     def load_state_dict(self, state_dict, strict: bool = False):
+        """Checks the checkpoint against what the engine consumes: a consumed key with the wrong shape always raises
+        (torch does too), missing consumed keys raise when `strict` (the engine raises on its first forward otherwise),
+        keys the engine ignores (the BBoxHead's unused fc_cls / fc_reg, gaze heads of stages 0-2, BN counters) are
+        tolerated, anything else is reported as unexpected."""
+        want = consumed_keys()
+        bad = [f'{k}: {tuple(state_dict[k].shape)} != {want[k]}' for k in want
+               if k in state_dict and hasattr(state_dict[k], 'shape') and tuple(state_dict[k].shape) != want[k]]
+        if bad:
+            raise RuntimeError('size mismatch for ' + '; '.join(bad[:8]))
+        missing = [k for k in want if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in want and not tolerated_key(k)]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f'state_dict mismatch: missing {missing[:8]}, unexpected {unexpected[:8]}')
+        self.load_report = dict(missing=missing, unexpected=unexpected)
         self._sd = OrderedDict(state_dict)
         self._engine = None
         self._ranges_checked = False

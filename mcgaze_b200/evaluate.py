@@ -12,7 +12,15 @@ the gaze configs because `Gaze360Dataset.__getitem__` raises NotImplementedError
                        clips go through one forward (`clips_per_batch`), results are all-gathered ONCE and put back
                        in dataset order (the `zip(*part_list)` re-ordering of :204-206)
   videos_from_clips    overlap merge + JSON records exactly as tools/test_gaze360_gaze.py:129-260
-  evaluate             tools/calculate_mae_gaze360.py on those records
+  evaluate             tools/calculate_mae_gaze360.py / calculate_mae_l2cs.py on those records
+  multi_gpu_test_videos  the sharded run SURVEY section 8e describes: VIDEOS are sharded over the ranks, each rank
+                       merges the overlaps of its videos and scores them ON ITS DEVICE (mcg_merge_clips,
+                       mcg_gaze_error), the MAE needs one all-reduce of 6 doubles; per-video arrays are gathered only
+                       when the caller wants the JSON
+
+Batches hold clips of ONE length and ONE padded canvas: the reference collates one clip at a time, so a clip's frames are
+padded to that clip's own largest frame (tools/test_gaze360_gaze.py:102-105) - a clip must never inherit a larger canvas
+from its batch neighbours (zero padding changes the convolutions' border behaviour and the proposal boxes).
 
 `model` is anything with the reference's call contract `model(return_loss=False, rescale=True, format=False,
 img=[Tensor], img_metas=[[meta...]], clip_length=T)` (mcgaze_b200.detector.MultiClueGaze); `pipeline` is a
@@ -120,26 +128,81 @@ def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging
     return infos[0]['n'], [block[k].copy() if o is None else o for k, o in enumerate(odd)], names
 
 
+def _canvas_groups(pipeline, frames, names: Sequence[str], T: int):
+    """Split the clips of a loaded batch by their OWN padded canvas.  -> [(frames, names, rands, clip positions)], one
+    entry per canvas; `rands` are the CenterCrop draws of those frames (drawn once per batch, in frame order, so the
+    grouping does not change which draw a frame gets)."""
+    n = len(names)
+    nclips = n // T
+    if not hasattr(pipeline, 'clip_canvases') or not hasattr(pipeline, 'draw'):
+        return [(frames, names, None, list(range(nclips)))]          # foreign pipeline object: nothing to plan with
+    if hasattr(frames, 'shape'):
+        shapes = [(int(frames.shape[1]), int(frames.shape[2]))] * n
+    else:
+        shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]
+    rands = pipeline.draw(n)
+    canvases = pipeline.clip_canvases(shapes, rands, T)
+    if len(set(canvases)) == 1:
+        return [(frames, names, rands, list(range(nclips)))]
+    groups = []
+    for cv in sorted(set(canvases)):
+        clips = [k for k in range(nclips) if canvases[k] == cv]
+        idx = [k * T + t for k in clips for t in range(T)]
+        sub = frames[idx] if hasattr(frames, 'shape') else [frames[i] for i in idx]
+        groups.append((sub, [names[i] for i in idx], rands[idx], clips))
+    return groups
+
+
 def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[int], clips_per_batch: int = 32,
-              workers: int = 0) -> Dict[int, np.ndarray]:
-    """-> {clip index: float32 [n_frames, ROW]} for the given clips; frames of a batch go through ONE pipeline call
-    and ONE forward.  With `workers` > 0 the frames of batch k+1 are decoded on a thread pool while the GPU works on
-    batch k (the role of the DataLoader workers in mmdet/apis/test.py:107-109)."""
+              workers: int = 0, to_host: bool = True, batch_sink: Optional[List[Any]] = None) -> Dict[int, Any]:
+    """-> {clip index: float32 [n_frames, ROW]} for the given clips (numpy; torch tensors on the model's device with
+    to_host=False); frames of a batch go through ONE pipeline call and ONE forward per padded canvas.  With `workers` > 0
+    the frames of batch k+1 are decoded on a thread pool while the GPU works on batch k (the role of the DataLoader
+    workers in mmdet/apis/test.py:107-109); on a GPU the uint8 block of batch k+1 crosses PCIe on a copy stream while
+    batch k computes, and results come back through pinned buffers gated by per-batch events, so the host never waits
+    for the batch it has just queued."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
-    results: Dict[int, np.ndarray] = {}
+    results: Dict[int, Any] = {}
     batches = _batches(dataset, indices, clips_per_batch)
     pool = ThreadPoolExecutor(workers) if workers > 0 else None
     feeder = ThreadPoolExecutor(1) if workers > 0 else None
     # pinned staging, three slots: batch k+2 is decoded into slot (k+2) % 3 while batch k+1 is being launched and batch
-    # k still runs; the last user of that slot, batch k-1, has been read back (a stream sync) by then
+    # k still runs; the upload of the last user of that slot, batch k-1, was issued (copy stream) before batch k's
+    # forward was queued and is complete once batch k-1's results have been collected
     staging: Optional[Dict[Any, Any]] = {} if workers > 0 else None
-    pending = None                                # results of the previous batch, still on the device
+    pending = None                                # results of the previous batch: (clip ids, T, rows, event)
+    cuda = torch.cuda.is_available()
+    copy_stream = None
+
+    def upload(frames):
+        """pinned uint8 block -> device on a side stream; the compute stream waits for the copy only"""
+        nonlocal copy_stream
+        if not (cuda and hasattr(frames, 'is_pinned') and frames.is_pinned() and hasattr(pipeline, 'device')):
+            return frames
+        dev = torch.device('cuda', pipeline.device)
+        if copy_stream is None:
+            copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            d = frames.to(dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        cur.wait_event(done)
+        d.record_stream(cur)
+        return d
 
     def collect(p):
-        batch, T, rows = p
-        rows = rows.cpu().numpy().astype(np.float32)                                 # ONE device->host read per batch
-        for k, i in enumerate(batch):
+        ids, T, rows, ev = p
+        if ev is not None:
+            ev.synchronize()                      # this batch's read-back only; later batches keep running
+        if batch_sink is not None:                # whole batches for the caller (no per-clip slicing of device tensors)
+            batch_sink.append((ids, T, rows))
+            return
+        if to_host:
+            rows = rows.numpy() if hasattr(rows, 'numpy') else np.asarray(rows)
+            rows = rows.astype(np.float32, copy=False)
+        for k, i in enumerate(ids):
             results[i] = rows[k * T:(k + 1) * T]
 
     try:
@@ -151,16 +214,30 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
                     if bi + 1 < len(batches) else None
             else:
                 T, frames, names = _load_batch(dataset, batch, None)
-            data = pipeline.batch(frames, filenames=names)
-            (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
-            n = len(names)
-            det = torch.stack(list(det_bboxes)).float()                              # [B*T, 3, 5]
-            gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
-            rows = torch.cat([det[..., :4].reshape(n, 12), det[..., 4], gaze.reshape(n, 12).float()], 1)
-            # read the PREVIOUS batch back only now, with this batch already queued: the GPU never waits for the host
+            frames = upload(frames)
+            parts = []
+            for sub, sub_names, rands, clips in _canvas_groups(pipeline, frames, names, T):
+                data = pipeline.batch(sub, filenames=sub_names) if rands is None else \
+                    pipeline.batch(sub, rands=rands, filenames=sub_names)
+                (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
+                n = len(sub_names)
+                det = torch.stack(list(det_bboxes)).float()                              # [B*T, 3, 5]
+                gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
+                rows = torch.cat([det[..., :4].reshape(n, 12), det[..., 4], gaze.reshape(n, 12).float()], 1)
+                parts.append(([batch[k] for k in clips], rows))
+            ids = [i for p_ids, _ in parts for i in p_ids]
+            rows = parts[0][1] if len(parts) == 1 else torch.cat([r for _, r in parts])
+            ev = None
+            if rows.is_cuda and to_host:
+                host = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
+                host.copy_(rows, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(rows.device))
+                rows = host
+            # hand the PREVIOUS batch over only now, with this batch already queued: the GPU never waits for the host
             if pending is not None:
                 collect(pending)
-            pending = (batch, T, rows)
+            pending = (ids, T, rows, ev)
         if pending is not None:
             collect(pending)
     finally:
@@ -223,22 +300,142 @@ def ground_truth_videos(dataset: Gaze360ClipDataset) -> Optional[List[np.ndarray
     return gt
 
 
-def evaluate(dataset: Gaze360ClipDataset, records: Sequence[Dict[str, Any]], key: str = 'fusion_gazes') -> Dict[str, float]:
-    gt = ground_truth_videos(dataset)
+def ground_truth(dataset: Gaze360ClipDataset, variant: str = 'gaze360') -> Optional[List[np.ndarray]]:
+    """Per-video ground truth for a scorer variant: Gaze360 = annotation k, l2cs = annotation 3k
+    (tools/calculate_mae_l2cs.py:110)."""
+    if variant == 'l2cs':
+        if not dataset.anno.get('annotations'):
+            return None
+        gt = metric.l2cs_ground_truth(dataset.anno)
+        if len(gt) < len(dataset.videos) or any(len(g) != len(v) for g, v in zip(gt, dataset.videos)):
+            raise ValueError('l2cs annotations do not match the videos (annotation 3k belongs to video k)')
+        return gt[:len(dataset.videos)]
+    return ground_truth_videos(dataset)
+
+
+def evaluate(dataset: Gaze360ClipDataset, records: Sequence[Dict[str, Any]], key: str = 'fusion_gazes',
+             variant: str = 'gaze360') -> Dict[str, float]:
+    gt = ground_truth(dataset, variant)
     if gt is None:
         raise ValueError('the annotation file carries no ground-truth gazes')
-    return metric.gaze_error([np.asarray(r[key], dtype=np.float64) for r in records], gt)
+    return metric.gaze_error([np.asarray(r[key], dtype=np.float64) for r in records], gt, variant=variant)
 
 
 def evaluate_on_device(dataset: Gaze360ClipDataset, merged: Sequence[Dict[str, np.ndarray]], clue: int = 0,
-                       device: str = 'cuda:0') -> Dict[str, float]:
+                       device: str = 'cuda:0', variant: str = 'gaze360') -> Dict[str, float]:
     """The same numbers from mcg_gaze_error: the merged per-video gaze arrays of `videos_from_clips`
     (clue 0 = fused, 1 / 2 / 3 = face / eyes / head) are scored by one kernel launch on the device."""
     import torch
     from . import lib
-    gt = ground_truth_videos(dataset)
+    gt = ground_truth(dataset, variant)
     if gt is None:
         raise ValueError('the annotation file carries no ground-truth gazes')
     pred = np.concatenate([m['gaze'][:, clue] for m in merged]).astype(np.float32)
     gt_all = np.concatenate(gt).astype(np.float32)
-    return lib.gaze_error(torch.from_numpy(pred).to(device), torch.from_numpy(gt_all).to(device), [len(g) for g in gt])
+    return lib.gaze_error(torch.from_numpy(pred).to(device), torch.from_numpy(gt_all).to(device), [len(g) for g in gt],
+                          variant=variant)
+
+
+def multi_gpu_test_videos(model, dataset: Gaze360ClipDataset, pipeline, clips_per_batch: int = 32, group=None,
+                          workers: int = 0, variant: str = 'gaze360', clue: int = 0, gather_videos: bool = True,
+                          merge: str = 'auto') -> Dict[str, Any]:
+    """The sharded evaluation of SURVEY section 8e: rank r takes VIDEOS r, r + W, ... (smoothing and the overlap merge
+    need whole videos on one rank), runs their clips in batches, merges the overlaps and scores its videos where the
+    results are - on its device through mcg_merge_clips / mcg_gaze_error when the forward returns CUDA tensors
+    (`merge='device'`), with the host restatements otherwise (`'host'`: CPU stand-in models in the gloo tests) - and the
+    MAE of the whole split costs ONE all-reduce of 6 doubles ({sum, frames} x {360, front-180, front-20}).
+    -> dict(mae=..., sums=[6], merged=[per-video dict(det [L,3,5], gaze [L,4,3])] in dataset order when gather_videos
+    (one all-gather of the merged rows), else only this rank's videos under 'merged_local' / 'videos_local')."""
+    import torch
+    import torch.distributed as tdist
+    dist_on = tdist.is_available() and tdist.is_initialized()
+    rank = tdist.get_rank(group) if dist_on else 0
+    world = tdist.get_world_size(group) if dist_on else 1
+    nv = len(dataset.videos)
+    mine = mdist.shard_indices(nv, rank, world)
+    first = np.concatenate([[0], np.cumsum([len(p) for p in dataset.plans])]).astype(np.int64)
+    clip_ids = [int(c) for v in mine for c in range(first[v], first[v + 1])]
+    done: List[Any] = []
+    if clip_ids:
+        run_clips(model, dataset, pipeline, clip_ids, clips_per_batch, workers, to_host=False, batch_sink=done)
+    T, L = dataset.clip_len, [len(dataset.videos[v]) for v in mine]
+    on_device = bool(done) and hasattr(done[0][2], 'is_cuda') and done[0][2].is_cuda
+    if merge == 'auto':
+        merge = 'device' if on_device else 'host'
+    gt = ground_truth(dataset, variant)
+    sums = torch.zeros(6, dtype=torch.float64)
+    det = gz = None
+    # per-clip rows [n_clips, clip_len, ROW] in dataset order from the batches: one cat + one index_select
+    order, blocks = [], []
+    for ids, t, r in done:
+        r = torch.as_tensor(r).reshape(len(ids), t, ROW)
+        blocks.append(r if t == T else torch.nn.functional.pad(r, (0, 0, 0, T - t)))
+        order += ids
+    rows = None
+    if blocks:
+        pos = {c: k for k, c in enumerate(order)}
+        rows = torch.cat(blocks).index_select(0, torch.tensor([pos[c] for c in clip_ids], device=blocks[0].device))
+    if mine and merge == 'device':
+        from . import lib
+        dev = rows.device
+        det, gz = lib.merge_clips(rows.contiguous(), [len(dataset.plans[v]) for v in mine], L, T, dataset.stride)
+        if gt is not None:
+            gt_dev = torch.from_numpy(np.concatenate([gt[v] for v in mine]).astype(np.float32)).to(dev)
+            sums = lib.gaze_error_sums(gz[:, clue].contiguous(), gt_dev, L, variant)
+    elif mine:
+        merged_local = []
+        host_rows = rows.cpu().numpy()
+        at = 0
+        for v in mine:
+            r = [host_rows[at + k, :n] for k, (_, n, _) in enumerate(dataset.plans[v])]
+            at += len(dataset.plans[v])
+            merged_local.append(slicer.merge_video(dataset.plans[v], [x[:, :12].reshape(-1, 3, 4) for x in r],
+                                                   [x[:, 12:15] for x in r], [x[:, 15:].reshape(-1, 4, 3) for x in r]))
+        det = torch.from_numpy(np.concatenate([m['det'] for m in merged_local]))
+        gz = torch.from_numpy(np.concatenate([m['gaze'] for m in merged_local]))
+        if gt is not None:
+            m = metric.gaze_error([x['gaze'][:, clue] for x in merged_local], [gt[v] for v in mine], variant=variant)
+            sums = torch.tensor([m[f'mae_{k}'] * m[f'frames_{k}'] if j == 0 else m[f'frames_{k}']
+                                 for k in ('360', 'front90', 'front20') for j in (0, 1)], dtype=torch.float64)
+    if dist_on and world > 1:
+        backend = tdist.get_backend(group)
+        sums = sums.cuda() if backend == 'nccl' and not sums.is_cuda else (sums.cpu() if backend != 'nccl' else sums)
+        tdist.all_reduce(sums, group=group)                         # THE collective of a sharded MAE run
+    out: Dict[str, Any] = dict(sums=[float(v) for v in sums.cpu()], videos_local=mine)
+    if gt is not None:
+        o = out['sums']
+        out['mae'] = {f'mae_{k}': o[2 * j] / max(o[2 * j + 1], 1.0) for j, k in enumerate(('360', 'front90', 'front20'))} | \
+                     {f'frames_{k}': int(o[2 * j + 1]) for j, k in enumerate(('360', 'front90', 'front20'))}
+    off = np.concatenate([[0], np.cumsum(L)]).astype(np.int64)
+    local = [dict(det=det[off[k]:off[k + 1]], gaze=gz[off[k]:off[k + 1]]) for k in range(len(mine))] if mine else []
+    if not gather_videos:
+        out['merged_local'] = local
+        return out
+    # JSON wanted: ONE all-gather of the merged per-frame rows (27 floats per frame), back to dataset order
+    fmax = -(-sum(len(v) for v in dataset.videos) // world) + max(len(v) for v in dataset.videos)
+    packed = torch.zeros(fmax, 27, dtype=torch.float32, device=det.device if det is not None else 'cpu')
+    if mine:
+        packed[:off[-1], :15] = det.reshape(-1, 15)
+        packed[:off[-1], 15:] = gz.reshape(-1, 12)
+    if dist_on and world > 1:
+        if tdist.get_backend(group) != 'nccl':
+            packed = packed.cpu()
+        bufs = [torch.empty_like(packed) for _ in range(world)]
+        tdist.all_gather(bufs, packed, group=group)
+    else:
+        bufs = [packed]
+    merged: List[Optional[Dict[str, np.ndarray]]] = [None] * nv
+    for r, b in enumerate(bufs):
+        b = b.cpu().numpy()
+        o = 0
+        for v in mdist.shard_indices(nv, r, world):
+            n = len(dataset.videos[v])
+            merged[v] = dict(det=b[o:o + n, :15].reshape(n, 3, 5).copy(), gaze=b[o:o + n, 15:].reshape(n, 4, 3).copy())
+            o += n
+    out['merged'] = merged
+    return out
+
+
+def records_from_merged(dataset: Gaze360ClipDataset, merged: Sequence[Dict[str, np.ndarray]]) -> List[Dict[str, Any]]:
+    """Merged per-video arrays -> the JSON records of tools/test_gaze360_gaze.py:210-260."""
+    return [slicer.video_record(dataset.anno['videos'][vi].get('id', vi + 1), m) for vi, m in enumerate(merged)]

@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
            'mcg_last_launch_count', 'mcg_range_report', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
-           'mcg_preprocess', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
+           'mcg_preprocess', 'mcg_merge_clips', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
 
 
 class McgError(RuntimeError):
@@ -66,7 +66,8 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_range_report.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_preprocess.argtypes = [ctypes.POINTER(mcg_frame), ci, cf, cf, ci, vp, ci, ci, vp]
-    lib.mcg_gaze_error.argtypes = [vp, vp, vp, ci, vp, vp]
+    lib.mcg_gaze_error.argtypes = [vp, vp, vp, ci, ci, vp, vp]
+    lib.mcg_merge_clips.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -130,13 +131,19 @@ def preprocess(frames, geometry, mean, std, to_rgb, out, stream: Optional[int] =
                               out.data_ptr(), out.shape[2], out.shape[3], st), 'mcg_preprocess')
 
 
-def gaze_error(pred, gt, lengths, stream: Optional[int] = None) -> Dict[str, float]:
-    """mcg_gaze_error: `pred`, `gt` = CUDA fp32 [F, 3] (frames of all videos concatenated), `lengths` = frames per
-    video.  Returns the keys of mcgaze_b200.metric.gaze_error (mae_360 / mae_front90 / mae_front20 + frame counts)."""
+SCORER_VARIANTS = {'gaze360': 0, 'l2cs': 1}
+
+
+def gaze_error_sums(pred, gt, lengths, variant: str = 'gaze360', stream: Optional[int] = None):
+    """mcg_gaze_error, raw form: -> CUDA float64 [6] = {sum of (per-video mean error in degrees x frames), frames} for
+    360 / front-180 / front-20.  The sums of disjoint sets of videos add up, so a sharded run needs one all-reduce of
+    these six numbers.  `pred`, `gt` = CUDA fp32 [F, 3], `lengths` = frames per video."""
     import numpy as np
     import torch
     if not torch.cuda.is_available():
         raise McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    if variant not in SCORER_VARIANTS:
+        raise McgError(f'unknown scorer variant {variant!r}; choose from {sorted(SCORER_VARIANTS)}')
     lib = load_library()
     lengths = np.asarray(lengths, dtype=np.int64)
     for t in (pred, gt):
@@ -148,14 +155,54 @@ def gaze_error(pred, gt, lengths, stream: Optional[int] = None) -> Dict[str, flo
     start = torch.from_numpy(np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)).to(pred.device)
     out = torch.empty(6, dtype=torch.float64, device=pred.device)
     st = torch.cuda.current_stream(pred.device).cuda_stream if stream is None else stream
-    _check(lib.mcg_gaze_error(pred.data_ptr(), gt.data_ptr(), start.data_ptr(), len(lengths), out.data_ptr(), st),
-           'mcg_gaze_error')
-    o = out.cpu().numpy()
+    with torch.cuda.device(pred.device):
+        _check(lib.mcg_gaze_error(pred.data_ptr(), gt.data_ptr(), start.data_ptr(), len(lengths), SCORER_VARIANTS[variant],
+                                  out.data_ptr(), st), 'mcg_gaze_error')
+    return out
+
+
+def sums_to_mae(sums) -> Dict[str, float]:
+    o = [float(v) for v in sums]
     res = {}
     for k, name in enumerate(('360', 'front90', 'front20')):
         res[f'mae_{name}'] = float(o[2 * k] / max(o[2 * k + 1], 1.0))
         res[f'frames_{name}'] = int(o[2 * k + 1])
     return res
+
+
+def gaze_error(pred, gt, lengths, variant: str = 'gaze360', stream: Optional[int] = None) -> Dict[str, float]:
+    """mcg_gaze_error: `pred`, `gt` = CUDA fp32 [F, 3] (frames of all videos concatenated), `lengths` = frames per
+    video.  Returns the keys of mcgaze_b200.metric.gaze_error (mae_360 / mae_front90 / mae_front20 + frame counts)."""
+    return sums_to_mae(gaze_error_sums(pred, gt, lengths, variant, stream).cpu().numpy())
+
+
+def merge_clips(rows, clips_per_video, frames_per_video, clip_len: int = 7, stride: int = 4, stream: Optional[int] = None):
+    """mcg_merge_clips: `rows` = CUDA fp32 [n_clips, clip_len, 27] (per clip and frame: boxes [3,4], scores [3], gaze
+    [4,3]; clips of a video consecutive, short clips padded), `clips_per_video` / `frames_per_video` = per-video counts.
+    -> (det CUDA fp32 [F, 3, 5], gaze CUDA fp32 [F, 4, 3]) with the reference's overlap merge applied."""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    lib = load_library()
+    cpv = np.asarray(clips_per_video, dtype=np.int64)
+    fpv = np.asarray(frames_per_video, dtype=np.int64)
+    if not rows.is_cuda or rows.dtype != torch.float32 or not rows.is_contiguous() or rows.dim() != 3 \
+            or rows.shape[0] != int(cpv.sum()) or rows.shape[1] != clip_len or rows.shape[2] != 27:
+        raise McgError('merge_clips: rows must be a contiguous CUDA fp32 tensor [sum(clips_per_video), clip_len, 27]')
+    if len(cpv) == 0 or len(cpv) != len(fpv) or np.any(cpv <= 0) or np.any(fpv <= 0):
+        raise McgError('merge_clips: every video needs at least one clip and one frame')
+    dev = rows.device
+    cs = torch.from_numpy(np.concatenate([[0], np.cumsum(cpv)]).astype(np.int32)).to(dev)
+    fs = torch.from_numpy(np.concatenate([[0], np.cumsum(fpv)]).astype(np.int32)).to(dev)
+    F = int(fpv.sum())
+    det = torch.empty(F, 3, 5, dtype=torch.float32, device=dev)
+    gaze = torch.empty(F, 4, 3, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    with torch.cuda.device(dev):
+        _check(lib.mcg_merge_clips(rows.data_ptr(), cs.data_ptr(), fs.data_ptr(), len(cpv), clip_len, stride, det.data_ptr(),
+                                   gaze.data_ptr(), st), 'mcg_merge_clips')
+    return det, gaze
 
 
 class Engine:

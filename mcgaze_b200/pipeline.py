@@ -83,6 +83,13 @@ class GpuTestPipeline:
     def _draw(self) -> float:
         return float((self._rng.rand(1) if self._rng is not None else np.random.rand(1))[0])
 
+    def draw(self, n: int) -> np.ndarray:
+        """The CenterCrop draws of n frames, in frame order (zeros when the pipeline has no random crop): n draws of
+        rand(1) and one draw of rand(n) consume the generator identically."""
+        if self.crop is not None and self.crop[0] == 'relative_range':
+            return (self._rng if self._rng is not None else np.random).rand(n)
+        return np.zeros(n)
+
     def crop_window(self, h: int, w: int, rand: float) -> Tuple[int, int, int, int]:
         """-> (y, x, crop_h, crop_w) of the CenterCrop slice, clipped to the image like the numpy slice is."""
         if self.crop is None:
@@ -117,17 +124,39 @@ class GpuTestPipeline:
             return int(np.ceil(h / d)) * d, int(np.ceil(w / d)) * d
         return h, w
 
+    def clip_canvases(self, shapes: Sequence[Tuple[int, int]], rands: Sequence[float], T: int) -> List[Tuple[int, int]]:
+        """Padded canvas (Hp, Wp) of every T-frame clip of a frame list: what the reference's per-clip collate pads the
+        clip's frames to (tools/test_gaze360_gaze.py:102-105)."""
+        ph, pw = self._arrays(shapes, rands)[-2:]
+        Hp = ph.reshape(-1, T).max(1)
+        Wp = pw.reshape(-1, T).max(1)
+        Wp = Wp + (-Wp) % 4
+        return list(zip(Hp.tolist(), Wp.tolist()))
+
     def plan(self, shapes: Sequence[Tuple[int, int]], rands: Optional[Sequence[float]] = None):
         """Per-frame geometry + metas for frames of the given (h, w); -> (geometry, metas, (Hp, Wp)).
         Vectorised over the frames in float64 / int64 numpy: the same IEEE operations, in the same order, as the
         scalar methods above (`plan_scalar` keeps the literal per-frame form; the tests compare the two)."""
         n = len(shapes)
+        h, w, y, x, ch, cw, nh, nw, ph, pw = self._arrays(shapes, rands)
+        Hp, Wp = int(ph.max()), int(pw.max())
+        geometry = np.stack([y, x, ch, cw, nh, nw], 1)
+        ws, hs = nw / cw, nh / ch
+        scale = np.stack([ws, hs, ws, hs], 1).astype(np.float32)
+        norm_cfg = dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb)
+        hl, wl, nhl, nwl, phl, pwl = (a.tolist() for a in (h, w, nh, nw, ph, pw))
+        metas = [dict(filename=None, ori_filename=None, ori_shape=(hl[i], wl[i], 3), img_shape=(nhl[i], nwl[i], 3),
+                      pad_shape=(phl[i], pwl[i], 3), scale_factor=scale[i], flip=False, flip_direction=None,
+                      img_norm_cfg=norm_cfg) for i in range(n)]
+        if Wp % 4:
+            Wp += 4 - Wp % 4                   # the kernel stores float4; configs pad to 32 anyway
+        return list(map(tuple, geometry.tolist())), metas, (Hp, Wp)
+
+    def _arrays(self, shapes: Sequence[Tuple[int, int]], rands: Optional[Sequence[float]] = None):
+        """-> int64 arrays (h, w, crop_y, crop_x, crop_h, crop_w, new_h, new_w, pad_h, pad_w), one entry per frame."""
+        n = len(shapes)
         if rands is None:
-            if self.crop is not None and self.crop[0] == 'relative_range':
-                # n draws of rand(1) and one draw of rand(n) consume the generator identically
-                rands = (self._rng if self._rng is not None else np.random).rand(n)
-            else:
-                rands = np.zeros(n)
+            rands = self.draw(n)
         hw = np.asarray(shapes, dtype=np.int64).reshape(n, 2)
         h, w = hw[:, 0], hw[:, 1]
         r = np.asarray(rands, dtype=np.float64).reshape(n)
@@ -162,18 +191,7 @@ class GpuTestPipeline:
             ph, pw = np.ceil(nh / d).astype(np.int64) * d, np.ceil(nw / d).astype(np.int64) * d
         else:
             ph, pw = nh, nw
-        Hp, Wp = int(ph.max()), int(pw.max())
-        geometry = np.stack([y, x, ch, cw, nh, nw], 1)
-        ws, hs = nw / cw, nh / ch
-        scale = np.stack([ws, hs, ws, hs], 1).astype(np.float32)
-        norm_cfg = dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb)
-        hl, wl, nhl, nwl, phl, pwl = (a.tolist() for a in (h, w, nh, nw, ph, pw))
-        metas = [dict(filename=None, ori_filename=None, ori_shape=(hl[i], wl[i], 3), img_shape=(nhl[i], nwl[i], 3),
-                      pad_shape=(phl[i], pwl[i], 3), scale_factor=scale[i], flip=False, flip_direction=None,
-                      img_norm_cfg=norm_cfg) for i in range(n)]
-        if Wp % 4:
-            Wp += 4 - Wp % 4                   # the kernel stores float4; configs pad to 32 anyway
-        return list(map(tuple, geometry.tolist())), metas, (Hp, Wp)
+        return h, w, y, x, ch, cw, nh, nw, ph, pw
 
     def plan_scalar(self, shapes: Sequence[Tuple[int, int]], rands: Sequence[float]):
         """The literal per-frame form of plan() (python floats, as the reference's transforms compute)."""

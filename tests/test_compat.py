@@ -105,3 +105,42 @@ def test_collate_scatter_like_the_slicer():
     out = scatter(b, [-1])[0]
     assert out['img'][0].shape == (T, 3, 6, 6) and out['img'][0][0, :, 4:, :].abs().sum() == 0
     assert [m['filename'] for m in out['img_metas'][0]] == ['0.png', '1.png', '2.png']
+
+
+def test_detector_checks_the_checkpoint_against_what_the_engine_consumes(synthetic_sd):
+    """ADVICE (round 1): load_state_dict reports missing / unexpected keys and refuses wrong shapes; unknown
+    architecture options are rejected instead of loading a checkpoint into the wrong network."""
+    import pytest
+    import torch
+    from mcgaze_b200 import detector as D
+    from mcgaze_b200.compat import Config
+    from mcgaze_b200.compat.checkpoint import load_state_dict
+    from mcgaze_b200.registry import build_detector
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, 'configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'))
+    model = build_detector(cfg.model.to_dict())
+    assert set(model.state_dict()) == set(D.consumed_keys())                     # before a load: the consumed keys
+    rep = load_state_dict(model, synthetic_sd, strict=True)                      # the reference layout: nothing to report
+    assert rep == {'missing': [], 'unexpected': []} and model.load_report == dict(missing=[], unexpected=[])
+    sd = dict(synthetic_sd)
+    del sd['backbone.layer2.0.conv1.weight']
+    sd['backbone.layer1.0.conv2.conv_offset.weight'] = torch.zeros(18, 64, 3, 3)   # a DCN checkpoint
+    model2 = build_detector(cfg.model.to_dict())
+    model2.load_state_dict(sd)
+    assert model2.load_report == dict(missing=['backbone.layer2.0.conv1.weight'],
+                                      unexpected=['backbone.layer1.0.conv2.conv_offset.weight'])
+    with pytest.raises(RuntimeError, match='state_dict mismatch'):
+        build_detector(cfg.model.to_dict()).load_state_dict(sd, strict=True)
+    bad = dict(synthetic_sd)
+    bad['neck.fpn_convs.0.conv.weight'] = torch.zeros(256, 256, 1, 1)
+    with pytest.raises(RuntimeError, match='size mismatch'):
+        build_detector(cfg.model.to_dict()).load_state_dict(bad)
+    for key, value in (('dcn', dict(type='DCNv2')), ('deep_stem', True), ('norm_cfg', dict(type='GN', num_groups=32))):
+        m = cfg.model.to_dict()
+        m['backbone'][key] = value
+        with pytest.raises(NotImplementedError):
+            build_detector(m)
+    m = cfg.model.to_dict()
+    m['neck']['norm_cfg'] = dict(type='BN')
+    with pytest.raises(NotImplementedError):
+        build_detector(m)

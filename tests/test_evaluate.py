@@ -253,3 +253,175 @@ def test_gpu_device_scorer_matches_host_scorer_on_driver_output():
     dev = ev.evaluate_on_device(ds, merged)
     for k in host:
         assert abs(host[k] - dev[k]) < 2e-3, (k, host[k], dev[k])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# video-sharded run: merge + score where the results are, one all-reduce of 6 doubles
+# ------------------------------------------------------------------------------------------------------------------
+def _video_worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    ds = ev.Gaze360ClipDataset(make_anno(), loader=fake_loader)
+    model = StubModel()
+    out = ev.multi_gpu_test_videos(model, ds, StubPipeline(), clips_per_batch=3)
+    out_q.put((rank, out['mae'], out['sums'], out['videos_local'], [(m['det'].tolist(), m['gaze'].tolist()) for m in out['merged']],
+               sum(n // T for n, T in model.calls)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_video_sharded_mae():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_video_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        item = q.get(timeout=180)
+        got[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ds = ev.Gaze360ClipDataset(make_anno(), loader=fake_loader)
+    rows = ev.single_gpu_test(StubModel(), ds, StubPipeline(), clips_per_batch=5)
+    records, merged = ev.videos_from_clips(ds, rows)
+    want = ev.evaluate(ds, records)
+    assert got[0][2] == [0, 2, 4, 6, 8] and got[1][2] == [1, 3, 5, 7]           # videos, not clips, are sharded
+    assert got[0][4] + got[1][4] == len(ds) and max(got[0][4], got[1][4]) < len(ds)
+    for r in range(2):
+        mae, sums, _, merged_r, _ = got[r]
+        assert len(sums) == 6 and sums[1] == sum(LENGTHS)
+        for k in want:
+            assert abs(mae[k] - want[k]) < 1e-6, (r, k, mae[k], want[k])
+        for (det, gz), m in zip(merged_r, merged):
+            assert np.allclose(np.asarray(det, np.float32), m['det'], rtol=1e-6, atol=1e-6)
+            assert np.allclose(np.asarray(gz, np.float32), m['gaze'], rtol=1e-6, atol=1e-6)
+
+
+def test_video_sharded_run_without_a_process_group_and_l2cs_variant():
+    """world = 1 (no torch.distributed): same numbers as the clip-level driver; the l2cs variant reads annotation 3k."""
+    anno = make_anno()
+    ds = ev.Gaze360ClipDataset(anno, loader=fake_loader)
+    out = ev.multi_gpu_test_videos(StubModel(), ds, StubPipeline(), clips_per_batch=4)
+    rows = ev.single_gpu_test(StubModel(), ds, StubPipeline(), clips_per_batch=4)
+    records, merged = ev.videos_from_clips(ds, rows)
+    want = ev.evaluate(ds, records)
+    assert all(abs(out['mae'][k] - want[k]) < 1e-6 for k in want)
+    recs = ev.records_from_merged(ds, out['merged'])
+    assert [r['video_id'] for r in recs] == [r['video_id'] for r in records]
+    assert all(np.allclose(a['fusion_gazes'], b['fusion_gazes'], atol=1e-6) for a, b in zip(recs, records))
+    l2 = dict(videos=anno['videos'], annotations=[a if k == 0 else dict(gaze=a['gaze'][::-1]) for a in anno['annotations'] for k in range(3)])
+    ds2 = ev.Gaze360ClipDataset(l2, loader=fake_loader)
+    o2 = ev.multi_gpu_test_videos(StubModel(), ds2, StubPipeline(), clips_per_batch=4, variant='l2cs')
+    w2 = ev.evaluate(ds2, records, variant='l2cs')
+    assert all(abs(o2['mae'][k] - w2[k]) < 1e-6 for k in w2)
+    assert o2['mae']['mae_360'] == pytest.approx(want['mae_360'], abs=1e-6)          # same GT for the 360 class
+    assert o2['mae']['frames_front20'] <= want['frames_front20']                      # the extra pitch condition
+
+
+def test_batches_keep_every_clip_on_its_own_canvas():
+    """ADVICE (round 1, high): a clip must be padded to ITS OWN largest frame, never to its batch neighbours'.  A
+    pipeline stand-in whose canvas depends on the frame size shows the driver splitting a mixed batch per canvas."""
+    seen = []
+
+    class CanvasPipeline(StubPipeline):
+        device = 0
+
+        def draw(self, n):
+            return np.zeros(n)
+
+        def clip_canvases(self, shapes, rands, T):
+            hw = np.asarray(shapes).reshape(-1, T, 2).max(1)
+            return [(int(h), int(w)) for h, w in hw]
+
+        def batch(self, frames, rands=None, filenames=None):
+            shapes = {tuple(np.asarray(f).shape[:2]) for f in frames}
+            seen.append(shapes)
+            imgs = [torch.from_numpy(np.asarray(f)[:4, :4].astype(np.float32)).permute(2, 0, 1) for f in frames]
+            metas = [dict(img_shape=(4, 4, 3), scale_factor=np.ones(4, np.float32), filename=n) for n in filenames]
+            return dict(img=[torch.stack(imgs)], img_metas=[metas])
+
+    def loader(path):                    # videos 1 and 3 have taller frames
+        img = fake_loader(path)
+        return np.pad(img, ((0, 2), (0, 0), (0, 0))) if path[:4] in ('v001', 'v003') else img
+
+    lengths = [7, 7, 7, 7]
+    ds = ev.Gaze360ClipDataset(make_anno(lengths), loader=loader)
+    rows = ev.single_gpu_test(StubModel(), ds, CanvasPipeline(), clips_per_batch=4)
+    assert all(len(s) == 1 for s in seen) and len(seen) == 2            # one call per canvas, never mixed
+    ref = ev.single_gpu_test(StubModel(), ev.Gaze360ClipDataset(make_anno(lengths), loader=fake_loader), StubPipeline(), clips_per_batch=1)
+    assert all(np.allclose(a, b, rtol=1e-6, atol=1e-6) for a, b in zip(rows, ref))
+
+
+@pytest.mark.gpu
+def test_gpu_mixed_aspect_ratios_batched_equals_per_clip(synthetic_sd):
+    """Videos of different aspect ratios in one batch: every clip still runs on its own padded canvas, so batched ==
+    one clip per forward (the reference's collate pads a clip to its own largest frame)."""
+    from mcgaze_b200.apis import init_detector
+    from mcgaze_b200.pipeline import GpuTestPipeline
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    model = init_detector(os.path.join(root, 'configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'), None, 'cuda:0')
+    model.load_state_dict(synthetic_sd)
+    rng = np.random.default_rng(0)
+    bases = {0: rng.integers(0, 256, (96, 96, 3), dtype=np.uint8), 1: rng.integers(0, 256, (120, 96, 3), dtype=np.uint8),
+             2: rng.integers(0, 256, (90, 130, 3), dtype=np.uint8)}
+
+    def loader(path):
+        v, t = path.split('/')[-2:]
+        k = int(v[1:]) * 37 + int(t.split('.')[0])
+        return np.roll(bases[int(v[1:]) % 3], k, axis=1) ^ np.uint8(k & 31)
+
+    ds = ev.Gaze360ClipDataset(make_anno([7, 7, 7, 11]), loader=loader)
+    rands = {}
+
+    class FixedCrops(GpuTestPipeline):
+        def draw(self, n):
+            return np.full(n, 0.5)
+
+    pipe = FixedCrops(model.cfg.data.test.pipeline)
+    canv = {pipe.clip_canvases([bases[v % 3].shape[:2]] * 7, np.full(7, 0.5), 7)[0] for v in range(3)}
+    assert len(canv) == 3, canv                                                      # three different canvases
+    batched = ev.single_gpu_test(model, ds, pipe, clips_per_batch=8)
+    single = [ev.run_clips(model, ds, pipe, [i], clips_per_batch=1)[i] for i in range(len(ds))]
+    for a, b in zip(batched, single):
+        assert a.shape == b.shape and np.allclose(a, b, atol=1e-4, rtol=1e-4)
+    del rands
+
+
+@pytest.mark.gpu
+def test_gpu_video_sharded_run_merges_and_scores_on_the_device(synthetic_sd):
+    """multi_gpu_test_videos on one GPU (world = 1): device merge + device scorer == host merge + host scorer."""
+    from mcgaze_b200.apis import init_detector
+    from mcgaze_b200.pipeline import GpuTestPipeline
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    model = init_detector(os.path.join(root, 'configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'), None, 'cuda:0')
+    model.load_state_dict(synthetic_sd)
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 256, (96, 88, 3), dtype=np.uint8)
+
+    def loader(path):
+        v, t = path.split('/')[-2:]
+        k = int(v[1:]) * 37 + int(t.split('.')[0])
+        return np.roll(base, k, axis=1) ^ np.uint8(k & 31)
+
+    class FixedCrops(GpuTestPipeline):
+        def draw(self, n):
+            return np.full(n, 0.3)
+
+    ds = ev.Gaze360ClipDataset(make_anno([7, 12, 3, 9]), loader=loader)
+    pipe = FixedCrops(model.cfg.data.test.pipeline)
+    out = ev.multi_gpu_test_videos(model, ds, pipe, clips_per_batch=3, workers=2)
+    rows = ev.single_gpu_test(model, ds, pipe, clips_per_batch=3)
+    records, merged = ev.videos_from_clips(ds, rows)
+    want = ev.evaluate(ds, records)
+    for k in want:
+        assert abs(out['mae'][k] - want[k]) < 2e-3, (k, out['mae'][k], want[k])
+    for a, b in zip(out['merged'], merged):
+        assert np.allclose(a['det'], b['det'], atol=1e-4, rtol=1e-4) and np.allclose(a['gaze'], b['gaze'], atol=1e-5)

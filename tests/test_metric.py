@@ -43,7 +43,8 @@ def test_device_scorer_has_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip('GPU present')
     so = lib.load_library()
-    assert so.mcg_gaze_error(None, None, None, 1, None, None) == -2
+    assert so.mcg_gaze_error(None, None, None, 1, 0, None, None) == -2
+    assert so.mcg_merge_clips(None, None, None, 1, 7, 4, None, None, None) == -2
     assert b'no CPU fallback' in so.mcg_last_error()
     with pytest.raises(lib.McgError):
         lib.gaze_error(torch.zeros(2, 3), torch.zeros(2, 3), [2])
@@ -91,3 +92,91 @@ def test_gpu_scorer_edge_cases():
         assert abs(got[k] - ref[k]) < 1e-3, (k, got[k], ref[k])
     with pytest.raises(lib.McgError):
         lib.gaze_error(torch.zeros(3, 3).cuda(), torch.zeros(3, 3).cuda(), [2])          # lengths do not add up
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# both scorer variants against what the reference's OWN scripts print (oracle/gen_golden_scorer.py executes
+# tools/calculate_mae_gaze360.py and tools/calculate_mae_l2cs.py on seeded synthetic videos)
+# ------------------------------------------------------------------------------------------------------------------
+def _synthetic_scorer_case():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('gen_golden_scorer', os.path.join(root, 'oracle', 'gen_golden_scorer.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize('variant', ['gaze360', 'l2cs'])
+def test_scorer_variants_match_the_reference_scripts(golden_dir, variant):
+    gen = _synthetic_scorer_case()
+    gold = json.load(open(os.path.join(golden_dir, 'golden_scorer.json')))
+    results, a360, al2 = gen.synthetic(gold['seed'], gold['n_videos'])
+    pred = [np.asarray(r['fusion_gazes']) for r in results]
+    gt = metric.l2cs_ground_truth(al2) if variant == 'l2cs' else [np.asarray(a['gaze']) for a in a360['annotations']]
+    got = metric.gaze_error(pred, gt, variant=variant)
+    for k, want in gold[variant].items():
+        assert abs(got[k] - want) < 0.0075, (variant, k, got[k], want)          # printed with %.2f
+    assert gold['l2cs']['mae_front20'] != gold['gaze360']['mae_front20']         # the pitch condition matters here
+    if os.path.isdir(gen.REF):                                                   # live against the reference script
+        script = 'calculate_mae_l2cs.py' if variant == 'l2cs' else 'calculate_mae_gaze360.py'
+        assert gen.run_reference(script, results, al2 if variant == 'l2cs' else a360) == gold[variant]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('variant', ['gaze360', 'l2cs'])
+def test_gpu_scorer_variants(golden_dir, variant):
+    import torch
+    from mcgaze_b200 import lib
+    gen = _synthetic_scorer_case()
+    gold = json.load(open(os.path.join(golden_dir, 'golden_scorer.json')))
+    results, a360, al2 = gen.synthetic(gold['seed'], gold['n_videos'])
+    pred = [np.asarray(r['fusion_gazes'], dtype=np.float32) for r in results]
+    gt = metric.l2cs_ground_truth(al2) if variant == 'l2cs' else [np.asarray(a['gaze']) for a in a360['annotations']]
+    lengths = [len(p) for p in pred]
+    got = lib.gaze_error(torch.from_numpy(np.concatenate(pred)).cuda(),
+                         torch.from_numpy(np.concatenate(gt).astype(np.float32)).cuda(), lengths, variant=variant)
+    ref = metric.gaze_error(pred, gt, variant=variant)
+    for k, want in gold[variant].items():
+        assert abs(got[k] - want) < 0.0075 and abs(got[k] - ref[k]) < 1e-3, (variant, k, got[k], want, ref[k])
+    for k in ('frames_360', 'frames_front90', 'frames_front20'):
+        assert got[k] == ref[k], k
+    # sums of disjoint shards add up to the whole: the one all-reduce of a sharded run
+    cut = len(lengths) // 3
+    off = int(np.sum(lengths[:cut]))
+    p_all = torch.from_numpy(np.concatenate(pred)).cuda()
+    g_all = torch.from_numpy(np.concatenate(gt).astype(np.float32)).cuda()
+    a = lib.gaze_error_sums(p_all[:off].contiguous(), g_all[:off].contiguous(), lengths[:cut], variant)
+    b = lib.gaze_error_sums(p_all[off:].contiguous(), g_all[off:].contiguous(), lengths[cut:], variant)
+    whole = lib.sums_to_mae((a + b).cpu().numpy())
+    for k in ref:
+        assert abs(whole[k] - got[k]) < 1e-9 * max(1.0, abs(got[k])), k
+
+
+@pytest.mark.gpu
+def test_gpu_overlap_merge_matches_the_host_merger():
+    """mcg_merge_clips against mcgaze_b200.slicer.merge_video (itself pinned against the reference's loop) on videos of
+    every length class: single short clip, exact window, right-aligned last window with overlap 4 / 5 / 6 / 3 -
+    including frames covered by THREE clips - and scores on both sides of the 0.5 threshold.  Bit-exact."""
+    import torch
+    from mcgaze_b200 import lib, slicer
+    rng = np.random.default_rng(5)
+    lengths = [1, 3, 7, 8, 9, 10, 11, 12, 15, 23, 50, 101]
+    rows, cpv = [], []
+    want_det, want_gaze = [], []
+    for L in lengths:
+        plan = slicer.plan_clips(L)
+        boxes = [rng.uniform(0, 200, (n, 3, 4)).astype(np.float32) for _, n, _ in plan]
+        scores = [rng.uniform(0.2, 0.9, (n, 3)).astype(np.float32) for _, n, _ in plan]
+        gaze = [rng.normal(size=(n, 4, 3)).astype(np.float32) for _, n, _ in plan]
+        m = slicer.merge_video(plan, boxes, scores, gaze)
+        want_det.append(m['det'])
+        want_gaze.append(m['gaze'])
+        cpv.append(len(plan))
+        for (_, n, _), b, s, g in zip(plan, boxes, scores, gaze):
+            r = np.zeros((7, 27), np.float32)
+            r[:n] = np.concatenate([b.reshape(n, 12), s, g.reshape(n, 12)], 1)
+            rows.append(r)
+    det, gz = lib.merge_clips(torch.from_numpy(np.stack(rows)).cuda(), cpv, lengths)
+    assert np.array_equal(det.cpu().numpy(), np.concatenate(want_det))
+    assert np.array_equal(gz.cpu().numpy(), np.concatenate(want_gaze))

@@ -24,7 +24,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def main():
-    a = [int(v) for v in sys.argv[1:]]
+    mode = 'video'
+    argv = sys.argv[1:]
+    if argv and argv[0] in ('video', 'clip'):
+        mode, argv = argv[0], argv[1:]
+    a = [int(v) for v in argv]
     cpb = a[0] if len(a) > 0 else 32
     workers = a[1] if len(a) > 1 else 8
     sh, sw = (a[2], a[3]) if len(a) > 3 else (300, 300)
@@ -38,7 +42,9 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device(device))
     lengths = np.load(os.path.join(ROOT, 'tests/golden/golden_gaze360_results.npz'))['lengths'].tolist()
-    anno = dict(videos=[dict(id=i + 1, file_names=[f'{i:04d}/{t:05d}.png' for t in range(L)]) for i, L in enumerate(lengths)])
+    grng = np.random.default_rng(1)
+    anno = dict(videos=[dict(id=i + 1, file_names=[f'{i:04d}/{t:05d}.png' for t in range(L)]) for i, L in enumerate(lengths)],
+                annotations=[dict(gaze=grng.normal(size=(L, 3)).tolist()) for L in lengths])
     rng = np.random.default_rng(0)
     bank = [rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8) for _ in range(64)]
     ds = ev.Gaze360ClipDataset(anno, loader=lambda p: bank[hash(p) % 64])
@@ -50,15 +56,23 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    rows = ev.multi_gpu_test(model, ds, pipe, cpb, device=device, workers=workers) if world > 1 else \
-        ev.single_gpu_test(model, ds, pipe, cpb, workers)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    records, _ = ev.videos_from_clips(ds, rows)
+    mae = None
+    if mode == 'video':      # videos sharded, merge + MAE on each device, one all-reduce (+ one all-gather for the JSON)
+        out = ev.multi_gpu_test_videos(model, ds, pipe, cpb, workers=workers)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        records = ev.records_from_merged(ds, out['merged'])
+        mae = out['mae']
+    else:                    # clips sharded, one all-gather of the per-clip rows, merge on the host
+        rows = ev.multi_gpu_test(model, ds, pipe, cpb, device=device, workers=workers) if world > 1 else \
+            ev.single_gpu_test(model, ds, pipe, cpb, workers)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        records, _ = ev.videos_from_clips(ds, rows)
     t2 = time.perf_counter()
     if rank == 0:
         print(json.dumps(dict(workload='Gaze360 test split stand-in (BASELINE configs[3])', videos=len(lengths), frames=int(sum(lengths)),
-                              clips=len(ds), n_gpus=world, clips_per_batch=cpb, workers=workers, source=[sh, sw],
+                              clips=len(ds), n_gpus=world, shard=mode, mae=mae, clips_per_batch=cpb, workers=workers, source=[sh, sw],
                               forward_s=t1 - t0, merge_json_s=t2 - t1, clips_per_s=len(ds) / (t1 - t0),
                               note='wall clock incl. host frame hand-over, H2D of uint8, GPU pipeline, forward, D2H, gather; '
                                    'PNG decoding excluded (frames come from a RAM bank); short clips (T < 7) run in their own batches')))
