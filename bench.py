@@ -225,6 +225,101 @@ def preprocess_extras(eng, dev, steps: int, graph: bool):
                        'api': 'pinned uint8 frames -> H2D (copy stream, overlapped) -> mcg_preprocess -> mcg_forward -> D2H'}}
 
 
+GFLOP_PER_CLIP_BY_SHAPE = {(224, 1): 14.22, (224, 3): 42.66, (224, 7): 99.55, (224, 15): 213.32, (320, 1): 28.64,
+                           (320, 3): 85.93, (320, 7): 200.51, (320, 15): 429.67, (448, 7): 390.57}
+
+
+def _time_shape(eng, dev, res: int, clip_len: int, clips: int, steps: int, graph: bool):
+    """Device time of one forward of `clips` clips of clip_len x res x res (inputs resident, like `value`)."""
+    import torch
+    img = torch.randn(clips * clip_len, 3, res, res, device=dev)
+    out = eng.forward(img, clip_length=clip_len)
+    eng.set_graph_mode(graph)
+    for _ in range(3):
+        eng.forward_into(img, clip_len, out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.forward_into(img, clip_len, out)
+    e1.record()
+    torch.cuda.synchronize()
+    eng.set_graph_mode(False)
+    ms = e0.elapsed_time(e1) / steps
+    cps = clips / (ms * 1e-3)
+    del img, out
+    torch.cuda.empty_cache()
+    return {'resolution': res, 'T': clip_len, 'clips_per_step': clips, 'ms_per_step': ms, 'clips_per_s': cps,
+            'frames_per_s': cps * clip_len, 'algorithmic_tflops': cps * GFLOP_PER_CLIP_BY_SHAPE[(res, clip_len)] / 1e3}
+
+
+def config_extras(eng, dev, graph: bool):
+    """BASELINE configs[2] (l2cs setting: bs = 32 clips x 7 frames x 448 x 448, multiclue_gaze_r50_l2cs.py:31-43) and
+    configs[4] (clip-length sweep T in {1, 3, 7, 15} x resolution {224, 320}, ~224 / ~112 frames per step) as side
+    measurements next to the headline: device-resident synthetic inputs, CUDA-graph replay, 5 timed steps each.
+    Parity of these shapes: tests/test_gpu_forward.py (test_l2cs_batch_8x7x448_vs_oracle, test_config_sweep_shapes_vs_oracle)."""
+    l2cs = _time_shape(eng, dev, 448, 7, 32, 5, graph)
+    l2cs['workload'] = 'multiclue_gaze_r50 l2cs-setting inference, bs=32 clips x 7 frames x 448x448 (BASELINE configs[2])'
+    sweep = [_time_shape(eng, dev, res, t, frames // t, 5, graph)
+             for res, t, frames in [(224, 1, 224), (224, 3, 222), (224, 7, 224), (224, 15, 225), (320, 1, 112), (320, 3, 111),
+                                    (320, 7, 112), (320, 15, 105)]]
+    return {'l2cs_bs32_448': l2cs, 'sweep': {'workload': 'clip-length sweep T x resolution (BASELINE configs[4])', 'rows': sweep}}
+
+
+def testsplit_extra(eng, sd, local_rank: int, world: int):
+    """BASELINE configs[3]: the Gaze360 test split (517 videos with the REAL length list of the shipped results JSON =
+    25 969 frames = 6365 clips, synthetic 300 x 300 uint8 frames from a RAM bank, PNG decoding excluded) through the
+    sharded evaluation driver on ALL ranks: videos sharded round-robin, uint8 H2D on a copy stream, mcg_preprocess,
+    batched forward, overlap merge + MAE on each device, ONE all-reduce of 6 doubles (+ one all-gather of the merged
+    rows, as a JSON writer needs).  Wall clock, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mcgaze_b200 import evaluate as ev
+    from mcgaze_b200.apis import init_detector
+    from mcgaze_b200.pipeline import GpuTestPipeline
+    lengths = np.load(os.path.join(ROOT, 'tests/golden/golden_gaze360_results.npz'))['lengths'].tolist()
+    grng = np.random.default_rng(1)
+    anno = dict(videos=[dict(id=i + 1, file_names=[f'{i:04d}/{t:05d}.png' for t in range(L)]) for i, L in enumerate(lengths)],
+                annotations=[dict(gaze=grng.normal(size=(L, 3)).tolist()) for L in lengths])
+    rng = np.random.default_rng(0)
+    bank = [rng.integers(0, 256, (300, 300, 3), dtype=np.uint8) for _ in range(64)]
+    ds = ev.Gaze360ClipDataset(anno, loader=lambda p: bank[hash(p) % 64])
+    model = init_detector(os.path.join(ROOT, 'configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'), None, f'cuda:{local_rank}')
+    model.load_state_dict(sd)
+    model._engine = eng                    # the engine of the headline measurement (same weights)
+    eng.set_graph_mode(True)
+    pipe = GpuTestPipeline(model.cfg.data.test.pipeline, device=local_rank, seed=0)
+    ok = 1
+    try:
+        ev.run_clips(model, ds, pipe, list(range(64)), 32, 8)          # warm-up: plans, graph capture, staging buffers
+        torch.cuda.synchronize()
+    except Exception:
+        ok = 0
+    if world > 1:      # every rank enters the sharded run (it holds collectives) or none does
+        t = torch.tensor([ok], device=f'cuda:{local_rank}')
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = int(t.item())
+    if not ok:
+        eng.set_graph_mode(False)
+        raise RuntimeError('warm-up of the evaluation driver failed on a rank')
+    t0 = time.perf_counter()
+    out = ev.multi_gpu_test_videos(model, ds, pipe, 32, workers=8, gather_videos=True)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([el], device=f'cuda:{local_rank}')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    eng.set_graph_mode(False)
+    return {'workload': 'Gaze360 test split stand-in, sharded by video over the ranks (BASELINE configs[3])', 'videos': len(lengths),
+            'frames': int(sum(lengths)), 'clips': len(ds), 'n_gpus': world, 'seconds': el, 'clips_per_s': len(ds) / el,
+            'collectives': 'one all-reduce of 6 doubles (MAE) + one all-gather of the merged per-frame rows (JSON)',
+            'mae_360_of_random_gt': out['mae']['mae_360'], 'frames_scored': out['mae']['frames_360'],
+            'note': 'wall clock, max over ranks; host frame hand-over, uint8 H2D, GPU pipeline, forward, device merge + scorer, '
+                    'collectives; PNG decoding excluded (frames come from a RAM bank)'}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -418,7 +513,18 @@ def main():
 
     extras = {}
     cpu_baseline = None
+    if not args.skip_extras:
+        # BASELINE configs[3] on every rank (it contains the sharded run's collectives); never takes the headline down
+        try:
+            ts = testsplit_extra(eng, sd, local_rank, world)
+        except Exception as e:
+            ts = {'unavailable': f'{type(e).__name__}: {e}'}
+        extras['testsplit'] = ts
     if rank == 0 and world == 1 and not args.skip_extras:
+        try:
+            extras.update(config_extras(eng, dev, not args.no_graph))
+        except Exception as e:
+            extras['l2cs_bs32_448'] = {'unavailable': f'{type(e).__name__}: {e}'}
         eng.set_option('time_kernels', 0)
         try:
             extras['preprocess'] = preprocess_extras(eng, dev, args.steps, not args.no_graph)
