@@ -82,6 +82,16 @@ __host__ __device__ inline long long res_row(const Epilogue& e, long long m) {
   return (n * (e.P / 2) + (p >> 1)) * (e.Q / 2) + (q >> 1);
 }
 
+// first pixel of the source ROW that res_row(e, m) lies in: no pixel at or after m maps to an earlier source pixel, so
+// it is the start of the window of source pixels a tile beginning at m needs (RES_UP2X prefetch)
+__host__ __device__ inline long long res_row_window_start(const Epilogue& e, long long m) {
+  long long pq = static_cast<long long>(e.P) * e.Q;
+  long long n = m / pq;
+  int rem = static_cast<int>(m - n * pq);
+  int p = rem / e.Q;
+  return (n * (e.P / 2) + (p >> 1)) * (e.Q / 2);
+}
+
 __device__ __forceinline__ void split_store(float v, __half* hi, __half* lo, long long idx, uint8_t* lo8 = nullptr,
                                             uint8_t* hi8 = nullptr) {
   __half h = __float2half_rn(v);

@@ -36,6 +36,7 @@
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue groups), per-group
 // residual mbarriers.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -81,7 +82,9 @@ struct UmmaParams {
   int acc_cols = 256;
   int out_tma = 0;  // planes output through smem staging + TMA store
   int out_sets = 1; // staging sets per epilogue group for the TMA-store epilogue (2 = double buffered)
-  int res_tma = 0;  // RES_SAME residual planes prefetched by TMA
+  int res_tma = 0;  // residual planes prefetched by TMA: RES_SAME chunks, or (res_up) the window of the coarser level
+  int res_up = 0;   // res_tma with RES_UP2X: the [128 x 32] box starts at the source pixel of the tile's first row; all
+                    // source pixels of a 128-row tile lie within 128 consecutive source rows (checked on the host)
   int res_bufs = 2; // ... this many [128 x 32] chunks ahead per epilogue group
   int out_fmt = 0;  // planes written by the epilogue: 0 hi, 1 hi + fp16 lo, 2 hi + e4m3 lo8 (+ e4m3 hi8 if out_hi8)
   int out_hi8 = 0;
@@ -564,9 +567,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
         ptx::mbar_arrive_expect_tx(&rbar[b], static_cast<uint32_t>(kFmt == 2   ? kEpiPlaneBytes + kEpiPlaneBytes / 2
                                                                    : kFmt == 1 ? 2 * kEpiPlaneBytes
                                                                                     : kEpiPlaneBytes));
-        ptx::tma_load_2d(dst, &tm.r_hi, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
+        const int r0 = p.res_up ? static_cast<int>(res_row_window_start(ep, static_cast<long long>(mt) * kBlockM)) : mt * kBlockM;
+        ptx::tma_load_2d(dst, &tm.r_hi, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, r0);
         if (kFmt != 0)  // fp16 lo chunk or e4m3 lo8 chunk
-          ptx::tma_load_2d(dst + kEpiPlaneBytes, &tm.r_lo, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, mt * kBlockM);
+          ptx::tma_load_2d(dst + kEpiPlaneBytes, &tm.r_lo, &rbar[b], nt * p.block_n + ri_c * kEpiChunk, r0);
       }
       ++r_issued;
       if (++ri_c == nchunks) {
@@ -594,6 +598,13 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const long long rrow = (valid && ep.res_mode != RES_NONE && !p.res_tma) ? res_row(ep, m) : 0;
+      // row of this thread's residual inside a TMA-prefetched slot: its own row, or (nearest-2x upsampling) the offset
+      // of its source pixel from the tile's first source pixel
+      int srow = row;
+      if (p.res_up) {
+        const long long first = res_row_window_start(ep, static_cast<long long>(m_tile_cta) * kBlockM);
+        srow = valid ? static_cast<int>(res_row(ep, m) - first) : 0;
+      }
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.acc_cols);
       // gathered residual (FPN nearest-2x top-down add): per-thread vector loads, software-pipelined
@@ -653,15 +664,15 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
           if (rcur) {
             if (kFmt == 2) {
               const uint8_t* r8 = rcur + kEpiLo8Off;
-              add_lo8x16(v, *reinterpret_cast<const uint4*>(r8 + sw32_off(row, 0)));
-              add_lo8x16(v + 16, *reinterpret_cast<const uint4*>(r8 + sw32_off(row, 1)));
+              add_lo8x16(v, *reinterpret_cast<const uint4*>(r8 + sw32_off(srow, 0)));
+              add_lo8x16(v + 16, *reinterpret_cast<const uint4*>(r8 + sw32_off(srow, 1)));
             }
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
               if (pl == 1 && kFmt != 1) break;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiPlaneBytes + sw64_off(row, j));
+                const uint4 u = *reinterpret_cast<const uint4*>(rcur + pl * kEpiPlaneBytes + sw64_off(srow, j));
                 ptx::add_half2(v[8 * j + 0], v[8 * j + 1], u.x);
                 ptx::add_half2(v[8 * j + 2], v[8 * j + 3], u.y);
                 ptx::add_half2(v[8 * j + 4], v[8 * j + 5], u.z);
@@ -995,6 +1006,26 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   // prefetch buffers for the same-shape residual
   p.out_tma = (ep.out_f32 == nullptr && ep.ldo % 16 == 0) ? 1 : 0;
   p.res_tma = (p.out_tma && ep.res_mode == RES_SAME && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0) ? 1 : 0;
+  // nearest-2x upsampled residual (FPN top-down add): the source pixels of 128 consecutive output pixels form a window
+  // of at most (rows touched / 2 + 1) * Q / 2 consecutive source pixels; when that is <= 128 for every tile the window
+  // is TMA-prefetched like a same-shape residual instead of gathered with per-thread loads
+  static const int tune_no_res_up = tune_env("MCG_TUNE_NO_RES_UP");
+  if (p.out_tma && !tune_no_res_up && ep.res_mode == RES_UP2X && ep.res_f32 == nullptr && ep.res_hi != nullptr && ep.ldr % 16 == 0 &&
+      ep.P % 2 == 0 && ep.Q % 2 == 0) {
+    // exact check over every distinct tile offset inside a frame (the geometry repeats per frame)
+    const long long pq = static_cast<long long>(ep.P) * ep.Q;
+    long long worst = 0;
+    for (long long t = 0; t * kBlockM < M && t < pq; ++t) {
+      const long long m0 = t * kBlockM;
+      const long long first = res_row_window_start(ep, m0);
+      for (long long m = m0; m < m0 + kBlockM && m < M; ++m) worst = std::max(worst, res_row(ep, m) - first);
+      if (worst >= kBlockM) break;
+    }
+    if (worst < kBlockM) {
+      p.res_tma = 1;
+      p.res_up = 1;
+    }
+  }
   p.out_hi8 = (p.out_tma && ep.out_hi8 != nullptr) ? 1 : 0;
   const int set_bytes = epi_set_bytes(p.out_fmt);
   // residual chunks in flight per epilogue group (more chunks cost pipeline stages: measured slower)
@@ -1145,9 +1176,10 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
     if (p.out_hi8) tm.o_hi8 = make_tmap_2d_u8(ep.out_hi8, M, N, ep.ldo, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_32B);
   }
   if (p.res_tma) {
-    tm.r_hi = make_tmap_2d(ep.res_hi, M, N, ep.ldr, kBlockM, kEpiChunk, sw64);
-    if (p.res_fmt == 1) tm.r_lo = make_tmap_2d(ep.res_lo, M, N, ep.ldr, kBlockM, kEpiChunk, sw64);
-    if (p.res_fmt == 2) tm.r_lo = make_tmap_2d_u8(ep.res_lo8, M, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_32B);
+    const long long RM = p.res_up ? M / 4 : M;   // rows of the residual tensor
+    tm.r_hi = make_tmap_2d(ep.res_hi, RM, N, ep.ldr, kBlockM, kEpiChunk, sw64);
+    if (p.res_fmt == 1) tm.r_lo = make_tmap_2d(ep.res_lo, RM, N, ep.ldr, kBlockM, kEpiChunk, sw64);
+    if (p.res_fmt == 2) tm.r_lo = make_tmap_2d_u8(ep.res_lo8, RM, N, ep.ldr, kBlockM, kEpiChunk, CU_TENSOR_MAP_SWIZZLE_32B);
   }
   return pl;
 }

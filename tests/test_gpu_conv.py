@@ -32,6 +32,14 @@ CASES = [
     ('multi_3x3_c64', 8, 64, 56, 56, 64, 3, 1, 1, 0, 1, 0, 0),
     ('multi_fpn_topdown', 8, 256, 28, 28, 256, 1, 1, 0, 2, 0, 0, 0),
     ('multi_3x3_c128_bn128', 8, 128, 28, 28, 256, 3, 1, 1, 0, 0, 0, 128),
+    # nearest-2x top-down add with the TMA-prefetched source window (round 2): the FPN's own shapes at 224^2 (56 / 28 /
+    # 14 wide) and 448^2 (112 wide), tiles crossing image rows and frames, a non-square map, and a map too wide for the
+    # 128-row window (falls back to per-thread gathers)
+    ('fpn_topdown_56', 5, 256, 56, 56, 256, 1, 1, 0, 2, 0, 0, 0),
+    ('fpn_topdown_112', 1, 256, 112, 112, 256, 1, 1, 0, 2, 0, 0, 0),
+    ('fpn_topdown_nonsquare', 3, 512, 24, 40, 256, 1, 1, 0, 2, 0, 0, 0),
+    ('fpn_topdown_odd_frames', 3, 256, 14, 14, 256, 1, 1, 0, 2, 0, 0, 128),
+    ('fpn_topdown_wide_gather', 1, 256, 8, 288, 256, 1, 1, 0, 2, 0, 0, 0),
 ]
 # max |err| relative to max |ref|: split-fp16 x3 and the fp32 CUDA-core kernel are fp32-class,
 # single fp16 carries 2^-11 operand rounding
@@ -98,6 +106,8 @@ PAIR_CASES = [
     ('pair_1x1_residual', 8, 64, 56, 56, 256, 1, 1, 0, 1, 1, 0, 1000),
     ('pair_1x1_residual_bn128', 8, 64, 56, 56, 256, 1, 1, 0, 1, 1, 0, 1128),
     ('pair_fpn_topdown', 8, 256, 28, 28, 256, 1, 1, 0, 2, 0, 0, 1000),
+    ('pair_fpn_topdown_56', 5, 256, 56, 56, 256, 1, 1, 0, 2, 0, 0, 1000),
+    ('pair_fpn_topdown_nonsquare', 3, 512, 24, 40, 256, 1, 1, 0, 2, 0, 0, 1128),
     ('pair_odd_tiles', 1, 256, 30, 30, 128, 1, 1, 0, 0, 1, 0, 1000),          # M = 900: 3.5 pair tiles, last half empty
     ('pair_tiny_M', 1, 64, 3, 3, 64, 1, 1, 0, 0, 0, 0, 1000),                  # M = 9: the second CTA has no rows
     ('pair_bigK', 2, 2048, 14, 14, 512, 1, 1, 0, 0, 1, 0, 1000),
