@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, 'build')
 API_H = os.path.join('..', '..', 'include', 'mcgaze_b200.h')
 # source -> headers it depends on (each source is compiled to its own object, then linked)
 SOURCES = {
-    'mcg_api.cu': ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh', API_H],
+    'mcg_api.cu': ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'bneck_fused.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh', API_H],
     'preprocess.cu': ['common.cuh', API_H],
     'metric.cu': ['common.cuh', API_H],
 }

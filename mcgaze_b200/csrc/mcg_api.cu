@@ -19,6 +19,7 @@
 #include "head_kernels.cuh"
 #include "simt_gemm.cuh"
 #include "umma_gemm.cuh"
+#include "bneck_fused.cuh"
 #include "stem_fused.cuh"
 
 namespace mcg {
@@ -211,6 +212,7 @@ class Engine {
     else if (k == "head_tensor_cores") { head_tc_ = v != 0; drop_graph(true); }
     else if (k == "fused_stem") { fused_stem_ = v != 0; drop_graph(); }
     else if (k == "fuse_downsample") { fuse_ds_ = v != 0; drop_graph(); }
+    else if (k == "fuse_bottleneck") { fuse_bneck_ = v != 0; drop_graph(); }
     else throw CudaError("check failed: unknown option " + k);
   }
 
@@ -420,8 +422,8 @@ class Engine {
     for (int l = 0; l < 4; ++l)
       for (size_t b = 0; b < blk_act_[l].size(); ++b) {
         const std::string k = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
-        if (!fused_tail_used(l, b)) acts.emplace_back(k + ".t1", &blk_act_[l][b].t1), acts.emplace_back(k + ".t2", &blk_act_[l][b].t2);
-        else acts.emplace_back(k + ".t1", &blk_act_[l][b].t1);
+        acts.emplace_back(k + ".t1", &blk_act_[l][b].t1);
+        if (!fused_tail_used(l, b)) acts.emplace_back(k + ".t2", &blk_act_[l][b].t2);
         if (blocks_[l][b].has_ds && !(fuse_ds_ && trunk_terms() != 0)) acts.emplace_back(k + ".ds", &blk_act_[l][b].ds);
         acts.emplace_back(k, &blk_act_[l][b].out);
       }
@@ -464,8 +466,11 @@ class Engine {
   }
 
  private:
-  // whether block (l, b) ran conv2 -> conv3 as one fused kernel in the last forward (its t2 tensor then stays on chip)
-  bool fused_tail_used(int, size_t) const { return false; }
+  // whether block (l, b) runs conv2 -> conv3 as one fused kernel (its t2 tensor then stays on chip)
+  bool fused_tail_used(int l, size_t b) const {
+    const BlockW& bw = blocks_[l][b];
+    return fuse_bneck_ && precision_ == MCG_PRECISION_FP16C8 && bneck_supported(bw.c2.Cout, bw.c2.stride, bw.has_ds);
+  }
 
   // -------------------------------------------------------------------------- weight loading
   struct HostT {
@@ -746,11 +751,13 @@ class Engine {
     if (ws_NB_ > 0) {
       ShapeCtx& old = ctx_[std::make_tuple(ws_NB_, ws_T_, ws_H_, ws_W_)];
       old.plans.swap(plans_);
+      old.bneck_plans.swap(bneck_plans_);
       old.graphs.swap(graphs_);
       old.stem_plan = stem_plan_;
       old.stem_valid = stem_plan_valid_;
     }
     plans_.clear();
+    bneck_plans_.clear();
     graphs_.clear();
     stem_plan_valid_ = false;
     interm_.clear();
@@ -769,6 +776,7 @@ class Engine {
       auto it = ctx_.find(std::make_tuple(NB, T, H, W));
       if (it != ctx_.end()) {
         plans_.swap(it->second.plans);
+        bneck_plans_.swap(it->second.bneck_plans);
         graphs_.swap(it->second.graphs);
         stem_plan_ = it->second.stem_plan;
         stem_plan_valid_ = it->second.stem_valid;
@@ -874,11 +882,13 @@ class Engine {
       kv.second.graphs.clear();
       if (plans) {
         kv.second.plans.clear();
+        kv.second.bneck_plans.clear();
         kv.second.stem_valid = false;
       }
     }
     if (plans) {
       plans_.clear();
+      bneck_plans_.clear();
       stem_plan_valid_ = false;
     }
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
@@ -1023,6 +1033,36 @@ class Engine {
       return;
     }
     gemm(key, &x.pl, nullptr, g, cw.g, y.rows(), ep, st, trunk_terms());
+  }
+
+  // fused bottleneck tail: y = relu(conv3(relu(conv2(t1))) + x)
+  void bneck(const std::string& key, const Act& t1, const BlockW& bw, const Act& idn, const Act& y, cudaStream_t st) {
+    auto it = bneck_plans_.find(key);
+    if (it == bneck_plans_.end()) {
+      static const int tune_pair = std::getenv("MCG_TUNE_BF_PAIR") ? std::atoi(std::getenv("MCG_TUNE_BF_PAIR")) : 1;
+      const long long M = y.rows();
+      const int pair = (tune_pair && M >= 2 * kBlockM * ((num_sms_ * 40) / 148)) ? 1 : 0;
+      BneckPlan pl = make_bneck_plan(t1.pl, t1.NB, t1.H, t1.W, bw.c2.Cout, bw.c2.g.w, bw.c2.g.bias, bw.c3.g.w, bw.c3.g.bias,
+                                     idn.pl, y.pl, num_sms_, pair);
+      it = bneck_plans_.emplace(key, pl).first;
+    }
+    const bool timed = time_kernels_ && !graph_mode_;
+    if (timed) {
+      if (ev_used_ + 2 > ev_pool_.size()) {
+        ev_pool_.resize(ev_used_ + 2);
+        MCG_CUDA(cudaEventCreate(&ev_pool_[ev_used_]));
+        MCG_CUDA(cudaEventCreate(&ev_pool_[ev_used_ + 1]));
+      }
+      MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_], st));
+    }
+    launch_bneck(it->second, st);
+    if (timed) {
+      MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_ + 1], st));
+      ev_used_ += 2;
+    }
+    ++umma_launches_;
+    umma_flops_ += it->second.flops;
+    count(("bneck:" + key).c_str());
   }
 
   // fp32 linear on (possibly strided) rows: y = x W^T + b (+res) (relu)
@@ -1254,6 +1294,13 @@ class Engine {
         BlkAct& ba = blk_act_[l][b];
         const std::string k = "l" + std::to_string(l) + "b" + std::to_string(b);
         conv(k + "c1", *x, bw.c1, ba.t1, true, nullptr, RES_NONE, st);
+        if (fused_tail_used(l, b)) {
+          // conv2 -> conv3 + identity as one kernel, t2 stays in shared memory (bneck_fused.cuh)
+          bneck(k + "c2c3", ba.t1, bw, *x, ba.out, st);
+          x = &ba.out;
+          reg_act("layer" + std::to_string(l + 1) + "." + std::to_string(b), ba.out);
+          continue;
+        }
         conv(k + "c2", ba.t1, bw.c2, ba.t2, true, nullptr, RES_NONE, st);
         const Act* idn = x;
         if (bw.has_ds && fuse_ds_ && trunk_terms() != 0) {
@@ -1500,6 +1547,7 @@ class Engine {
   bool head_tc_ = true;
   bool fused_stem_ = true;
   bool fuse_ds_ = true;  // conv3 + downsample branch of a layer's first bottleneck as one K-concatenated GEMM
+  bool fuse_bneck_ = true;  // conv2 -> conv3 + identity of the other bottlenecks of layer1 / layer2 as one kernel (fp16c8)
   StemFusedPlan stem_plan_;
   bool stem_plan_valid_ = false;
   bool keep_stage_interm_ = false;
@@ -1550,6 +1598,7 @@ class Engine {
   bool has_scale_ = false;
 
   std::map<std::string, UmmaPlan> plans_;
+  std::map<std::string, BneckPlan> bneck_plans_;
   std::map<std::string, Interm> interm_;
   int launches_ = 0;
 
@@ -1565,6 +1614,7 @@ class Engine {
   std::map<GraphKey, cudaGraphExec_t> graphs_;
   struct ShapeCtx {  // launch plans / graphs of a (NB, T, H, W) seen before (valid while the arena is not re-allocated)
     std::map<std::string, UmmaPlan> plans;
+    std::map<std::string, BneckPlan> bneck_plans;
     std::map<GraphKey, cudaGraphExec_t> graphs;
     StemFusedPlan stem_plan;
     bool stem_valid = false;

@@ -415,3 +415,32 @@ def test_k_concatenated_downsample_matches_separate_branch(engines, synthetic_sd
         assert (f[n] - p[n]).abs().max() < tol * p[n].abs().max(), n
     if precision != 'fp16':
         assert yaw_pitch_err(fused['gaze'][:, 0].cpu(), plain['gaze'][:, 0].cpu()) < 2e-4
+
+
+@pytest.mark.parametrize('shape', [(1, 4, 224, 224), (8, 7, 224, 224), (1, 3, 96, 128), (2, 2, 448, 448)],
+                         ids=['T4_224', 'B8_T7_224_pairs', 'T3_96x128', 'B2_T2_448'])
+def test_fused_bottleneck_tail_matches_separate_convolutions(engines, synthetic_sd, shape):
+    """Default fp16c8 schedule: conv2 -> conv3 + identity of layer1.1-2 / layer2.1-3 as ONE kernel (bneck_fused.cuh,
+    t2 stays in shared memory as tensor-core operand planes; resnet.py:277-302).  Against the separate convolutions
+    (option fuse_bottleneck = 0; same operands, same accumulation order per layer -> the block outputs agree to the
+    storage rounding) and against the oracle's block outputs; single-CTA tiles (small M) and CTA pairs (large M)."""
+    B, T, H, W = shape
+    img = torch.cat([O.make_clip(300 + b, T, H, W) for b in range(B)])
+    taps = {}
+    ref = O.forward(synthetic_sd, img, clip_length=T, hk=O.Hooks(tap=lambda n, t: taps.__setitem__(n, t.clone())))
+    eng = engines('fp16c8')
+    names = ['layer1.1', 'layer1.2', 'layer2.1', 'layer2.2', 'layer2.3', 'layer3.5', 'layer4.2']
+    try:
+        fused = eng.forward(img.cuda(), clip_length=T)
+        f = {n: eng.intermediate(n).cpu() for n in names}
+        eng.set_option('fuse_bottleneck', 0)
+        plain = eng.forward(img.cuda(), clip_length=T)
+        p = {n: eng.intermediate(n).cpu() for n in names}
+    finally:
+        eng.set_option('fuse_bottleneck', 1)
+    for n in names:
+        assert (f[n] - taps[n]).abs().max() < 4e-4 * taps[n].abs().max(), n
+        assert (f[n] - p[n]).abs().max() < 2e-4 * p[n].abs().max(), n
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(fused['gaze'][:, i].cpu(), ref[k]) < 1e-3, k
+    assert yaw_pitch_err(fused['gaze'][:, 0].cpu(), plain['gaze'][:, 0].cpu()) < 2e-4
