@@ -398,7 +398,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        # a rank that dies must not cost the others the default 10-minute collective timeout
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local_rank)
 
     sd = O.make_state_dict(0)
@@ -565,6 +567,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+                'ms_per_step_over_ranks': rank_ms,
                 'config': {'workload': 'multiclue_gaze_r50 Gaze360-setting inference, bs=32 clips x 7 frames x 224x224 '
                                        'per GPU (BASELINE configs[1])', 'clips_per_step_per_gpu': CLIPS_PER_STEP,
                            'clip_length': T, 'height': H, 'width': W, 'weights': 'seeded random (reference key layout)',

@@ -412,7 +412,8 @@ def multi_gpu_test_videos(model, dataset: Gaze360ClipDataset, pipeline, clips_pe
         out['merged_local'] = local
         return out
     # JSON wanted: ONE all-gather of the merged per-frame rows (27 floats per frame), back to dataset order
-    fmax = -(-sum(len(v) for v in dataset.videos) // world) + max(len(v) for v in dataset.videos)
+    # same buffer size on every rank, computed from what every rank knows (lengths + sharding rule): the largest shard
+    fmax = max(sum(len(dataset.videos[v]) for v in mdist.shard_indices(nv, r, world)) for r in range(world))
     packed = torch.zeros(fmax, 27, dtype=torch.float32, device=det.device if det is not None else 'cpu')
     if mine:
         packed[:off[-1], :15] = det.reshape(-1, 15)

@@ -258,12 +258,12 @@ def test_gpu_device_scorer_matches_host_scorer_on_driver_output():
 # ------------------------------------------------------------------------------------------------------------------
 # video-sharded run: merge + score where the results are, one all-reduce of 6 doubles
 # ------------------------------------------------------------------------------------------------------------------
-def _video_worker(rank, world, port, out_q):
+def _video_worker(rank, world, port, out_q, lengths=None):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    ds = ev.Gaze360ClipDataset(make_anno(), loader=fake_loader)
+    ds = ev.Gaze360ClipDataset(make_anno(lengths or LENGTHS), loader=fake_loader)
     model = StubModel()
     out = ev.multi_gpu_test_videos(model, ds, StubPipeline(), clips_per_batch=3)
     out_q.put((rank, out['mae'], out['sums'], out['videos_local'], [(m['det'].tolist(), m['gaze'].tolist()) for m in out['merged']],
@@ -303,6 +303,39 @@ def test_two_rank_gloo_video_sharded_mae():
         for (det, gz), m in zip(merged_r, merged):
             assert np.allclose(np.asarray(det, np.float32), m['det'], rtol=1e-6, atol=1e-6)
             assert np.allclose(np.asarray(gz, np.float32), m['gaze'], rtol=1e-6, atol=1e-6)
+
+
+def test_three_rank_gloo_video_sharding_with_skewed_shards():
+    """Round-robin over videos of very different lengths: one rank holds far more frames than total / world + longest
+    video (the bound a first version of the gather buffer used: a rank failed before the all-gather and the others
+    waited for it until the NCCL timeout).  Every rank must come back with all videos."""
+    import torch.multiprocessing as mp
+    lengths = [30, 1, 1, 30, 2, 1, 30, 1, 3, 23]
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_video_worker, args=(r, 3, port, q, lengths)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(3):
+        item = q.get(timeout=180)
+        got[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ds = ev.Gaze360ClipDataset(make_anno(lengths), loader=fake_loader)
+    rows = ev.single_gpu_test(StubModel(), ds, StubPipeline(), clips_per_batch=5)
+    records, merged = ev.videos_from_clips(ds, rows)
+    want = ev.evaluate(ds, records)
+    for r in range(3):
+        mae, sums, mine, merged_r, _ = got[r]
+        assert mine == list(range(r, len(lengths), 3)) and sums[1] == sum(lengths)
+        assert all(abs(mae[k] - want[k]) < 1e-6 for k in want)
+        assert all(np.allclose(np.asarray(det, np.float32), m['det'], rtol=1e-6, atol=1e-6) for (det, _), m in zip(merged_r, merged))
 
 
 def test_video_sharded_run_without_a_process_group_and_l2cs_variant():
