@@ -431,12 +431,14 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_mid = torch.cuda.Event(enable_timing=True)
     keep = []
     barrier()
     e0.record()
     for _ in range(args.steps):
         eng.forward_into(img, T, out)
         keep.append(out['gaze'].clone())
+    e_mid.record()     # end of this rank's own forwards (reported per rank; the timed region goes on to e1)
     if world > 1:      # the one collective of the sharded test path: gather every rank's results
         mine = torch.stack(keep)
         gathered = [torch.empty_like(mine) for _ in range(world)]
@@ -447,12 +449,13 @@ def main():
     ms_total = e0.elapsed_time(e1)
     rank_ms = None
     if world > 1:
-        t = torch.tensor([ms_total], device=dev)
+        t = torch.tensor([ms_total, e0.elapsed_time(e_mid)], device=dev)
         all_t = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(all_t, t)
-        per_rank = sorted(float(x.item()) for x in all_t)
+        per_rank = sorted(float(x[0].item()) for x in all_t)
+        fwd = [float(x[1].item()) / args.steps for x in all_t]       # by rank: forwards only, before the all-gather
         rank_ms = {'min': per_rank[0] / args.steps, 'median': per_rank[len(per_rank) // 2] / args.steps,
-                   'max': per_rank[-1] / args.steps}
+                   'max': per_rank[-1] / args.steps, 'forwards_only_by_rank': fwd}
         ms_total = per_rank[-1]            # max over ranks
     ms_per_step = ms_total / args.steps
     value = world * CLIPS_PER_STEP * args.steps / (ms_total * 1e-3)
