@@ -970,10 +970,16 @@ __global__ void __launch_bounds__(kSlThreads) small_linear_kernel(const LinGroup
 // towers, gaze towers).  A CTA owns 8 complete rows (256 columns x 4 k-slices = 1024 threads),
 // so the row statistics never leave the SM.
 // ---------------------------------------------------------------------------------------
+// attn_qkv != null (K must be 256): the input rows are not read from grp.x but computed here as the self-attention
+// core over qkv [M, 768] (the body of attention_kernel: 8 heads x 32 channels, one warp per (row, head), online
+// softmax over the 3 clues of the row's frame (attn_mode 0) or the T frames of its clip and clue (attn_mode 1)), so
+// `attention core -> out_proj -> + identity -> attention_norm` (gaze_stqi_head.py:148-166) is one launch.
 __global__ void __launch_bounds__(1024) linear256_ln_kernel(const LinGroups grp, long long ldx,
                                                             const float* __restrict__ res, long long ldres,
                                                             long long ldy, long long M, int K, int relu,
-                                                            __half* __restrict__ yh, __half* __restrict__ yl) {
+                                                            __half* __restrict__ yh, __half* __restrict__ yl,
+                                                            const float* __restrict__ attn_qkv = nullptr, int attn_T = 0,
+                                                            int attn_mode = 0) {
   const float* __restrict__ x = grp.x[blockIdx.y];
   const float* __restrict__ wt = grp.wt[blockIdx.y];  // [K, 256]
   const float* __restrict__ bias = grp.bias[blockIdx.y];
@@ -991,9 +997,49 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const LinGroups grp,
   float w[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) w[j] = (k0 + j < k1) ? __ldg(wt + static_cast<long long>(k0 + j) * 256 + n) : 0.f;
-  for (int i = tid; i < kSlRows * K; i += 1024) {
-    const int rr = i / K, k = i - rr * K;
-    xs[i] = (m0 + rr < M) ? x[(m0 + rr) * ldx + k] : 0.f;
+  if (attn_qkv != nullptr) {
+    // 8 rows x 8 heads = 64 (row, head) pairs over the 32 warps; lane = channel of the head
+    const int aw = tid >> 5, al = tid & 31;
+    for (int pair = aw; pair < kSlRows * 8; pair += 32) {
+      const int rr = pair >> 3, head = pair & 7;
+      const long long row = m0 + rr;
+      float o = 0.f;
+      if (row < M) {
+        const long long frame = row / 3;
+        const int clue = static_cast<int>(row - frame * 3);
+        long long first;
+        int step, L;
+        if (attn_mode == 0) {
+          first = frame * 3;
+          step = 1;
+          L = 3;
+        } else {
+          first = (frame / attn_T) * attn_T * 3 + clue;
+          step = 3;
+          L = attn_T;
+        }
+        const float qv = attn_qkv[row * 768 + head * 32 + al] * 0.17677669529663687f;  // 1/sqrt(32)
+        float mx = -INFINITY, den = 0.f, acc_v = 0.f;
+        for (int l = 0; l < L; ++l) {
+          const long long kr = (first + static_cast<long long>(l) * step) * 768;
+          float sc = qv * attn_qkv[kr + 256 + head * 32 + al];
+          for (int off = 16; off; off >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);
+          const float nm = fmaxf(mx, sc);
+          const float corr = __expf(mx - nm);
+          const float pexp = __expf(sc - nm);
+          den = den * corr + pexp;
+          acc_v = acc_v * corr + pexp * attn_qkv[kr + 512 + head * 32 + al];
+          mx = nm;
+        }
+        o = acc_v / den;
+      }
+      xs[rr * K + head * 32 + al] = o;
+    }
+  } else {
+    for (int i = tid; i < kSlRows * K; i += 1024) {
+      const int rr = i / K, k = i - rr * K;
+      xs[i] = (m0 + rr < M) ? x[(m0 + rr) * ldx + k] : 0.f;
+    }
   }
   __syncthreads();
   float acc[kSlRows];

@@ -1113,17 +1113,21 @@ class Engine {
 
   // y = act(LN(x W^T + b (+res)))  for N == 256 Linears followed by a LayerNorm; optionally also written as
   // split-fp16 planes (input of a following tensor-core Linear)
+  // attn_qkv != null: x is computed in the kernel as the attention core over qkv (mode 0 spatial / 1 temporal)
   void linear_ln(const float* x, long long ldx, const GemmW& w, const LnW& n, long long M, float* y, long long ldy,
-                 bool relu, const float* res, long long ldres, cudaStream_t st, const Planes* planes = nullptr) {
+                 bool relu, const float* res, long long ldres, cudaStream_t st, const Planes* planes = nullptr,
+                 const float* attn_qkv = nullptr, int attn_T = 0, int attn_mode = 0) {
     const GemmW* ws[1] = {&w};
     const LnW* ns[1] = {&n};
     const float* xs[1] = {x};
     float* ys[1] = {y};
-    linear_ln_grouped(1, xs, ldx, ws, ns, M, ys, ldy, relu, res, ldres, st, planes);
+    linear_ln_grouped(1, xs, ldx, ws, ns, M, ys, ldy, relu, res, ldres, st, planes, attn_qkv, attn_T, attn_mode);
   }
   void linear_ln_grouped(int cnt, const float* const* x, long long ldx, const GemmW* const* w, const LnW* const* n,
                          long long M, float* const* y, long long ldy, bool relu, const float* res, long long ldres,
-                         cudaStream_t st, const Planes* planes = nullptr) {
+                         cudaStream_t st, const Planes* planes = nullptr, const float* attn_qkv = nullptr, int attn_T = 0,
+                         int attn_mode = 0) {
+    MCG_CHECK(attn_qkv == nullptr || (cnt == 1 && w[0]->K == 256), "the fused attention core feeds one 256 -> 256 Linear");
     MCG_CHECK(cnt >= 1 && cnt <= kMaxLinGroups && ((res == nullptr && planes == nullptr) || cnt == 1), "bad Linear+LN group");
     LinGroups g = {};
     for (int i = 0; i < cnt; ++i) {
@@ -1140,7 +1144,8 @@ class Engine {
     const size_t smem = (static_cast<size_t>(kSlRows) * K + 4 * kSlRows * 256) * sizeof(float);
     dim3 grid(static_cast<unsigned>((M + kSlRows - 1) / kSlRows), cnt);
     linear256_ln_kernel<<<grid, 1024, smem, st>>>(g, ldx, res, ldres, ldy, M, K, relu ? 1 : 0,
-                                                  planes ? planes->hi : nullptr, planes ? planes->lo : nullptr);
+                                                  planes ? planes->hi : nullptr, planes ? planes->lo : nullptr, attn_qkv,
+                                                  attn_T, attn_mode);
     MCG_CUDA(cudaGetLastError());
     count("linear256_ln_kernel");
   }
@@ -1377,13 +1382,10 @@ class Engine {
         // that produced xin (init proposals / the previous stage's ffn_norm / the spatial pass's out_proj + LN)
         linear_tc(sk + (mode == 0 ? "inproj_s" : "inproj_t"), xin, 256, mode == 0 ? hobj_ : hx1_, tc, sw.in_proj, R, qkv_,
                   false, nullptr, st);
-        attention_kernel<<<(R * 8 * 32 + 255) / 256, 256, 0, st>>>(qkv_, att_, R, T, mode);
-        MCG_CUDA(cudaGetLastError());
-        count("attention_kernel");
-        // out_proj + identity (mmcv MHA) + attention_norm in one kernel; the temporal pass also emits the
-        // split-fp16 planes the dynamic_layer GEMM reads
-        linear_ln(att_, 256, sw.out_proj, sw.attn_norm, R, xout[mode], 256, false, xin, 256, st,
-                  tc ? (mode == 1 ? &hq_ : &hx1_) : nullptr);
+        // attention core + out_proj + identity (mmcv MHA) + attention_norm in one kernel; it also emits the split-fp16
+        // planes the next tensor-core Linear reads (temporal in_proj resp. dynamic_layer)
+        linear_ln(nullptr, 256, sw.out_proj, sw.attn_norm, R, xout[mode], 256, false, xin, 256, st,
+                  tc ? (mode == 1 ? &hq_ : &hx1_) : nullptr, qkv_, T, mode);
         xin = xout[mode];
       }
       const float* attn = xb_;
