@@ -365,7 +365,7 @@ def run_reference(args, rank, world):
 
 
 # measured DRAM traffic (bytes) of the dominant GEMM launch, from the ncu capture committed under profiles/
-NCU_TRAFFIC = {'fp16c8': 722255616 + 505873152}
+NCU_TRAFFIC = {'fp16c8': 722660864 + 504889856}
 
 
 def main():
@@ -505,7 +505,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the step (FPN 3x3 on P2, 26 % of
                 # the step's FLOPs) from the committed `ncu --set full` capture; its algorithmic bytes are 1259 MB
                 'traffic': NCU_TRAFFIC.get(args.precision),
-                'traffic_source': 'profiles/r01_ncu_umma_fp16c8_summary.md (fpn0 launch: 722 MB read + 506 MB written)'
+                'traffic_source': 'profiles/r02_ncu_summary.md (fpn0 launch, the largest of the step: 723 MB read + 505 MB written; algorithmic bytes 1259 MB)'
                 if args.precision in NCU_TRAFFIC else None,
                 'peak_source': peaks['source'] + ', bf16 dense sustained (kernel timed inside a long step)',
                 'launches_per_step': um_n // 3, 'algorithmic_gflop_per_step': um_fl / 3 / 1e9,
