@@ -40,6 +40,7 @@ struct BneckParams {
   int stage_bytes = 0;
   int nbuf1 = 2;     // acc1 buffers
   int out_sets = 1;
+  int res_slots = 2; // identity chunks in flight per E3 group (1 or 2)
   int out_hi8 = 1;
   AGeom a;           // im2col geometry of conv2 (3x3, stride 1, pad 1)
   const float* bias2 = nullptr;
@@ -441,7 +442,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
     constexpr int nchunks = kBfN3Tile / kEpiChunk;   // 4
     const uint32_t osets = static_cast<uint32_t>(p.out_sets);
     uint8_t* obuf = obuf_base + grp * p.out_sets * kBfSet;
-    uint8_t* rbuf = rbuf_base + grp * 2 * kBfRSet;
+    uint8_t* rbuf = rbuf_base + grp * p.res_slots * kBfRSet;
+    const uint32_t rslots = static_cast<uint32_t>(p.res_slots);
     uint64_t* rbar = res_bar + grp * 2;
     const int total_q = n_local * nt3;
     // residual chunk stream of this group's tasks, prefetched two chunks ahead
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
     uint32_t r_issued = 0, r_consumed = 0;
     auto res_issue = [&]() {
       if (ri_q >= total_q) return;
-      const uint32_t b = r_issued & 1u;
+      const uint32_t b = r_issued % rslots;
       if (leader) {
         const int i = ri_q / nt3, j = ri_q - i * nt3;
         const int tile = walker + i * walkers;
@@ -466,8 +468,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
         ri_q += 2;
       }
     };
-    res_issue();
-    res_issue();
+    for (int k = 0; k < p.res_slots; ++k) res_issue();
     uint32_t ostores = 0;
     int n = 0;
     for (int q = grp; q < total_q; q += 2, ++n) {
@@ -483,8 +484,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
         const int ncol = j * kBfN3Tile + c * kEpiChunk;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr0 + static_cast<uint32_t>(c * kEpiChunk), r);
-        const uint32_t rb = r_consumed & 1u;
-        ptx::mbar_wait(&rbar[rb], (r_consumed >> 1) & 1u);
+        const uint32_t rb = r_consumed % rslots;
+        ptx::mbar_wait(&rbar[rb], (r_consumed / rslots) & 1u);
         const uint8_t* rcur = rbuf + rb * kBfRSet;
         ++r_consumed;
         ptx::tmem_ld_wait();
@@ -634,7 +635,10 @@ inline BneckPlan make_bneck_plan(const Planes& t1, int NB, int H, int W, int pla
   const int c2_stage = kATileBytes + w2_rows * kBlockK * 2;
   const int c3_stage = w3_rows * kBlockK * 2;
   p.stage_bytes = ((c2_stage > c3_stage ? c2_stage : c3_stage) + 1023) & ~1023;
-  const int fixed = 1024 + kSmemBarrierBytes + (planes / kBlockK) * kBfT2KbBytes + 2 * 2 * kBfRSet;   // + residual slots
+  static const int tune_rslots = tune_env("MCG_TUNE_BF_RES_SLOTS");
+  // measured (same box, graph replay): 1 slot 9.49 ms per step, 2 slots 9.64 - the 24 KB are worth more as a ring stage
+  p.res_slots = tune_rslots == 1 || tune_rslots == 2 ? tune_rslots : 1;
+  const int fixed = 1024 + kSmemBarrierBytes + (planes / kBlockK) * kBfT2KbBytes + 2 * p.res_slots * kBfRSet;   // + residual slots
   // staging sets per E3 group: a second set only when it does not cost the ring its 4th stage (conv2 is L2-bound: the
   // bytes in flight matter more than the store overlap); env MCG_TUNE_BF_OUT_SETS forces it
   static const int tune_sets = tune_env("MCG_TUNE_BF_OUT_SETS");

@@ -1030,7 +1030,7 @@ inline UmmaPlan make_umma_plan(int terms, Planes A, const AGeom& a, Planes W, lo
   const int set_bytes = epi_set_bytes(p.out_fmt);
   // residual chunks in flight per epilogue group (more chunks cost pipeline stages: measured slower)
   static const int tune_res_bufs = tune_env("MCG_TUNE_RES_BUFS");
-  p.res_bufs = tune_res_bufs >= 2 && tune_res_bufs <= kMaxResBufs ? tune_res_bufs : 2;  // measured: 2 > 3 > 4 (ring depth matters more)
+  p.res_bufs = tune_res_bufs >= 1 && tune_res_bufs <= kMaxResBufs ? tune_res_bufs : 2;  // measured: 2 > 3 > 4 (ring depth matters more)
   // ... as long as two stages of the widest usable tile (block_n >= 128 where N allows) still fit
   while (p.res_tma && p.res_bufs > 2) {
     const int wide = force_block_n ? force_block_n : (N % 128 == 0 ? 128 : 64);
