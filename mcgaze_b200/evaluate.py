@@ -175,7 +175,9 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
     cuda = torch.cuda.is_available()
     copy_stream = None
 
-    def upload(frames):
+    upload_done: Dict[int, Any] = {}              # staging slot -> event of the last H2D copy that read it
+
+    def upload(frames, slot):
         """pinned uint8 block -> device on a side stream; the compute stream waits for the copy only"""
         nonlocal copy_stream
         if not (cuda and hasattr(frames, 'is_pinned') and frames.is_pinned() and hasattr(pipeline, 'device')):
@@ -188,6 +190,7 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
             d = frames.to(dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record(copy_stream)
+        upload_done[slot] = done
         cur.wait_event(done)
         d.record_stream(cur)
         return d
@@ -210,11 +213,18 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
         for bi, batch in enumerate(batches):
             if feeder:
                 T, frames, names = nxt.result()
-                nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool, staging, (bi + 1) % 3) \
-                    if bi + 1 < len(batches) else None
+                if bi + 1 < len(batches):
+                    # the loader is about to overwrite pinned slot (bi + 1) % 3: the copy of its last user (batch bi - 2)
+                    # must have left it - nothing else orders the two when the results stay on the device
+                    prev = upload_done.pop((bi + 1) % 3, None)
+                    if prev is not None:
+                        prev.synchronize()
+                    nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool, staging, (bi + 1) % 3)
+                else:
+                    nxt = None
             else:
                 T, frames, names = _load_batch(dataset, batch, None)
-            frames = upload(frames)
+            frames = upload(frames, bi % 3)
             parts = []
             for sub, sub_names, rands, clips in _canvas_groups(pipeline, frames, names, T):
                 data = pipeline.batch(sub, filenames=sub_names) if rands is None else \
@@ -421,6 +431,8 @@ def multi_gpu_test_videos(model, dataset: Gaze360ClipDataset, pipeline, clips_pe
     if dist_on and world > 1:
         if tdist.get_backend(group) != 'nccl':
             packed = packed.cpu()
+        elif not packed.is_cuda:           # a rank without videos still takes part in the NCCL collective
+            packed = packed.cuda()
         bufs = [torch.empty_like(packed) for _ in range(world)]
         tdist.all_gather(bufs, packed, group=group)
     else:
