@@ -417,8 +417,9 @@ def test_k_concatenated_downsample_matches_separate_branch(engines, synthetic_sd
         assert yaw_pitch_err(fused['gaze'][:, 0].cpu(), plain['gaze'][:, 0].cpu()) < 2e-4
 
 
-@pytest.mark.parametrize('shape', [(1, 4, 224, 224), (8, 7, 224, 224), (1, 3, 96, 128), (2, 2, 448, 448)],
-                         ids=['T4_224', 'B8_T7_224_pairs', 'T3_96x128', 'B2_T2_448'])
+@pytest.mark.parametrize('shape', [(1, 4, 224, 224), (8, 7, 224, 224), (1, 3, 96, 128), (2, 2, 448, 448), (1, 5, 224, 224),
+                                   (1, 1, 32, 64)],
+                         ids=['T4_224', 'B8_T7_224_pairs', 'T3_96x128', 'B2_T2_448', 'T5_224_ragged_pair_tiles', 'T1_32x64_one_tile'])
 def test_fused_bottleneck_tail_matches_separate_convolutions(engines, synthetic_sd, shape):
     """Default fp16c8 schedule: conv2 -> conv3 + identity of layer1.1-2 / layer2.1-3 as ONE kernel (bneck_fused.cuh,
     t2 stays in shared memory as tensor-core operand planes; resnet.py:277-302).  Against the separate convolutions
