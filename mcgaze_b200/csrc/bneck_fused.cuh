@@ -41,6 +41,7 @@ struct BneckParams {
   int nbuf1 = 2;     // acc1 buffers
   int out_sets = 1;
   int res_slots = 2; // identity chunks in flight per E3 group (1 or 2)
+  int reverse = 0;   // walk the tiles from the end (see UmmaParams::reverse)
   int out_hi8 = 1;
   AGeom a;           // im2col geometry of conv2 (3x3, stride 1, pad 1)
   const float* bias2 = nullptr;
@@ -90,6 +91,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
   const int walkers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int n_local = walker < p.m_tiles ? (p.m_tiles - walker + walkers - 1) / walkers : 0;
   const int rows_per_tile = kPair ? 2 * kBlockM : kBlockM;
+  // i-th tile of this walker
+  auto tile_of = [&](int i) {
+    const int t = walker + i * walkers;
+    return p.reverse ? p.m_tiles - 1 - t : t;
+  };
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm.a_hi);
@@ -233,8 +239,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
       }
     };
     for (int i = 0; i <= n_local; ++i) {
-      if (i < n_local) load_c2(walker + i * walkers);
-      if (i >= 1) load_c3(walker + (i - 1) * walkers);
+      if (i < n_local) load_c2(tile_of(i));
+      if (i >= 1) load_c3(tile_of(i - 1));
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
       const uint32_t b = r_issued % rslots;
       if (leader) {
         const int i = ri_q / nt3, j = ri_q - i * nt3;
-        const int tile = walker + i * walkers;
+        const int tile = tile_of(i);
         const int mt = tile * (kPair ? 2 : 1) + static_cast<int>(cta_rank);
         uint8_t* dst = rbuf + b * kBfRSet;
         ptx::fence_proxy_async();
@@ -473,7 +479,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bneck_tail_kernel(const __grid_
     int n = 0;
     for (int q = grp; q < total_q; q += 2, ++n) {
       const int i = q / nt3, j = q - i * nt3;
-      const int tile = walker + i * walkers;
+      const int tile = tile_of(i);
       const int m_tile_cta = tile * (kPair ? 2 : 1) + static_cast<int>(cta_rank);
       ptx::mbar_wait(&a3full[grp], static_cast<uint32_t>(n) & 1u);
       ptx::tc_fence_after();

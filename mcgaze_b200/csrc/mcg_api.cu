@@ -941,6 +941,7 @@ class Engine {
         const bool big = M >= 2 * kBlockM * pair_min && k_split == 1 && ep.out_f32 == nullptr;
         const int pair = (big && ((pair_mode == 1 && geom.kind == 1) || pair_mode == 2)) ? 1 : 0;
         UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, pair, A2, geom2);
+        pl.p.reverse = alternate_ ? ((tc_launch_index_ & 1) ^ 1) : 0;   // launch 0 reads what the stem wrote last
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -953,6 +954,7 @@ class Engine {
         MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_], st));
       }
       launch_umma(it->second, st);
+      ++tc_launch_index_;
       if (timed) {
         MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_ + 1], st));
         ev_used_ += 2;
@@ -1044,6 +1046,7 @@ class Engine {
       const int pair = (tune_pair && M >= 2 * kBlockM * ((num_sms_ * 40) / 148)) ? 1 : 0;
       BneckPlan pl = make_bneck_plan(t1.pl, t1.NB, t1.H, t1.W, bw.c2.Cout, bw.c2.g.w, bw.c2.g.bias, bw.c3.g.w, bw.c3.g.bias,
                                      idn.pl, y.pl, num_sms_, pair);
+      pl.p.reverse = alternate_ ? ((tc_launch_index_ & 1) ^ 1) : 0;
       it = bneck_plans_.emplace(key, pl).first;
     }
     const bool timed = time_kernels_ && !graph_mode_;
@@ -1056,6 +1059,7 @@ class Engine {
       MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_], st));
     }
     launch_bneck(it->second, st);
+    ++tc_launch_index_;
     if (timed) {
       MCG_CUDA(cudaEventRecord(ev_pool_[ev_used_ + 1], st));
       ev_used_ += 2;
@@ -1239,6 +1243,7 @@ class Engine {
   // -------------------------------------------------------------------------- the forward schedule
   void schedule(const float* img, float* out_gaze, float* out_boxes, float* out_scores, cudaStream_t st) {
     launches_ = 0;
+    tc_launch_index_ = 0;
     umma_launches_ = 0;
     umma_flops_ = 0.0;
     ev_used_ = 0;
@@ -1549,6 +1554,9 @@ class Engine {
   bool head_tc_ = true;
   bool fused_stem_ = true;
   bool fuse_ds_ = true;  // conv3 + downsample branch of a layer's first bottleneck as one K-concatenated GEMM
+  // consecutive tcgen05 launches walk their tile lists in opposite directions (env MCG_TUNE_NO_ALTERNATE=1: all forward)
+  bool alternate_ = std::getenv("MCG_TUNE_NO_ALTERNATE") == nullptr;
+  int tc_launch_index_ = 0;
   bool fuse_bneck_ = true;  // conv2 -> conv3 + identity of the other bottlenecks of layer1 / layer2 as one kernel (fp16c8)
   StemFusedPlan stem_plan_;
   bool stem_plan_valid_ = false;

@@ -94,6 +94,8 @@ struct UmmaParams {
   // K-concatenated second A operand: k-blocks [kb2_begin, num_kb) read the tensor described by `a2` (maps a2_*)
   // instead of `a`; W is the [N, K1 + K2] concatenation.  D = A1 W1^T + A2 W2^T in one accumulator: a bottleneck's
   // conv3 and its downsample branch (resnet.py:286-295) as ONE GEMM, the identity never round-trips through HBM.
+  int reverse = 0;    // walk the tile list from its end: consecutive launches alternate, so a launch starts on the tiles
+                      // its producer wrote last (still in L2) instead of the ones written first (long evicted)
   int kb2_begin = 0;  // 0 = single A operand
   AGeom a;
   AGeom a2;
@@ -265,7 +267,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     const long long dbg_p0 = clock64();
     const uint32_t full_a = ptx::smem_u32(full_bar), empty_a = ptx::smem_u32(empty_bar);
     const uint32_t ring_a = ptx::smem_u32(stage_base);
-    for (int tile = walker; tile < num_tiles; tile += walkers) {
+    for (int tile_i = walker; tile_i < num_tiles; tile_i += walkers) {
+      const int tile = p.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int ks = tile / mn_tiles;
       const int mn = tile - ks * mn_tiles;
       const int m_tile = mn / p.n_tiles;
@@ -447,7 +450,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
       dbg_c0 = clock64();
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     }
-    for (int tile = walker; tile < num_tiles && leader_cta; tile += walkers, ++local) {
+    for (int tile_i = walker; tile_i < num_tiles && leader_cta; tile_i += walkers, ++local) {
+      const int tile = p.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int acc = local % p.num_acc;
       const uint32_t acc_phase = static_cast<uint32_t>(local / p.num_acc) & 1u;
       if (kDbg && (p.dbg & 128)) {
@@ -552,8 +556,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     int ri_local = grp, ri_c = 0;
     uint32_t r_issued = 0, r_consumed = 0;
     auto res_issue = [&]() {
-      const int t = walker + ri_local * walkers;
-      if (t >= num_tiles) return;
+      const int t_i = walker + ri_local * walkers;
+      if (t_i >= num_tiles) return;
+      const int t = p.reverse ? num_tiles - 1 - t_i : t_i;
       const uint32_t b = r_issued % res_bufs;
       if (leader && (kDbg && (p.dbg & 32))) {
         ptx::mbar_arrive(&rbar[b]);
@@ -583,8 +588,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaMaps tm, const UmmaParams p) {
     }
     uint32_t ostores = 0;  // chunks handed to TMA so far (staging set = ostores % osets)
     for (int local = grp;; local += kEpiGroups) {
-      const int tile = walker + local * walkers;
-      if (tile >= num_tiles) break;
+      const int tile_i = walker + local * walkers;
+      if (tile_i >= num_tiles) break;
+      const int tile = p.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int ks = tile / mn_tiles;
       const int mn = tile - ks * mn_tiles;
       const int m_tile = mn / p.n_tiles;
