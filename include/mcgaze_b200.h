@@ -168,7 +168,55 @@ typedef struct {
 int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const float* std, int to_rgb, float* out,
                    int Hp, int Wp, void* stream);
 
-/* ---- overlap merge ------------------------------------------------------------------
+/* ---- PNG decode on the device ("decode -> ...") -------------------------------------
+ * Replaces the decode inside LoadImageFromFile (mmdet/datasets/pipelines/loading.py:58-69: mmcv.imfrombytes ->
+ * cv2.imdecode(IMREAD_COLOR)) for the frames data/gaze360/<split>_rawframes/<vid>/<00000>.png holds
+ * (tools/gaze360_img_reorganize.py:108,137 writes them with cv2.imwrite): 8-bit, non-interlaced PNG of colour type
+ * 0 (gray), 2 (RGB), 3 (palette), 4 (gray + alpha) or 6 (RGBA).  Output = what cv2 returns for the file, bit for bit:
+ * BGR uint8, gray replicated, palette expanded, alpha (and tRNS) dropped, gamma / colour-space chunks ignored.
+ * The host only walks the chunk list; inflate and scanline reconstruction run on the device. */
+typedef struct {
+  int32_t width, height;
+  int32_t bit_depth, color_type, interlace;
+  int32_t channels;      /* samples per scanline pixel */
+  int32_t has_palette;
+  int32_t supported;     /* 1 when mcg_png_decode takes the image (bit depth 8, not interlaced) */
+  int64_t idat_bytes;    /* total IDAT payload = length of the zlib stream */
+  uint8_t palette[768];  /* PLTE entries (RGB), zero padded */
+} mcg_png_info;
+
+/* HOST function (no GPU needed).  Walks the chunks of one PNG file image: signature, IHDR first, PLTE, IDAT, IEND;
+ * checks every chunk CRC when check_crc != 0 (libpng does).  Fills `info`; when zdata != NULL the IDAT payloads are
+ * concatenated there (zcap bytes available; MCG_ERR_INVALID with info->idat_bytes set when it is too small, so a
+ * first call with zdata == NULL sizes the buffer).  The H2D copy of zdata is the caller's. */
+int mcg_png_parse(const uint8_t* file, int64_t nbytes, int check_crc, mcg_png_info* info, uint8_t* zdata, int64_t zcap);
+
+typedef struct {
+  const uint8_t* zdata;  /* DEVICE zlib stream (the concatenated IDAT payloads) */
+  int64_t zbytes;
+  int32_t width, height;
+  int32_t color_type;    /* 0, 2, 3, 4, 6; bit depth 8, not interlaced */
+  int32_t reserved;
+  const uint8_t* palette;/* DEVICE [768] RGB for colour type 3, else NULL */
+  uint8_t* scan;         /* DEVICE scratch, height * (1 + width * channels) bytes: the filtered scanlines */
+  uint8_t* dst;          /* DEVICE uint8 [height, width, 3] BGR (the `src` of mcg_frame) */
+  int64_t dst_stride;    /* bytes per output row (>= 3 * width) */
+} mcg_png_job;
+
+/* per-image results in `status` (DEVICE int32 [n], written asynchronously): 0 = decoded */
+enum {
+  MCG_PNG_OK = 0, MCG_PNG_BAD_ZLIB_HEADER = 1, MCG_PNG_BAD_BLOCK_TYPE = 2, MCG_PNG_BAD_STORED_LEN = 3,
+  MCG_PNG_BAD_CODE_LENGTHS = 4, MCG_PNG_BAD_SYMBOL = 5, MCG_PNG_BAD_DISTANCE = 6, MCG_PNG_OUTPUT_OVERFLOW = 7,
+  MCG_PNG_INPUT_EXHAUSTED = 8, MCG_PNG_OUTPUT_SHORT = 9, MCG_PNG_BAD_FILTER = 10
+};
+
+/* n images, one warp each: inflate (RFC 1950 / 1951: stored, fixed and dynamic blocks) into `scan`, then scanline
+ * reconstruction (None / Sub / Up / Average / Paeth) + colour conversion into `dst`.  jobs: HOST array (device pointers
+ * inside).  Asynchronous on `stream`; needs no engine handle.  A corrupt stream sets its status and leaves `dst`
+ * undefined, it never writes outside `scan` / `dst`.  The zlib Adler-32 trailer is not verified. */
+int mcg_png_decode(const mcg_png_job* jobs, int n, int32_t* status, void* stream);
+
+/* ---- overlap merge------------------------------------------------------------------
  * Replaces the clip-to-video merge of tools/test_gaze360_gaze.py:129-201 for per-clip results that are on the device:
  * windows of clip_len frames every `stride` frames, the last one right-aligned (:73-86); frames a clip adds are copied
  * with their boxes zeroed where that clip's score < 0.5 (:135-141), frames it shares with earlier clips are averaged

@@ -19,6 +19,7 @@ SOURCES = {
     'mcg_api.cu': ['common.cuh', 'ptx.cuh', 'umma_gemm.cuh', 'bneck_fused.cuh', 'stem_fused.cuh', 'simt_gemm.cuh', 'head_kernels.cuh', API_H],
     'preprocess.cu': ['common.cuh', API_H],
     'metric.cu': ['common.cuh', API_H],
+    'png_decode.cu': ['common.cuh', 'png_core.cuh', API_H],
 }
 
 

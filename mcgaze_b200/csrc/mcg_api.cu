@@ -259,7 +259,10 @@ class Engine {
       meta_slot_ = (meta_slot_ + 1) % kMetaSlots;
       if (!meta_ev_[slot]) MCG_CUDA(cudaEventCreateWithFlags(&meta_ev_[slot], cudaEventDisableTiming));
       else MCG_CUDA(cudaEventSynchronize(meta_ev_[slot]));
-      float* pin = pin_meta_ + static_cast<size_t>(slot) * meta.size();
+      // slots have ONE stride whatever NB is (the ring's capacity / kMetaSlots): with a per-call stride a short batch's
+      // slot overlapped the still-pending copy of the longer batch queued before it (seen once the host stopped waiting
+      // for uploads: device-side PNG decode)
+      float* pin = pin_meta_ + static_cast<size_t>(slot) * (pin_meta_bytes_ / sizeof(float) / kMetaSlots);
       std::memcpy(pin, meta.data(), meta.size() * sizeof(float));
       MCG_CUDA(cudaMemcpyAsync(d_meta_, pin, meta.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
       MCG_CUDA(cudaEventRecord(meta_ev_[slot], stream));
@@ -1654,6 +1657,9 @@ namespace mcg {
 // preprocess.cu
 void preprocess_launch(const mcg_frame* frames, int n, const float* mean, const float* std_, int to_rgb, float* out,
                        int Hp, int Wp, cudaStream_t st, int* launches);
+// png_decode.cu
+int png_parse(const uint8_t* f, int64_t n, int check_crc, mcg_png_info* info, uint8_t* z, int64_t zcap, const char** why);
+void png_decode_launch(const mcg_png_job* jobs, int n, int32_t* status, cudaStream_t st, int* launches);
 // metric.cu
 void gaze_error_launch(const float* pred, const float* gt, const int32_t* video_start, int n_videos, int variant,
                        double* out, cudaStream_t st);
@@ -1774,6 +1780,27 @@ int mcg_preprocess(const mcg_frame* frames, int n, const float* mean, const floa
       return MCG_ERR_CUDA;
     }
     mcg::preprocess_launch(frames, n, mean, std, to_rgb, out, Hp, Wp, static_cast<cudaStream_t>(stream), nullptr);
+    return MCG_OK;
+  });
+}
+
+int mcg_png_parse(const uint8_t* file, int64_t nbytes, int check_crc, mcg_png_info* info, uint8_t* zdata, int64_t zcap) {
+  return guarded([&]() -> int {
+    const char* why = "";
+    const int rc = mcg::png_parse(file, nbytes, check_crc, info, zdata, zcap, &why);
+    if (rc != MCG_OK) mcg::g_last_error = std::string("mcg_png_parse: ") + why;
+    return rc;
+  });
+}
+
+int mcg_png_decode(const mcg_png_job* jobs, int n, int32_t* status, void* stream) {
+  return guarded([&]() -> int {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      mcg::g_last_error = "mcg_png_decode: no CUDA device visible (this library has no CPU fallback)";
+      return MCG_ERR_CUDA;
+    }
+    mcg::png_decode_launch(jobs, n, status, static_cast<cudaStream_t>(stream), nullptr);
     return MCG_OK;
   });
 }

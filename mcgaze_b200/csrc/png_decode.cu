@@ -1,0 +1,234 @@
+// mcg_png_parse / mcg_png_decode (include/mcgaze_b200.h): PNG files -> BGR uint8 frames in HBM, the part of
+// LoadImageFromFile (mmdet/datasets/pipelines/loading.py:58-69 -> mmcv.imfrombytes -> cv2.imdecode) that used to stay on
+// the host.  The host only walks the chunk list (signature, IHDR, PLTE, IDAT payloads, optional CRC check); inflate and
+// scanline reconstruction run on the device, one warp per image (png_core.cuh).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/mcgaze_b200.h"
+#include "common.cuh"
+#include "png_core.cuh"
+
+namespace mcg {
+
+struct PngDevJob {
+  const uint8_t* zdata;
+  long long zbytes;
+  uint8_t* scan;
+  uint8_t* dst;
+  long long dst_stride;
+  const uint8_t* palette;
+  int width, height, color_type, pad_;
+};
+static_assert(sizeof(PngDevJob) == 64, "descriptor layout");
+
+constexpr int kPngChunk = 448;          // jobs per launch: 28 KB of kernel parameters (CUDA >= 12.1 takes up to 32764 B)
+constexpr int kPngWarps = 4;            // images per CTA
+struct PngBatch {
+  int n, base;
+  long long pad_;
+  PngDevJob j[kPngChunk];
+};
+
+__global__ void __launch_bounds__(32 * kPngWarps) png_inflate_kernel(const __grid_constant__ PngBatch b, int32_t* __restrict__ status) {
+  __shared__ png::Tables tables[kPngWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kPngWarps + warp;
+  if (idx >= b.n) return;
+  const PngDevJob& job = b.j[idx];
+  const long long expected = static_cast<long long>(job.height) * (1 + static_cast<long long>(job.width) * png::channels_of(job.color_type));
+  long long produced = 0;
+  int st = png::inflate_warp(job.zdata, job.zbytes, job.scan, expected, tables[warp], lane, &produced);
+  if (st == png::ST_OK && produced != expected) st = png::ST_OUTPUT_SHORT;
+  if (lane == 0) status[b.base + idx] = st;
+}
+
+__global__ void __launch_bounds__(32 * kPngWarps) png_unfilter_kernel(const __grid_constant__ PngBatch b, int32_t* __restrict__ status) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kPngWarps + warp;
+  if (idx >= b.n) return;
+  if (status[b.base + idx] != png::ST_OK) return;     // uniform per warp: the inflate kernel wrote it
+  const PngDevJob& job = b.j[idx];
+  const int ct = job.color_type, bpp = png::channels_of(ct);
+  const int H = job.height;
+  const int rowbytes = job.width * bpp;
+  const long long stride = 1 + static_cast<long long>(rowbytes);
+  bool bad = false;
+  for (int band = 0; band * 32 < H; ++band) {
+    const int r = band * 32 + lane;
+    const bool valid = r < H;
+    uint8_t* row = job.scan + static_cast<long long>(valid ? r : 0) * stride + 1;
+    uint8_t* dst_row = job.dst + static_cast<long long>(valid ? r : 0) * job.dst_stride;
+    int ft = valid ? row[-1] : 0;
+    if (ft > 4) {
+      bad = true;
+      ft = 0;
+    }
+    png::LaneState s = {0u, 0u, 0u, 0, 0};
+    for (int t = 0; t < rowbytes + 31; ++t) {
+      uint32_t up = __shfl_up_sync(0xffffffffu, s.last, 1);
+      const int j = t - lane;
+      const bool active = valid && j >= 0 && j < rowbytes;
+      if (lane == 0) up = (active && r > 0) ? png::load_cg(row - stride + j) : 0u;   // last row of the band before
+      if (active) {
+        png::unfilter_byte(s, ft, row[j], up, bpp, ct, job.palette, dst_row);
+        if (lane == 31) row[j] = static_cast<uint8_t>(s.last);                         // ... which lane 31 leaves here
+      }
+    }
+    __syncwarp();
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) status[b.base + idx] = png::ST_BAD_FILTER;
+}
+
+// ---- host: chunk walk ---------------------------------------------------------------------------------------
+namespace {
+uint32_t g_crc_table[4][256];
+std::once_flag g_crc_once;
+void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+    g_crc_table[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 4; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 255u];
+}
+uint32_t crc32_update(uint32_t crc, const uint8_t* p, int64_t n) {
+  crc = ~crc;
+  while (n >= 4) {
+    crc ^= static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) |
+           (static_cast<uint32_t>(p[3]) << 24);
+    crc = g_crc_table[3][crc & 255u] ^ g_crc_table[2][(crc >> 8) & 255u] ^ g_crc_table[1][(crc >> 16) & 255u] ^
+          g_crc_table[0][crc >> 24];
+    p += 4;
+    n -= 4;
+  }
+  while (n-- > 0) crc = g_crc_table[0][(crc ^ *p++) & 255u] ^ (crc >> 8);
+  return ~crc;
+}
+inline uint32_t be32(const uint8_t* p) {
+  return (static_cast<uint32_t>(p[0]) << 24) | (static_cast<uint32_t>(p[1]) << 16) | (static_cast<uint32_t>(p[2]) << 8) | p[3];
+}
+
+}  // namespace
+
+// -> MCG_OK, or MCG_ERR_INVALID with g_last_error-style message in `why`
+int png_parse(const uint8_t* f, int64_t n, int check_crc, mcg_png_info* info, uint8_t* z, int64_t zcap, const char** why) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  *why = "";
+  if (!f || !info || n < 8 + 25 || std::memcmp(f, sig, 8) != 0) {
+    *why = "not a PNG file (signature)";
+    return MCG_ERR_INVALID;
+  }
+  if (check_crc) std::call_once(g_crc_once, crc_init);
+  std::memset(info, 0, sizeof(*info));
+  int64_t pos = 8, zpos = 0;
+  bool have_ihdr = false, have_end = false, overflow = false;
+  while (pos + 12 <= n) {
+    const uint32_t len = be32(f + pos);
+    const uint8_t* type = f + pos + 4;
+    const uint8_t* data = f + pos + 8;
+    if (len > 0x7fffffffu || pos + 12 + static_cast<int64_t>(len) > n) {
+      *why = "truncated chunk";
+      return MCG_ERR_INVALID;
+    }
+    if (check_crc && crc32_update(0u, type, 4 + static_cast<int64_t>(len)) != be32(data + len)) {
+      *why = "chunk CRC mismatch";
+      return MCG_ERR_INVALID;
+    }
+    if (!have_ihdr) {
+      if (std::memcmp(type, "IHDR", 4) != 0 || len != 13) {
+        *why = "first chunk is not IHDR";
+        return MCG_ERR_INVALID;
+      }
+      info->width = static_cast<int32_t>(be32(data));
+      info->height = static_cast<int32_t>(be32(data + 4));
+      info->bit_depth = data[8];
+      info->color_type = data[9];
+      info->interlace = data[12];
+      if (info->width <= 0 || info->height <= 0 || data[10] != 0 || data[11] != 0) {
+        *why = "bad IHDR";
+        return MCG_ERR_INVALID;
+      }
+      const int ct = info->color_type;
+      info->channels = ct == 0 ? 1 : ct == 2 ? 3 : ct == 3 ? 1 : ct == 4 ? 2 : ct == 6 ? 4 : 0;
+      if (info->channels == 0) {
+        *why = "bad colour type";
+        return MCG_ERR_INVALID;
+      }
+      have_ihdr = true;
+    } else if (std::memcmp(type, "PLTE", 4) == 0) {
+      if (len % 3 != 0 || len > 768) {
+        *why = "bad PLTE";
+        return MCG_ERR_INVALID;
+      }
+      std::memcpy(info->palette, data, len);
+      info->has_palette = 1;
+    } else if (std::memcmp(type, "IDAT", 4) == 0) {
+      if (z != nullptr && zpos + static_cast<int64_t>(len) <= zcap)
+        std::memcpy(z + zpos, data, len);
+      else if (z != nullptr)
+        overflow = true;
+      zpos += len;
+    } else if (std::memcmp(type, "IEND", 4) == 0) {
+      have_end = true;
+      break;
+    }
+    pos += 12 + static_cast<int64_t>(len);
+  }
+  info->idat_bytes = zpos;
+  if (!have_ihdr || !have_end || zpos == 0) {
+    *why = "missing IHDR / IDAT / IEND";
+    return MCG_ERR_INVALID;
+  }
+  if (info->color_type == 3 && !info->has_palette) {
+    *why = "palette image without PLTE";
+    return MCG_ERR_INVALID;
+  }
+  info->supported = (info->bit_depth == 8 && info->interlace == 0) ? 1 : 0;
+  if (overflow) {
+    *why = "IDAT buffer too small (see idat_bytes)";
+    return MCG_ERR_INVALID;
+  }
+  return MCG_OK;
+}
+
+void png_decode_launch(const mcg_png_job* jobs, int n, int32_t* status, cudaStream_t st, int* launches) {
+  MCG_CHECK(jobs != nullptr && n > 0 && status != nullptr, "null argument");
+  int count = 0;
+  for (int base = 0; base < n; base += kPngChunk) {
+    PngBatch b;
+    b.n = std::min(kPngChunk, n - base);
+    b.base = base;
+    b.pad_ = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const mcg_png_job& s = jobs[base + i];
+      const int ch = s.color_type == 0 ? 1 : s.color_type == 2 ? 3 : s.color_type == 3 ? 1 : s.color_type == 4 ? 2 : s.color_type == 6 ? 4 : 0;
+      MCG_CHECK(ch != 0, "colour type must be 0, 2, 3, 4 or 6");
+      MCG_CHECK(s.zdata != nullptr && s.zbytes > 0 && s.scan != nullptr && s.dst != nullptr, "null buffer in a PNG job");
+      MCG_CHECK(s.width > 0 && s.height > 0 && s.dst_stride >= 3LL * s.width, "bad image geometry");
+      MCG_CHECK(s.color_type != 3 || s.palette != nullptr, "palette image without a palette");
+      PngDevJob& d = b.j[i];
+      d.zdata = s.zdata;
+      d.zbytes = s.zbytes;
+      d.scan = s.scan;
+      d.dst = s.dst;
+      d.dst_stride = s.dst_stride;
+      d.palette = s.palette;
+      d.width = s.width;
+      d.height = s.height;
+      d.color_type = s.color_type;
+      d.pad_ = 0;
+    }
+    const unsigned grid = static_cast<unsigned>((b.n + kPngWarps - 1) / kPngWarps);
+    png_inflate_kernel<<<grid, 32 * kPngWarps, 0, st>>>(b, status);
+    MCG_CUDA(cudaGetLastError());
+    png_unfilter_kernel<<<grid, 32 * kPngWarps, 0, st>>>(b, status);
+    MCG_CUDA(cudaGetLastError());
+    count += 2;
+  }
+  if (launches) *launches = count;
+}
+
+}  // namespace mcg

@@ -51,9 +51,18 @@ def _default_loader(path: str) -> np.ndarray:
 
 class Gaze360ClipDataset:
     def __init__(self, ann_file, img_prefix: str = '', clip_len: int = slicer.CLIP_LEN, stride: int = slicer.STRIDE,
-                 loader: Optional[Callable[[str], np.ndarray]] = None, test_mode: bool = True):
+                 loader: Optional[Callable[[str], np.ndarray]] = None, test_mode: bool = True, decode: str = 'host'):
+        """decode='host': LoadImageFromFile on the host (cv2, in the loader threads); decode='gpu': the batched drivers
+        below only read the files and decode them on the device (mcgaze_b200/png.py: mcg_png_parse + mcg_png_decode);
+        batches holding a file that decoder does not take (JPEG, 16-bit or interlaced PNG) go through the host loader."""
         if not test_mode:
             raise NotImplementedError('training is out of scope for the B200 inference backend')
+        if decode not in ('host', 'gpu'):
+            raise ValueError("decode must be 'host' or 'gpu'")
+        if decode == 'gpu' and loader is not None:
+            raise ValueError("decode='gpu' reads the files itself; it does not combine with a custom loader")
+        self.decode = decode
+        self.host_decoded_batches = 0             # decode='gpu': batches that fell back to the host loader
         self.anno = json.load(open(ann_file)) if isinstance(ann_file, (str, os.PathLike)) else ann_file
         self.img_prefix = img_prefix
         self.clip_len, self.stride = clip_len, stride
@@ -98,6 +107,13 @@ def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging
     names = [f for it in infos for f in it['filenames']]
     paths = [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
     n = len(paths)
+    if getattr(dataset, 'decode', 'host') == 'gpu':
+        from . import png
+        try:
+            # host part only: read the files, walk their chunks into one pinned block; run_clips launches the decode
+            return infos[0]['n'], png.GpuPngDecoder(check_crc=True).stage(paths, pool), names
+        except png.UnsupportedPng:
+            dataset.host_decoded_batches += 1
     if pool is None or staging is None:
         frames = [dataset.loader(p) for p in paths]
         return infos[0]['n'], (np.stack(frames) if len({f.shape for f in frames}) == 1 else frames), names
@@ -176,10 +192,22 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
     copy_stream = None
 
     upload_done: Dict[int, Any] = {}              # staging slot -> event of the last H2D copy that read it
+    decoder = None
+    decode_check = None                           # decode='gpu': (staged files, pinned status copy, event) of the batch in upload()
 
     def upload(frames, slot):
-        """pinned uint8 block -> device on a side stream; the compute stream waits for the copy only"""
-        nonlocal copy_stream
+        """pinned uint8 block -> device on a side stream; the compute stream waits for the copy only.  Staged PNG files
+        (decode='gpu'): compressed bytes -> device + mcg_png_decode on the compute stream, status checked at collect()."""
+        nonlocal copy_stream, decoder, decode_check
+        decode_check = None
+        if hasattr(frames, 'zoff'):               # png.StagedPngs
+            from . import png
+            if decoder is None:
+                decoder = png.GpuPngDecoder(getattr(pipeline, 'device', 0))
+            with torch.cuda.device(decoder.device):
+                dframes, status = decoder.launch(frames)
+                decode_check = (frames,) + decoder.status_async(status)
+            return dframes
         if not (cuda and hasattr(frames, 'is_pinned') and frames.is_pinned() and hasattr(pipeline, 'device')):
             return frames
         dev = torch.device('cuda', pipeline.device)
@@ -196,7 +224,10 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
         return d
 
     def collect(p):
-        ids, T, rows, ev = p
+        ids, T, rows, ev, chk = p
+        if chk is not None:                       # per-image status of this batch's PNG decode (queued before its forward)
+            chk[2].synchronize()
+            decoder.check(chk[0], chk[1])
         if ev is not None:
             ev.synchronize()                      # this batch's read-back only; later batches keep running
         if batch_sink is not None:                # whole batches for the caller (no per-clip slicing of device tensors)
@@ -247,7 +278,7 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
             # hand the PREVIOUS batch over only now, with this batch already queued: the GPU never waits for the host
             if pending is not None:
                 collect(pending)
-            pending = (ids, T, rows, ev)
+            pending = (ids, T, rows, ev, decode_check)
         if pending is not None:
             collect(pending)
     finally:

@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
            'mcg_last_launch_count', 'mcg_range_report', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
-           'mcg_preprocess', 'mcg_merge_clips', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
+           'mcg_preprocess', 'mcg_png_parse', 'mcg_png_decode', 'mcg_merge_clips', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
 
 
 class McgError(RuntimeError):
@@ -36,6 +36,20 @@ class mcg_frame(ctypes.Structure):
                 ('src_w', ctypes.c_int32), ('crop_y', ctypes.c_int32), ('crop_x', ctypes.c_int32),
                 ('crop_h', ctypes.c_int32), ('crop_w', ctypes.c_int32), ('dst_h', ctypes.c_int32),
                 ('dst_w', ctypes.c_int32)]
+
+
+class mcg_png_info(ctypes.Structure):
+    _fields_ = [('width', ctypes.c_int32), ('height', ctypes.c_int32), ('bit_depth', ctypes.c_int32),
+                ('color_type', ctypes.c_int32), ('interlace', ctypes.c_int32), ('channels', ctypes.c_int32),
+                ('has_palette', ctypes.c_int32), ('supported', ctypes.c_int32), ('idat_bytes', ctypes.c_int64),
+                ('palette', ctypes.c_uint8 * 768)]
+
+
+class mcg_png_job(ctypes.Structure):
+    _fields_ = [('zdata', ctypes.c_void_p), ('zbytes', ctypes.c_int64), ('width', ctypes.c_int32),
+                ('height', ctypes.c_int32), ('color_type', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('palette', ctypes.c_void_p), ('scan', ctypes.c_void_p), ('dst', ctypes.c_void_p),
+                ('dst_stride', ctypes.c_int64)]
 
 
 _lib = None
@@ -66,6 +80,8 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_range_report.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_preprocess.argtypes = [ctypes.POINTER(mcg_frame), ci, cf, cf, ci, vp, ci, ci, vp]
+    lib.mcg_png_parse.argtypes = [vp, ctypes.c_int64, ci, ctypes.POINTER(mcg_png_info), vp, ctypes.c_int64]
+    lib.mcg_png_decode.argtypes = [ctypes.POINTER(mcg_png_job), ci, vp, vp]
     lib.mcg_gaze_error.argtypes = [vp, vp, vp, ci, ci, vp, vp]
     lib.mcg_merge_clips.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
     lib.mcg_debug_conv.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]

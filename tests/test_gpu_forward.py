@@ -445,3 +445,34 @@ def test_fused_bottleneck_tail_matches_separate_convolutions(engines, synthetic_
     for i, k in enumerate(KEYS):
         assert yaw_pitch_err(fused['gaze'][:, i].cpu(), ref[k]) < 1e-3, k
     assert yaw_pitch_err(fused['gaze'][:, 0].cpu(), plain['gaze'][:, 0].cpu()) < 2e-4
+
+
+def test_queued_forwards_of_different_batch_sizes_keep_their_own_metadata(engines):
+    """The per-call metadata (img_hw, scale_factor) is staged in a pinned ring and copied asynchronously: a forward that
+    is still queued behind other work must not see the metadata of a later, shorter batch (ring slots had a per-call
+    stride, so slot 3 of a 4-frame batch overlapped slot 2 of a 7-frame one - found when the evaluation driver stopped
+    waiting for uploads).  A long sleep kernel keeps the first copies pending while the host stages the later ones."""
+    eng = engines('fp16c8')
+    T = 7
+    img7 = O.make_clip(3, T, 96, 128).cuda()
+    img4 = O.make_clip(4, 4, 96, 128).cuda()
+    rng = np.random.default_rng(0)
+
+    def metas(n):
+        hw = np.stack([rng.integers(60, 97, n), rng.integers(80, 129, n)], 1).astype(np.float32)
+        sf = rng.uniform(0.4, 2.5, (n, 4)).astype(np.float32)
+        return hw, sf
+
+    m = [metas(7), metas(7), metas(7), metas(4)]
+    want = []
+    for k, (hw, sf) in enumerate(m):                      # one at a time, synchronised
+        out = eng.forward(img4 if k == 3 else img7, clip_length=4 if k == 3 else T, img_hw=hw, scale_factor=sf)
+        torch.cuda.synchronize()
+        want.append({n: t.clone() for n, t in out.items()})
+    torch.cuda._sleep(int(2e9))                           # ~1 s: everything below is queued behind it
+    got = [eng.forward(img4 if k == 3 else img7, clip_length=4 if k == 3 else T, img_hw=hw, scale_factor=sf)
+           for k, (hw, sf) in enumerate(m)]
+    torch.cuda.synchronize()
+    for k in range(4):
+        for n in ('gaze', 'boxes', 'scores'):
+            assert torch.equal(got[k][n], want[k][n]), (k, n)

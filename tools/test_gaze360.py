@@ -33,6 +33,9 @@ def main():
                     help='which of the reference scorers to print (default: l2cs when the config name says so)')
     ap.add_argument('--shard', default='video', choices=['video', 'clip'],
                     help='multi-GPU sharding: videos (merge + MAE on each device, one all-reduce) or clips (one all-gather)')
+    ap.add_argument('--decode', default='gpu', choices=['gpu', 'host'],
+                    help='PNG frames decoded on the device (mcg_png_decode; the loader threads only read files) or by cv2 '
+                         'on the host like LoadImageFromFile; other formats always take the host path')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -45,7 +48,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device(device))
     model = init_detector(args.config, args.checkpoint, device=device, cfg_options=args.cfg_options)
     pipe = GpuTestPipeline(model.cfg.data.test.pipeline, device=int(device.split(':')[1]), seed=args.seed)
-    ds = ev.Gaze360ClipDataset(args.json, img_prefix=args.root)
+    ds = ev.Gaze360ClipDataset(args.json, img_prefix=args.root, decode=args.decode)
     scorer = args.scorer or ('l2cs' if 'l2cs' in os.path.basename(args.config) else 'gaze360')
     sharded = None
     if args.shard == 'video':
