@@ -207,13 +207,21 @@ typedef struct {
 enum {
   MCG_PNG_OK = 0, MCG_PNG_BAD_ZLIB_HEADER = 1, MCG_PNG_BAD_BLOCK_TYPE = 2, MCG_PNG_BAD_STORED_LEN = 3,
   MCG_PNG_BAD_CODE_LENGTHS = 4, MCG_PNG_BAD_SYMBOL = 5, MCG_PNG_BAD_DISTANCE = 6, MCG_PNG_OUTPUT_OVERFLOW = 7,
-  MCG_PNG_INPUT_EXHAUSTED = 8, MCG_PNG_OUTPUT_SHORT = 9, MCG_PNG_BAD_FILTER = 10
+  MCG_PNG_INPUT_EXHAUSTED = 8, MCG_PNG_OUTPUT_SHORT = 9, MCG_PNG_BAD_FILTER = 10, MCG_PNG_BAD_JOB = 11,
+  MCG_PNG_BAD_CHECKSUM = 12
 };
 
-/* n images, one warp each: inflate (RFC 1950 / 1951: stored, fixed and dynamic blocks) into `scan`, then scanline
- * reconstruction (None / Sub / Up / Average / Paeth) + colour conversion into `dst`.  jobs: HOST array (device pointers
- * inside).  Asynchronous on `stream`; needs no engine handle.  A corrupt stream sets its status and leaves `dst`
- * undefined, it never writes outside `scan` / `dst`.  The zlib Adler-32 trailer is not verified. */
+/* n images, one warp each, ONE launch per stage whatever n is: inflate (RFC 1950 / 1951: stored, fixed and dynamic
+ * blocks) into `scan`, then scanline reconstruction (None / Sub / Up / Average / Paeth) + colour conversion into `dst`.
+ *   jobs    DEVICE array [n] (upload it with the compressed bytes; the kernels read the descriptors from HBM, so a batch
+ *           of thousands of images is one launch and fills the GPU: a single stream is a serial decode, the throughput
+ *           is in the number of images in flight)
+ *   status  DEVICE int32 [n]: MCG_PNG_OK, a stream error, or MCG_PNG_BAD_JOB for a descriptor with a null buffer, a
+ *           colour type outside {0, 2, 3, 4, 6}, a non-positive size or dst_stride < 3 * width
+ * Asynchronous on `stream`; needs no engine handle.  A corrupt stream sets its status and leaves `dst` undefined, it
+ * never writes outside `scan` / `dst`.  The zlib stream's Adler-32 trailer is verified on the device against the inflated
+ * bytes (MCG_PNG_BAD_CHECKSUM), so a caller may skip the host-side chunk CRCs (check_crc = 0) and still catch corrupt
+ * pixel data. */
 int mcg_png_decode(const mcg_png_job* jobs, int n, int32_t* status, void* stream);
 
 /* ---- overlap merge------------------------------------------------------------------

@@ -12,44 +12,42 @@
 
 namespace mcg {
 
-struct PngDevJob {
-  const uint8_t* zdata;
-  long long zbytes;
-  uint8_t* scan;
-  uint8_t* dst;
-  long long dst_stride;
-  const uint8_t* palette;
-  int width, height, color_type, pad_;
-};
-static_assert(sizeof(PngDevJob) == 64, "descriptor layout");
+constexpr int kInflateWarps = 1;   // one image per CTA: the decoding tables sit at a constant shared-memory offset
+constexpr int kUnfilterWarps = 4;
 
-constexpr int kPngChunk = 448;          // jobs per launch: 28 KB of kernel parameters (CUDA >= 12.1 takes up to 32764 B)
-constexpr int kPngWarps = 4;            // images per CTA
-struct PngBatch {
-  int n, base;
-  long long pad_;
-  PngDevJob j[kPngChunk];
-};
+__device__ __forceinline__ bool png_job_ok(const mcg_png_job& j) {
+  return png::channels_of(j.color_type) != 0 && j.zdata != nullptr && j.zbytes > 0 && j.scan != nullptr && j.dst != nullptr &&
+         j.width > 0 && j.height > 0 && j.dst_stride >= 3LL * j.width && (j.color_type != 3 || j.palette != nullptr);
+}
 
-__global__ void __launch_bounds__(32 * kPngWarps) png_inflate_kernel(const __grid_constant__ PngBatch b, int32_t* __restrict__ status) {
-  __shared__ png::Tables tables[kPngWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kPngWarps + warp;
-  if (idx >= b.n) return;
-  const PngDevJob& job = b.j[idx];
+// The job table lives in HBM (the caller uploads it with the compressed bytes), so ONE launch covers a whole batch:
+// a warp spends ~10 ms on a 300 x 300 photograph whatever else runs, and throughput comes from the thousands of warps a
+// B200 keeps resident (148 SMs x 32 one-warp CTAs), not from the speed of one stream.
+__global__ void __launch_bounds__(32 * kInflateWarps) png_inflate_kernel(const mcg_png_job* __restrict__ jobs, int n,
+                                                                          int32_t* __restrict__ status) {
+  __shared__ png::Tables tables[kInflateWarps];
+  const int warp = kInflateWarps == 1 ? 0 : threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kInflateWarps + warp;
+  if (idx >= n) return;
+  const mcg_png_job job = jobs[idx];
+  if (!png_job_ok(job)) {
+    if (lane == 0) status[idx] = MCG_PNG_BAD_JOB;
+    return;
+  }
   const long long expected = static_cast<long long>(job.height) * (1 + static_cast<long long>(job.width) * png::channels_of(job.color_type));
   long long produced = 0;
   int st = png::inflate_warp(job.zdata, job.zbytes, job.scan, expected, tables[warp], lane, &produced);
   if (st == png::ST_OK && produced != expected) st = png::ST_OUTPUT_SHORT;
-  if (lane == 0) status[b.base + idx] = st;
+  if (lane == 0) status[idx] = st;
 }
 
-__global__ void __launch_bounds__(32 * kPngWarps) png_unfilter_kernel(const __grid_constant__ PngBatch b, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(32 * kUnfilterWarps) png_unfilter_kernel(const mcg_png_job* __restrict__ jobs, int n,
+                                                                            int32_t* __restrict__ status) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kPngWarps + warp;
-  if (idx >= b.n) return;
-  if (status[b.base + idx] != png::ST_OK) return;     // uniform per warp: the inflate kernel wrote it
-  const PngDevJob& job = b.j[idx];
+  const int idx = blockIdx.x * kUnfilterWarps + warp;
+  if (idx >= n) return;
+  if (status[idx] != png::ST_OK) return;     // uniform per warp: the inflate kernel wrote it
+  const mcg_png_job job = jobs[idx];
   const int ct = job.color_type, bpp = png::channels_of(ct);
   const int H = job.height;
   const int rowbytes = job.width * bpp;
@@ -66,19 +64,33 @@ __global__ void __launch_bounds__(32 * kPngWarps) png_unfilter_kernel(const __gr
       ft = 0;
     }
     png::LaneState s = {0u, 0u, 0u, 0, 0};
+    // Row above the band (lane 0's "up" bytes; lane 31 of the band before left it in `scan`): the warp fetches it 32
+    // bytes at a time, one coalesced load 32 steps ahead of use, and hands lane 0 its byte by shuffle - a load per step
+    // in lane 0 would put an L2 round trip on every step of the wavefront.
+    const uint8_t* above = job.scan + (static_cast<long long>(band) * 32 - 1) * stride + 1;
+    uint32_t cur32 = (band > 0 && lane < rowbytes) ? png::load_cg(above + lane) : 0u;
+    uint32_t nxt32 = (band > 0 && 32 + lane < rowbytes) ? png::load_cg(above + 32 + lane) : 0u;
+    uint32_t raw_next = (valid && lane == 0 && rowbytes > 0) ? row[0] : 0u;    // this row's next filtered byte, one step ahead
     for (int t = 0; t < rowbytes + 31; ++t) {
+      if ((t & 31) == 0 && t > 0) {
+        cur32 = nxt32;
+        nxt32 = (band > 0 && t + 32 + lane < rowbytes) ? png::load_cg(above + t + 32 + lane) : 0u;
+      }
+      const uint32_t up0 = __shfl_sync(0xffffffffu, cur32, t & 31);
       uint32_t up = __shfl_up_sync(0xffffffffu, s.last, 1);
+      if (lane == 0) up = up0;
       const int j = t - lane;
       const bool active = valid && j >= 0 && j < rowbytes;
-      if (lane == 0) up = (active && r > 0) ? png::load_cg(row - stride + j) : 0u;   // last row of the band before
+      const uint32_t raw = raw_next;
+      if (valid && j + 1 >= 0 && j + 1 < rowbytes) raw_next = row[j + 1];
       if (active) {
-        png::unfilter_byte(s, ft, row[j], up, bpp, ct, job.palette, dst_row);
-        if (lane == 31) row[j] = static_cast<uint8_t>(s.last);                         // ... which lane 31 leaves here
+        png::unfilter_byte(s, ft, raw, up, bpp, ct, job.palette, dst_row);
+        if (lane == 31) row[j] = static_cast<uint8_t>(s.last);                         // ... for the next band's lane 0
       }
     }
     __syncwarp();
   }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) status[b.base + idx] = png::ST_BAD_FILTER;
+  if (__any_sync(0xffffffffu, bad) && lane == 0) status[idx] = png::ST_BAD_FILTER;
 }
 
 // ---- host: chunk walk ---------------------------------------------------------------------------------------
@@ -196,39 +208,14 @@ int png_parse(const uint8_t* f, int64_t n, int check_crc, mcg_png_info* info, ui
 
 void png_decode_launch(const mcg_png_job* jobs, int n, int32_t* status, cudaStream_t st, int* launches) {
   MCG_CHECK(jobs != nullptr && n > 0 && status != nullptr, "null argument");
-  int count = 0;
-  for (int base = 0; base < n; base += kPngChunk) {
-    PngBatch b;
-    b.n = std::min(kPngChunk, n - base);
-    b.base = base;
-    b.pad_ = 0;
-    for (int i = 0; i < b.n; ++i) {
-      const mcg_png_job& s = jobs[base + i];
-      const int ch = s.color_type == 0 ? 1 : s.color_type == 2 ? 3 : s.color_type == 3 ? 1 : s.color_type == 4 ? 2 : s.color_type == 6 ? 4 : 0;
-      MCG_CHECK(ch != 0, "colour type must be 0, 2, 3, 4 or 6");
-      MCG_CHECK(s.zdata != nullptr && s.zbytes > 0 && s.scan != nullptr && s.dst != nullptr, "null buffer in a PNG job");
-      MCG_CHECK(s.width > 0 && s.height > 0 && s.dst_stride >= 3LL * s.width, "bad image geometry");
-      MCG_CHECK(s.color_type != 3 || s.palette != nullptr, "palette image without a palette");
-      PngDevJob& d = b.j[i];
-      d.zdata = s.zdata;
-      d.zbytes = s.zbytes;
-      d.scan = s.scan;
-      d.dst = s.dst;
-      d.dst_stride = s.dst_stride;
-      d.palette = s.palette;
-      d.width = s.width;
-      d.height = s.height;
-      d.color_type = s.color_type;
-      d.pad_ = 0;
-    }
-    const unsigned grid = static_cast<unsigned>((b.n + kPngWarps - 1) / kPngWarps);
-    png_inflate_kernel<<<grid, 32 * kPngWarps, 0, st>>>(b, status);
-    MCG_CUDA(cudaGetLastError());
-    png_unfilter_kernel<<<grid, 32 * kPngWarps, 0, st>>>(b, status);
-    MCG_CUDA(cudaGetLastError());
-    count += 2;
-  }
-  if (launches) *launches = count;
+  cudaPointerAttributes attr;
+  MCG_CHECK(cudaPointerGetAttributes(&attr, jobs) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged),
+            "the job table must be in device memory (upload it with the compressed bytes)");
+  png_inflate_kernel<<<static_cast<unsigned>((n + kInflateWarps - 1) / kInflateWarps), 32 * kInflateWarps, 0, st>>>(jobs, n, status);
+  MCG_CUDA(cudaGetLastError());
+  png_unfilter_kernel<<<static_cast<unsigned>((n + kUnfilterWarps - 1) / kUnfilterWarps), 32 * kUnfilterWarps, 0, st>>>(jobs, n, status);
+  MCG_CUDA(cudaGetLastError());
+  if (launches) *launches = 2;
 }
 
 }  // namespace mcg

@@ -51,10 +51,13 @@ def _default_loader(path: str) -> np.ndarray:
 
 class Gaze360ClipDataset:
     def __init__(self, ann_file, img_prefix: str = '', clip_len: int = slicer.CLIP_LEN, stride: int = slicer.STRIDE,
-                 loader: Optional[Callable[[str], np.ndarray]] = None, test_mode: bool = True, decode: str = 'host'):
+                 loader: Optional[Callable[[str], np.ndarray]] = None, test_mode: bool = True, decode: str = 'host',
+                 check_crc: bool = False):
         """decode='host': LoadImageFromFile on the host (cv2, in the loader threads); decode='gpu': the batched drivers
         below only read the files and decode them on the device (mcgaze_b200/png.py: mcg_png_parse + mcg_png_decode);
-        batches holding a file that decoder does not take (JPEG, 16-bit or interlaced PNG) go through the host loader."""
+        batches holding a file that decoder does not take (JPEG, 16-bit or interlaced PNG) go through the host loader.
+        check_crc: also verify every chunk CRC on the host (libpng does; ~0.2 ms per frame and core) - the device always
+        verifies the Adler-32 of the pixel data, which is what a damaged file most likely breaks."""
         if not test_mode:
             raise NotImplementedError('training is out of scope for the B200 inference backend')
         if decode not in ('host', 'gpu'):
@@ -62,6 +65,7 @@ class Gaze360ClipDataset:
         if decode == 'gpu' and loader is not None:
             raise ValueError("decode='gpu' reads the files itself; it does not combine with a custom loader")
         self.decode = decode
+        self.check_crc = bool(check_crc)
         self.host_decoded_batches = 0             # decode='gpu': batches that fell back to the host loader
         self.anno = json.load(open(ann_file)) if isinstance(ann_file, (str, os.PathLike)) else ann_file
         self.img_prefix = img_prefix
@@ -107,13 +111,6 @@ def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging
     names = [f for it in infos for f in it['filenames']]
     paths = [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
     n = len(paths)
-    if getattr(dataset, 'decode', 'host') == 'gpu':
-        from . import png
-        try:
-            # host part only: read the files, walk their chunks into one pinned block; run_clips launches the decode
-            return infos[0]['n'], png.GpuPngDecoder(check_crc=True).stage(paths, pool), names
-        except png.UnsupportedPng:
-            dataset.host_decoded_batches += 1
     if pool is None or staging is None:
         frames = [dataset.loader(p) for p in paths]
         return infos[0]['n'], (np.stack(frames) if len({f.shape for f in frames}) == 1 else frames), names
@@ -144,6 +141,26 @@ def _load_batch(dataset: Gaze360ClipDataset, batch: Sequence[int], pool, staging
     return infos[0]['n'], [block[k].copy() if o is None else o for k, o in enumerate(odd)], names
 
 
+def _stage_unit(dataset: Gaze360ClipDataset, unit: Sequence[Sequence[int]], pool):
+    """decode='gpu': the host part for SEVERAL batches at once - read the files and walk their chunks into one pinned
+    block (mcgaze_b200/png.py).  One mcg_png_decode launch then covers the whole unit: a warp needs ~10 ms for a frame
+    whatever else runs, so the decode is paid once per unit instead of once per batch.
+    -> (StagedPngs, [(clip length, frame names, first frame, end frame) per batch]) or None when a file is not a PNG the
+    device decoder takes (the unit then goes through the host loader)."""
+    from . import png
+    paths, parts = [], []
+    for batch in unit:
+        infos = [dataset.clip_info(i) for i in batch]
+        names = [f for it in infos for f in it['filenames']]
+        parts.append((infos[0]['n'], names, len(paths), len(paths) + len(names)))
+        paths += [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
+    try:
+        return png.GpuPngDecoder(check_crc=dataset.check_crc).stage(paths, pool), parts
+    except png.UnsupportedPng:
+        dataset.host_decoded_batches += len(unit)
+        return None
+
+
 def _canvas_groups(pipeline, frames, names: Sequence[str], T: int):
     """Split the clips of a loaded batch by their OWN padded canvas.  -> [(frames, names, rands, clip positions)], one
     entry per canvas; `rands` are the CenterCrop draws of those frames (drawn once per batch, in frame order, so the
@@ -170,13 +187,15 @@ def _canvas_groups(pipeline, frames, names: Sequence[str], T: int):
 
 
 def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[int], clips_per_batch: int = 32,
-              workers: int = 0, to_host: bool = True, batch_sink: Optional[List[Any]] = None) -> Dict[int, Any]:
+              workers: int = 0, to_host: bool = True, batch_sink: Optional[List[Any]] = None,
+              decode_group: int = 8) -> Dict[int, Any]:
     """-> {clip index: float32 [n_frames, ROW]} for the given clips (numpy; torch tensors on the model's device with
     to_host=False); frames of a batch go through ONE pipeline call and ONE forward per padded canvas.  With `workers` > 0
     the frames of batch k+1 are decoded on a thread pool while the GPU works on batch k (the role of the DataLoader
     workers in mmdet/apis/test.py:107-109); on a GPU the uint8 block of batch k+1 crosses PCIe on a copy stream while
     batch k computes, and results come back through pinned buffers gated by per-batch events, so the host never waits
-    for the batch it has just queued."""
+    for the batch it has just queued.  With a decode='gpu' dataset the workers only read files; the PNG streams of
+    `decode_group` batches cross PCIe compressed and are decoded by ONE mcg_png_decode launch."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
     results: Dict[int, Any] = {}
@@ -239,46 +258,73 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
         for k, i in enumerate(ids):
             results[i] = rows[k * T:(k + 1) * T]
 
+    gpu_decode = getattr(dataset, 'decode', 'host') == 'gpu'
+    per_unit = max(1, int(decode_group)) if gpu_decode else 1
+    units = [batches[k:k + per_unit] for k in range(0, len(batches), per_unit)]
+
+    def load_unit(ui: int):
+        """-> ('gpu', (staged files, parts)) or ('host', [(T, frames, names) per batch])"""
+        if gpu_decode:
+            r = _stage_unit(dataset, units[ui], pool)
+            if r is not None:
+                return 'gpu', r
+            return 'host', [_load_batch(dataset, b, pool) for b in units[ui]]       # rare: plain arrays, no pinned slots
+        return 'host', [_load_batch(dataset, units[ui][0], pool, staging, ui % 3)]
+
     try:
-        nxt = feeder.submit(_load_batch, dataset, batches[0], pool, staging, 0) if feeder and batches else None
-        for bi, batch in enumerate(batches):
+        nxt = feeder.submit(load_unit, 0) if feeder and units else None
+        bi = -1
+        for ui, unit in enumerate(units):
             if feeder:
-                T, frames, names = nxt.result()
-                if bi + 1 < len(batches):
-                    # the loader is about to overwrite pinned slot (bi + 1) % 3: the copy of its last user (batch bi - 2)
-                    # must have left it - nothing else orders the two when the results stay on the device
-                    prev = upload_done.pop((bi + 1) % 3, None)
+                kind, payload = nxt.result()
+                if ui + 1 < len(units):
+                    # (host decode: units are single batches) the loader is about to overwrite pinned slot (ui + 1) % 3:
+                    # the copy of its last user (batch ui - 2) must have left it - nothing else orders the two when the
+                    # results stay on the device
+                    prev = upload_done.pop((ui + 1) % 3, None)
                     if prev is not None:
                         prev.synchronize()
-                    nxt = feeder.submit(_load_batch, dataset, batches[bi + 1], pool, staging, (bi + 1) % 3)
+                    nxt = feeder.submit(load_unit, ui + 1)
                 else:
                     nxt = None
             else:
-                T, frames, names = _load_batch(dataset, batch, None)
-            frames = upload(frames, bi % 3)
-            parts = []
-            for sub, sub_names, rands, clips in _canvas_groups(pipeline, frames, names, T):
-                data = pipeline.batch(sub, filenames=sub_names) if rands is None else \
-                    pipeline.batch(sub, rands=rands, filenames=sub_names)
-                (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
-                n = len(sub_names)
-                det = torch.stack(list(det_bboxes)).float()                              # [B*T, 3, 5]
-                gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
-                rows = torch.cat([det[..., :4].reshape(n, 12), det[..., 4], gaze.reshape(n, 12).float()], 1)
-                parts.append(([batch[k] for k in clips], rows))
-            ids = [i for p_ids, _ in parts for i in p_ids]
-            rows = parts[0][1] if len(parts) == 1 else torch.cat([r for _, r in parts])
-            ev = None
-            if rows.is_cuda and to_host:
-                host = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
-                host.copy_(rows, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(rows.device))
-                rows = host
-            # hand the PREVIOUS batch over only now, with this batch already queued: the GPU never waits for the host
-            if pending is not None:
-                collect(pending)
-            pending = (ids, T, rows, ev, decode_check)
+                kind, payload = load_unit(ui)
+            if kind == 'gpu':
+                staged, descr = payload
+                dframes = upload(staged, 0)                                    # one H2D copy + one decode launch per unit
+                items = [(T, dframes[a:b], names) for T, names, a, b in descr]
+            else:
+                items = payload
+            for k, (T, frames, names) in enumerate(items):
+                bi += 1
+                batch = unit[k]
+                if kind != 'gpu':
+                    frames = upload(frames, bi % 3)
+                elif k > 0:
+                    decode_check = None                                            # the unit's status rides on its first batch
+                parts = []
+                for sub, sub_names, rands, clips in _canvas_groups(pipeline, frames, names, T):
+                    data = pipeline.batch(sub, filenames=sub_names) if rands is None else \
+                        pipeline.batch(sub, rands=rands, filenames=sub_names)
+                    (det_bboxes, _), gz = model(return_loss=False, rescale=True, format=False, clip_length=T, **data)
+                    n = len(sub_names)
+                    det = torch.stack(list(det_bboxes)).float()                              # [B*T, 3, 5]
+                    gaze = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
+                    rows = torch.cat([det[..., :4].reshape(n, 12), det[..., 4], gaze.reshape(n, 12).float()], 1)
+                    parts.append(([batch[k] for k in clips], rows))
+                ids = [i for p_ids, _ in parts for i in p_ids]
+                rows = parts[0][1] if len(parts) == 1 else torch.cat([r for _, r in parts])
+                ev = None
+                if rows.is_cuda and to_host:
+                    host = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
+                    host.copy_(rows, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(rows.device))
+                    rows = host
+                # hand the PREVIOUS batch over only now, with this batch already queued: the GPU never waits for the host
+                if pending is not None:
+                    collect(pending)
+                pending = (ids, T, rows, ev, decode_check)
         if pending is not None:
             collect(pending)
     finally:

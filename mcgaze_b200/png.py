@@ -32,7 +32,8 @@ _ALIGN = 16
 _CHANNELS = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
 STATUS_NAMES = ('ok', 'bad zlib header', 'reserved block type', 'bad stored-block length', 'bad code lengths',
                 'bad symbol', 'match distance before the start of the data', 'more data than the image holds',
-                'compressed stream ends early', 'less data than the image holds', 'bad filter type')
+                'compressed stream ends early', 'less data than the image holds', 'bad filter type', 'bad job descriptor',
+                'Adler-32 of the decoded data does not match the stream trailer')
 
 
 class UnsupportedPng(lib.McgError):
@@ -44,7 +45,8 @@ def _up(n: int) -> int:
 
 
 class StagedPngs:
-    """host side of one batch: the pinned block (zlib streams + palettes), per-image header fields and offsets"""
+    """host side of one batch: the pinned block (zlib streams + palettes + room for the job table at `used`), per-image
+    header fields and offsets"""
     __slots__ = ('block', 'used', 'infos', 'zoff', 'zlen', 'paloff', 'names')
 
     def __init__(self, block, used, infos, zoff, zlen, paloff, names):
@@ -92,7 +94,10 @@ class GpuPngDecoder:
         offs = np.zeros(n + 1, dtype=np.int64)
         for i, d in enumerate(datas):
             offs[i + 1] = offs[i] + _up(int(d.size)) + 768
-        block = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        # ... and the job table behind them (64-byte descriptors, filled by launch() once the device addresses exist): the
+        # kernels read it from HBM, so it travels in the same copy
+        jobs_off = (int(offs[-1]) + 63) // 64 * 64
+        block = torch.empty(jobs_off + 64 * n, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
         base = block.numpy()
         names = [str(f) if isinstance(f, (str, os.PathLike)) else f'<image {i}>' for i, f in enumerate(files)]
 
@@ -113,7 +118,7 @@ class GpuPngDecoder:
             return (int(info.width), int(info.height), int(info.color_type)), int(info.idat_bytes), pal
 
         res = [one(i) for i in range(n)] if pool is None else list(pool.map(one, range(n)))
-        return StagedPngs(block, int(offs[-1]), [r[0] for r in res], offs[:-1].copy(), np.array([r[1] for r in res], dtype=np.int64),
+        return StagedPngs(block, jobs_off, [r[0] for r in res], offs[:-1].copy(), np.array([r[1] for r in res], dtype=np.int64),
                           np.array([r[2] for r in res], dtype=np.int64), names)
 
     # ------------------------------------------------------------------------------------------------ device phase
@@ -128,7 +133,7 @@ class GpuPngDecoder:
         dev = torch.device('cuda', self.device)
         n = len(staged)
         with torch.cuda.device(dev):
-            zdev = staged.block.to(dev, non_blocking=True)
+            zdev = torch.empty(staged.block.shape, dtype=torch.uint8, device=dev)
             w = np.array([i[0] for i in staged.infos], dtype=np.int64)
             h = np.array([i[1] for i in staged.infos], dtype=np.int64)
             ch = np.array([_CHANNELS[i[2]] for i in staged.infos], dtype=np.int64)
@@ -150,7 +155,8 @@ class GpuPngDecoder:
                 dst_off = np.concatenate([[0], np.cumsum((dst_bytes + _ALIGN - 1) // _ALIGN * _ALIGN)])
                 dst = torch.empty(int(dst_off[-1]), dtype=torch.uint8, device=dev)
             status = torch.empty(n, dtype=torch.int32, device=dev)
-            jobs = np.zeros(n, dtype=self._job_dtype)
+            jobs = staged.block.numpy()[staged.used:staged.used + 64 * n].view(self._job_dtype)
+            jobs[:] = 0
             zbase = zdev.data_ptr()
             jobs['zdata'] = zbase + staged.zoff.astype(np.uint64)
             jobs['zbytes'] = staged.zlen
@@ -160,8 +166,9 @@ class GpuPngDecoder:
             jobs['scan'] = scan.data_ptr() + scan_off[:-1].astype(np.uint64)
             jobs['dst'] = dst.data_ptr() + dst_off[:-1].astype(np.uint64)
             jobs['dst_stride'] = 3 * w
+            zdev.copy_(staged.block, non_blocking=True)            # compressed bytes + palettes + job table: one copy
             st = torch.cuda.current_stream().cuda_stream if stream is None else stream
-            lib._check(so.mcg_png_decode(ctypes.cast(jobs.ctypes.data, ctypes.POINTER(lib.mcg_png_job)), n, status.data_ptr(), st),
+            lib._check(so.mcg_png_decode(ctypes.cast(zbase + staged.used, ctypes.POINTER(lib.mcg_png_job)), n, status.data_ptr(), st),
                        'mcg_png_decode')
             cur = torch.cuda.current_stream()
             for t in (zdev, scan):           # freed at return: the caching allocator must not hand them out before the kernels ran

@@ -17,7 +17,7 @@ extern "C" long long sim_slow_symbols() { return g_slow_symbols; }
 
 extern "C" int sim_unfilter(uint8_t* scan, int W, int H, int color_type, const uint8_t* palette, uint8_t* dst, long long dst_stride) {
   const int bpp = channels_of(color_type);
-  if (bpp == 0) return ST_UNSUPPORTED;
+  if (bpp == 0) return ST_BAD_JOB;
   const int rowbytes = W * bpp;
   const long long stride = 1 + static_cast<long long>(rowbytes);
   bool bad = false;

@@ -160,17 +160,23 @@ def test_host_build_flags_corrupt_streams(sim, name):
     assert st != 0 or st2 != 0
 
 
-def test_host_build_survives_random_corruption(sim):
-    """bit flips anywhere in the stream: an error or a (wrong) image, never a write outside the buffers (canary)"""
+def test_host_build_flags_random_corruption(sim):
+    """bit flips anywhere in the stream: flagged (a code error, a size mismatch, or the Adler-32 of the inflated bytes
+    against the stream trailer) unless the decoded image is unchanged (padding bits); never a write outside the buffers"""
     rng = np.random.default_rng(0)
-    base = bytearray(P.parse(CASES['cv2_level9'])['zdata'])
     p = P.parse(CASES['cv2_level9'])
-    for _ in range(200):
+    base = bytearray(p['zdata'])
+    want = _cv2(CASES['cv2_level9'])
+    ihdr = P._chunk(b'IHDR', p['width'].to_bytes(4, 'big') + p['height'].to_bytes(4, 'big') + bytes([8, 2, 0, 0, 0]))
+    statuses = set()
+    for _ in range(300):
         z = bytearray(base)
         for _ in range(int(rng.integers(1, 4))):
             z[int(rng.integers(2, len(z)))] ^= 1 << int(rng.integers(0, 8))
-        ihdr = P._chunk(b'IHDR', p['width'].to_bytes(4, 'big') + p['height'].to_bytes(4, 'big') + bytes([8, 2, 0, 0, 0]))
-        _sim_decode(sim, P.SIGNATURE + ihdr + P._chunk(b'IDAT', bytes(z)) + P._chunk(b'IEND', b''))
+        st, st2, img = _sim_decode(sim, P.SIGNATURE + ihdr + P._chunk(b'IDAT', bytes(z)) + P._chunk(b'IEND', b''))
+        assert st != 0 or st2 != 0 or np.array_equal(img, want)
+        statuses.add(st)
+    assert 12 in statuses          # MCG_PNG_BAD_CHECKSUM: a flipped literal decodes "fine" and only the checksum sees it
 
 
 def test_decoder_needs_a_gpu_and_never_falls_back():
@@ -251,6 +257,9 @@ def test_gpu_decode_random_corruption_stays_inside_its_buffers():
     want = torch.from_numpy(_cv2(CASES['cv2_level9'])).cuda()
     st = status.cpu().numpy()
     assert (st[1::2] == 0).all() and bool((frames[1::2] == want[None]).all())
+    # ... and every damaged stream is flagged unless its pixels are unchanged (Adler-32 verified on the device)
+    same = (frames[0::2] == want[None]).flatten(1).all(1).cpu().numpy()
+    assert ((st[0::2] != 0) | same).all() and (st[0::2] == 12).any()
 
 
 @pytest.mark.gpu
@@ -311,12 +320,8 @@ def test_gpu_evaluation_driver_with_device_decode_equals_host_decode(synthetic_s
     ihdr = P._chunk(b'IHDR', p['width'].to_bytes(4, 'big') + p['height'].to_bytes(4, 'big') + bytes([8, 2, 0, 0, 0]))
     open(bad, 'wb').write(P.SIGNATURE + ihdr + P._chunk(b'IDAT', bytes(z)) + P._chunk(b'IEND', b''))
     ds = ev.Gaze360ClipDataset(anno, img_prefix=str(tmp_path), decode='gpu')
-    try:
-        got = ev.single_gpu_test(model, ds, GpuTestPipeline(model.cfg.data.test.pipeline, seed=3), clips_per_batch=2, workers=2)
-        # a flipped bit inside a literal decodes to a wrong pixel without tripping any check: then only that clip differs
-        assert not np.array_equal(got[0], rows['gpu'][0]) and np.array_equal(got[-1], rows['gpu'][-1])
-    except lib.McgError as e:
-        assert '00003.png' in str(e)
+    with pytest.raises(lib.McgError, match='00003.png'):      # a code error or the Adler-32 check, reported by file name
+        ev.single_gpu_test(model, ds, GpuTestPipeline(model.cfg.data.test.pipeline, seed=3), clips_per_batch=2, workers=2)
     # a JPEG among the frames: that batch is decoded by cv2 on the host, as the reference does
     open(bad, 'wb').write(keep)
     jpg = tmp_path / 'v002' / '00001.png'
