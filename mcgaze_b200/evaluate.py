@@ -224,7 +224,9 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
             if decoder is None:
                 decoder = png.GpuPngDecoder(getattr(pipeline, 'device', 0))
             with torch.cuda.device(decoder.device):
-                dframes, status = decoder.launch(frames)
+                if copy_stream is None:
+                    copy_stream = torch.cuda.Stream(device=decoder.device)
+                dframes, status = decoder.launch(frames, copy_stream=copy_stream)
                 decode_check = (frames,) + decoder.status_async(status)
             return dframes
         if not (cuda and hasattr(frames, 'is_pinned') and frames.is_pinned() and hasattr(pipeline, 'device')):

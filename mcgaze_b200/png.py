@@ -122,10 +122,12 @@ class GpuPngDecoder:
                           np.array([r[2] for r in res], dtype=np.int64), names)
 
     # ------------------------------------------------------------------------------------------------ device phase
-    def launch(self, staged: StagedPngs, stream: Optional[int] = None, out: Any = None):
+    def launch(self, staged: StagedPngs, stream: Optional[int] = None, out: Any = None, copy_stream: Any = None):
         """-> (frames, status): `frames` = list of CUDA uint8 [h, w, 3] tensors (views of one allocation; or ONE
         [n, h, w, 3] tensor when all images have the same size), `status` = CUDA int32 [n] (0 = decoded), both valid in
-        stream order.  `out`: optional CUDA uint8 [n, h, w, 3] tensor to decode into (images of one size)."""
+        stream order.  `out`: optional CUDA uint8 [n, h, w, 3] tensor to decode into (images of one size).
+        `copy_stream`: a torch.cuda.Stream for the H2D copy of the compressed bytes (the current stream then only waits
+        for it, so the copy runs beside whatever the current stream is still computing)."""
         import torch
         if not torch.cuda.is_available():
             raise lib.McgError('mcgaze_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
@@ -133,7 +135,11 @@ class GpuPngDecoder:
         dev = torch.device('cuda', self.device)
         n = len(staged)
         with torch.cuda.device(dev):
-            zdev = torch.empty(staged.block.shape, dtype=torch.uint8, device=dev)
+            if copy_stream is not None:      # from the copy stream's pool: a block this stream may overwrite at once
+                with torch.cuda.stream(copy_stream):
+                    zdev = torch.empty(staged.block.shape, dtype=torch.uint8, device=dev)
+            else:
+                zdev = torch.empty(staged.block.shape, dtype=torch.uint8, device=dev)
             w = np.array([i[0] for i in staged.infos], dtype=np.int64)
             h = np.array([i[1] for i in staged.infos], dtype=np.int64)
             ch = np.array([_CHANNELS[i[2]] for i in staged.infos], dtype=np.int64)
@@ -166,7 +172,15 @@ class GpuPngDecoder:
             jobs['scan'] = scan.data_ptr() + scan_off[:-1].astype(np.uint64)
             jobs['dst'] = dst.data_ptr() + dst_off[:-1].astype(np.uint64)
             jobs['dst_stride'] = 3 * w
-            zdev.copy_(staged.block, non_blocking=True)            # compressed bytes + palettes + job table: one copy
+            if copy_stream is not None:                            # compressed bytes + palettes + job table: one copy
+                cur = torch.cuda.current_stream()
+                with torch.cuda.stream(copy_stream):
+                    zdev.copy_(staged.block, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                cur.wait_event(done)
+            else:
+                zdev.copy_(staged.block, non_blocking=True)
             st = torch.cuda.current_stream().cuda_stream if stream is None else stream
             lib._check(so.mcg_png_decode(ctypes.cast(zbase + staged.used, ctypes.POINTER(lib.mcg_png_job)), n, status.data_ptr(), st),
                        'mcg_png_decode')
