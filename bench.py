@@ -382,6 +382,17 @@ def png_decode_extra(eng, sd, dev):
         for k, f in enumerate(files):
             with open(os.path.join(tmp, f'{k:02d}.png'), 'wb') as fh:
                 fh.write(f)
+        # host side of a unit of 8 batches from FILES: mcg_png_file_sizes + mcg_png_stage_files (read, chunk walk, copy into
+        # the pinned block on 8 worker threads inside the C call)
+        from concurrent.futures import ThreadPoolExecutor
+        paths = [os.path.join(tmp, f'{k % 64:02d}.png') for k in range(1792)]
+        with ThreadPoolExecutor(8) as tp:
+            dec_nocrc = GpuPngDecoder(dev.index, check_crc=False)
+            dec_nocrc.stage(paths, tp)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dec_nocrc.stage(paths, tp)
+            out['host_stage_files_ms_per_1792_8_threads'] = 1e3 * (time.perf_counter() - t0) / 3
         grng = np.random.default_rng(1)
         anno = dict(videos=[dict(id=i + 1, file_names=[f'{(i * 131 + t) % 64:02d}.png' for t in range(L)]) for i, L in enumerate(lengths)],
                     annotations=[dict(gaze=grng.normal(size=(L, 3)).tolist()) for L in lengths])

@@ -191,6 +191,17 @@ typedef struct {
  * first call with zdata == NULL sizes the buffer).  The H2D copy of zdata is the caller's. */
 int mcg_png_parse(const uint8_t* file, int64_t nbytes, int check_crc, mcg_png_info* info, uint8_t* zdata, int64_t zcap);
 
+/* HOST functions for a batch of FILES (what a loader thread does for LoadImageFromFile's `filename`): sizes first, so the
+ * caller can lay out one pinned staging block (slot i needs sizes[i] bytes: a file's IDAT payload is shorter than the
+ * file), then every file is mapped, parsed like mcg_png_parse and its payload copied from the page cache straight into
+ * block + slot_off[i], on `threads` worker threads inside the call (no per-file work in the caller's language).
+ *   results[i]  0 = staged (infos[i] valid), 1 = unreadable, 2 = not a PNG / malformed, 3 = valid PNG that
+ *               mcg_png_decode does not take (infos[i].supported == 0: decode it on the host)
+ * Returns MCG_OK when every file was staged, else MCG_ERR_INVALID (mcg_last_error names the first one). */
+int mcg_png_file_sizes(const char* const* paths, int n, int64_t* sizes);
+int mcg_png_stage_files(const char* const* paths, int n, int check_crc, int threads, const int64_t* slot_off,
+                        const int64_t* slot_cap, uint8_t* block, mcg_png_info* infos, int32_t* results);
+
 typedef struct {
   const uint8_t* zdata;  /* DEVICE zlib stream (the concatenated IDAT payloads) */
   int64_t zbytes;

@@ -1660,6 +1660,9 @@ void preprocess_launch(const mcg_frame* frames, int n, const float* mean, const 
 // png_decode.cu
 int png_parse(const uint8_t* f, int64_t n, int check_crc, mcg_png_info* info, uint8_t* z, int64_t zcap, const char** why);
 void png_decode_launch(const mcg_png_job* jobs, int n, int32_t* status, cudaStream_t st, int* launches);
+void png_file_sizes(const char* const* paths, int n, int64_t* sizes);
+int png_stage_files(const char* const* paths, int n, int check_crc, int threads, const int64_t* slot_off,
+                    const int64_t* slot_cap, uint8_t* block, mcg_png_info* infos, int32_t* results);
 // metric.cu
 void gaze_error_launch(const float* pred, const float* gt, const int32_t* video_start, int n_videos, int variant,
                        double* out, cudaStream_t st);
@@ -1790,6 +1793,39 @@ int mcg_png_parse(const uint8_t* file, int64_t nbytes, int check_crc, mcg_png_in
     const int rc = mcg::png_parse(file, nbytes, check_crc, info, zdata, zcap, &why);
     if (rc != MCG_OK) mcg::g_last_error = std::string("mcg_png_parse: ") + why;
     return rc;
+  });
+}
+
+int mcg_png_file_sizes(const char* const* paths, int n, int64_t* sizes) {
+  return guarded([&]() -> int {
+    if (!paths || !sizes || n <= 0) {
+      mcg::g_last_error = "mcg_png_file_sizes: null argument";
+      return MCG_ERR_INVALID;
+    }
+    mcg::png_file_sizes(paths, n, sizes);
+    return MCG_OK;
+  });
+}
+
+int mcg_png_stage_files(const char* const* paths, int n, int check_crc, int threads, const int64_t* slot_off,
+                        const int64_t* slot_cap, uint8_t* block, mcg_png_info* infos, int32_t* results) {
+  return guarded([&]() -> int {
+    if (!paths || !slot_off || !slot_cap || !block || !infos || !results || n <= 0) {
+      mcg::g_last_error = "mcg_png_stage_files: null argument";
+      return MCG_ERR_INVALID;
+    }
+    const int bad = mcg::png_stage_files(paths, n, check_crc, threads, slot_off, slot_cap, block, infos, results);
+    if (bad) {
+      for (int i = 0; i < n; ++i)
+        if (results[i]) {
+          static const char* what[] = {"", "cannot read", "not a PNG file or malformed", "a PNG the device decoder does not take"};
+          mcg::g_last_error = std::string("mcg_png_stage_files: ") + (paths[i] ? paths[i] : "(null)") + ": " + what[results[i] & 3] +
+                              " (" + std::to_string(bad) + " of " + std::to_string(n) + " files)";
+          break;
+        }
+      return MCG_ERR_INVALID;
+    }
+    return MCG_OK;
   });
 }
 

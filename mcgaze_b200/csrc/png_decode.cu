@@ -2,9 +2,17 @@
 // LoadImageFromFile (mmdet/datasets/pipelines/loading.py:58-69 -> mmcv.imfrombytes -> cv2.imdecode) that used to stay on
 // the host.  The host only walks the chunk list (signature, IHDR, PLTE, IDAT payloads, optional CRC check); inflate and
 // scanline reconstruction run on the device, one warp per image (png_core.cuh).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/mcgaze_b200.h"
 #include "common.cuh"
@@ -204,6 +212,67 @@ int png_parse(const uint8_t* f, int64_t n, int check_crc, mcg_png_info* info, ui
     return MCG_ERR_INVALID;
   }
   return MCG_OK;
+}
+
+// File sizes (bytes; -1 = cannot stat): what the caller needs to lay out the staging block.
+void png_file_sizes(const char* const* paths, int n, int64_t* sizes) {
+  for (int i = 0; i < n; ++i) {
+    struct stat sb;
+    sizes[i] = (paths[i] && ::stat(paths[i], &sb) == 0 && S_ISREG(sb.st_mode)) ? static_cast<int64_t>(sb.st_size) : -1;
+  }
+}
+
+// The host side of a batch in one call: every file is read, its chunks are walked and its IDAT payload is copied into
+// the caller's (pinned) block at slot_off[i] (slot_cap[i] bytes), on `threads` worker threads.  results[i]: 0 = staged, 1 = unreadable, 2 = not a PNG / malformed, 3 = a PNG the device decoder does not take.
+// -> number of files with results != 0.
+int png_stage_files(const char* const* paths, int n, int check_crc, int threads, const int64_t* slot_off,
+                    const int64_t* slot_cap, uint8_t* block, mcg_png_info* infos, int32_t* results) {
+  std::atomic<int> next(0), failed(0);
+  auto work = [&]() {
+    std::vector<uint8_t> buf;
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) return;
+      results[i] = 1;
+      std::memset(&infos[i], 0, sizeof(mcg_png_info));
+      const int fd = paths[i] ? ::open(paths[i], O_RDONLY | O_CLOEXEC) : -1;
+      struct stat sb;
+      if (fd < 0 || ::fstat(fd, &sb) != 0 || sb.st_size <= 0) {
+        if (fd >= 0) ::close(fd);
+        failed.fetch_add(1);
+        continue;
+      }
+      // read() into a per-thread buffer: one sequential copy out of the page cache (mapping every file costs a page
+      // fault per 4 KB and a munmap: measured 2.5x slower for 200 KB frames)
+      const size_t size = static_cast<size_t>(sb.st_size);
+      if (buf.size() < size) buf.resize(size + (size >> 2));
+      size_t got = 0;
+      while (got < size) {
+        const ssize_t r = ::read(fd, buf.data() + got, size - got);
+        if (r <= 0) break;
+        got += static_cast<size_t>(r);
+      }
+      ::close(fd);
+      if (got != size) {
+        failed.fetch_add(1);
+        continue;
+      }
+      const char* why = "";
+      const int rc = png_parse(buf.data(), static_cast<int64_t>(size), check_crc, &infos[i], block + slot_off[i], slot_cap[i], &why);
+      results[i] = rc != MCG_OK ? 2 : (infos[i].supported ? 0 : 3);
+      if (results[i] != 0) failed.fetch_add(1);
+    }
+  };
+  const int nt = std::max(1, std::min(threads, n));
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  return failed.load();
 }
 
 void png_decode_launch(const mcg_png_job* jobs, int n, int32_t* status, cudaStream_t st, int* launches) {

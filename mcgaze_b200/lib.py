@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 0, 'fp16': 1, 'simt': 2, 'fp16c8': 3}
 EXPORTS = ('mcg_create', 'mcg_destroy', 'mcg_forward', 'mcg_forward_host', 'mcg_submit_host', 'mcg_wait_host',
            'mcg_get_intermediate',
            'mcg_last_launch_count', 'mcg_range_report', 'mcg_last_umma_stats', 'mcg_last_umma_times', 'mcg_last_kernel_profile', 'mcg_set_graph_mode', 'mcg_set_option', 'mcg_debug_conv',
-           'mcg_preprocess', 'mcg_png_parse', 'mcg_png_decode', 'mcg_merge_clips', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
+           'mcg_preprocess', 'mcg_png_parse', 'mcg_png_file_sizes', 'mcg_png_stage_files', 'mcg_png_decode', 'mcg_merge_clips', 'mcg_gaze_error', 'mcg_last_error', 'mcg_version')
 
 
 class McgError(RuntimeError):
@@ -81,6 +81,8 @@ def load_library() -> ctypes.CDLL:
     lib.mcg_range_report.argtypes = [vp, ctypes.c_char_p, ci]
     lib.mcg_preprocess.argtypes = [ctypes.POINTER(mcg_frame), ci, cf, cf, ci, vp, ci, ci, vp]
     lib.mcg_png_parse.argtypes = [vp, ctypes.c_int64, ci, ctypes.POINTER(mcg_png_info), vp, ctypes.c_int64]
+    lib.mcg_png_file_sizes.argtypes = [ctypes.POINTER(ctypes.c_char_p), ci, vp]
+    lib.mcg_png_stage_files.argtypes = [ctypes.POINTER(ctypes.c_char_p), ci, ci, ci, vp, vp, vp, ctypes.POINTER(mcg_png_info), vp]
     lib.mcg_png_decode.argtypes = [ctypes.POINTER(mcg_png_job), ci, vp, vp]
     lib.mcg_gaze_error.argtypes = [vp, vp, vp, ci, ci, vp, vp]
     lib.mcg_merge_clips.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]

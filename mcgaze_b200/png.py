@@ -78,11 +78,57 @@ class GpuPngDecoder:
             return np.ascontiguousarray(f, dtype=np.uint8).reshape(-1)
         return np.frombuffer(f, dtype=np.uint8)
 
-    def stage(self, files: Sequence[FileLike], pool=None) -> StagedPngs:
-        """Read and parse `files` (paths or file images).  The IDAT payloads land in one pinned host block (pageable
-        without a GPU).  `pool`: optional ThreadPoolExecutor - mcg_png_parse releases the GIL."""
+    def _stage_paths(self, paths: Sequence[str], threads: int) -> StagedPngs:
+        """all inputs are file names: sizes, layout, then ONE C call maps, parses and copies every file on its own worker
+        threads (mcg_png_stage_files) - no per-file python work"""
         import torch
         so = lib.load_library()
+        n = len(paths)
+        cpaths = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        sizes = np.zeros(n, dtype=np.int64)
+        lib._check(so.mcg_png_file_sizes(cpaths, n, sizes.ctypes.data), 'mcg_png_file_sizes')
+        if (sizes < 0).any():
+            raise FileNotFoundError(paths[int(np.nonzero(sizes < 0)[0][0])])
+        slot = (sizes + _ALIGN - 1) // _ALIGN * _ALIGN
+        offs = np.concatenate([[0], np.cumsum(slot + 768)]).astype(np.int64)
+        jobs_off = (int(offs[-1]) + 63) // 64 * 64
+        block = torch.empty(jobs_off + 64 * n, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        base = block.numpy()
+        infos = (lib.mcg_png_info * n)()
+        results = np.zeros(n, dtype=np.int32)
+        rc = so.mcg_png_stage_files(cpaths, n, 1 if self.check_crc else 0, max(1, int(threads)), offs.ctypes.data, sizes.ctypes.data,
+                                    base.ctypes.data, infos, results.ctypes.data)
+        if rc != 0:
+            msg = (so.mcg_last_error() or b'mcg_png_stage_files failed').decode()
+            first = int(results[np.nonzero(results)[0][0]]) if results.any() else 0
+            if first == 1:
+                raise FileNotFoundError(msg)
+            raise (UnsupportedPng if first == 3 or self._not_png(paths[int(np.nonzero(results)[0][0])]) else lib.McgError)(msg)
+        arr = np.frombuffer(infos, dtype=np.uint8).reshape(n, ctypes.sizeof(lib.mcg_png_info))
+        head = arr[:, :32].copy().view(np.int32)                     # width, height, bit_depth, color_type, ...
+        zlen = arr[:, 32:40].copy().view(np.int64).reshape(n)
+        paloff = np.full(n, -1, dtype=np.int64)
+        for i in np.nonzero(head[:, 3] == 3)[0]:
+            paloff[i] = int(offs[i] + slot[i])
+            base[paloff[i]:paloff[i] + 768] = arr[i, 40:808]
+        triples = [(int(w), int(h), int(c)) for w, h, c in zip(head[:, 0], head[:, 1], head[:, 3])]
+        return StagedPngs(block, jobs_off, triples, offs[:-1].copy(), zlen, paloff, [str(p) for p in paths])
+
+    @staticmethod
+    def _not_png(path) -> bool:
+        try:
+            with open(path, 'rb') as fh:
+                return fh.read(8) != b'\x89PNG\r\n\x1a\n'
+        except OSError:
+            return False
+
+    def stage(self, files: Sequence[FileLike], pool=None) -> StagedPngs:
+        """Read and parse `files` (paths or file images).  The IDAT payloads land in one pinned host block (pageable
+        without a GPU).  `pool`: optional ThreadPoolExecutor (its size = the worker threads used)."""
+        import torch
+        so = lib.load_library()
+        if len(files) and all(isinstance(f, (str, os.PathLike)) for f in files):
+            return self._stage_paths([os.fspath(f) for f in files], getattr(pool, '_max_workers', 1) if pool is not None else 1)
         datas = [self._bytes(f) for f in files] if pool is None else list(pool.map(self._bytes, files))
         n = len(datas)
         if n == 0:

@@ -179,6 +179,45 @@ def test_host_build_flags_random_corruption(sim):
     assert 12 in statuses          # MCG_PNG_BAD_CHECKSUM: a flipped literal decodes "fine" and only the checksum sees it
 
 
+def test_staging_files_in_one_c_call_equals_staging_file_images(tmp_path):
+    """mcg_png_file_sizes + mcg_png_stage_files (the loader-thread side of decode='gpu': read, chunk walk, copy into the
+    staging block on worker threads inside the call) against the per-image mcg_png_parse path; and what they report for
+    files the device decoder cannot take"""
+    from concurrent.futures import ThreadPoolExecutor
+    from mcgaze_b200.png import GpuPngDecoder, UnsupportedPng
+    names = sorted(CASES)
+    paths = []
+    for n in names:
+        (tmp_path / f'{n}.png').write_bytes(CASES[n])
+        paths.append(str(tmp_path / f'{n}.png'))
+    dec = GpuPngDecoder(check_crc=True)
+    a = dec.stage([CASES[n] for n in names])
+    with ThreadPoolExecutor(4) as pool:
+        b = dec.stage(paths, pool)
+    assert a.infos == b.infos and (a.zlen == b.zlen).all() and ((a.paloff >= 0) == (b.paloff >= 0)).all()
+    for i, n in enumerate(names):
+        za = a.block.numpy()[a.zoff[i]:a.zoff[i] + a.zlen[i]]
+        zb = b.block.numpy()[b.zoff[i]:b.zoff[i] + b.zlen[i]]
+        assert np.array_equal(za, zb), n
+        if a.paloff[i] >= 0:
+            assert np.array_equal(a.block.numpy()[a.paloff[i]:a.paloff[i] + 768], b.block.numpy()[b.paloff[i]:b.paloff[i] + 768])
+    assert b.names == paths
+    # not a PNG (a JPEG behind a .png name), a 16-bit PNG: the caller's cue to use the host loader; a missing file; a bad CRC
+    assert cv2.imwrite(str(tmp_path / 'x.jpg'), np.zeros((10, 10, 3), np.uint8))
+    os.replace(tmp_path / 'x.jpg', tmp_path / 'fake.png')
+    with pytest.raises(UnsupportedPng, match='fake.png'):
+        dec.stage([paths[0], str(tmp_path / 'fake.png')])
+    assert cv2.imwrite(str(tmp_path / 's16.png'), (np.arange(600, dtype=np.uint16) * 97).reshape(20, 10, 3))
+    with pytest.raises(UnsupportedPng, match='s16.png'):
+        dec.stage([str(tmp_path / 's16.png')])
+    with pytest.raises(FileNotFoundError):
+        dec.stage([str(tmp_path / 'missing.png')])
+    (tmp_path / 'crc.png').write_bytes(CORRUPT['bad_crc'][0])
+    with pytest.raises(lib.McgError, match='crc.png'):
+        dec.stage([str(tmp_path / 'crc.png')])
+    assert len(GpuPngDecoder(check_crc=False).stage([str(tmp_path / 'crc.png')])) == 1
+
+
 def test_decoder_needs_a_gpu_and_never_falls_back():
     import torch
     if torch.cuda.is_available():
