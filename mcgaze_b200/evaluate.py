@@ -145,17 +145,24 @@ def _stage_unit(dataset: Gaze360ClipDataset, unit: Sequence[Sequence[int]], pool
     """decode='gpu': the host part for SEVERAL batches at once - read the files and walk their chunks into one pinned
     block (mcgaze_b200/png.py).  One mcg_png_decode launch then covers the whole unit: a warp needs ~10 ms for a frame
     whatever else runs, so the decode is paid once per unit instead of once per batch.
-    -> (StagedPngs, [(clip length, frame names, first frame, end frame) per batch]) or None when a file is not a PNG the
-    device decoder takes (the unit then goes through the host loader)."""
+    -> (StagedPngs of the unit's DISTINCT files, [(clip length, frame names, first frame, end frame) per batch], index of
+    every frame into the distinct files) or None when a file is not a PNG the device decoder takes (the unit then goes
+    through the host loader)."""
     from . import png
-    paths, parts = [], []
+    paths, parts, index, where = [], [], [], {}
     for batch in unit:
         infos = [dataset.clip_info(i) for i in batch]
         names = [f for it in infos for f in it['filenames']]
-        parts.append((infos[0]['n'], names, len(paths), len(paths) + len(names)))
-        paths += [os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f for f in names]
+        first = len(index)
+        for f in names:                       # overlapping clips share frames (stride 4 of 7): a file is staged and decoded once
+            k = where.get(f)
+            if k is None:
+                k = where[f] = len(paths)
+                paths.append(os.path.join(dataset.img_prefix, f) if dataset.img_prefix else f)
+            index.append(k)
+        parts.append((infos[0]['n'], names, first, len(index)))
     try:
-        return png.GpuPngDecoder(check_crc=dataset.check_crc).stage(paths, pool), parts
+        return png.GpuPngDecoder(check_crc=dataset.check_crc).stage(paths, pool), parts, np.asarray(index, dtype=np.int64)
     except png.UnsupportedPng:
         dataset.host_decoded_batches += len(unit)
         return None
@@ -292,9 +299,13 @@ def run_clips(model, dataset: Gaze360ClipDataset, pipeline, indices: Sequence[in
             else:
                 kind, payload = load_unit(ui)
             if kind == 'gpu':
-                staged, descr = payload
+                staged, descr, index = payload
                 dframes = upload(staged, 0)                                    # one H2D copy + one decode launch per unit
-                items = [(T, dframes[a:b], names) for T, names, a, b in descr]
+                if hasattr(dframes, 'shape'):                                  # frames of one size: gather on the device
+                    didx = torch.from_numpy(index).to(dframes.device, non_blocking=True)
+                    items = [(T, dframes.index_select(0, didx[a:b]), names) for T, names, a, b in descr]
+                else:
+                    items = [(T, [dframes[i] for i in index[a:b]], names) for T, names, a, b in descr]
             else:
                 items = payload
             for k, (T, frames, names) in enumerate(items):
