@@ -869,72 +869,6 @@ __global__ void finalize_kernel(const float* __restrict__ gvec, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// acc[i] += sum_k xs[i][k] * Wt[k][n] for one 256 x 256 transposed weight matrix, K split over the 4 k-slices of a
-// 1024-thread CTA (thread = (n = tid & 255, kq = tid >> 8); slice kq owns rows [kq * 8, kq * 8 + 8) of every 32-row
-// chunk).  The weights stream through shared memory in 32-row chunks (32 KB) with cp.async, two chunks in flight:
-// the per-thread dependent global loads of the first version paid the L2 latency 8 times per layer (~9 us per layer
-// at 84 CTAs); with the stream a layer is bound by its FMAs (~4 us).
-// `wbuf` = [2][32][256] floats.  The caller has issued chunks 0 and 1 of THIS matrix (stream256_prefetch) before; on
-// return chunks 0 and 1 of `next` (if any) are in flight.  Contains __syncthreads: call from all 1024 threads.
-// ---------------------------------------------------------------------------------------
-constexpr int kW256ChunkRows = 32;
-constexpr int kW256Chunks = 256 / kW256ChunkRows;                 // 8
-constexpr int kW256BufFloats = 2 * kW256ChunkRows * 256;          // 64 KB
-
-__device__ __forceinline__ void stream256_issue(float* wbuf, const float* __restrict__ wt, int chunk) {
-  // 32 rows x 1 KB = 2048 x 16 B: two per thread
-  float* dst = wbuf + (chunk & 1) * kW256ChunkRows * 256;
-  const float* src = wt + static_cast<long long>(chunk) * kW256ChunkRows * 256;
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int i = threadIdx.x + t * 1024;
-    cp_async16(dst + i * 4, src + i * 4);
-  }
-  cp_async_commit();
-}
-__device__ __forceinline__ void stream256_prefetch(float* wbuf, const float* __restrict__ wt) {
-  stream256_issue(wbuf, wt, 0);
-  stream256_issue(wbuf, wt, 1);
-}
-__device__ __forceinline__ void stream256_layer(const float* xs /*[8][256] smem*/, float* wbuf, const float* __restrict__ wt,
-                                                const float* __restrict__ next, float (&acc)[8]) {
-  const int n = threadIdx.x & 255, kq = threadIdx.x >> 8;
-#pragma unroll 1
-  for (int c = 0; c < kW256Chunks; ++c) {
-    if (c + 1 < kW256Chunks || next != nullptr)
-      cp_async_wait<1>();   // chunk c has landed (one younger group may still be in flight)
-    else
-      cp_async_wait<0>();
-    __syncthreads();
-    const float* wb = wbuf + (c & 1) * kW256ChunkRows * 256 + (kq * 8) * 256 + n;
-    const int k = c * kW256ChunkRows + kq * 8;
-    float w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = wb[j * 256];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 x0 = *reinterpret_cast<const float4*>(xs + i * 256 + k);
-      const float4 x1 = *reinterpret_cast<const float4*>(xs + i * 256 + k + 4);
-      float a = acc[i];
-      a = fmaf(x0.x, w[0], a);
-      a = fmaf(x0.y, w[1], a);
-      a = fmaf(x0.z, w[2], a);
-      a = fmaf(x0.w, w[3], a);
-      a = fmaf(x1.x, w[4], a);
-      a = fmaf(x1.y, w[5], a);
-      a = fmaf(x1.z, w[6], a);
-      a = fmaf(x1.w, w[7], a);
-      acc[i] = a;
-    }
-    __syncthreads();   // everyone is done with buffer c & 1 before it is refilled
-    if (c + 2 < kW256Chunks)
-      stream256_issue(wbuf, wt, c + 2);
-    else if (next != nullptr)
-      stream256_issue(wbuf, next, c + 2 - kW256Chunks);
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // Small fp32 Linear for the head's latency-bound layers (M = 3*frames rows, K = 256, N <= 768):
 // y[m, n] = act( sum_k x[m, k] * Wt[k, n] + b[n] (+ res[m, n]) ).  Weights are stored transposed
 // ([K, N]) so a warp reads 128 contiguous bytes per k; a CTA owns 8 rows x 64 columns and splits
@@ -1183,7 +1117,7 @@ __global__ void __launch_bounds__(1024) linear256_ln_kernel(const LinGroups grp,
 // independent): the activations never leave shared memory, the weights stream from L2.  blockIdx.y = chain.
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxChains = 6;
-constexpr int kChainSmemBytes = (8 * 256 + 4 * 8 * 256 + 2 * 32 * 256) * 4;  // xs + k-slice partial sums + weight chunks = 104 KB
+constexpr int kChainSmemBytes = (8 * 256 + 4 * 8 * 256) * 4;  // xs + k-slice partial sums = 40 KB
 struct ChainArgs {
   const float* x;            // [M, 256] rows with stride ldx
   long long ldx;
@@ -1214,18 +1148,54 @@ __global__ void __launch_bounds__(1024) mlp_chain_kernel(const ChainGroups grp, 
   const int n = tid & 255, kq = tid >> 8;
   const int k0 = kq * 64;
   const int warp = tid >> 5, lane = tid & 31;
-  float* wbuf = ch_smem + kSlRows * 256 + 4 * kSlRows * 256;   // [2][32][256] weight chunks
-  stream256_prefetch(wbuf, a.wt[0]);
+  float w[8];
+  {
+    const float* __restrict__ wt = a.wt[0];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = __ldg(wt + static_cast<long long>(k0 + j) * 256 + n);
+  }
   for (int i = tid; i < kSlRows * 256; i += 1024) {
     const int rr = i >> 8, k = i & 255;
     xs[i] = (m0 + rr < M) ? a.x[(m0 + rr) * a.ldx + k] : 0.f;
   }
   __syncthreads();
   for (int layer = 0; layer < a.n_layers; ++layer) {
+    const float* __restrict__ wt = a.wt[layer];
     float acc[kSlRows];
 #pragma unroll
     for (int i = 0; i < kSlRows; ++i) acc[i] = 0.f;
-    stream256_layer(xs, wbuf, a.wt[layer], layer + 1 < a.n_layers ? a.wt[layer + 1] : nullptr, acc);
+#pragma unroll 1
+    for (int k = k0; k < k0 + 64; k += 8) {
+      float wn[8];
+      if (k + 8 < k0 + 64) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wt + static_cast<long long>(k + 8 + j) * 256 + n);
+      } else if (layer + 1 < a.n_layers) {  // first batch of the next layer's weights
+        const float* __restrict__ wt2 = a.wt[layer + 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wt2 + static_cast<long long>(k0 + j) * 256 + n);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wn[j] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kSlRows; ++i) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xs + i * 256 + k);
+        const float4 x1 = *reinterpret_cast<const float4*>(xs + i * 256 + k + 4);
+        float c = acc[i];
+        c = fmaf(x0.x, w[0], c);
+        c = fmaf(x0.y, w[1], c);
+        c = fmaf(x0.z, w[2], c);
+        c = fmaf(x0.w, w[3], c);
+        c = fmaf(x1.x, w[4], c);
+        c = fmaf(x1.y, w[5], c);
+        c = fmaf(x1.z, w[6], c);
+        c = fmaf(x1.w, w[7], c);
+        acc[i] = c;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = wn[j];
+    }
 #pragma unroll
     for (int i = 0; i < kSlRows; ++i) red[(kq * kSlRows + i) * 256 + n] = acc[i];
     __syncthreads();  // partial sums complete; every thread is done reading xs
