@@ -3,6 +3,7 @@
 dist_params = dict(backend='nccl')
 log_level = 'INFO'
 load_from = None
-# precision of the CUDA engine: 'fp16x3' (parity mode, <=1e-3 rad vs the fp32 reference),
-# 'fp16' (fast mode) or 'simt' (fp32 CUDA cores, bring-up)
-engine = dict(precision='fp16x3', cuda_graph=True)
+# precision of the CUDA engine (read by init_detector): 'fp16c8' (default parity mode: fp16 products + e4m3 correction
+# MMAs, <= 1e-3 rad against the fp32 reference), 'fp16x3' (three fp16 products per MMA, same bar), 'fp16' (fast mode,
+# 1-3e-3 rad) or 'simt' (fp32 CUDA cores, bring-up)
+engine = dict(precision='fp16c8')

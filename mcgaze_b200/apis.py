@@ -10,7 +10,7 @@ from . import detector as _detector  # noqa: F401  (registers the model classes)
 
 
 def init_detector(config: Union[str, Config], checkpoint: Optional[str] = None, device: str = 'cuda:0',
-                  cfg_options: Optional[dict] = None, precision: str = 'fp16c8'):
+                  cfg_options: Optional[dict] = None, precision: Optional[str] = None):
     if isinstance(config, str):
         config = Config.fromfile(config)
     elif not isinstance(config, Config):
@@ -23,7 +23,9 @@ def init_detector(config: Union[str, Config], checkpoint: Optional[str] = None, 
         config.model.backbone.init_cfg = None
     config.model.train_cfg = None
     model_cfg = dict(config.model.to_dict())
-    model_cfg['precision'] = precision
+    # engine precision: the argument, else the config's `engine = dict(precision=...)` (configs/_base_/default_runtime.py),
+    # else the parity mode fp16c8
+    model_cfg['precision'] = precision or (config.get('engine') or {}).get('precision', 'fp16c8')
     model = build_detector(model_cfg, test_cfg=config.get('test_cfg'))
     if checkpoint is not None:
         ckpt = load_checkpoint(model, checkpoint, map_location='cpu',

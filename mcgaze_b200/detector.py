@@ -280,12 +280,19 @@ class MultiClueGaze:
         s = str(device)
         if s.startswith('cpu'):
             raise RuntimeError('mcgaze_b200 has no CPU path; use a cuda device')
-        self.device_index = int(s.split(':')[1]) if ':' in s else 0
-        self._engine = None
+        index = int(s.split(':')[1]) if ':' in s else 0
+        if index != self.device_index:
+            self._engine = None                   # packed weights and workspace live on one device
+        self.device_index = index
         return self
 
-    def cuda(self, device=0):
-        return self.to(f'cuda:{device}')
+    def cuda(self, device=None):
+        """torch.nn.Module.cuda(): the current device unless one is named (tools/test.py:214 calls `model.cuda()` after
+        init_dist has selected the rank's GPU)."""
+        if device is None:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        return self.to(device if isinstance(device, str) and device.startswith('cuda') else f'cuda:{int(device)}')
 
     def eval(self):
         self.training = False

@@ -1,4 +1,7 @@
-"""mmdet.datasets: what the inference tools import (tools/test_gaze360_gaze.py:14-15)."""
+"""mmdet.datasets: what the inference tools import (tools/test_gaze360_gaze.py:14-15, tools/test.py:16-17)."""
+from mcgaze_b200.datasets import (DATASETS, PIPELINES, Gaze360Dataset, build_dataloader,  # noqa: F401
+                                  build_dataset)
+
 from . import pipelines  # noqa: F401
 from .pipelines import Compose  # noqa: F401
 

@@ -78,3 +78,42 @@ class StubBatchPipeline:
         img = torch.from_numpy(np.asarray(frames).astype(np.float32)).permute(0, 3, 1, 2).contiguous()
         metas = [dict(img_shape=(4, 4, 3), scale_factor=np.ones(4, np.float32), filename=f) for f in filenames]
         return dict(img=[img], img_metas=[metas])
+
+
+class StubDetector(StubModel):
+    """StubModel behind the surface tools/test.py:196-217 touches when it builds a detector from `cfg.model`
+    (build_detector kwargs, load_checkpoint, `.cuda()`, `.eval()`, `.CLASSES`) - registered under a stub name by the tests."""
+
+    CLASSES = ('face', 'eyes', 'head')
+
+    def __init__(self, train_cfg=None, test_cfg=None, **model_cfg):
+        super().__init__(cfg=None)
+        self.model_cfg = model_cfg
+        self.device_index = 0
+
+    def state_dict(self):
+        return {}
+
+    def load_state_dict(self, state_dict, strict=False):
+        return self
+
+    def to(self, device):
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    def eval(self):
+        return self
+
+
+def make_anno_with_gt(lengths=LENGTHS, seed=0):
+    """make_anno + one ground-truth gaze per frame (annotation k belongs to video k, tools/calculate_mae_gaze360.py:118-121)."""
+    rng = np.random.default_rng(seed)
+    anno = make_anno(lengths)
+    anno['annotations'] = []
+    for L in lengths:
+        g = rng.normal(size=(L, 3))
+        g /= np.linalg.norm(g, axis=1, keepdims=True)
+        anno['annotations'].append(dict(gaze=g.tolist()))
+    return anno
