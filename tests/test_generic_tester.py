@@ -278,3 +278,41 @@ def test_shims_export_every_mmcv_mmdet_name_the_reference_tools_import(tool, shi
                     importlib.import_module(a.name)
                     seen += 1
     assert seen >= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+def test_gpu_two_ranks_nccl_generic_tester(synthetic_sd, tmp_path):
+    """The distributed branch of tools/test.py (dist_test.sh): init_dist over NCCL, MMDistributedDataParallel(model.cuda()),
+    multi_gpu_test - one process per GPU under torch.distributed.run; the gathered per-clip rows equal a one-GPU run."""
+    cv2 = pytest.importorskip('cv2')
+    from mcgaze_b200.apis import init_detector
+    from mcgaze_b200.pipeline import GpuTestPipeline
+    rng = np.random.default_rng(4)
+    anno = S.make_anno_with_gt([3, 9, 12, 23, 7])
+    for v in anno['videos']:
+        for f in v['file_names']:
+            os.makedirs(tmp_path / 'frames' / os.path.dirname(f), exist_ok=True)
+            assert cv2.imwrite(str(tmp_path / 'frames' / f), rng.integers(0, 256, (120, 100, 3), dtype=np.uint8))
+    json.dump(anno, open(tmp_path / 'test.json', 'w'))
+    torch.save({'state_dict': synthetic_sd, 'meta': {}}, tmp_path / 'ckpt.pth')
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'dist_generic_tester.py'),
+                        str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    outputs = pickle.load(open(tmp_path / 'dist_out.pkl', 'rb'))
+    model = init_detector(CFG, str(tmp_path / 'ckpt.pth'), device='cuda:0')
+    ds = ev.Gaze360ClipDataset(anno, img_prefix=str(tmp_path / 'frames'))
+    pipe_cfg = [dict(t) for t in model.cfg.data.test.pipeline]
+    pipe_cfg[1]['crop_type'] = 'relative'                             # the deterministic crop the ranks used
+    want = ev.single_gpu_test(model, ds, GpuTestPipeline(pipe_cfg, device=0), clips_per_batch=32)
+    assert len(outputs) == len(want) == len(ds)
+    for a, b in zip(outputs, want):                                   # other batches, other GPU: a clip's rows do not change
+        assert np.allclose(np.asarray(a), b, rtol=0, atol=1e-4)
+    res = json.load(open(tmp_path / 'dist_res.json'))
+    assert [len(v['fusion_gazes']) for v in res] == [3, 9, 12, 23, 7]
+    assert 'fusion_mae_360' in r.stdout
