@@ -129,7 +129,11 @@ int mcg_set_graph_mode(mcg_handle h, int on);
  * "fused_stem" (0: im2col -> GEMM -> max-pool chain instead of the fused stem kernel; exposes "stem"),
  * "fuse_downsample" (0: a layer's first bottleneck runs its downsample branch as its own convolution and conv3 adds
  * it as a residual, like mmdet/models/backbones/resnet.py:286-295 literally; default 1: conv3 and the downsample
- * branch are one GEMM over the concatenated K). */
+ * branch are one GEMM over the concatenated K),
+ * "fuse_bottleneck" (0: conv2 and conv3 + identity of layer1 / layer2 bottlenecks as separate launches),
+ * "split_layers" (bit l set: the bottlenecks of layer l+1 run as two chains over the two halves of the frames, on two
+ * streams - the other half's launches fill the idle last wave of a persistent launch; results are bit-identical;
+ * -1: default), "split_min_frames" (smallest batch that is split; -1: default 64). */
 int mcg_set_option(mcg_handle h, const char* key, int value);
 
 /* Stand-alone convolution / GEMM with the fused epilogue, for kernel-level parity tests.

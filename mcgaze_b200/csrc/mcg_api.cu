@@ -138,6 +138,7 @@ struct GazeW {
 
 constexpr int kFcSplit = 14;  // 196 k-blocks -> 14 per slice
 constexpr int kFfnSplit = 4;  // second FFN Linear (K = 2048): 32 k-blocks -> 8 per slice, 24 -> 96 tiles
+constexpr int kDefaultSplitLayers = 0;  // Engine::split_layers_: bit l = layer l+1 runs as two half-batch chains
 
 struct Interm {
   int kind = 0;  // 0 = fp32 dense, 1 = NHWC planes
@@ -197,6 +198,8 @@ class Engine {
         cudaEventDestroy(fork_ev_[i]);
         cudaEventDestroy(join_ev_[i]);
       }
+      cudaEventDestroy(split_fork_ev_);
+      cudaEventDestroy(split_join_ev_);
     }
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
@@ -213,6 +216,8 @@ class Engine {
     else if (k == "fused_stem") { fused_stem_ = v != 0; drop_graph(); }
     else if (k == "fuse_downsample") { fuse_ds_ = v != 0; drop_graph(); }
     else if (k == "fuse_bottleneck") { fuse_bneck_ = v != 0; drop_graph(); }
+    else if (k == "split_layers") { split_layers_ = v < 0 ? default_split_layers() : (v & 0xf); drop_graph(); }
+    else if (k == "split_min_frames") { split_min_frames_ = v < 0 ? default_split_min_frames() : v; drop_graph(); }
     else throw CudaError("check failed: unknown option " + k);
   }
 
@@ -876,6 +881,8 @@ class Engine {
       MCG_CUDA(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming));
       MCG_CUDA(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming));
     }
+    MCG_CUDA(cudaEventCreateWithFlags(&split_fork_ev_, cudaEventDisableTiming));
+    MCG_CUDA(cudaEventCreateWithFlags(&split_join_ev_, cudaEventDisableTiming));
   }
 
   // forget every captured graph and (plans = true) every launch plan, of the current shape and of the stashed ones
@@ -944,7 +951,7 @@ class Engine {
         const bool big = M >= 2 * kBlockM * pair_min && k_split == 1 && ep.out_f32 == nullptr;
         const int pair = (big && ((pair_mode == 1 && geom.kind == 1) || pair_mode == 2)) ? 1 : 0;
         UmmaPlan pl = make_umma_plan(terms, *A, geom, w.w, M, w.N, w.K, ep, num_sms_, 0, k_split, split_stride, pair, A2, geom2);
-        pl.p.reverse = alternate_ ? ((tc_launch_index_ & 1) ^ 1) : 0;   // launch 0 reads what the stem wrote last
+        pl.p.reverse = reverse_override_ >= 0 ? reverse_override_ : (alternate_ ? ((tc_launch_index_ & 1) ^ 1) : 0);   // launch 0 reads what the stem wrote last
         it = plans_.emplace(key, pl).first;
       }
       const bool timed = time_kernels_ && !graph_mode_;
@@ -1038,6 +1045,58 @@ class Engine {
       return;
     }
     gemm(key, &x.pl, nullptr, g, cw.g, y.rows(), ep, st, trunk_terms());
+  }
+
+  // frames [f0, f0 + nf) of an NHWC tensor
+  static Act slice_frames(const Act& a, int f0, int nf) {
+    Act s = a;
+    const size_t off = static_cast<size_t>(f0) * a.H * a.W * a.C;
+    s.NB = nf;
+    s.pl.hi = a.pl.hi + off;
+    if (a.pl.lo) s.pl.lo = a.pl.lo + off;
+    if (a.pl.lo8) s.pl.lo8 = a.pl.lo8 + off;
+    if (a.pl.hi8) s.pl.hi8 = a.pl.hi8 + off;
+    return s;
+  }
+
+  // One bottleneck (resnet.py:263-302) as two independent chains over the two halves of the frames, chain 0 on `s0`, chain 1
+  // on `s1` (see split_layers_).  `chain` numbers the convolutions of a chain for the alternating tile order; -> next number.
+  int block_two_chains(int l, size_t b, const Act& x, cudaStream_t s0, cudaStream_t s1, int chain) {
+    const BlockW& bw = blocks_[l][b];
+    BlkAct& ba = blk_act_[l][b];
+    const std::string k = "l" + std::to_string(l) + "b" + std::to_string(b);
+    const int n0 = x.NB / 2;
+    int c = chain;
+    for (int h = 0; h < 2; ++h) {
+      cudaStream_t s = h ? s1 : s0;
+      const int f0 = h ? n0 : 0, nf = h ? x.NB - n0 : n0;
+      const std::string tag = h ? "#1" : "#0";
+      const Act xs = slice_frames(x, f0, nf), t1 = slice_frames(ba.t1, f0, nf), t2 = slice_frames(ba.t2, f0, nf),
+                out = slice_frames(ba.out, f0, nf);
+      c = chain;
+      auto order = [&]() { reverse_override_ = alternate_ ? ((c++ & 1) ^ 1) : 0; };
+      order();
+      conv(k + "c1" + tag, xs, bw.c1, t1, true, nullptr, RES_NONE, s);
+      order();
+      conv(k + "c2" + tag, t1, bw.c2, t2, true, nullptr, RES_NONE, s);
+      if (bw.has_ds && fuse_ds_) {
+        order();
+        conv(k + "c3ds" + tag, t2, bw.c3ds, out, true, nullptr, RES_NONE, s, &xs, bw.ds.stride);
+      } else {
+        Act ds;
+        const Act* idn = &xs;
+        if (bw.has_ds) {
+          ds = slice_frames(ba.ds, f0, nf);
+          order();
+          conv(k + "ds" + tag, xs, bw.ds, ds, false, nullptr, RES_NONE, s);
+          idn = &ds;
+        }
+        order();
+        conv(k + "c3" + tag, t2, bw.c3, out, true, idn, RES_SAME, s);
+      }
+    }
+    reverse_override_ = -1;
+    return c;
   }
 
   // fused bottleneck tail: y = relu(conv3(relu(conv2(t1))) + x)
@@ -1301,11 +1360,37 @@ class Engine {
     reg_act("pool", pool_out_);
     // ---- layer1..4 (resnet.py:263-302)
     const Act* x = &pool_out_;
+    // two-chain region (split_layers_): per-kernel timing mode keeps everything on one stream
+    const bool may_split = split_layers_ != 0 && NB >= split_min_frames_ && NB >= 2 && trunk_terms() != 0 &&
+                           !(time_kernels_ && !graph_mode_);
+    bool forked = false;
+    int chain = 0;
+    auto join_chains = [&]() {
+      if (!forked) return;
+      MCG_CUDA(cudaEventRecord(split_join_ev_, side_stream_));
+      MCG_CUDA(cudaStreamWaitEvent(st, split_join_ev_, 0));
+      reverse_override_ = -1;
+      forked = false;
+    };
     for (int l = 0; l < 4; ++l) {
       for (size_t b = 0; b < blocks_[l].size(); ++b) {
         const BlockW& bw = blocks_[l][b];
         BlkAct& ba = blk_act_[l][b];
         const std::string k = "l" + std::to_string(l) + "b" + std::to_string(b);
+        if (may_split && ((split_layers_ >> l) & 1) && !fused_tail_used(l, b)) {
+          if (!forked) {
+            ensure_side_stream();
+            MCG_CUDA(cudaEventRecord(split_fork_ev_, st));
+            MCG_CUDA(cudaStreamWaitEvent(side_stream_, split_fork_ev_, 0));
+            forked = true;
+            chain = tc_launch_index_;
+          }
+          chain = block_two_chains(l, b, *x, st, side_stream_, chain);
+          x = &ba.out;
+          reg_act("layer" + std::to_string(l + 1) + "." + std::to_string(b), ba.out);
+          continue;
+        }
+        join_chains();
         conv(k + "c1", *x, bw.c1, ba.t1, true, nullptr, RES_NONE, st);
         if (fused_tail_used(l, b)) {
           // conv2 -> conv3 + identity as one kernel, t2 stays in shared memory (bneck_fused.cuh)
@@ -1331,6 +1416,7 @@ class Engine {
         reg_act("layer" + std::to_string(l + 1) + "." + std::to_string(b), ba.out);
       }
     }
+    join_chains();
     // ---- FPN (fpn.py:151-180): lateral 1x1 (+ top-down nearest-2x add fused), then 3x3
     for (int i = 3; i >= 0; --i) {
       const Act& c = blk_act_[i].back().out;
@@ -1561,6 +1647,22 @@ class Engine {
   bool alternate_ = std::getenv("MCG_TUNE_NO_ALTERNATE") == nullptr;
   int tc_launch_index_ = 0;
   bool fuse_bneck_ = true;  // conv2 -> conv3 + identity of the other bottlenecks of layer1 / layer2 as one kernel (fp16c8)
+  // Layers (bit l = layer l+1) whose bottlenecks run as TWO chains, one per half of the frames, on two streams: with
+  // 172 (layer3) / 86-172 (layer4) tiles for 74 SM pairs a single persistent launch leaves a quarter of the machine idle in
+  // its last wave (ncu: sm__cycles_active min / max = 0.70-0.75 over the SMs); the other half's launches fill it.  Frames
+  // are independent through the trunk and a tile's k order does not depend on the tiling, so the results are bit-identical.
+  // Option "split_layers" / env MCG_TUNE_SPLIT_LAYERS; batches below split_min_frames_ keep one chain.
+  static int default_split_layers() {
+    const char* e = std::getenv("MCG_TUNE_SPLIT_LAYERS");
+    return e ? (std::atoi(e) & 0xf) : kDefaultSplitLayers;
+  }
+  static int default_split_min_frames() {
+    const char* e = std::getenv("MCG_TUNE_SPLIT_MIN_NB");
+    return e ? std::atoi(e) : 64;
+  }
+  int split_layers_ = default_split_layers();
+  int split_min_frames_ = default_split_min_frames();
+  int reverse_override_ = -1;  // >= 0: tile order of the next plan (the two chains alternate on their own)
   StemFusedPlan stem_plan_;
   bool stem_plan_valid_ = false;
   bool keep_stage_interm_ = false;
@@ -1637,6 +1739,7 @@ class Engine {
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t side_stream_ = nullptr;  // forked branch of the head (RoIAlign beside the attention block)
   cudaEvent_t fork_ev_[4] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t split_fork_ev_ = nullptr, split_join_ev_ = nullptr;  // two-chain region of the trunk (split_layers_)
   cudaStream_t cap_stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   struct HostSlot {

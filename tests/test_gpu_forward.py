@@ -417,6 +417,44 @@ def test_k_concatenated_downsample_matches_separate_branch(engines, synthetic_sd
         assert yaw_pitch_err(fused['gaze'][:, 0].cpu(), plain['gaze'][:, 0].cpu()) < 2e-4
 
 
+@pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3'])
+@pytest.mark.parametrize('shape', [(3, 7, 224, 224), (16, 7, 224, 224), (1, 2, 96, 128)], ids=['21_frames_10+11', '112_frames', '2_frames_1+1'])
+def test_two_chain_trunk_is_bit_identical(engines, precision, shape):
+    """Option split_layers: the bottlenecks of layer3 / layer4 as two half-batch chains on two streams (the other half's
+    launches fill the idle last wave of a persistent launch).  Frames are independent through the trunk and an output
+    element's k order does not depend on the tiling: every output and the block outputs are BIT-identical to the one-chain
+    schedule, eager and graph replay, for even and uneven halves and for layer3 only / layer3 + layer4."""
+    B, T, H, W = shape
+    img = torch.cat([O.make_clip(500 + b, T, H, W) for b in range(B)]).cuda()
+    eng = engines(precision)
+    names = ['layer3.0', 'layer3.5', 'layer4.0', 'layer4.2', 'fpn3']
+    try:
+        eng.set_option('split_layers', 0)
+        one = {k: v.clone() for k, v in eng.forward(img, clip_length=T).items()}
+        n_one = eng.last_launch_count
+        ref = {n: eng.intermediate(n).clone() for n in names}
+        eng.set_option('split_min_frames', 2)
+        for layers, extra in ((4, 18), (12, 27)):
+            eng.set_option('split_layers', layers)
+            two = eng.forward(img, clip_length=T)
+            assert eng.last_launch_count == n_one + extra                  # every convolution of the region twice
+            for k in one:
+                assert torch.equal(one[k], two[k]), (layers, k)
+            for n in names:
+                assert torch.equal(ref[n], eng.intermediate(n)), (layers, n)
+        out = {k: torch.empty_like(v) for k, v in one.items()}
+        eng.set_graph_mode(True)
+        for _ in range(3):
+            eng.forward_into(img, T, out)
+        torch.cuda.synchronize()
+        for k in one:
+            assert torch.equal(one[k], out[k]), ('graph', k)
+    finally:
+        eng.set_graph_mode(False)
+        eng.set_option('split_layers', -1)                                 # back to the defaults
+        eng.set_option('split_min_frames', -1)
+
+
 @pytest.mark.parametrize('shape', [(1, 4, 224, 224), (8, 7, 224, 224), (1, 3, 96, 128), (2, 2, 448, 448), (1, 5, 224, 224),
                                    (1, 1, 32, 64)],
                          ids=['T4_224', 'B8_T7_224_pairs', 'T3_96x128', 'B2_T2_448', 'T5_224_ragged_pair_tiles', 'T1_32x64_one_tile'])
