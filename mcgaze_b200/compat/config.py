@@ -141,10 +141,27 @@ class Config:
         return self._cfg_dict.get(key, default)
 
     def __getattr__(self, name):
+        if name.startswith('__') or name in ('_cfg_dict', '_filename'):     # copy / pickle probe blank instances
+            raise AttributeError(name)
         return getattr(self._cfg_dict, name)
 
     def __setattr__(self, name, value):
         self._cfg_dict[name] = _wrap(value)
+
+    def __deepcopy__(self, memo):
+        """tools/analysis_tools/benchmark.py:148 deep-copies the config per repetition (mmcv.Config supports it)."""
+        import copy
+        return Config(copy.deepcopy(_unwrap(self._cfg_dict), memo), filename=self._filename)
+
+    def __copy__(self):
+        return Config(_unwrap(self._cfg_dict), filename=self._filename)
+
+    def __getstate__(self):
+        return (_unwrap(self._cfg_dict), self._filename)
+
+    def __setstate__(self, state):
+        object.__setattr__(self, '_cfg_dict', _wrap(state[0]))
+        object.__setattr__(self, '_filename', state[1])
 
     def __getitem__(self, name):
         return self._cfg_dict[name]

@@ -144,15 +144,21 @@ def build_dataset(cfg, default_args=None):
 
 
 class ClipLoader:
-    """What `build_dataloader` returns: the handle tools/test.py passes to single_gpu_test / multi_gpu_test.  Iterating
-    it yields the decoded clips one by one (dict(video, clip, start, n, overlap, filenames, frames)); the test drivers do
-    not iterate - they hand `dataset` to the batched driver, which overlaps loading with the forward itself."""
+    """What `build_dataloader` returns: the handle tools/test.py passes to single_gpu_test / multi_gpu_test, which hand its
+    `dataset` to the batched driver (loading overlapped with the forward: decode threads, pinned blocks, copy stream).
+
+    Iterating it gives what a loop like tools/analysis_tools/benchmark.py:105-112 expects from an mmdet DataLoader - the
+    keyword arguments of one model call, `model(return_loss=False, rescale=True, **data)`: `img=[Tensor[n, 3, H, W]]` on the
+    device, `img_metas=[[meta] * n]`, already unwrapped (there are no DataContainers to scatter), one clip per item at
+    `samples_per_gpu=1`; with more samples per GPU an item holds several clips of one length and one canvas and carries
+    `clip_length`.  With `dist=True` inside a process group a rank iterates the clips DistributedSampler(shuffle=False)
+    gives it.  Frames are decoded on the host here (the synchronous path; the batched driver has the device decoder)."""
 
     def __init__(self, dataset, samples_per_gpu: int = 1, workers_per_gpu: int = 0, dist: bool = False, shuffle: bool = False):
         if shuffle:
             raise NotImplementedError('shuffle=True is a training-side option')
         self.dataset = dataset
-        self.samples_per_gpu = int(samples_per_gpu)
+        self.samples_per_gpu = max(int(samples_per_gpu), 1)
         self.workers_per_gpu = int(workers_per_gpu)
         self.dist = bool(dist)
         self.batch_size = self.samples_per_gpu
@@ -161,12 +167,30 @@ class ClipLoader:
     def clips_per_batch(self) -> int:
         return max(self.samples_per_gpu, int(os.environ.get('MCG_CLIPS_PER_BATCH', '32')))
 
+    def _indices(self):
+        n = len(self.dataset)
+        if self.dist:
+            import torch.distributed as tdist
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+                return ev.mdist.padded_shard(n, tdist.get_rank(), tdist.get_world_size())
+        return list(range(n))
+
     def __len__(self):
-        return -(-len(self.dataset) // self.samples_per_gpu)
+        return -(-len(self._indices()) // self.samples_per_gpu)
 
     def __iter__(self):
-        for i in range(len(self.dataset)):
-            yield self.dataset[i]
+        import torch
+        ds = self.dataset
+        pipe = ds.make_pipeline(torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        idx = self._indices()
+        batches = [[i] for i in idx] if self.samples_per_gpu == 1 else ev._batches(ds, idx, self.samples_per_gpu)
+        for batch in batches:
+            T, frames, names = ev._load_batch(ds, batch, None)
+            for sub, sub_names, rands, clips in ev._canvas_groups(pipe, frames, names, T):
+                data = pipe.batch(sub, filenames=sub_names) if rands is None else pipe.batch(sub, rands=rands, filenames=sub_names)
+                if len(clips) > 1:
+                    data = dict(data, clip_length=T)
+                yield data
 
 
 def build_dataloader(dataset, samples_per_gpu, workers_per_gpu, num_gpus=1, dist=True, shuffle=True, seed=None,

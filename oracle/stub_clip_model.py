@@ -27,7 +27,7 @@ class StubModel:
         self.cfg = cfg
         self.calls = []
 
-    def __call__(self, return_loss, rescale, format, img, img_metas, clip_length=None):
+    def __call__(self, return_loss=True, rescale=False, format=False, img=None, img_metas=None, clip_length=None):
         assert return_loss is False and rescale is True and format is False
         x = img[0]
         n = x.shape[0]

@@ -152,7 +152,8 @@ def test_test_py_call_sequence_with_stand_ins(golden, shim_path, tmp_path):
                                   dist=False, shuffle=False)
         assert loader.dataset is dataset and len(loader) == len(dataset) and loader.clips_per_batch == 32
         first = next(iter(loader))
-        assert first['n'] == 1 and first['frames'][0].shape == (4, 4, 3)
+        assert first['img'][0].shape == (1, 3, 4, 4) and len(first['img_metas'][0]) == 1         # video 0 has one frame
+        assert dataset[0]['n'] == 1 and dataset[0]['frames'][0].shape == (4, 4, 3)
         model = S.StubDetector()
         torch.save({'state_dict': {}, 'meta': {'CLASSES': ('face', 'eyes', 'head')}}, tmp_path / 'c.pth')
         ckpt = load_checkpoint(model, str(tmp_path / 'c.pth'), map_location='cpu')
@@ -316,3 +317,95 @@ def test_gpu_two_ranks_nccl_generic_tester(synthetic_sd, tmp_path):
     res = json.load(open(tmp_path / 'dist_res.json'))
     assert [len(v['fusion_gazes']) for v in res] == [3, 9, 12, 23, 7]
     assert 'fusion_mae_360' in r.stdout
+
+
+@needs_ref
+def test_reference_benchmark_tool_runs_unmodified(tmp_path):
+    """tools/analysis_tools/benchmark.py (tracing / profiling): deep-copies the config, builds dataset /
+    loader / detector, wraps it in MMDistributedDataParallel and times `model(return_loss=False, rescale=True, **data)`
+    over the loader - one clip per item."""
+    args = _files(tmp_path)
+    cfg_opts = args[args.index('--cfg-options') + 1:]
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, RANK='0', LOCAL_RANK='0', WORLD_SIZE='1', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    r = subprocess.run([sys.executable, WORKER, REF, 'tools/analysis_tools/benchmark.py', CFG, str(tmp_path / 'none.pth'),
+                        '--launcher', 'pytorch', '--max-iter', '12', '--log-interval', '4', '--repeat-num', '2',
+                        '--cfg-options'] + cfg_opts + ['dist_params.backend=gloo'],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.count('Overall fps') == 3 and 'Done image [12 ' in r.stdout
+
+
+def test_loader_iterates_model_ready_clips(golden):
+    """`for data in data_loader: model(return_loss=False, rescale=True, **data)` - the DataLoader protocol of
+    mmdet/apis/test.py:26-34 and tools/analysis_tools/benchmark.py:105-112."""
+    import copy
+    from mcgaze_b200.compat import Config
+    from mcgaze_b200.datasets import Gaze360Dataset, build_dataloader, build_dataset
+    cfg = copy.deepcopy(Config.fromfile(CFG))
+    assert isinstance(cfg, Config) and cfg.filename == CFG
+    saved = (Gaze360Dataset.frame_loader, Gaze360Dataset.pipeline_factory)
+    Gaze360Dataset.frame_loader = staticmethod(S.encode_frame)
+    Gaze360Dataset.pipeline_factory = staticmethod(lambda c: S.StubBatchPipeline())
+    try:
+        ds = build_dataset(dict(cfg.data.test.to_dict(), ann_file=S.make_anno(), img_prefix='frames', test_mode=True))
+        want = ev.single_gpu_test(S.StubModel(), ds, S.StubBatchPipeline(), clips_per_batch=1)
+        # one clip per item, dataset order, no clip_length (the reference's model call takes T from the tensor)
+        model = S.StubModel()
+        loader = build_dataloader(ds, samples_per_gpu=1, workers_per_gpu=0, dist=True, shuffle=False)
+        assert len(loader) == len(ds) == golden['forwards']
+        rows = []
+        for data in loader:
+            assert set(data) == {'img', 'img_metas'} and len(data['img']) == 1 and len(data['img_metas'][0]) == data['img'][0].shape[0]
+            (det, _), gz = model(return_loss=False, rescale=True, **data)
+            det = torch.stack(det)
+            g = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
+            rows.append(torch.cat([det[..., :4].reshape(-1, 12), det[..., 4], g.reshape(-1, 12)], 1).numpy())
+        assert all(np.array_equal(a, b) for a, b in zip(rows, want))
+        # several clips per item: one length per item, clip_length set, every clip exactly once
+        loader = build_dataloader(ds, samples_per_gpu=4, workers_per_gpu=0, dist=False, shuffle=False)
+        seen = 0
+        for data in loader:
+            n = data['img'][0].shape[0]
+            T = data.get('clip_length', n)
+            assert n % T == 0 and n // T <= 4 and (n // T == 1 or 'clip_length' in data)
+            model(return_loss=False, rescale=True, **data)
+            seen += n // T
+        assert seen == len(ds)
+    finally:
+        Gaze360Dataset.frame_loader, Gaze360Dataset.pipeline_factory = saved
+
+
+@pytest.mark.gpu
+def test_gpu_loader_iteration_matches_the_batched_driver(synthetic_sd, tmp_path):
+    """The synchronous loop of tools/analysis_tools/benchmark.py on the real engine: iterating the loader and calling the
+    model per clip gives the rows the batched driver gives (same crop: deterministic `relative` CenterCrop)."""
+    cv2 = pytest.importorskip('cv2')
+    from mcgaze_b200.apis import init_detector
+    from mcgaze_b200.datasets import build_dataloader, build_dataset
+    rng = np.random.default_rng(6)
+    anno = S.make_anno([3, 9])
+    for v in anno['videos']:
+        for f in v['file_names']:
+            os.makedirs(tmp_path / 'frames' / os.path.dirname(f), exist_ok=True)
+            assert cv2.imwrite(str(tmp_path / 'frames' / f), rng.integers(0, 256, (110, 96, 3), dtype=np.uint8))
+    model = init_detector(CFG, None, device='cuda:0')
+    model.load_state_dict(synthetic_sd)
+    pipe_cfg = [dict(t) for t in model.cfg.data.test.pipeline]
+    pipe_cfg[1]['crop_type'] = 'relative'
+    ds = build_dataset(dict(type='Gaze360Dataset', ann_file=anno, img_prefix=str(tmp_path / 'frames'), pipeline=pipe_cfg,
+                            clip_length=7, test_mode=True))
+    want = ev.single_gpu_test(model, ds, ds.make_pipeline(0), clips_per_batch=8)
+    rows = []
+    for data in build_dataloader(ds, samples_per_gpu=1, workers_per_gpu=0, dist=False, shuffle=False):
+        assert data['img'][0].is_cuda
+        (det, _), gz = model(return_loss=False, rescale=True, **data)
+        det = torch.stack(list(det)).float()
+        g = torch.stack([gz['gaze_score'], gz['face_gaze_score'], gz['eyes_gaze_score'], gz['head_gaze_score']], 1)
+        rows.append(torch.cat([det[..., :4].reshape(-1, 12), det[..., 4], g.reshape(-1, 12).float()], 1).cpu().numpy())
+    assert len(rows) == len(want) == 3
+    for a, b in zip(rows, want):
+        assert np.array_equal(a, b)
