@@ -86,6 +86,19 @@ def test_config_sweep_shapes_vs_oracle(engines, synthetic_sd, precision, shape):
     assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
 
 
+def test_long_clip_like_the_demo_vs_oracle(engines, synthetic_sd):
+    """The reference's demo pushes a whole track - up to ~101 frames - through ONE forward as one clip (MCGaze_demo/demo.ipynb
+    cell 4, max_len = 100): the temporal attention is dense over all T frames.  T = 41 against the oracle."""
+    T = 41
+    img = O.make_clip(61, T)
+    ref = O.forward(synthetic_sd, img, clip_length=T)
+    out = engines('fp16c8').forward(img.cuda(), clip_length=T)
+    for i, k in enumerate(KEYS):
+        assert yaw_pitch_err(out['gaze'][:, i].cpu(), ref[k]) < 1e-3, k
+    assert (out['boxes'].cpu() - ref['boxes']).abs().max() < 0.1
+    assert (out['scores'].cpu() - ref['scores']).abs().max() < 1e-3
+
+
 @pytest.mark.parametrize('precision', ['fp16c8', 'fp16x3'])
 def test_batched_clips_and_ragged_meta(engines, synthetic_sd, precision):
     """B=2 clips of T=3 on a non-square padded image with unpadded img_shape and rescale."""
