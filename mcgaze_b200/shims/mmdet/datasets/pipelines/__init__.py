@@ -1,7 +1,8 @@
 """mmdet.datasets.pipelines.Compose for the reference's TEST pipelines (configs/_base_/datasets/gaze360.py:27-36,
 multiclue_gaze_r50_l2cs.py:31-39), as tools/test_gaze360_gaze.py:58,96-105 drives it: one call per frame with
 `dict(img_info=dict(filename=...), img_prefix=...)`, the results of a clip are sorted by `img_metas.data['filename']`,
-collated and scattered.
+collated and scattered - and as MCGaze_demo/demo.ipynb cells 3-4 drive it: `Compose(cfg.data.test.pipeline[1:])` on
+`dict(filename=j, img=<decoded crop>, ...)`, up to ~101 frames of different sizes collated into one clip.
 
 LoadImageFromFile (mmdet/datasets/pipelines/loading.py:58-69) runs on the host (cv2 decode); every later step is
 mcgaze_b200.pipeline.GpuTestPipeline (one mcg_preprocess launch on the decoded uint8 frame).  The output has the
@@ -37,9 +38,16 @@ class Compose:
             data['img'] = img
         elif data.get('img_info'):
             name = ori = data['img_info'].get('filename')
+        else:
+            # a caller that decodes (and crops) itself, like MCGaze_demo/demo.ipynb cell 4: dict(filename=j, ori_filename=...,
+            # img=head_crop, img_shape=..., ori_shape=..., img_fields=['img']) through Compose(pipeline[1:]); Collect copies
+            # these keys into the meta (formatting.py:331-333) and the caller sorts the frames by meta['filename']
+            name, ori = data.get('filename'), data.get('ori_filename')
         res = self.pipeline.batch([data['img']], filenames=[name])
         meta = res['img_metas'][0][0]
         meta['ori_filename'] = ori
+        if 'img_info' not in data and data.get('ori_shape') is not None:
+            meta['ori_shape'] = tuple(data['ori_shape'])
         return dict(img_metas=DataContainer(meta, cpu_only=True), img=DataContainer(res['img'][0][0], stack=True))
 
     def __repr__(self):

@@ -162,3 +162,50 @@ def test_gpu_shims_in_the_reference_scripts_call_sequence(synthetic_sd, tmp_path
     rows = ev.single_gpu_test(model, ds, pipe, clips_per_batch=4)[0]
     assert np.allclose(rows[:, :12].reshape(7, 3, 4), det[..., :4].cpu().numpy(), atol=1e-4)
     assert np.allclose(rows[:, 15:18], det_gazes['gaze_score'].cpu().numpy(), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_demo_notebook_call_sequence(synthetic_sd):
+    """MCGaze_demo/demo.ipynb cells 2-4 on the shims: init_detector with the l2cs config, Compose(pipeline[1:]) on head crops
+    the caller decoded itself (`dict(filename=j, ori_filename=111, img=crop, img_shape=..., ori_shape=..., img_fields=['img'])`,
+    crops of DIFFERENT sizes), sort by meta['filename'], collate(samples_per_gpu=<clip length>), scatter, ONE model call over
+    the whole track - against GpuTestPipeline.batch + the same model on the same crops."""
+    from mcgaze_b200 import shims
+    sys.path.insert(0, shims.PATH)
+    try:
+        from mmcv.parallel import collate, scatter
+        from mmdet.apis import init_detector
+        from mmdet.datasets.pipelines import Compose
+    finally:
+        sys.path.remove(shims.PATH)
+    cfg_path = os.path.join(ROOT, 'configs/multiclue_gaze/multiclue_gaze_r50_l2cs.py')
+    model = init_detector(cfg_path, None, device='cuda:0', cfg_options=None)
+    model.load_state_dict(synthetic_sd)
+    cfg = model.cfg
+    test_pipeline = Compose(cfg.data.test.pipeline[1:])
+    rng = np.random.default_rng(8)
+    sizes = [(90, 90), (96, 88), (90, 90), (101, 97), (84, 90)]
+    crops = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    datas = []
+    for j in reversed(range(len(crops))):                                      # out of order: the sort must restore it
+        c = crops[j]
+        datas.append(test_pipeline(dict(filename=j, ori_filename=111, img=c, img_shape=c.shape, ori_shape=(2 * 45, 2 * 45, 3),
+                                        img_fields=['img'])))
+    datas = sorted(datas, key=lambda x: x['img_metas'].data['filename'])
+    assert [d['img_metas'].data['filename'] for d in datas] == list(range(len(crops)))
+    assert datas[0]['img_metas'].data['ori_filename'] == 111 and datas[0]['img_metas'].data['ori_shape'] == (90, 90, 3)
+    datas = collate(datas, samples_per_gpu=len(crops))
+    datas['img_metas'] = datas['img_metas'].data
+    datas['img'] = datas['img'].data
+    datas = scatter(datas, ['cuda:0'])[0]
+    with torch.no_grad():
+        (det_bboxes, det_labels), det_gazes = model(return_loss=False, rescale=True, format=False, **datas)
+    g = det_gazes['gaze_score']
+    assert g.shape == (len(crops), 3) and len(det_bboxes) == len(crops) and det_bboxes[0].shape == (3, 5)
+    assert torch.allclose(g.norm(dim=1), torch.ones(len(crops), device=g.device), atol=1e-4)
+    # the same crops through the batched pipeline call (no crop step in the l2cs pipeline: nothing random)
+    from mcgaze_b200.pipeline import GpuTestPipeline
+    data = GpuTestPipeline(cfg.data.test.pipeline, device=0).batch(crops, filenames=list(range(len(crops))))
+    assert torch.equal(data['img'][0], datas['img'][0])
+    (det2, _), gz2 = model(return_loss=False, rescale=True, format=False, **data)
+    assert torch.equal(gz2['gaze_score'], g) and all(torch.equal(a, b) for a, b in zip(det2, det_bboxes))
