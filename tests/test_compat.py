@@ -144,3 +144,73 @@ def test_detector_checks_the_checkpoint_against_what_the_engine_consumes(synthet
     m['neck']['norm_cfg'] = dict(type='BN')
     with pytest.raises(NotImplementedError):
         build_detector(m)
+
+
+def test_runner_and_parallel_stand_ins(tmp_path, monkeypatch):
+    """mcgaze_b200/compat/runner.py: what tools/test.py:9-13 imports from mmcv.runner / mmcv.parallel / mmcv (fileio)."""
+    import numpy as np
+    from mcgaze_b200.compat import runner as R
+    assert R.get_dist_info() == (0, 1)
+    with pytest.raises(NotImplementedError):
+        R.init_dist('slurm')
+    monkeypatch.delenv('RANK', raising=False)
+    with pytest.raises(RuntimeError, match='RANK'):
+        R.init_dist('pytorch', backend='gloo')
+    if not torch.cuda.is_available():
+        monkeypatch.setenv('RANK', '0')
+        with pytest.raises(RuntimeError, match='nccl'):
+            R.init_dist('pytorch', backend='nccl')
+    with pytest.raises(NotImplementedError):
+        R.wrap_fp16_model(object())
+
+    class M:
+        CLASSES = ('a',)
+
+        def __init__(self):
+            self.dev, self.evals = None, 0
+
+        def to(self, d):
+            self.dev = d
+            return self
+
+        def eval(self):
+            self.evals += 1
+            return self
+
+        def __call__(self, x, k=1):
+            return x * k
+
+    m = M()
+    assert R.fuse_conv_bn(m) is m
+    w = R.MMDataParallel(m, device_ids=[1])
+    assert w.module is m and m.dev == 'cuda:1' and w(3, k=2) == 6 and w.CLASSES == ('a',) and w.eval() is w and m.evals == 1
+    with pytest.raises(AttributeError):
+        w.nonexistent
+    with pytest.raises(NotImplementedError):
+        R.MMDataParallel(m, device_ids=[0, 1])
+    d = R.MMDistributedDataParallel(m, device_ids=[0], broadcast_buffers=False)
+    assert d.module is m and m.dev == 'cuda:0'
+    R.mkdir_or_exist(str(tmp_path / 'a' / 'b'))
+    R.mkdir_or_exist(str(tmp_path / 'a' / 'b'))
+    obj = dict(x=[np.float32(1.5), np.arange(3)], y='z')
+    R.dump(obj, str(tmp_path / 'a' / 'o.json'))
+    assert R.load(str(tmp_path / 'a' / 'o.json')) == dict(x=[1.5, [0, 1, 2]], y='z')
+    R.dump([np.arange(4, dtype=np.float32)], str(tmp_path / 'a' / 'o.pkl'))
+    assert np.array_equal(R.load(str(tmp_path / 'a' / 'o.pkl'))[0], np.arange(4, dtype=np.float32))
+    assert R.load(str(tmp_path / 'a' / 'o.json')) and isinstance(R.dump(obj, file_format='json'), str)
+    with pytest.raises(TypeError):
+        R.dump(obj, str(tmp_path / 'o.yaml'))
+
+
+def test_config_copies_and_pickles_like_mmcv_config():
+    import copy
+    import pickle
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs/multiclue_gaze/multiclue_gaze_r50_gaze360.py'))
+    c2 = copy.deepcopy(cfg)
+    c2.data.test.test_mode = True
+    assert isinstance(c2, Config) and c2.filename == cfg.filename and 'test_mode' not in cfg.data.test
+    c3 = pickle.loads(pickle.dumps(cfg))
+    assert isinstance(c3, Config) and c3.to_dict() == cfg.to_dict()
+    assert isinstance(copy.copy(cfg), Config)
+    with pytest.raises(AttributeError):
+        cfg.no_such_key
