@@ -132,3 +132,58 @@ def test_two_rank_gloo_gather():
     want = np.array([[i, i * i] for i in range(n)], dtype=np.float32)
     for r in range(2):
         assert np.array_equal(got[r], want)
+
+
+# ---- properties over arbitrary lengths (hypothesis): the slicing of tools/test_gaze360_gaze.py:73-86 and the merge of :129-201
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(L=st.integers(1, 600), clip_len=st.integers(2, 16), stride_frac=st.integers(1, 15))
+def test_plan_covers_every_frame_and_counts_its_own_overlap(L, clip_len, stride_frac):
+    stride = 1 + stride_frac % (clip_len - 1) if clip_len > 2 else 1                     # 1 <= stride < clip_len
+    plan = slicer.plan_clips(L, clip_len, stride)
+    covered = np.zeros(L, dtype=int)
+    end_prev = 0
+    for i, (start, n, overlap) in enumerate(plan):
+        assert 0 <= start and start + n <= L and 1 <= n <= clip_len
+        assert (n == clip_len) or len(plan) == 1                                         # only a short video has a short clip
+        covered[start:start + n] += 1
+        # `overlap` is what the reference's merge treats as already present: the frames before the running end
+        assert overlap == (end_prev - start if i else 0) and 0 <= overlap < n
+        end_prev = max(end_prev, start + n)
+    assert covered.min() >= 1 and end_prev == L
+    if L > clip_len:
+        assert len(plan) == math.ceil((L - clip_len) / stride) + 1 and plan[-1][0] == L - clip_len
+
+
+@settings(max_examples=60, deadline=None)
+@given(L=st.integers(1, 90), seed=st.integers(0, 2 ** 16))
+def test_merge_of_frame_functions_is_the_function(L, seed):
+    """If a clip's output for a frame depends on the frame only (scores all >= 0.5), averaging the overlaps changes nothing:
+    the merged video equals the per-frame values, whatever the length class."""
+    rng = np.random.default_rng(seed)
+    boxes = rng.uniform(1, 100, (L, 3, 4)).astype(np.float32)
+    scores = rng.uniform(0.5, 1.0, (L, 3)).astype(np.float32)
+    gaze = rng.normal(size=(L, 4, 3)).astype(np.float32)
+    plan = slicer.plan_clips(L)
+    m = slicer.merge_video(plan, [boxes[s:s + n] for s, n, _ in plan], [scores[s:s + n] for s, n, _ in plan],
+                           [gaze[s:s + n] for s, n, _ in plan])
+    assert m['det'].shape == (L, 3, 5) and m['gaze'].shape == (L, 4, 3)
+    assert np.allclose(m['det'][..., :4], boxes, rtol=0, atol=1e-5) and np.allclose(m['det'][..., 4], scores, rtol=0, atol=1e-6)
+    assert np.allclose(m['gaze'], gaze, rtol=0, atol=1e-6)
+    rec = slicer.video_record(7, m)
+    assert rec['video_id'] == 7 and len(rec['fusion_gazes']) == L and all(b is not None and len(b) == 4 for b in rec['head_bboxes'])
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(1, 500), world=st.integers(1, 9))
+def test_shards_partition_the_items_and_interleave_restores_them(n, world):
+    parts = [mdist.shard_indices(n, r, world) for r in range(world)]
+    assert sorted(i for p in parts for i in p) == list(range(n))
+    padded = [mdist.padded_shard(n, r, world) for r in range(world)]
+    per = -(-n // world)
+    assert all(len(p) == per for p in padded) and all(p[:len(q)] == q for p, q in zip(padded, parts))
+    data = [np.asarray(p, dtype=np.float32)[:, None] * 2.0 for p in padded]            # item i carries 2 i
+    assert np.array_equal(mdist.interleave(data, n)[:, 0], 2.0 * np.arange(n, dtype=np.float32))
